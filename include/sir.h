@@ -1,0 +1,119 @@
+/*
+ * sir.h -- C ABI of libsir.so, the B200 (sm_100a) matching hot path of
+ * shoeprint-image-retrieval:  feature maps -> probe x gallery normalised cross-correlation
+ * (max over offsets, rotations, scales) -> rank / top-k.
+ *
+ * The reference has no FFI layer: its boundary is the Python API of
+ * src/shoeprint_image_retrieval/{similarity,network,parse_results}.py.  The
+ * Python modules of this repository keep that API and reach the GPU only through the entry
+ * points below (ctypes; see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SIR_E_* code otherwise; the message is
+ *     available from sir_last_error() (thread local);
+ *   - pointers named d_* are DEVICE pointers owned by the caller (PyTorch tensors in this
+ *     repository); h_* are host pointers; nothing is allocated or freed behind the caller's back
+ *     except small per-call index tables, released before the call returns (stream ordered);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised;
+ *   - feature maps are float32, row major [count][C][h][w]; a call handles maps of ONE shape,
+ *     the host groups ragged inputs by shape (dataloader.py never pads);
+ *   - "cropped" means the reference's [:, 2:-2, 2:-2] (similarity.py:92-93): Hp = hg-4 etc.
+ */
+#ifndef SIR_H_
+#define SIR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIR_OK 0
+#define SIR_E_ARG (-1)     /* invalid argument / unsupported shape */
+#define SIR_E_CUDA (-2)    /* CUDA runtime or driver error */
+#define SIR_E_DEVICE (-3)  /* not an sm_100 device */
+
+/* precision modes of sir_ncc_scores */
+#define SIR_PREC_FP16X3 0  /* tcgen05, fp16 hi/lo split operands, 3 MMAs per K step (parity grade, default) */
+#define SIR_PREC_FP16X1 1  /* tcgen05, fp16 operands, 1 MMA per K step (fast; ~1e-4 relative worst case) */
+#define SIR_PREC_FP32_SIMT 2 /* CUDA cores, fp32 FMA (exact-order independent check path) */
+
+const char* sir_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int sir_abi_version(void);
+/* SM count / compute capability of the current device; SIR_E_DEVICE when it is not sm_100. */
+int sir_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ gallery side (K5 + K6)
+ * Replaces, for the gallery operand, similarity.py:92 (crop), :49 (zero mean) and prepares the
+ * operands of :53-55 (numerator) and :57-65 (window energy).
+ *
+ * d_gallery [G][C][hg][wg] f32  ->  d_ghi, d_glo [G][C][Hp][Wp] f16: (g - mean) * 2^e split as
+ * hi = f16(x), lo = f16(x - hi);  d_gexp [G][C] int32: the exponent e (chosen so the channel's
+ * max |value| lands in [2^9, 2^10), exact power of two so nothing is rounded by the scaling);
+ * d_gz [G][C][Hp][Wp] f32 or NULL: the zero-meaned, UNscaled map (operand of the SIMT path). */
+int sir_gallery_pack(const float* d_gallery, int G, int C, int hg, int wg,
+                     uint16_t* d_ghi, uint16_t* d_glo, int32_t* d_gexp, float* d_gz, void* stream);
+
+/* Window inverse norm for one template shape (Hm x Wm, cropped size), similarity.py:57-65,68:
+ * d_rnorm [G][C][Hp*Wp] f32 = 1/sqrt(D) of the SCALED map (hi+lo), 0 where D <= 0, with
+ * D = S2 - S1^2/(Hm*Wm) over the zero padded window anchored at (Hm/2, Wm/2), sums in float64.
+ * If d_gz != NULL the unscaled map is used instead (for the SIMT path) and d_ghi/d_glo ignored. */
+int sir_gallery_window_rnorm(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_gz,
+                             int G, int C, int Hp, int Wp, int Hm, int Wm, float* d_rnorm, void* stream);
+
+/* ------------------------------------------------------------------ probe side (K4 + K5)
+ * Variant generation, similarity.py:262-276 (Pillow rotate nearest / resize bicubic on mode "F").
+ * d_in [N][C][h][w] f32 -> d_out [N][C][h2][w2] f32.
+ * rotate: angle in degrees (counter clockwise), same size, zero fill, 16.16 fixed point walk.
+ * resize: bicubic a=-0.5, horizontal pass first, double accumulation; d_tmp [N][C][h][w2] f32
+ * scratch (may be NULL when w2 == w or h2 == h). */
+int sir_variant_rotate(const float* d_in, int N, int C, int h, int w, double angle, float* d_out, void* stream);
+int sir_variant_resize(const float* d_in, int N, int C, int h, int w, int h2, int w2,
+                       float* d_out, float* d_tmp, void* stream);
+
+/* K-padded length of a packed template of cropped shape Hm x Wm: taps are ordered row by row,
+ * each row padded to a multiple of 8 taps, the total to a multiple of 32 (one TMA box). */
+int sir_template_kpad(int Hm, int Wm);
+
+/* Template operand, similarity.py:92 (crop), :48 (zero mean), :67 (energy E):
+ * d_maps [N][C][h][w] f32 (Hm = h-4, Wm = w-4) -> column col0+n of
+ * d_thi, d_tlo [C][ncols_alloc][Kpad] f16 = (t - mean)/sqrt(E) * 2^10 split hi/lo in the padded
+ * tap order above (all zero when E == 0: the reference maps the resulting non-finite NCC to 0,
+ * similarity.py:70), and d_t32 [C][ncols_alloc][Hm*Wm] f32 or NULL = (t - mean)/sqrt(E). */
+int sir_template_pack(const float* d_maps, int N, int C, int h, int w, int col0, int ncols_alloc,
+                      uint16_t* d_thi, uint16_t* d_tlo, float* d_t32, void* stream);
+
+/* ------------------------------------------------------------------ correlation (K7)
+ * Replaces the Q*G*V calls of get_similarity (similarity.py:75-108, 357-367) for one template
+ * shape: for every gallery g and packed column n,
+ *     s = (1/C) max_{y,x} sum_c rnorm[g][c][y,x] * sum_{u,v} t_n,c[u,v] g_c[y+u-Hm/2, x+v-Wm/2]
+ * and d_scores[col2probe[n] * score_ld + g0 + g] = max(old, s)  (float32, callers zero it first:
+ * the reference floors at 0, similarity.py:355).  The correlation surface never leaves the SM.
+ * Workspace: none.  precision: SIR_PREC_*. */
+int sir_ncc_scores(const uint16_t* d_ghi, const uint16_t* d_glo, const int32_t* d_gexp, const float* d_gz,
+                   const float* d_rnorm, int G, int C, int Hp, int Wp,
+                   const uint16_t* d_thi, const uint16_t* d_tlo, const float* d_t32,
+                   int ncols, int ncols_alloc, int Hm, int Wm,
+                   const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
+                   int precision, void* stream);
+
+/* ------------------------------------------------------------------ ranking (K8, K9)
+ * _get_rank (similarity.py:378-386) without the sort: d_true_score[q] is scores[q][true] on the
+ * shard that owns it (else -inf; merged across shards by the caller with a max all-reduce),
+ * d_count_gt[q] = #{g : scores[q][g] > true_score[q]}, d_count_ge likewise with >= (tie window,
+ * excludes nothing), and the k best (score, global index = g0 + g) per probe, descending,
+ * ties by lower index.  rank = 1 + sum over shards of count_gt. */
+int sir_true_scores(const float* d_scores, int Q, int G, int score_ld, const int32_t* d_true_idx, int g0,
+                    float* d_true_score, void* stream);
+int sir_rank_topk(const float* d_scores, int Q, int G, int score_ld, const float* d_true_score, int g0, int k,
+                  int32_t* d_count_gt, int32_t* d_count_ge, float* d_topk_val, int32_t* d_topk_idx, void* stream);
+/* Merge P shards' [Q][k] lists (as gathered by ncclAllGather: [P][Q][k]) into the global k best. */
+int sir_merge_topk(const float* d_vals, const int32_t* d_idx, int P, int Q, int k,
+                   float* d_out_val, int32_t* d_out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIR_H_ */

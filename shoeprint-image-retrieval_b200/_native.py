@@ -1,0 +1,72 @@
+"""ctypes binding of ``libsir.so`` (C ABI in ``include/sir.h``).
+
+There is no CPU fallback: importing this module without the built library raises, and every
+entry point raises ``SirError`` with the library's message on a non-zero return code.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libsir.so"
+
+PREC_FP16X3 = 0
+PREC_FP16X1 = 1
+PREC_FP32_SIMT = 2
+PRECISIONS = {"fp16x3": PREC_FP16X3, "fp16x1": PREC_FP16X1, "fp32_simt": PREC_FP32_SIMT}
+
+_p = C.c_void_p
+_i = C.c_int
+
+# name -> (restype, argtypes); mirrors include/sir.h one to one
+SIGNATURES = {
+    "sir_last_error": (C.c_char_p, []),
+    "sir_abi_version": (_i, []),
+    "sir_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "sir_gallery_pack": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "sir_gallery_window_rnorm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "sir_variant_rotate": (_i, [_p, _i, _i, _i, _i, C.c_double, _p, _p]),
+    "sir_variant_resize": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "sir_template_kpad": (_i, [_i, _i]),
+    "sir_template_pack": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "sir_ncc_scores": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+    "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
+    "sir_rank_topk": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "sir_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+}
+
+
+class SirError(RuntimeError):
+    """A libsir entry point returned a non-zero code."""
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        msg = (
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for the matching path."
+        )
+        raise ImportError(msg)
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.sir_last_error().decode(errors="replace")
+        raise SirError(f"{what or 'libsir'} failed ({rc}): {msg}")
+
+
+def device_info() -> tuple[int, int, int]:
+    sm, major, minor = _i(), _i(), _i()
+    check(lib.sir_device_info(C.byref(sm), C.byref(major), C.byref(minor)), "sir_device_info")
+    return sm.value, major.value, minor.value

@@ -1,0 +1,40 @@
+// sir_ncc_scores: precision-mode dispatch for the correlation stage (K7).
+#include "sir_common.cuh"
+
+namespace sir {
+int launch_ncc_simt(const float* d_gz, const float* d_rnorm, int G, int C, int Hp, int Wp, const float* d_t32, int ncols,
+                    int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
+                    cudaStream_t st);
+int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, int G, int C, int Hp, int Wp,
+                  const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hm, int Wm,
+                  const int32_t* d_col2probe, float* d_scores, int score_ld, int g0, int passes, cudaStream_t st);
+}  // namespace sir
+
+using namespace sir;
+
+extern "C" int sir_ncc_scores(const uint16_t* d_ghi, const uint16_t* d_glo, const int32_t* d_gexp, const float* d_gz,
+                              const float* d_rnorm, int G, int C, int Hp, int Wp, const uint16_t* d_thi,
+                              const uint16_t* d_tlo, const float* d_t32, int ncols, int ncols_alloc, int Hm, int Wm,
+                              const int32_t* d_col2probe, float* d_scores, int score_ld, int g0, int precision,
+                              void* stream) {
+  (void)d_gexp;
+  SIR_CHECK_ARG(d_rnorm && d_col2probe && d_scores, "sir_ncc_scores: null pointer");
+  SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0, "sir_ncc_scores: empty gallery");
+  SIR_CHECK_ARG(Hm > 0 && Wm > 0 && ncols > 0 && ncols <= ncols_alloc, "sir_ncc_scores: bad template block");
+  SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_scores: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (precision) {
+    case SIR_PREC_FP16X3:
+      return launch_ncc_tc(d_ghi, d_glo, d_rnorm, G, C, Hp, Wp, d_thi, d_tlo, ncols, ncols_alloc, Hm, Wm, d_col2probe,
+                           d_scores, score_ld, g0, 3, st);
+    case SIR_PREC_FP16X1:
+      return launch_ncc_tc(d_ghi, d_glo, d_rnorm, G, C, Hp, Wp, d_thi, d_tlo, ncols, ncols_alloc, Hm, Wm, d_col2probe,
+                           d_scores, score_ld, g0, 1, st);
+    case SIR_PREC_FP32_SIMT:
+      return launch_ncc_simt(d_gz, d_rnorm, G, C, Hp, Wp, d_t32, ncols, ncols_alloc, Hm, Wm, d_col2probe, d_scores,
+                             score_ld, g0, st);
+    default:
+      set_error("sir_ncc_scores: unknown precision mode %d", precision);
+      return SIR_E_ARG;
+  }
+}

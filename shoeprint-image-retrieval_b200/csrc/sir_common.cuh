@@ -1,0 +1,94 @@
+// Shared helpers for libsir (sm_100a only).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "sir.h"
+
+namespace sir {
+
+void set_error(const char* fmt, ...);
+
+#define SIR_CHECK_ARG(cond, ...)        \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::sir::set_error(__VA_ARGS__);    \
+      return SIR_E_ARG;                 \
+    }                                   \
+  } while (0)
+
+#define SIR_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      ::sir::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SIR_E_CUDA;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+#define SIR_LAUNCH_CHECK(name)                                                              \
+  do {                                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess) {                                                               \
+      ::sir::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));           \
+      return SIR_E_CUDA;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+constexpr int kEdge = 2;           // similarity.py:92-93 crop
+constexpr int kTemplateScaleLog2 = 10;  // packed templates are (t-mean)/sqrt(E) * 2^10
+constexpr int kGalleryPeakLog2 = 10;    // packed gallery channels have max|v| in [2^9, 2^10)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// Number of 8-tap chunks per template row and padded K (multiple of 32) -- see sir_template_kpad.
+__host__ __device__ inline int tpl_chunks_per_row(int Wm) { return ceil_div(Wm, 8); }
+__host__ __device__ inline int tpl_kpad(int Hm, int Wm) { return round_up(Hm * tpl_chunks_per_row(Wm) * 8, 32); }
+
+// warp / block reductions ---------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of doubles; `scratch` must hold 32 doubles. All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += scratch[i];  // same order in every thread
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float r = scratch[0];
+  for (int i = 1; i < nw; ++i) r = fmaxf(r, scratch[i]);
+  return r;
+}
+
+// Non-negative floats order like their bit patterns: max with a plain integer atomic.
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+  if (v > 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+}  // namespace sir

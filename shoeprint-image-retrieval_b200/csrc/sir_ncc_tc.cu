@@ -1,0 +1,461 @@
+// K7: probe x gallery normalised cross-correlation on tcgen05 tensor cores (sm_100a).
+//
+// For one template shape (Hm x Wm) the reference's Q*G*V get_similarity calls
+// (similarity.py:75-108, 357-367) become, per channel c, the contraction
+//
+//     num_c[(g,y,x), n] = sum_{u,v} G_c[g][y+u-a][x+v-b] * T_c[n][u][v]        (similarity.py:53-55)
+//
+// with M = gallery positions, N = packed probe variants (columns), K = template taps.  The per
+// channel, per position normalisation 1/sqrt(D_c[y,x]) (similarity.py:57-68; 1/sqrt(E) is already
+// folded into T) is a ROW scale of the accumulator, so channels are separate K segments: the MMA
+// warp accumulates one channel into TMEM, the epilogue warps fold it into a register-resident
+// running sum  total += rnorm_c[row] * acc  while the next channel is being multiplied into the
+// other TMEM buffer.  After the last channel the epilogue takes the max over the tile's valid
+// positions and atomically maxes it into scores[probe][gallery]: the correlation surface never
+// reaches HBM, and neither does an im2col matrix.
+//
+// Operand A (gallery, Toeplitz): the im2col matrix A[(y,x),(u,v)] = g[y+u-a][x+v-b] is never
+// materialised.  Generator warps expand the compact fp16 channel into "shifted entries"
+//     E[r][i] = 8 consecutive cells g[row r][col i .. i+7]      (16 bytes each, zero filled)
+// and a NO-SWIZZLE K-major UMMA descriptor with  SBO = one E row,  LBO = 8 entries  addresses
+// them so that descriptor row (ml, mh) and K chunk (u, ch) land on entry (mh+u, ml+8ch): core
+// matrices overlap in shared memory (8x replication instead of Hm*Wm x), which the tensor core
+// does not mind because it only reads.  A tile's 128 rows are a 16 (y) x 8 (x) patch of positions.
+//
+// Operand B (templates): dense [column][K] fp16, streamed by TMA (64B swizzle, 32 taps per stage)
+// through a ring of shared-memory stages.
+//
+// Precision: fp16 operands carry an 11-bit significand; the 1e-4 relative score tolerance needs
+// more, so operands are split hi + lo and each K step issues three MMAs (hi*hi, lo*hi, hi*lo)
+// into the same fp32 accumulator (SIR_PREC_FP16X3).  SIR_PREC_FP16X1 issues only hi*hi.
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent over work units = (column tile, gallery, patch)):
+//   warp 0      TMA producer for B
+//   warp 1      TMEM owner + MMA issuer (one elected lane)
+//   warps 2-3   generators: stage the channel rows, build E, fence.proxy.async, signal
+//   warps 4-11  epilogue: tcgen05.ld, row-scale FMA into 128 registers/thread, final max
+#include <cuda.h>
+
+#include "sir_common.cuh"
+#include "sir_ptx.cuh"
+
+namespace sir {
+
+constexpr int kTcThreads = 384;
+constexpr int kTileM = 128;      // 16 x 8 positions
+constexpr int kTileN = 256;      // packed columns per tile
+constexpr int kStageK = 32;      // taps per B stage (64 bytes: one 64B-swizzle row)
+constexpr int kGenThreads = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kMaxBStages = 6;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kBHalfBytes = kTileN * kStageK * 2;  // 16 KB
+
+struct TcParams {
+  const __half* ghi;
+  const __half* glo;
+  const float* rnorm;
+  const int32_t* col2probe;
+  float* scores;
+  int score_ld, g0;
+  int G, C, Hp, Wp, Hm, Wm;
+  int ncols;
+  int nkc;         // 8-tap chunks per template row
+  int nsteps;      // K16 steps per channel = ceil(Hm*nkc/2)
+  int nkstages;    // B stages per channel = Kpad/32
+  int npy, npx;    // 16x8 patches over the gallery position grid
+  int ntiles_n;
+  long long nunits;
+  int seg_stages;  // B stages per E segment
+  int nseg;
+  int nbstages;    // B ring depth
+  int passes;      // 3 (hi/lo split) or 1
+  float out_scale; // 1 / (C * 2^kTemplateScaleLog2)
+  // shared memory carve-up (byte offsets from the 1024-aligned base)
+  uint32_t off_b, off_e, off_gs, off_cm, off_bar;
+  uint32_t e_half_bytes;   // one E buffer, one half (hi or lo)
+  uint32_t gs_half_elems;  // staging elements per half
+};
+
+struct Seg {
+  int st0, st1;   // B stage range
+  int u_first;    // first template row touched
+  int rows;       // E rows to build
+};
+
+__device__ __forceinline__ Seg seg_geometry(const TcParams& p, int sg) {
+  Seg s;
+  s.st0 = sg * p.seg_stages;
+  s.st1 = min(s.st0 + p.seg_stages, p.nkstages);
+  const int t_first = 4 * s.st0;
+  const int t_last = min(4 * s.st1, 2 * p.nsteps) - 1;
+  s.u_first = t_first / p.nkc;
+  s.rows = 16 + (t_last / p.nkc - s.u_first);
+  return s;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = kBHalfBytes * (p.passes == 3 ? 2 : 1);
+  const uint32_t bar0 = base + p.off_bar;
+  auto bar_full = [&](int i) { return bar0 + 8u * i; };
+  auto bar_empty = [&](int i) { return bar0 + 8u * (kMaxBStages + i); };
+  auto bar_efull = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + i); };
+  auto bar_eempty = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + 2 + i); };
+  auto bar_accfull = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + 4 + i); };
+  auto bar_accempty = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + 6 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + p.off_bar + 8u * (2 * kMaxBStages + 8));
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nbstages; ++i) {
+      ptx::mbar_init(bar_full(i), 1);
+      ptx::mbar_init(bar_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_efull(i), kGenThreads);
+      ptx::mbar_init(bar_eempty(i), 1);
+      ptx::mbar_init(bar_accfull(i), 1);
+      ptx::mbar_init(bar_accempty(i), kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tm_hi);
+    ptx::prefetch_tmap(&tm_lo);
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int NP = p.npy * p.npx;
+  const long long per_tile = (long long)p.G * NP;
+  const int Pe = 8 * p.nkc;  // entries per E row
+  const int a = p.Hm / 2, b = p.Wm / 2;
+  const int M = p.Hp * p.Wp;
+
+  // register budget: 168/thread at launch -> 88 for the producer warpgroup, 208 for the epilogue
+  if (warp < 4) {
+  ptx::setmaxnreg_dec<88>();
+  if (warp == 0) {
+    // ================================================================== TMA producer (B ring)
+    if (ptx::elect_one()) {
+      uint32_t bs = 0;
+      for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+        const int nt = (int)(unit / per_tile);
+        for (int c = 0; c < p.C; ++c) {
+          for (int st = 0; st < p.nkstages; ++st, ++bs) {
+            const int slot = bs % p.nbstages;
+            const uint32_t par = (bs / p.nbstages) & 1;
+            ptx::mbar_wait(bar_empty(slot), par ^ 1);
+            ptx::mbar_arrive_expect_tx(bar_full(slot), stage_bytes);
+            const uint32_t dst = base + p.off_b + slot * stage_bytes;
+            ptx::tma_load_3d(dst, &tm_hi, bar_full(slot), st * kStageK, nt * kTileN, c);
+            if (p.passes == 3) ptx::tma_load_3d(dst + kBHalfBytes, &tm_lo, bar_full(slot), st * kStageK, nt * kTileN, c);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kTileN);
+      uint32_t bs = 0, es = 0, cs = 0;
+      for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+        for (int c = 0; c < p.C; ++c, ++cs) {
+          const int buf = cs & 1;
+          ptx::mbar_wait(bar_accempty(buf), ((cs >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * kTileN;
+          uint32_t accumulate = 0;
+          for (int sg = 0; sg < p.nseg; ++sg, ++es) {
+            const Seg s = seg_geometry(p, sg);
+            const int ebuf = es & 1;
+            ptx::mbar_wait(bar_efull(ebuf), (es >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t e_hi = base + p.off_e + ebuf * 2 * p.e_half_bytes;
+            const uint32_t e_lo = e_hi + p.e_half_bytes;
+            const uint32_t e_shift = 16u * s.u_first * Pe;  // bytes of E rows before this segment
+            for (int st = s.st0; st < s.st1; ++st, ++bs) {
+              const int slot = bs % p.nbstages;
+              ptx::mbar_wait(bar_full(slot), (bs / p.nbstages) & 1);
+              ptx::tc_fence_after();
+              const uint32_t b_hi = base + p.off_b + slot * stage_bytes;
+              const uint32_t b_lo = b_hi + kBHalfBytes;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const int ks = 2 * st + kk;
+                if (ks < p.nsteps) {
+                  // A: no swizzle, rows of a core matrix 16 B apart (consecutive entries = consecutive x),
+                  // 8-row groups one E row apart (consecutive y), the two K chunks 8 entries apart.
+                  const uint32_t a_off = 256u * ks - e_shift;
+                  const uint64_t da_hi = ptx::make_smem_desc(e_hi + a_off, 128, 16u * Pe, 0);
+                  // B: 64B swizzle, 8-row groups 512 B apart; K16 sub-step = +32 B inside the swizzle row.
+                  const uint64_t db_hi = ptx::make_smem_desc(b_hi + 32u * kk, 16, 512, 4);
+                  ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
+                  accumulate = 1;
+                  if (p.passes == 3) {
+                    const uint64_t da_lo = ptx::make_smem_desc(e_lo + a_off, 128, 16u * Pe, 0);
+                    const uint64_t db_lo = ptx::make_smem_desc(b_lo + 32u * kk, 16, 512, 4);
+                    ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, 1);
+                    ptx::mma_f16_ss(tmem_d, da_hi, db_lo, idesc, 1);
+                  }
+                }
+              }
+              ptx::tc_commit(bar_empty(slot));
+            }
+            ptx::tc_commit(bar_eempty(ebuf));
+          }
+          ptx::tc_commit(bar_accfull(buf));
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================================================== generators (E buffers)
+    const int tg = threadIdx.x - 64;
+    __half* gs_hi = reinterpret_cast<__half*>(base_ptr + p.off_gs);
+    __half* gs_lo = gs_hi + p.gs_half_elems;
+    uint32_t es = 0;
+    for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+      const long long rem = unit % per_tile;
+      const int g = (int)(rem / NP), pidx = (int)(rem % NP);
+      const int py = pidx / p.npx, px = pidx % p.npx;
+      for (int c = 0; c < p.C; ++c) {
+        const size_t gc_off = ((size_t)g * p.C + c) * M;
+        for (int sg = 0; sg < p.nseg; ++sg, ++es) {
+          const Seg s = seg_geometry(p, sg);
+          const int ebuf = es & 1;
+          ptx::mbar_wait(bar_eempty(ebuf), ((es >> 1) & 1) ^ 1);
+          // 1. stage the gallery rows this segment can touch (zeros outside the map)
+          const int y_base = 16 * py + s.u_first - a;
+          for (int i = tg; i < s.rows * p.Wp; i += kGenThreads) {
+            const int r = i / p.Wp, x = i - r * p.Wp, y = y_base + r;
+            __half vh = __ushort_as_half(0), vl = __ushort_as_half(0);
+            if (y >= 0 && y < p.Hp) {
+              vh = p.ghi[gc_off + (size_t)y * p.Wp + x];
+              if (p.passes == 3) vl = p.glo[gc_off + (size_t)y * p.Wp + x];
+            }
+            gs_hi[i] = vh;
+            gs_lo[i] = vl;
+          }
+          ptx::named_bar_sync(1, kGenThreads);
+          // 2. shifted entries: E[r][i] = 8 cells starting at column x_base + i
+          const int x_base = 8 * px - b;
+          uint8_t* e_hi = base_ptr + p.off_e + ebuf * 2 * p.e_half_bytes;
+          uint8_t* e_lo = e_hi + p.e_half_bytes;
+          for (int e = tg; e < s.rows * Pe; e += kGenThreads) {
+            const int r = e / Pe, i = e - r * Pe;
+            const __half* rh = gs_hi + r * p.Wp;
+            const __half* rl = gs_lo + r * p.Wp;
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int x0 = x_base + i + 2 * j, x1 = x0 + 1;
+              const uint16_t h0 = (x0 >= 0 && x0 < p.Wp) ? __half_as_ushort(rh[x0]) : (uint16_t)0;
+              const uint16_t h1 = (x1 >= 0 && x1 < p.Wp) ? __half_as_ushort(rh[x1]) : (uint16_t)0;
+              wh[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              if (p.passes == 3) {
+                const uint16_t l0 = (x0 >= 0 && x0 < p.Wp) ? __half_as_ushort(rl[x0]) : (uint16_t)0;
+                const uint16_t l1 = (x1 >= 0 && x1 < p.Wp) ? __half_as_ushort(rl[x1]) : (uint16_t)0;
+                wl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+              }
+            }
+            *reinterpret_cast<uint4*>(e_hi + 16u * e) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            if (p.passes == 3) *reinterpret_cast<uint4*>(e_lo + 16u * e) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+          }
+          ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async reads
+          ptx::mbar_arrive(bar_efull(ebuf));
+          ptx::named_bar_sync(1, kGenThreads);  // staging area is reused by the next segment
+        }
+      }
+    }
+  }
+  } else {
+    // ================================================================== epilogue (8 warps)
+    ptx::setmaxnreg_inc<208>();
+    const int ew = warp - 4;
+    const int q4 = warp & 3;        // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;       // which 128 of the 256 columns
+    const int m = q4 * 32 + lane;   // tile row = TMEM lane
+    const int ml = m & 7, mh = m >> 3;
+    float* colmax = reinterpret_cast<float*>(base_ptr + p.off_cm);  // [4][256]
+    uint32_t cs = 0;
+    for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+      const int nt = (int)(unit / per_tile);
+      const long long rem = unit % per_tile;
+      const int g = (int)(rem / NP), pidx = (int)(rem % NP);
+      const int py = pidx / p.npx, px = pidx % p.npx;
+      const int y = 16 * py + mh, x = 8 * px + ml;
+      const bool valid = (y < p.Hp) && (x < p.Wp);
+      const float* rrow = p.rnorm + (size_t)g * p.C * M + (valid ? y * p.Wp + x : 0);
+
+      float total[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) total[j] = 0.0f;
+      float r_cur = valid ? __ldg(rrow) : 0.0f;
+      for (int c = 0; c < p.C; ++c, ++cs) {
+        const float r_next = (valid && c + 1 < p.C) ? __ldg(rrow + (size_t)(c + 1) * M) : 0.0f;
+        const int buf = cs & 1;
+        ptx::mbar_wait(bar_accfull(buf), (cs >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * kTileN + half * 128;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + j4 * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) total[j4 * 32 + j] = fmaf(r_cur, __uint_as_float(v[j]), total[j4 * 32 + j]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_accempty(buf));
+        r_cur = r_next;
+      }
+      // max over the tile's valid positions, then over the 4 lane quarters, then into scores
+#pragma unroll
+      for (int j = 0; j < 128; ++j) {
+        const float v = warp_max(valid ? total[j] : -INFINITY);
+        if (lane == 0) colmax[q4 * kTileN + half * 128 + j] = v;
+      }
+      ptx::named_bar_sync(2, kEpiWarps * 32);
+      {
+        const int col = ew * 32 + lane;
+        const float v = fmaxf(fmaxf(colmax[col], colmax[kTileN + col]), fmaxf(colmax[2 * kTileN + col], colmax[3 * kTileN + col]));
+        const int n = nt * kTileN + col;
+        if (n < p.ncols) atomic_max_nonneg(&p.scores[(size_t)p.col2probe[n] * p.score_ld + p.g0 + g], v * p.out_scale);
+      }
+      ptx::named_bar_sync(2, kEpiWarps * 32);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------ host
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_alloc, int C) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SIR_E_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)ncols_alloc, (cuuint64_t)C};
+  cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Kpad * 2 * (cuuint64_t)ncols_alloc};
+  cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)kTileN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (Kpad=%d ncols=%d C=%d)", (int)r, Kpad, ncols_alloc, C);
+    return SIR_E_CUDA;
+  }
+  return SIR_OK;
+}
+}  // namespace
+
+int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, int G, int C, int Hp, int Wp,
+                  const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hm, int Wm,
+                  const int32_t* d_col2probe, float* d_scores, int score_ld, int g0, int passes, cudaStream_t st) {
+  SIR_CHECK_ARG(d_ghi && d_glo && d_thi && d_tlo, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
+  SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_thi) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_tlo) & 15) == 0,
+                "sir_ncc_scores: template operands must be 16-byte aligned");
+  TcParams p{};
+  p.ghi = (const __half*)d_ghi;
+  p.glo = (const __half*)d_glo;
+  p.rnorm = d_rnorm;
+  p.col2probe = d_col2probe;
+  p.scores = d_scores;
+  p.score_ld = score_ld;
+  p.g0 = g0;
+  p.G = G; p.C = C; p.Hp = Hp; p.Wp = Wp; p.Hm = Hm; p.Wm = Wm;
+  p.ncols = ncols;
+  p.nkc = tpl_chunks_per_row(Wm);
+  const int Kpad = tpl_kpad(Hm, Wm);
+  p.nsteps = ceil_div(Hm * p.nkc, 2);
+  p.nkstages = Kpad / kStageK;
+  p.npy = ceil_div(Hp, 16);
+  p.npx = ceil_div(Wp, 8);
+  p.ntiles_n = ceil_div(ncols, kTileN);
+  p.nunits = (long long)p.ntiles_n * G * p.npy * p.npx;
+  p.passes = passes;
+  p.out_scale = 1.0f / ((float)C * (float)(1 << kTemplateScaleLog2));
+
+  // shared memory plan: B ring, 2 E buffers (x halves), row staging, column maxima, barriers
+  const int halves = passes == 3 ? 2 : 1;
+  const uint32_t stage_bytes = kBHalfBytes * halves;
+  const int Pe = 8 * p.nkc;
+  const size_t limit = 227 * 1024 - 1024;  // alignment slack
+  bool ok = false;
+  for (int nb = 4; nb >= 2 && !ok; --nb) {
+    for (int seg = p.nkstages; seg >= 1; --seg) {
+      // rows touched by a segment of `seg` stages: worst case over alignments
+      const int max_rows = 16 + (4 * seg - 1) / p.nkc + 1;
+      const size_t e_half = (size_t)(max_rows + 1) * Pe * 16;
+      const size_t gs_half = (size_t)(max_rows + 1) * Wp;
+      const size_t total = (size_t)nb * stage_bytes + 2 * halves * e_half + 2 * gs_half * 2 + 4 * kTileN * 4 + 256;
+      if (total <= limit) {
+        p.nbstages = nb;
+        p.seg_stages = seg;
+        p.e_half_bytes = (uint32_t)round_up((int)e_half, 128);
+        p.gs_half_elems = (uint32_t)round_up((int)gs_half, 8);
+        ok = true;
+        break;
+      }
+      if (seg > 64) seg -= seg / 8;  // coarse search for very long K
+    }
+  }
+  SIR_CHECK_ARG(ok, "sir_ncc_scores: template %dx%d does not fit the shared-memory plan", Hm, Wm);
+  p.nseg = ceil_div(p.nkstages, p.seg_stages);
+  p.off_b = 0;
+  p.off_e = p.off_b + p.nbstages * stage_bytes;
+  p.off_gs = p.off_e + 2 * 2 * p.e_half_bytes;
+  p.off_cm = (uint32_t)round_up((int)(p.off_gs + 2 * p.gs_half_elems * 2), 16);
+  p.off_bar = p.off_cm + 4 * kTileN * 4;
+  const size_t smem = 1024 + p.off_bar + 256;
+  SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_scores: shared-memory plan overflow (%zu bytes)", smem);
+
+  CUtensorMap tm_hi, tm_lo;
+  int rc = make_template_map(&tm_hi, d_thi, Kpad, ncols_alloc, C);
+  if (rc) return rc;
+  rc = make_template_map(&tm_lo, d_tlo, Kpad, ncols_alloc, C);
+  if (rc) return rc;
+
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    SIR_CUDA(cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int dev = 0, sms = 0;
+  SIR_CUDA(cudaGetDevice(&dev));
+  SIR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = (unsigned)std::min<long long>(p.nunits, sms);
+  ncc_tc_kernel<<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, p);
+  SIR_LAUNCH_CHECK("ncc_tc_kernel");
+  return SIR_OK;
+}
+
+}  // namespace sir

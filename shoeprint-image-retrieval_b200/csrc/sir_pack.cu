@@ -1,0 +1,398 @@
+// HBM-bound preparation kernels: gallery pack (K5), window inverse norm (K6), probe variants
+// (K4: Pillow-exact rotate / bicubic resize) and template pack (K5).
+//
+// Reference semantics restated (reference repo paths):
+//   similarity.py:92-93   crop [:, 2:-2, 2:-2]
+//   similarity.py:48-49   zero mean per channel over the cropped map
+//   similarity.py:57-65   D = box(g^2) - box(g)^2 / (Hm*Wm), clamped at 0, float64
+//   similarity.py:67      E = sum(t^2)
+//   similarity.py:262-276 Image.rotate (nearest) / Image.resize (bicubic) per channel
+#include "sir_common.cuh"
+
+namespace sir {
+
+// ------------------------------------------------------------------------------------------
+// K5 gallery: one CTA per (gallery, channel).  Reads 4 B/cell, writes 4 B/cell (hi+lo) [+4 gz].
+__global__ void __launch_bounds__(256) gallery_pack_kernel(const float* __restrict__ gal, int C, int hg, int wg,
+                                                           __half* __restrict__ ghi, __half* __restrict__ glo,
+                                                           int32_t* __restrict__ gexp, float* __restrict__ gz) {
+  __shared__ double sred[32];
+  __shared__ float fred[32];
+  const int Hp = hg - 2 * kEdge, Wp = wg - 2 * kEdge, M = Hp * Wp;
+  const size_t gc = blockIdx.x;  // g*C + c
+  const float* src = gal + gc * (size_t)hg * wg;
+
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const int y = i / Wp, x = i - y * Wp;
+    acc += (double)src[(y + kEdge) * wg + x + kEdge];
+  }
+  const float mean = (float)(block_sum(acc, sred) / (double)M);
+
+  float amax = 0.0f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const int y = i / Wp, x = i - y * Wp;
+    amax = fmaxf(amax, fabsf(src[(y + kEdge) * wg + x + kEdge] - mean));
+  }
+  amax = block_max(amax, fred);
+  int e = 0;
+  if (amax > 0.0f && isfinite(amax)) {
+    int ex;
+    (void)frexpf(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
+    e = kGalleryPeakLog2 - ex;
+  }
+  if (threadIdx.x == 0) gexp[gc] = e;
+
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const int y = i / Wp, x = i - y * Wp;
+    const float z = src[(y + kEdge) * wg + x + kEdge] - mean;
+    const float s = ldexpf(z, e);
+    const __half h = __float2half_rn(s);
+    const __half l = __float2half_rn(s - __half2float(h));
+    ghi[gc * M + i] = h;
+    glo[gc * M + i] = l;
+    if (gz) gz[gc * M + i] = z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: window inverse norm through float64 summed-area tables held in shared memory.
+// One CTA per (gallery, channel); dynamic smem = 2 * (Hp+1)*(Wp+1) doubles.
+__global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo,
+                                                           const float* __restrict__ gz, int Hp, int Wp, int Hm, int Wm,
+                                                           float* __restrict__ rnorm) {
+  extern __shared__ double sat[];
+  const int W1 = Wp + 1, M = Hp * Wp;
+  double* s1 = sat;
+  double* s2 = sat + (size_t)(Hp + 1) * W1;
+  const size_t gc = blockIdx.x;
+
+  for (int i = threadIdx.x; i < (Hp + 1) * W1; i += blockDim.x) {
+    const int y = i / W1, x = i - y * W1;
+    double v = 0.0;
+    if (y > 0 && x > 0) {
+      const size_t j = gc * M + (size_t)(y - 1) * Wp + (x - 1);
+      v = gz ? (double)gz[j] : (double)__half2float(ghi[j]) + (double)__half2float(glo[j]);
+    }
+    s1[i] = v;
+    s2[i] = v * v;
+  }
+  __syncthreads();
+  for (int y = 1 + threadIdx.x; y <= Hp; y += blockDim.x) {  // prefix along x
+    double a = 0.0, b = 0.0;
+    for (int x = 1; x <= Wp; ++x) {
+      a += s1[y * W1 + x];
+      b += s2[y * W1 + x];
+      s1[y * W1 + x] = a;
+      s2[y * W1 + x] = b;
+    }
+  }
+  __syncthreads();
+  for (int x = 1 + threadIdx.x; x <= Wp; x += blockDim.x) {  // prefix along y
+    double a = 0.0, b = 0.0;
+    for (int y = 1; y <= Hp; ++y) {
+      a += s1[y * W1 + x];
+      b += s2[y * W1 + x];
+      s1[y * W1 + x] = a;
+      s2[y * W1 + x] = b;
+    }
+  }
+  __syncthreads();
+  const int a = Hm / 2, b = Wm / 2;
+  const double inv_n = 1.0 / ((double)Hm * (double)Wm);
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const int y = i / Wp, x = i - y * Wp;
+    const int r0 = max(y - a, 0), r1 = min(y - a + Hm, Hp);
+    const int c0 = max(x - b, 0), c1 = min(x - b + Wm, Wp);
+    float r = 0.0f;
+    if (r1 > r0 && c1 > c0) {
+      const double t1 = s1[r1 * W1 + c1] - s1[r0 * W1 + c1] - s1[r1 * W1 + c0] + s1[r0 * W1 + c0];
+      const double t2 = s2[r1 * W1 + c1] - s2[r0 * W1 + c1] - s2[r1 * W1 + c0] + s2[r0 * W1 + c0];
+      const double d = t2 - t1 * t1 * inv_n;
+      if (d > 0.0) r = (float)(1.0 / sqrt(d));
+    }
+    rnorm[gc * M + i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 rotate: Pillow affine_fixed (Geometry.c) nearest neighbour.  mode 0 copy, 1 flip (180),
+// 2 transpose-90, 3 transpose-270 (square maps only), 4 general 16.16 fixed point.
+struct RotateCoeffs {
+  int mode;
+  long long a0, a1, a2, a3, a4, a5;
+};
+
+__global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                     size_t total, RotateCoeffs rc) {
+  const size_t hw = (size_t)h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t plane = i / hw;
+    const int p = (int)(i - plane * hw);
+    const int y = p / w, x = p - y * w;
+    int sy, sx;
+    bool ok = true;
+    switch (rc.mode) {
+      case 0: sy = y; sx = x; break;
+      case 1: sy = h - 1 - y; sx = w - 1 - x; break;
+      case 2: sy = x; sx = w - 1 - y; break;
+      case 3: sy = h - 1 - x; sx = y; break;
+      default: {
+        const long long xs = (rc.a2 + rc.a1 * y + rc.a0 * x) >> 16;
+        const long long ys = (rc.a5 + rc.a4 * y + rc.a3 * x) >> 16;
+        ok = xs >= 0 && xs < w && ys >= 0 && ys < h;
+        sx = (int)xs;
+        sy = (int)ys;
+      }
+    }
+    out[i] = ok ? in[plane * hw + (size_t)sy * w + sx] : 0.0f;
+  }
+}
+
+// K4 resize: one separable bicubic pass (Pillow Resample.c, 32bpc float path): sequential double
+// accumulation of float32 pixel * double weight, no FMA contraction, cast to float32.
+// axis 1: along w (in [P][h][n_in] -> out [P][h][n_out]); axis 0: along h.
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ in, float* __restrict__ out, int planes,
+                                                       int h_in, int w_in, int h_out, int w_out, int axis,
+                                                       const int* __restrict__ xmin, const int* __restrict__ cnt,
+                                                       const double* __restrict__ kk, int ksize) {
+  const size_t total = (size_t)planes * h_out * w_out;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t plane = i / ((size_t)h_out * w_out);
+    const int p = (int)(i - plane * (size_t)h_out * w_out);
+    const int y = p / w_out, x = p - y * w_out;
+    const float* src = in + plane * (size_t)h_in * w_in;
+    const int o = axis ? x : y;
+    const int lo = xmin[o], n = cnt[o];
+    const double* k = kk + (size_t)o * ksize;
+    double ss = 0.0;
+    for (int j = 0; j < n; ++j) {
+      const float px = axis ? src[(size_t)y * w_in + lo + j] : src[(size_t)(lo + j) * w_in + x];
+      ss = __dadd_rn(ss, __dmul_rn((double)px, k[j]));
+    }
+    out[i] = (float)ss;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 templates: one CTA per (map n, channel c).
+__global__ void __launch_bounds__(128) template_pack_kernel(const float* __restrict__ maps, int C, int h, int w, int col0,
+                                                            int ncols_alloc, __half* __restrict__ thi,
+                                                            __half* __restrict__ tlo, float* __restrict__ t32) {
+  __shared__ double sred[32];
+  const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm;
+  const int nkc = tpl_chunks_per_row(Wm), Kpad = tpl_kpad(Hm, Wm), rowk = nkc * 8;
+  const int n = blockIdx.x / C, c = blockIdx.x - n * C;
+  const float* src = maps + ((size_t)n * C + c) * (size_t)h * w;
+
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int u = i / Wm, v = i - u * Wm;
+    acc += (double)src[(u + kEdge) * w + v + kEdge];
+  }
+  const float mean = (float)(block_sum(acc, sred) / (double)K);
+  double e = 0.0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int u = i / Wm, v = i - u * Wm;
+    const double z = (double)(src[(u + kEdge) * w + v + kEdge] - mean);
+    e += z * z;
+  }
+  e = block_sum(e, sred);
+  const double inv = e > 0.0 ? 1.0 / sqrt(e) : 0.0;
+
+  const size_t col = (size_t)c * ncols_alloc + col0 + n;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    const int u = k / rowk, v = k - u * rowk;
+    float tn = 0.0f;
+    if (u < Hm && v < Wm) {
+      tn = (float)((double)(src[(u + kEdge) * w + v + kEdge] - mean) * inv);
+      if (t32) t32[col * K + u * Wm + v] = tn;
+    }
+    const float s = ldexpf(tn, kTemplateScaleLog2);
+    const __half hi = __float2half_rn(s);
+    thi[col * Kpad + k] = hi;
+    tlo[col * Kpad + k] = __float2half_rn(s - __half2float(hi));
+  }
+}
+
+}  // namespace sir
+
+// =========================================================================== C ABI launchers
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+using namespace sir;
+
+extern "C" int sir_gallery_pack(const float* d_gallery, int G, int C, int hg, int wg, uint16_t* d_ghi, uint16_t* d_glo,
+                                int32_t* d_gexp, float* d_gz, void* stream) {
+  SIR_CHECK_ARG(d_gallery && d_ghi && d_glo && d_gexp, "sir_gallery_pack: null pointer");
+  SIR_CHECK_ARG(G > 0 && C > 0, "sir_gallery_pack: empty gallery (G=%d C=%d)", G, C);
+  SIR_CHECK_ARG(hg > 2 * kEdge && wg > 2 * kEdge, "sir_gallery_pack: map %dx%d vanishes after the 2-cell crop", hg, wg);
+  gallery_pack_kernel<<<(unsigned)((size_t)G * C), 256, 0, (cudaStream_t)stream>>>(
+      d_gallery, C, hg, wg, (__half*)d_ghi, (__half*)d_glo, d_gexp, d_gz);
+  SIR_LAUNCH_CHECK("gallery_pack_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_gallery_window_rnorm(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_gz, int G, int C,
+                                        int Hp, int Wp, int Hm, int Wm, float* d_rnorm, void* stream) {
+  SIR_CHECK_ARG((d_gz || (d_ghi && d_glo)) && d_rnorm, "sir_gallery_window_rnorm: null pointer");
+  SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0 && Hm > 0 && Wm > 0, "sir_gallery_window_rnorm: bad shape");
+  const size_t smem = 2 * (size_t)(Hp + 1) * (Wp + 1) * sizeof(double);
+  SIR_CHECK_ARG(smem <= 227 * 1024, "sir_gallery_window_rnorm: map %dx%d too large for the smem SAT", Hp, Wp);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SIR_CUDA(cudaFuncSetAttribute(window_rnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  window_rnorm_kernel<<<(unsigned)((size_t)G * C), 256, smem, (cudaStream_t)stream>>>(
+      (const __half*)d_ghi, (const __half*)d_glo, d_gz, Hp, Wp, Hm, Wm, d_rnorm);
+  SIR_LAUNCH_CHECK("window_rnorm_kernel");
+  return SIR_OK;
+}
+
+// Python's round(x, 15) == correctly rounded decimal with 15 fractional digits, re-parsed.
+static double round15(double v) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.15f", v);
+  return strtod(buf, nullptr);
+}
+static long long fix16(double v) { return (long long)std::floor(v * 65536.0 + 0.5); }
+
+extern "C" int sir_variant_rotate(const float* d_in, int N, int C, int h, int w, double angle, float* d_out,
+                                  void* stream) {
+  SIR_CHECK_ARG(d_in && d_out, "sir_variant_rotate: null pointer");
+  SIR_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0, "sir_variant_rotate: bad shape");
+  SIR_CHECK_ARG(h < 32768 && w < 32768, "sir_variant_rotate: map too large for the 16.16 fixed point walk");
+  RotateCoeffs rc{};
+  double a = std::fmod(angle, 360.0);
+  if (a < 0) a += 360.0;  // Python's % on floats
+  if (a == 0.0) rc.mode = 0;
+  else if (a == 180.0) rc.mode = 1;
+  else if (a == 90.0 && w == h) rc.mode = 2;
+  else if (a == 270.0 && w == h) rc.mode = 3;
+  else {
+    rc.mode = 4;
+    const double r = -(a * (M_PI / 180.0));
+    // math.radians(a) is a * (pi / 180); keep the same association
+    const double m0 = round15(std::cos(r)), m1 = round15(std::sin(r));
+    const double m3 = round15(-std::sin(r)), m4 = round15(std::cos(r));
+    const double cx = w / 2.0, cy = h / 2.0;
+    const double m2 = m0 * (-cx) + m1 * (-cy) + 0.0 + cx;
+    const double m5 = m3 * (-cx) + m4 * (-cy) + 0.0 + cy;
+    rc.a0 = fix16(m0); rc.a1 = fix16(m1); rc.a3 = fix16(m3); rc.a4 = fix16(m4);
+    rc.a2 = fix16(m2 + m0 * 0.5 + m1 * 0.5);
+    rc.a5 = fix16(m5 + m3 * 0.5 + m4 * 0.5);
+  }
+  const size_t total = (size_t)N * C * h * w;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  rotate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, h, w, total, rc);
+  SIR_LAUNCH_CHECK("rotate_kernel");
+  return SIR_OK;
+}
+
+namespace {
+struct Coeffs {
+  int ksize;
+  std::vector<int> xmin, cnt;
+  std::vector<double> kk;
+};
+double bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+// Pillow Resample.c precompute_coeffs, bicubic (support 2.0).
+Coeffs precompute(int n_in, int n_out) {
+  Coeffs c;
+  const double scale = (double)n_in / n_out;
+  const double fscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * fscale;
+  c.ksize = (int)std::ceil(support) * 2 + 1;
+  c.xmin.assign(n_out, 0);
+  c.cnt.assign(n_out, 0);
+  c.kk.assign((size_t)n_out * c.ksize, 0.0);
+  const double ss = 1.0 / fscale;
+  for (int xx = 0; xx < n_out; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int lo = (int)(center - support + 0.5);
+    if (lo < 0) lo = 0;
+    int hi = (int)(center + support + 0.5);
+    if (hi > n_in) hi = n_in;
+    const int n = hi - lo;
+    double* k = &c.kk[(size_t)xx * c.ksize];
+    double ww = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double wgt = bicubic((i + lo - center + 0.5) * ss);
+      k[i] = wgt;
+      ww += wgt;
+    }
+    if (ww != 0.0)
+      for (int i = 0; i < n; ++i) k[i] /= ww;
+    c.xmin[xx] = lo;
+    c.cnt[xx] = n;
+  }
+  return c;
+}
+
+int run_pass(const float* in, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int axis,
+             cudaStream_t st) {
+  const Coeffs c = precompute(axis ? w_in : h_in, axis ? w_out : h_out);
+  const int n_out = axis ? w_out : h_out;
+  int *d_xmin = nullptr, *d_cnt = nullptr;
+  double* d_kk = nullptr;
+  SIR_CUDA(cudaMallocAsync(&d_xmin, sizeof(int) * n_out, st));
+  SIR_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * n_out, st));
+  SIR_CUDA(cudaMallocAsync(&d_kk, sizeof(double) * c.kk.size(), st));
+  // pageable sources: the runtime stages them before returning, so the vectors may die here
+  SIR_CUDA(cudaMemcpyAsync(d_xmin, c.xmin.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice, st));
+  SIR_CUDA(cudaMemcpyAsync(d_cnt, c.cnt.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice, st));
+  SIR_CUDA(cudaMemcpyAsync(d_kk, c.kk.data(), sizeof(double) * c.kk.size(), cudaMemcpyHostToDevice, st));
+  const size_t total = (size_t)planes * h_out * w_out;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  resample_kernel<<<blocks, 256, 0, st>>>(in, out, planes, h_in, w_in, h_out, w_out, axis, d_xmin, d_cnt, d_kk, c.ksize);
+  SIR_LAUNCH_CHECK("resample_kernel");
+  SIR_CUDA(cudaFreeAsync(d_xmin, st));
+  SIR_CUDA(cudaFreeAsync(d_cnt, st));
+  SIR_CUDA(cudaFreeAsync(d_kk, st));
+  return SIR_OK;
+}
+}  // namespace
+
+extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w, int h2, int w2, float* d_out,
+                                  float* d_tmp, void* stream) {
+  SIR_CHECK_ARG(d_in && d_out, "sir_variant_resize: null pointer");
+  SIR_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && h2 > 0 && w2 > 0, "sir_variant_resize: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = N * C;
+  if (h2 == h && w2 == w) {  // Image.resize with an unchanged size is a copy
+    SIR_CUDA(cudaMemcpyAsync(d_out, d_in, sizeof(float) * (size_t)planes * h * w, cudaMemcpyDeviceToDevice, st));
+    return SIR_OK;
+  }
+  if (w2 != w && h2 != h) {
+    SIR_CHECK_ARG(d_tmp, "sir_variant_resize: two-pass resize needs d_tmp");
+    int rc = run_pass(d_in, d_tmp, planes, h, w, h, w2, 1, st);
+    if (rc) return rc;
+    return run_pass(d_tmp, d_out, planes, h, w2, h2, w2, 0, st);
+  }
+  if (w2 != w) return run_pass(d_in, d_out, planes, h, w, h, w2, 1, st);
+  return run_pass(d_in, d_out, planes, h, w, h2, w, 0, st);
+}
+
+extern "C" int sir_template_kpad(int Hm, int Wm) { return (Hm > 0 && Wm > 0) ? tpl_kpad(Hm, Wm) : 0; }
+
+extern "C" int sir_template_pack(const float* d_maps, int N, int C, int h, int w, int col0, int ncols_alloc,
+                                 uint16_t* d_thi, uint16_t* d_tlo, float* d_t32, void* stream) {
+  SIR_CHECK_ARG(d_maps && d_thi && d_tlo, "sir_template_pack: null pointer");
+  SIR_CHECK_ARG(N > 0 && C > 0, "sir_template_pack: empty input");
+  SIR_CHECK_ARG(h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack: map %dx%d vanishes after the 2-cell crop", h, w);
+  SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack: columns [%d,%d) outside %d", col0, col0 + N,
+                ncols_alloc);
+  template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, (cudaStream_t)stream>>>(
+      d_maps, C, h, w, col0, ncols_alloc, (__half*)d_thi, (__half*)d_tlo, d_t32);
+  SIR_LAUNCH_CHECK("template_pack_kernel");
+  return SIR_OK;
+}

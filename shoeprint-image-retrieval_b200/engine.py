@@ -1,0 +1,345 @@
+"""Device-side orchestration of the matching path (PyTorch owns memory and streams; every
+kernel is in ``libsir.so``).
+
+Flow (reference call sites in brackets):
+
+    gallery maps --sir_gallery_pack--> fp16 hi/lo operands            [similarity.py:92,49]
+    probe maps --sir_variant_rotate/resize--> variant maps            [similarity.py:262-276, 321-353]
+               --sir_template_pack--> column blocks per template shape [similarity.py:92,48,67]
+    per (template shape, gallery shape): sir_gallery_window_rnorm     [similarity.py:57-65]
+                                         sir_ncc_scores (max-fused)   [similarity.py:53-55,68,100-108,355-367]
+    scores --sir_true_scores / sir_rank_topk--> ranks, top-k          [similarity.py:378-386]
+
+Ragged inputs are grouped by shape on the host (the reference never pads: dataloader.py:231-237).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+__all__ = [
+    "MapGroup",
+    "MapSet",
+    "GalleryOperands",
+    "variant_plan",
+    "scaled_size",
+    "score_matrix",
+    "rank_true_matches",
+    "compare",
+    "launch_counter",
+]
+
+EDGE = 2  # similarity.py:92-93
+
+
+class _LaunchCounter:
+    """Counts libsir kernel launches (bench.py reports it as ``gpu_launches``)."""
+
+    def __init__(self) -> None:
+        self.n = 0
+
+    def add(self, k: int = 1) -> None:
+        self.n += k
+
+
+launch_counter = _LaunchCounter()
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("the matching path needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# --------------------------------------------------------------------------- inputs
+
+@dataclass
+class MapGroup:
+    """Feature maps of one shape: ``maps [n, C, h, w]`` float32 on the device, ``ids`` = their
+    positions in the caller's list."""
+
+    maps: torch.Tensor
+    ids: torch.Tensor  # int64 [n], host
+
+    @property
+    def shape_hw(self) -> tuple[int, int]:
+        return int(self.maps.shape[2]), int(self.maps.shape[3])
+
+
+@dataclass
+class MapSet:
+    groups: list[MapGroup]
+    count: int
+    channels: int
+    h2d_bytes: int = 0
+
+    @staticmethod
+    def from_host(maps: list[np.ndarray], pin: bool = True) -> "MapSet":
+        """Group a list of ``[C,h,w]`` float32 arrays by shape and upload each group."""
+        dev = _require_cuda()
+        if len(maps) == 0:
+            raise ValueError("empty list of feature maps")
+        by_shape: dict[tuple[int, int, int], list[int]] = {}
+        for i, m in enumerate(maps):
+            if m.ndim != 3:
+                raise ValueError(f"feature map {i} has shape {m.shape}, expected [C,h,w]")
+            by_shape.setdefault(tuple(m.shape), []).append(i)
+        chans = {s[0] for s in by_shape}
+        if len(chans) != 1:
+            raise ValueError(f"feature maps disagree on the channel count: {sorted(chans)}")
+        groups, nbytes = [], 0
+        for shp, idx in by_shape.items():
+            if shp[1] <= 2 * EDGE or shp[2] <= 2 * EDGE:
+                raise ValueError(f"feature map of shape {shp} vanishes after the 2-cell crop (similarity.py:92-93)")
+            host = torch.empty((len(idx), *shp), dtype=torch.float32, pin_memory=pin)
+            hv = host.numpy()
+            for j, i in enumerate(idx):
+                hv[j] = maps[i]
+            groups.append(MapGroup(host.to(dev, non_blocking=True), torch.tensor(idx, dtype=torch.int64)))
+            nbytes += host.numel() * 4
+        return MapSet(groups, len(maps), chans.pop(), nbytes)
+
+    @staticmethod
+    def from_device(maps: torch.Tensor) -> "MapSet":
+        """One uniform-shape group already resident on the device: ``[n, C, h, w]`` float32."""
+        if maps.dim() != 4 or maps.dtype != torch.float32 or not maps.is_cuda:
+            raise ValueError("expected a CUDA float32 tensor [n,C,h,w]")
+        maps = maps.contiguous()
+        return MapSet([MapGroup(maps, torch.arange(maps.shape[0]))], int(maps.shape[0]), int(maps.shape[1]))
+
+
+@dataclass
+class GalleryOperands:
+    """Packed gallery group (K5) + cache of window inverse norms per template shape (K6)."""
+
+    G: int
+    C: int
+    Hp: int
+    Wp: int
+    ghi: torch.Tensor
+    glo: torch.Tensor
+    gexp: torch.Tensor
+    gz: torch.Tensor | None
+    ids: torch.Tensor
+    _rnorm: dict = field(default_factory=dict)
+
+    @staticmethod
+    def pack(group: MapGroup, keep_fp32: bool) -> "GalleryOperands":
+        n, c, h, w = (int(v) for v in group.maps.shape)
+        hp, wp = h - 2 * EDGE, w - 2 * EDGE
+        dev = group.maps.device
+        ghi = torch.empty((n, c, hp, wp), dtype=torch.float16, device=dev)
+        glo = torch.empty_like(ghi)
+        gexp = torch.empty((n, c), dtype=torch.int32, device=dev)
+        gz = torch.empty((n, c, hp, wp), dtype=torch.float32, device=dev) if keep_fp32 else None
+        nat.check(
+            nat.lib.sir_gallery_pack(_ptr(group.maps), n, c, h, w, _ptr(ghi), _ptr(glo), _ptr(gexp), _ptr(gz), _stream()),
+            "sir_gallery_pack",
+        )
+        launch_counter.add()
+        return GalleryOperands(n, c, hp, wp, ghi, glo, gexp, gz, group.ids)
+
+    def rnorm(self, hm: int, wm: int, simt: bool) -> torch.Tensor:
+        key = (hm, wm, simt)
+        if key not in self._rnorm:
+            if len(self._rnorm) >= 2:  # a window table is as large as the gallery: keep few
+                self._rnorm.pop(next(iter(self._rnorm)))
+            out = torch.empty((self.G, self.C, self.Hp * self.Wp), dtype=torch.float32, device=self.ghi.device)
+            nat.check(
+                nat.lib.sir_gallery_window_rnorm(
+                    _ptr(self.ghi), _ptr(self.glo), _ptr(self.gz if simt else None),
+                    self.G, self.C, self.Hp, self.Wp, hm, wm, _ptr(out), _stream(),
+                ),
+                "sir_gallery_window_rnorm",
+            )
+            launch_counter.add()
+            self._rnorm[key] = out
+        return self._rnorm[key]
+
+
+# --------------------------------------------------------------------------- variants
+
+def variant_plan(rotations, scales) -> list[tuple[float | None, float | None]]:
+    """(rotation, scale) of every variant the reference scores (similarity.py:321-353 with the
+    list handling of :282): with both given, ``[id] + [scale_s(v) for v in (id, rot...) for s]``,
+    i.e. the rotated-only variants are not scored."""
+    if rotations is None and scales is None:
+        return [(None, None)]
+    if scales is None:
+        return [(None, None)] + [(float(r), None) for r in rotations]
+    if rotations is None:
+        return [(None, None)] + [(None, float(s)) for s in scales]
+    plan: list[tuple[float | None, float | None]] = [(None, None)]
+    for r in [None, *rotations]:
+        plan.extend((None if r is None else float(r), float(s)) for s in scales)
+    return plan
+
+
+def scaled_size(h: int, w: int, s: float) -> tuple[int, int]:
+    """Target size of ``Image.resize((int(w*s), int(h*s)))`` (similarity.py:269-274)."""
+    return int(h * s), int(w * s)
+
+
+def make_variant(maps: torch.Tensor, rot: float | None, scale: float | None) -> torch.Tensor:
+    """Rotate (nearest, Pillow fixed point) then resize (bicubic) a group ``[n,C,h,w]``."""
+    n, c, h, w = (int(v) for v in maps.shape)
+    out = maps
+    if rot is not None:
+        rotated = torch.empty_like(maps)
+        nat.check(nat.lib.sir_variant_rotate(_ptr(out), n, c, h, w, float(rot), _ptr(rotated), _stream()), "sir_variant_rotate")
+        launch_counter.add()
+        out = rotated
+    if scale is not None:
+        h2, w2 = scaled_size(h, w, scale)
+        if h2 <= 2 * EDGE or w2 <= 2 * EDGE:
+            raise ValueError(f"scale {scale} shrinks a {h}x{w} map below the 2-cell crop")
+        if (h2, w2) != (h, w):
+            resized = torch.empty((n, c, h2, w2), dtype=torch.float32, device=maps.device)
+            two_pass = h2 != h and w2 != w
+            tmp = torch.empty((n, c, h, w2), dtype=torch.float32, device=maps.device) if two_pass else None
+            nat.check(
+                nat.lib.sir_variant_resize(_ptr(out), n, c, h, w, h2, w2, _ptr(resized), _ptr(tmp), _stream()),
+                "sir_variant_resize",
+            )
+            launch_counter.add(2 if two_pass else 1)
+            out = resized
+    return out
+
+
+# --------------------------------------------------------------------------- scoring
+
+@dataclass
+class _Block:
+    """Pending columns of one template shape."""
+
+    maps: list[torch.Tensor] = field(default_factory=list)
+    ids: list[torch.Tensor] = field(default_factory=list)
+    ncols: int = 0
+
+
+def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperands], offsets: list[int],
+                 scores: torch.Tensor, precision: int) -> None:
+    h, w = hw
+    hm, wm = h - 2 * EDGE, w - 2 * EDGE
+    dev = scores.device
+    c = gallery[0].C
+    ncols = block.ncols
+    kpad = int(nat.lib.sir_template_kpad(hm, wm))
+    simt = precision == nat.PREC_FP32_SIMT
+    thi = torch.empty((c, ncols, kpad), dtype=torch.float16, device=dev)
+    tlo = torch.empty_like(thi)
+    t32 = torch.empty((c, ncols, hm * wm), dtype=torch.float32, device=dev) if simt else None
+    col0 = 0
+    for m in block.maps:
+        n = int(m.shape[0])
+        nat.check(
+            nat.lib.sir_template_pack(_ptr(m), n, c, h, w, col0, ncols, _ptr(thi), _ptr(tlo), _ptr(t32), _stream()),
+            "sir_template_pack",
+        )
+        launch_counter.add()
+        col0 += n
+    col2probe = torch.cat(block.ids).to(torch.int32).to(dev, non_blocking=True)
+    for ops, g0 in zip(gallery, offsets):
+        rn = ops.rnorm(hm, wm, simt)
+        nat.check(
+            nat.lib.sir_ncc_scores(
+                _ptr(ops.ghi), _ptr(ops.glo), _ptr(ops.gexp), _ptr(ops.gz), _ptr(rn),
+                ops.G, ops.C, ops.Hp, ops.Wp,
+                _ptr(thi), _ptr(tlo), _ptr(t32), ncols, ncols, hm, wm,
+                _ptr(col2probe), _ptr(scores), int(scores.stride(0)), g0, precision, _stream(),
+            ),
+            "sir_ncc_scores",
+        )
+        launch_counter.add()
+
+
+def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, precision: str = "fp16x3",
+                 col_block: int = 16384, packed_gallery: list[GalleryOperands] | None = None) -> torch.Tensor:
+    """float32 ``[Q, G]`` on the device: max over the variant set, floored at 0
+    (``similarities_all`` of similarity.py:355-367), columns in the caller's gallery order."""
+    dev = _require_cuda()
+    if probes.channels != gallery.channels:
+        raise ValueError(f"probe maps have {probes.channels} channels, gallery maps {gallery.channels}")
+    prec = nat.PRECISIONS[precision]
+    ops = packed_gallery or [GalleryOperands.pack(g, keep_fp32=(prec == nat.PREC_FP32_SIMT)) for g in gallery.groups]
+    offsets, g0 = [], 0
+    for o in ops:
+        offsets.append(g0)
+        g0 += o.G
+    ld = (gallery.count + 3) // 4 * 4  # 16-byte aligned rows for the vectorised rank kernel
+    grouped = torch.zeros((probes.count, ld), dtype=torch.float32, device=dev)
+
+    pending: dict[tuple[int, int], _Block] = {}
+    for rot, scale in variant_plan(rotations, scales):
+        for grp in probes.groups:
+            v = make_variant(grp.maps, rot, scale)
+            key = (int(v.shape[2]), int(v.shape[3]))
+            blk = pending.setdefault(key, _Block())
+            blk.maps.append(v)
+            blk.ids.append(grp.ids)
+            blk.ncols += int(v.shape[0])
+            if blk.ncols >= col_block:
+                _score_block(blk, key, ops, offsets, grouped, prec)
+                del pending[key]
+    for key, blk in pending.items():
+        _score_block(blk, key, ops, offsets, grouped, prec)
+
+    # un-group the gallery axis back to the caller's order
+    order = torch.cat([o.ids for o in ops])
+    if torch.equal(order, torch.arange(gallery.count)):
+        return grouped[:, : gallery.count]
+    out = torch.empty((probes.count, gallery.count), dtype=torch.float32, device=dev)
+    out[:, order.to(dev)] = grouped[:, : gallery.count]
+    return out
+
+
+def rank_true_matches(scores: torch.Tensor, true_idx, k: int = 0, g0: int = 0, true_score: torch.Tensor | None = None):
+    """(count_gt, count_ge, topk_val, topk_idx, true_score) for ``scores [Q, G_local]``.
+
+    ``rank = 1 + count_gt`` is the reference's ``_get_rank`` (similarity.py:378-386) up to the
+    order of exact ties.  ``g0`` is the global index of local column 0; ``true_score`` may be
+    supplied when the true match lives on another shard."""
+    q, g = int(scores.shape[0]), int(scores.shape[1])
+    dev = scores.device
+    if scores.stride(1) != 1:
+        scores = scores.contiguous()
+    ld = int(scores.stride(0))
+    tidx = torch.as_tensor(true_idx, dtype=torch.int32).to(dev)
+    if true_score is None:
+        true_score = torch.empty(q, dtype=torch.float32, device=dev)
+        nat.check(nat.lib.sir_true_scores(_ptr(scores), q, g, ld, _ptr(tidx), g0, _ptr(true_score), _stream()), "sir_true_scores")
+        launch_counter.add()
+    count_gt = torch.empty(q, dtype=torch.int32, device=dev)
+    count_ge = torch.empty(q, dtype=torch.int32, device=dev)
+    tv = torch.empty((q, max(k, 1)), dtype=torch.float32, device=dev)
+    ti = torch.empty((q, max(k, 1)), dtype=torch.int32, device=dev)
+    nat.check(
+        nat.lib.sir_rank_topk(_ptr(scores), q, g, ld, _ptr(true_score), g0, k, _ptr(count_gt), _ptr(count_ge), _ptr(tv), _ptr(ti), _stream()),
+        "sir_rank_topk",
+    )
+    launch_counter.add()
+    return count_gt, count_ge, tv[:, :k], ti[:, :k], true_score
+
+
+def compare(probe_maps, gallery_maps, matching_pairs, rotations=None, scales=None, precision: str = "fp16x3", k: int = 0):
+    """Host lists in, (ranks int32 [Q] on host, scores [Q,G] on device, top-k lists) out."""
+    probes = probe_maps if isinstance(probe_maps, MapSet) else MapSet.from_host(list(probe_maps))
+    gallery = gallery_maps if isinstance(gallery_maps, MapSet) else MapSet.from_host(list(gallery_maps))
+    scores = score_matrix(probes, gallery, rotations, scales, precision)
+    count_gt, _, tv, ti, _ = rank_true_matches(scores, matching_pairs, k)
+    ranks = (count_gt + 1).to("cpu").numpy().astype(np.int32)
+    return ranks, scores, (tv, ti)

@@ -1,0 +1,151 @@
+"""Feature-map comparison on B200: drop-in for the reference ``similarity.py``.
+
+Public names, arguments and results follow the reference (``similarity.py:26-386``):
+
+* ``compare_maps(shoemark_maps, shoeprint_maps, matching_pairs, config) -> ndarray[int32]``
+  1-based rank of each shoemark's true shoeprint (``similarity.py:129-227``);
+* ``get_similarity(shoemark, shoeprint) -> float`` (``similarity.py:75-108``);
+* ``normxcorr(template, image, mode="same") -> ndarray`` (``similarity.py:26-72``);
+* ``MultiProcessingTrackers`` kept importable (``similarity.py:111-126``).
+
+The work happens on the GPU through ``engine`` / ``libsir.so``; ``comparison.n_processes`` is
+accepted and ignored (one process drives one GPU).  Differences a caller can observe:
+
+* with both ``rotations`` and ``scales`` set the reference's progress loop never terminates
+  (it waits for ``(R+1)(S+1)*Q`` ticks while the workers produce ``(1+(R+1)S)*Q``; SURVEY.md
+  Appendix D2) -- this implementation scores the same variant set the workers score and returns;
+* exact score ties are ranked best-first (``1 + #{s > s_true}``) instead of numpy's unspecified
+  argsort order.
+"""
+
+from __future__ import annotations
+
+from multiprocessing import Array, Queue, Value
+from typing import TYPE_CHECKING, Literal
+
+import numpy as np
+from tqdm import tqdm
+
+from . import engine
+
+if TYPE_CHECKING:
+    from .config import Config
+    from .customtypes import FeatureMapsArrayType, ImageArrayType
+
+_PAD = engine.EDGE
+
+#: scores ``[Q, G]`` (torch, on the device) and top-k lists of the most recent ``compare_maps`` call
+last_result: dict = {}
+
+
+class MultiProcessingTrackers:
+    """Shared progress state of the reference's worker processes (``similarity.py:111-126``).
+    Unused by the GPU path; constructed on demand for callers that poke at it."""
+
+    def __init__(self, rankings_len: int) -> None:
+        self.counter = Value("i", 0)
+        self.queue: Queue = Queue()
+        self.rankings = Array("i", rankings_len)
+
+
+def _as_f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+def compare_maps(
+    shoemark_maps: list[FeatureMapsArrayType],
+    shoeprint_maps: list[FeatureMapsArrayType],
+    matching_pairs: list[int],
+    config: Config,
+) -> np.ndarray:
+    """Rank every shoemark's true shoeprint among all shoeprints by NCC similarity.
+
+    Args:
+        shoemark_maps: probe feature maps, each ``[C, h, w]`` float32 (shapes may differ).
+        shoeprint_maps: gallery feature maps, each ``[C, h, w]`` float32.
+        matching_pairs: ``matching_pairs[i]`` = index into ``shoeprint_maps`` of shoemark ``i``'s match.
+        config: system config; ``config["comparison"]`` supplies ``rotations`` / ``scales``.
+    """
+    comparison = config["comparison"]
+    rotations = comparison.get("rotations")
+    scales = comparison.get("scales")
+    precision = comparison.get("precision", "fp16x3")
+    top_k = int(comparison.get("top_k", 0))
+    if len(matching_pairs) < len(shoemark_maps):
+        raise IndexError("matching_pairs is shorter than shoemark_maps")
+
+    n_variants = len(engine.variant_plan(rotations, scales))
+    with tqdm(total=n_variants * len(shoemark_maps)) as pbar:
+        ranks, scores, topk = engine.compare(
+            [_as_f32(m) for m in shoemark_maps],
+            [_as_f32(m) for m in shoeprint_maps],
+            list(matching_pairs[: len(shoemark_maps)]),
+            rotations,
+            scales,
+            precision=precision,
+            k=top_k,
+        )
+        for shoemark_id, rank in enumerate(ranks):
+            pbar.write(f"Print {shoemark_id} true match ranked {rank}")  # similarity.py:375
+        pbar.update(pbar.total)
+    last_result.clear()
+    last_result.update(scores=scores, topk=topk)
+    return ranks
+
+
+def get_similarity(shoemark: FeatureMapsArrayType, shoeprint: FeatureMapsArrayType) -> np.floating:
+    """Similarity of one shoemark against one shoeprint (``similarity.py:75-108``): per-channel NCC
+    of the 2-cell-cropped maps, summed over channels, max over positions, divided by C."""
+    probes = engine.MapSet.from_host([_as_f32(shoemark)])
+    gallery = engine.MapSet.from_host([_as_f32(shoeprint)])
+    scores = engine.score_matrix(probes, gallery, None, None, "fp16x3")
+    # compare_maps floors at 0 (similarity.py:355); a lone get_similarity call in the reference does
+    # not, but a negative best NCC only arises for anti-correlated maps and ranks last either way.
+    return np.float64(scores[0, 0].item())
+
+
+def normxcorr(
+    template: ImageArrayType,
+    image: ImageArrayType,
+    mode: Literal["full", "valid", "same"] = "same",
+) -> ImageArrayType:
+    """Normalised cross-correlation surface of ``template`` over ``image`` (``similarity.py:26-72``).
+
+    Debug helper, not on the matching path: the fused GPU kernel never materialises the surface
+    (``compare_maps`` / ``get_similarity`` go through ``sir_ncc_scores``).  Here the zero-meaned
+    operands and the window norm come from the library's pack kernels (``sir_gallery_pack``,
+    ``sir_gallery_window_rnorm``) and only the numerator of this one surface is a plain
+    ``torch.nn.functional.conv2d`` on the device.  Only ``mode="same"`` -- the only mode the
+    reference uses (``similarity.py:104``) -- is supported.
+    """
+    if mode != "same":
+        raise NotImplementedError("only mode='same' is used by the matching path (similarity.py:104)")
+    import torch
+
+    t = _as_f32(template)
+    g = _as_f32(image)
+    hm, wm = t.shape
+    hp, wp = g.shape
+    # frame both so the library's 2-cell crop removes exactly the frame
+    tpad = np.pad(t, _PAD)[None]
+    gpad = np.pad(g, _PAD)[None]
+    probes = engine.MapSet.from_host([tpad])
+    gal = engine.MapSet.from_host([gpad])
+    ops = engine.GalleryOperands.pack(gal.groups[0], keep_fp32=True)
+    rn = ops.rnorm(hm, wm, simt=True).reshape(hp, wp)
+    # numerator: correlate on the device with the packed fp32 operands
+    gz = ops.gz.reshape(1, 1, hp, wp)
+    tz = torch.from_numpy(t - t.mean(dtype=np.float32)).to(gz.device)
+    e = float((tz.double() ** 2).sum())
+    a, b = hm // 2, wm // 2
+    padded = torch.nn.functional.pad(gz, (b, wm - 1 - b, a, hm - 1 - a))
+    num = torch.nn.functional.conv2d(padded.double(), tz.double().reshape(1, 1, hm, wm)).reshape(hp, wp)
+    out = num * rn.double() / np.sqrt(e) if e > 0 else torch.zeros_like(num)
+    out = torch.nan_to_num(out, nan=0.0, posinf=0.0, neginf=0.0)
+    return out.cpu().numpy()
+
+
+def _get_rank(similarities, matching_pairs: list[int], print_id: int) -> int:
+    """1-based rank of the true match in one score row (``similarity.py:378-386``)."""
+    row = np.asarray(similarities)
+    return int((row > row[matching_pairs[print_id]]).sum()) + 1

@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, host logic of the
+drop-in modules matches the reference-generated goldens / the oracle."""
+
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from src.shoeprint_image_retrieval import _native as nat
+
+    header = (ROOT / "include" / "sir.h").read_text()
+    declared = set(re.findall(r"\b(sir_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    for name in declared:
+        assert hasattr(nat.lib, name)
+    assert nat.lib.sir_abi_version() == 1
+
+
+def test_kpad_matches_layout_rule():
+    from src.shoeprint_image_retrieval import _native as nat
+
+    for hm, wm in [(46, 15), (55, 17), (1, 1), (7, 8), (7, 9), (60, 124)]:
+        chunks = (wm + 7) // 8
+        want = (hm * chunks * 8 + 31) // 32 * 32
+        assert nat.lib.sir_template_kpad(hm, wm) == want
+    assert nat.lib.sir_template_kpad(0, 5) == 0
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    import ctypes as C
+
+    from src.shoeprint_image_retrieval import _native as nat
+
+    rc = nat.lib.sir_gallery_pack(None, 1, 1, 8, 8, None, None, None, None, None)
+    assert rc == -1
+    assert b"null pointer" in nat.lib.sir_last_error()
+    with pytest.raises(nat.SirError):
+        nat.check(nat.lib.sir_rank_topk(C.c_void_p(8), 1, 1, 1, C.c_void_p(8), 0, 4096, C.c_void_p(8), C.c_void_p(8), None, None, None))
+
+
+def test_variant_plan_matches_oracle():
+    from oracle import variants as ov
+    from src.shoeprint_image_retrieval import engine
+
+    cases = [(None, None), ([-15, 9, 180], None), (None, [1.02, 1.08]), ([-15, -9, -3, 3, 9, 15, 180], [1.02, 1.04, 1.08])]
+    for rot, scl in cases:
+        assert engine.variant_plan(rot, scl) == [(None if r is None else float(r), None if s is None else float(s)) for r, s in ov.variant_plan(rot, scl)]
+    assert len(engine.variant_plan([-15, -9, -3, 3, 9, 15, 180], [1.02, 1.04, 1.08])) == 25
+    for h, w, s in [(59, 21, 1.02), (59, 21, 1.08), (50, 19, 1.04), (13, 9, 0.5)]:
+        assert engine.scaled_size(h, w, s) == ov.scaled_size(h, w, s)
+
+
+def test_s_scores_match_reference_vectors(golden, capsys):
+    from src.shoeprint_image_retrieval import parse_results as pr
+
+    ranks = [int(r) for r in golden["s_ranks"]]
+    tp, tm = int(golden["s_total_prints"]), int(golden["s_total_marks"])
+    got = [pr.cmp(ranks, p, tp, tm) for p in (1, 5, 10, 15, 20)]
+    np.testing.assert_array_equal(np.array(got), golden["s_values"])
+    pr.cmp_all(ranks, tp, tm)
+    line = capsys.readouterr().out.strip()
+    assert re.fullmatch(r"S1:\d+\.\d\d S5:\d+\.\d\d S10:\d+\.\d\d S15:\d+\.\d\d S20:\d+\.\d\d", line)
+    assert line.startswith(f"S1:{got[0] * 100:.2f} ")
+
+
+def test_load_config_normalises_empty_strings(tmp_path):
+    from src.shoeprint_image_retrieval.config import load_config
+
+    cfg = load_config(ROOT / "run.toml")
+    assert cfg["comparison"]["rotations"] == [-15, -9, -3, 3, 9, 15, 180]
+    assert cfg["model"]["type"] == "EfficientNetV2_M"
+    text = (ROOT / "run.toml").read_text()
+    text = re.sub(r"rotations\s*=.*", 'rotations = ""', text)
+    text = re.sub(r"scales\s*=.*", 'scales = ""', text)
+    p = tmp_path / "run.toml"
+    p.write_text(text)
+    cfg = load_config(p)
+    assert cfg["comparison"]["rotations"] is None and cfg["comparison"]["scales"] is None
+
+
+def test_matching_path_fails_loudly_without_cuda():
+    import torch
+
+    from src.shoeprint_image_retrieval import engine
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.MapSet.from_host([np.zeros((2, 8, 8), np.float32)])
