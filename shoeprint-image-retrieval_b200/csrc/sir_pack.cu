@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restr
       const double t1 = s1[r1 * W1 + c1] - s1[r0 * W1 + c1] - s1[r1 * W1 + c0] + s1[r0 * W1 + c0];
       const double t2 = s2[r1 * W1 + c1] - s2[r0 * W1 + c1] - s2[r1 * W1 + c0] + s2[r0 * W1 + c0];
       const double d = t2 - t1 * t1 * inv_n;
-      if (d > 0.0) r = (float)(1.0 / sqrt(d));
+      // A window that is flat up to SAT round-off is the reference's "division by ~0" case
+      // (similarity.py:69-70 zeroes the non-finite results; FFT noise decides the rest): call it 0.
+      if (d > 1e-10 * t2) r = (float)(1.0 / sqrt(d));
     }
     rnorm[gc * M + i] = r;
   }

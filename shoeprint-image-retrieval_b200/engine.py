@@ -50,6 +50,10 @@ class _LaunchCounter:
 
 launch_counter = _LaunchCounter()
 
+#: when set to a list, every sir_ncc_scores launch appends (start_event, end_event, algorithmic_flops)
+#: recorded on the launching stream (bench.py uses this for the roofline line)
+kernel_events: list | None = None
+
 
 def _ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
@@ -88,8 +92,10 @@ class MapSet:
     h2d_bytes: int = 0
 
     @staticmethod
-    def from_host(maps: list[np.ndarray], pin: bool = True) -> "MapSet":
-        """Group a list of ``[C,h,w]`` float32 arrays by shape and upload each group."""
+    def from_host(maps: list[np.ndarray]) -> "MapSet":
+        """Group a list of ``[C,h,w]`` float32 arrays by shape and upload them, one asynchronous copy
+        per map straight into the group's device tensor (no host-side staging copy; arrays that live
+        in pinned memory are copied without blocking the host)."""
         dev = _require_cuda()
         if len(maps) == 0:
             raise ValueError("empty list of feature maps")
@@ -105,12 +111,14 @@ class MapSet:
         for shp, idx in by_shape.items():
             if shp[1] <= 2 * EDGE or shp[2] <= 2 * EDGE:
                 raise ValueError(f"feature map of shape {shp} vanishes after the 2-cell crop (similarity.py:92-93)")
-            host = torch.empty((len(idx), *shp), dtype=torch.float32, pin_memory=pin)
-            hv = host.numpy()
+            dst = torch.empty((len(idx), *shp), dtype=torch.float32, device=dev)
             for j, i in enumerate(idx):
-                hv[j] = maps[i]
-            groups.append(MapGroup(host.to(dev, non_blocking=True), torch.tensor(idx, dtype=torch.int64)))
-            nbytes += host.numel() * 4
+                src = maps[i]
+                if src.dtype != np.float32 or not src.flags.c_contiguous:
+                    src = np.ascontiguousarray(src, dtype=np.float32)
+                dst[j].copy_(torch.from_numpy(src), non_blocking=True)
+            groups.append(MapGroup(dst, torch.tensor(idx, dtype=torch.int64)))
+            nbytes += dst.numel() * 4
         return MapSet(groups, len(maps), chans.pop(), nbytes)
 
     @staticmethod
@@ -205,8 +213,8 @@ def make_variant(maps: torch.Tensor, rot: float | None, scale: float | None) -> 
         out = rotated
     if scale is not None:
         h2, w2 = scaled_size(h, w, scale)
-        if h2 <= 2 * EDGE or w2 <= 2 * EDGE:
-            raise ValueError(f"scale {scale} shrinks a {h}x{w} map below the 2-cell crop")
+        if h2 < 1 or w2 < 1:
+            raise ValueError(f"scale {scale} shrinks a {h}x{w} map to nothing")
         if (h2, w2) != (h, w):
             resized = torch.empty((n, c, h2, w2), dtype=torch.float32, device=maps.device)
             two_pass = h2 != h and w2 != w
@@ -255,6 +263,9 @@ def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperan
     col2probe = torch.cat(block.ids).to(torch.int32).to(dev, non_blocking=True)
     for ops, g0 in zip(gallery, offsets):
         rn = ops.rnorm(hm, wm, simt)
+        if kernel_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         nat.check(
             nat.lib.sir_ncc_scores(
                 _ptr(ops.ghi), _ptr(ops.glo), _ptr(ops.gexp), _ptr(ops.gz), _ptr(rn),
@@ -265,6 +276,11 @@ def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperan
             "sir_ncc_scores",
         )
         launch_counter.add()
+        if kernel_events is not None:
+            ev1.record()
+            # 2 * C * (gallery positions) * (template taps) per (column, gallery)
+            flops = 2.0 * ops.C * (ops.Hp * ops.Wp) * (hm * wm) * ncols * ops.G
+            kernel_events.append((ev0, ev1, flops))
 
 
 def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, precision: str = "fp16x3",
