@@ -49,10 +49,12 @@ int sir_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Replaces, for the gallery operand, similarity.py:92 (crop), :49 (zero mean) and prepares the
  * operands of :53-55 (numerator) and :57-65 (window energy).
  *
- * d_gallery [G][C][hg][wg] f32  ->  d_ghi, d_glo [G][C][Hp][Wp] f16: (g - mean) * 2^e split as
- * hi = f16(x), lo = f16(x - hi);  d_gexp [G][C] int32: the exponent e (chosen so the channel's
+ * d_gallery [G][C][hg][wg] f32  ->  d_ghi, d_glo [G][C][Hp][WP] f16, WP = sir_gallery_pitch(Wp)
+ * (rows padded with zeros to a multiple of 8 cells so TMA can address them): (g - mean) * 2^e split
+ * as hi = f16(x), lo = f16(x - hi);  d_gexp [G][C] int32: the exponent e (chosen so the channel's
  * max |value| lands in [2^9, 2^10), exact power of two so nothing is rounded by the scaling);
  * d_gz [G][C][Hp][Wp] f32 or NULL: the zero-meaned, UNscaled map (operand of the SIMT path). */
+int sir_gallery_pitch(int Wp);
 int sir_gallery_pack(const float* d_gallery, int G, int C, int hg, int wg,
                      uint16_t* d_ghi, uint16_t* d_glo, int32_t* d_gexp, float* d_gz, void* stream);
 

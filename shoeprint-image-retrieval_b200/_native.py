@@ -25,6 +25,7 @@ SIGNATURES = {
     "sir_last_error": (C.c_char_p, []),
     "sir_abi_version": (_i, []),
     "sir_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "sir_gallery_pitch": (_i, [_i]),
     "sir_gallery_pack": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "sir_gallery_window_rnorm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "sir_variant_rotate": (_i, [_p, _i, _i, _i, _i, C.c_double, _p, _p]),

@@ -47,6 +47,10 @@ constexpr int kGalleryPeakLog2 = 10;    // packed gallery channels have max|v| i
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
+// Row pitch (cells) of the packed fp16 gallery operands: rows padded to 8 cells = 16 bytes so a TMA
+// tensor map can walk them (global strides must be multiples of 16 bytes).
+__host__ __device__ inline int gal_pitch(int Wp) { return round_up(Wp, 8); }
+
 // Number of 8-tap chunks per template row and padded K (multiple of 32) -- see sir_template_kpad.
 __host__ __device__ inline int tpl_chunks_per_row(int Wm) { return ceil_div(Wm, 8); }
 __host__ __device__ inline int tpl_kpad(int Hm, int Wm) { return round_up(Hm * tpl_chunks_per_row(Wm) * 8, 32); }

@@ -36,6 +36,8 @@
 //   warps 4-11  epilogue: tcgen05.ld, row-scale FMA into 128 registers/thread, final max
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "sir_common.cuh"
 #include "sir_ptx.cuh"
 
@@ -74,7 +76,9 @@ struct TcParams {
   // shared memory carve-up (byte offsets from the 1024-aligned base)
   uint32_t off_b, off_e, off_gs, off_cm, off_bar;
   uint32_t e_half_bytes;   // one E buffer, one half (hi or lo)
-  uint32_t gs_half_elems;  // staging elements per half
+  uint32_t gs_half_elems;  // staging cells per half per buffer >= gs_rows * (Pe + 16)
+  int gs_rows;             // rows of the staging TMA box (max rows any segment needs)
+  int gs_bufs;             // 2: stage one segment ahead; 1: no lookahead (very wide templates)
 };
 
 struct Seg {
@@ -83,19 +87,41 @@ struct Seg {
   int rows;       // E rows to build
 };
 
-__device__ __forceinline__ Seg seg_geometry(const TcParams& p, int sg) {
+// K range of one work unit.  Template rows whose 16 image rows all fall outside the gallery map
+// multiply zeros only ("same"-mode padding): they are skipped by every role, stage-aligned.
+struct KRange {
+  int ks_lo, ks_hi;  // K16 steps with a non-zero A operand
+  int st_lo, st_hi;  // B stages covering them
+  int nseg;
+};
+
+__device__ __forceinline__ KRange k_range(const TcParams& p, int py) {
+  const int a = p.Hm / 2;
+  const int u_lo = max(0, a - 16 * py - 15);
+  const int u_hi = min(p.Hm, p.Hp + a - 16 * py);
+  KRange r;
+  r.ks_lo = (u_lo * p.nkc) / 2;
+  r.ks_hi = min(p.nsteps, (u_hi * p.nkc + 1) / 2);
+  r.st_lo = r.ks_lo / 2;
+  r.st_hi = (r.ks_hi + 1) / 2;
+  r.nseg = (r.st_hi - r.st_lo + p.seg_stages - 1) / p.seg_stages;
+  return r;
+}
+
+__device__ __forceinline__ Seg seg_geometry(const TcParams& p, const KRange& kr, int sg) {
   Seg s;
-  s.st0 = sg * p.seg_stages;
-  s.st1 = min(s.st0 + p.seg_stages, p.nkstages);
+  s.st0 = kr.st_lo + sg * p.seg_stages;
+  s.st1 = min(s.st0 + p.seg_stages, kr.st_hi);
   const int t_first = 4 * s.st0;
-  const int t_last = min(4 * s.st1, 2 * p.nsteps) - 1;
+  const int t_last = min(4 * s.st1, 2 * kr.ks_hi) - 1;
   s.u_first = t_first / p.nkc;
   s.rows = 16 + (t_last / p.nkc - s.u_first);
   return s;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const TcParams p) {
+ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+              const __grid_constant__ CUtensorMap tm_ghi, const __grid_constant__ CUtensorMap tm_glo, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -109,7 +135,8 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   auto bar_eempty = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + 2 + i); };
   auto bar_accfull = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + 4 + i); };
   auto bar_accempty = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + 6 + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + p.off_bar + 8u * (2 * kMaxBStages + 8));
+  auto bar_gsfull = [&](int i) { return bar0 + 8u * (2 * kMaxBStages + 8 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + p.off_bar + 8u * (2 * kMaxBStages + 10));
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nbstages; ++i) {
@@ -121,10 +148,13 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       ptx::mbar_init(bar_eempty(i), 1);
       ptx::mbar_init(bar_accfull(i), 1);
       ptx::mbar_init(bar_accempty(i), kEpiWarps);
+      ptx::mbar_init(bar_gsfull(i), 1);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_hi);
     ptx::prefetch_tmap(&tm_lo);
+    ptx::prefetch_tmap(&tm_ghi);
+    ptx::prefetch_tmap(&tm_glo);
   }
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
   ptx::tc_fence_before();
@@ -132,6 +162,9 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Work units are dealt round-robin (unit = blockIdx.x + k * gridDim.x) in the order
+  // (column tile, patch, gallery): at any moment all CTAs work on the same column tile (one B stream
+  // shared through L2) and on the same patch row (equal cost once zero rows are skipped).
   const int NP = p.npy * p.npx;
   const long long per_tile = (long long)p.G * NP;
   const int Pe = 8 * p.nkc;  // entries per E row
@@ -147,8 +180,9 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       uint32_t bs = 0;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const int nt = (int)(unit / per_tile);
+        const KRange kr = k_range(p, (int)((unit % per_tile) / p.G) / p.npx);
         for (int c = 0; c < p.C; ++c) {
-          for (int st = 0; st < p.nkstages; ++st, ++bs) {
+          for (int st = kr.st_lo; st < kr.st_hi; ++st, ++bs) {
             const int slot = bs % p.nbstages;
             const uint32_t par = (bs / p.nbstages) & 1;
             ptx::mbar_wait(bar_empty(slot), par ^ 1);
@@ -166,14 +200,15 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kTileN);
       uint32_t bs = 0, es = 0, cs = 0;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+        const KRange kr = k_range(p, (int)((unit % per_tile) / p.G) / p.npx);
         for (int c = 0; c < p.C; ++c, ++cs) {
           const int buf = cs & 1;
           ptx::mbar_wait(bar_accempty(buf), ((cs >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * kTileN;
           uint32_t accumulate = 0;
-          for (int sg = 0; sg < p.nseg; ++sg, ++es) {
-            const Seg s = seg_geometry(p, sg);
+          for (int sg = 0; sg < kr.nseg; ++sg, ++es) {
+            const Seg s = seg_geometry(p, kr, sg);
             const int ebuf = es & 1;
             ptx::mbar_wait(bar_efull(ebuf), (es >> 1) & 1);
             ptx::tc_fence_after();
@@ -189,7 +224,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const int ks = 2 * st + kk;
-                if (ks < p.nsteps) {
+                if (ks >= kr.ks_lo && ks < kr.ks_hi) {
                   // A: no swizzle, rows of a core matrix 16 B apart (consecutive entries = consecutive x),
                   // 8-row groups one E row apart (consecutive y), the two K chunks 8 entries apart.
                   const uint32_t a_off = 256u * ks - e_shift;
@@ -216,61 +251,104 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     }
   } else if (warp < 4) {
     // ================================================================== generators (E buffers)
+    // Per (unit, channel, segment): TMA stages the window of the packed channel the segment can
+    // touch (out-of-map cells arrive as zeros), issued one segment ahead into the other staging
+    // buffer; the 64 threads then expand it into the shifted-entry array E.
     const int tg = threadIdx.x - 64;
-    __half* gs_hi = reinterpret_cast<__half*>(base_ptr + p.off_gs);
-    __half* gs_lo = gs_hi + p.gs_half_elems;
-    uint32_t es = 0;
-    for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-      const long long rem = unit % per_tile;
-      const int g = (int)(rem / NP), pidx = (int)(rem % NP);
-      const int py = pidx / p.npx, px = pidx % p.npx;
-      for (int c = 0; c < p.C; ++c) {
-        const size_t gc_off = ((size_t)g * p.C + c) * M;
-        for (int sg = 0; sg < p.nseg; ++sg, ++es) {
-          const Seg s = seg_geometry(p, sg);
-          const int ebuf = es & 1;
-          ptx::mbar_wait(bar_eempty(ebuf), ((es >> 1) & 1) ^ 1);
-          // 1. stage the gallery rows this segment can touch (zeros outside the map)
-          const int y_base = 16 * py + s.u_first - a;
-          for (int i = tg; i < s.rows * p.Wp; i += kGenThreads) {
-            const int r = i / p.Wp, x = i - r * p.Wp, y = y_base + r;
-            __half vh = __ushort_as_half(0), vl = __ushort_as_half(0);
-            if (y >= 0 && y < p.Hp) {
-              vh = p.ghi[gc_off + (size_t)y * p.Wp + x];
-              if (p.passes == 3) vl = p.glo[gc_off + (size_t)y * p.Wp + x];
-            }
-            gs_hi[i] = vh;
-            gs_lo[i] = vl;
-          }
-          ptx::named_bar_sync(1, kGenThreads);
-          // 2. shifted entries: E[r][i] = 8 cells starting at column x_base + i
-          const int x_base = 8 * px - b;
-          uint8_t* e_hi = base_ptr + p.off_e + ebuf * 2 * p.e_half_bytes;
-          uint8_t* e_lo = e_hi + p.e_half_bytes;
-          for (int e = tg; e < s.rows * Pe; e += kGenThreads) {
-            const int r = e / Pe, i = e - r * Pe;
-            const __half* rh = gs_hi + r * p.Wp;
-            const __half* rl = gs_lo + r * p.Wp;
-            uint32_t wh[4], wl[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int x0 = x_base + i + 2 * j, x1 = x0 + 1;
-              const uint16_t h0 = (x0 >= 0 && x0 < p.Wp) ? __half_as_ushort(rh[x0]) : (uint16_t)0;
-              const uint16_t h1 = (x1 >= 0 && x1 < p.Wp) ? __half_as_ushort(rh[x1]) : (uint16_t)0;
-              wh[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              if (p.passes == 3) {
-                const uint16_t l0 = (x0 >= 0 && x0 < p.Wp) ? __half_as_ushort(rl[x0]) : (uint16_t)0;
-                const uint16_t l1 = (x1 >= 0 && x1 < p.Wp) ? __half_as_ushort(rl[x1]) : (uint16_t)0;
-                wl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-              }
-            }
-            *reinterpret_cast<uint4*>(e_hi + 16u * e) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-            if (p.passes == 3) *reinterpret_cast<uint4*>(e_lo + 16u * e) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-          }
-          ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async reads
-          ptx::mbar_arrive(bar_efull(ebuf));
-          ptx::named_bar_sync(1, kGenThreads);  // staging area is reused by the next segment
+    // staged cells per row: TMA needs a 16-byte aligned start column, so the window starts at the
+    // multiple of 8 at or below (8*px - b) and is 8 cells wider than the entries need
+    const int SP = Pe + 16;
+    const uint32_t gs_bytes_half = 2u * p.gs_half_elems;
+    const uint32_t gs_tx = 2u * SP * p.gs_rows * (p.passes == 3 ? 2 : 1);  // bytes one staging TMA round delivers
+
+    struct Cursor {
+      long long unit;
+      int c, sg, g, py, px;
+      KRange kr;
+    };
+    auto decode = [&](Cursor& cu) {
+      const long long rem = cu.unit % per_tile;
+      const int pidx = (int)(rem / p.G);
+      cu.g = (int)(rem % p.G);
+      cu.py = pidx / p.npx;
+      cu.px = pidx % p.npx;
+      cu.kr = k_range(p, cu.py);
+    };
+    auto advance = [&](Cursor& cu) {
+      if (++cu.sg < cu.kr.nseg) return;
+      cu.sg = 0;
+      if (++cu.c < p.C) return;
+      cu.c = 0;
+      cu.unit += gridDim.x;
+      if (cu.unit < p.nunits) decode(cu);
+    };
+    auto issue_stage = [&](const Cursor& cu, int sbuf) {  // one thread
+      const Seg sgm = seg_geometry(p, cu.kr, cu.sg);
+      const uint32_t dst = base + p.off_gs + sbuf * 2 * gs_bytes_half;
+      ptx::fence_proxy_async_smem();  // earlier generic reads of this buffer precede the async write
+      ptx::mbar_arrive_expect_tx(bar_gsfull(sbuf), gs_tx);
+      const int x0 = (8 * cu.px - b) & ~7, y0 = 16 * cu.py + sgm.u_first - a, z0 = cu.g * p.C + cu.c;
+      ptx::tma_load_3d(dst, &tm_ghi, bar_gsfull(sbuf), x0, y0, z0);
+      if (p.passes == 3) ptx::tma_load_3d(dst + gs_bytes_half, &tm_glo, bar_gsfull(sbuf), x0, y0, z0);
+    };
+
+    Cursor cur{};
+    cur.unit = blockIdx.x;
+    if (cur.unit < p.nunits) {
+      decode(cur);
+      Cursor nxt = cur;
+      advance(nxt);
+      const bool ahead = p.gs_bufs == 2;
+      if (tg == 0 && ahead) issue_stage(cur, 0);
+      uint32_t es = 0;
+      while (cur.unit < p.nunits) {
+        const int ebuf = es & 1, sbuf = ahead ? (es & 1) : 0;
+        if (tg == 0) {
+          if (!ahead) issue_stage(cur, 0);
+          else if (nxt.unit < p.nunits) issue_stage(nxt, sbuf ^ 1);
         }
+        const Seg s = seg_geometry(p, cur.kr, cur.sg);
+        ptx::mbar_wait(bar_eempty(ebuf), ((es >> 1) & 1) ^ 1);
+        ptx::mbar_wait(bar_gsfull(sbuf), ahead ? ((es >> 1) & 1) : (es & 1));
+        const __half* gs_hi = reinterpret_cast<const __half*>(base_ptr + p.off_gs + sbuf * 2 * gs_bytes_half);
+        const __half* gs_lo = gs_hi + p.gs_half_elems;
+        // shifted entries E[r][i] = gs[r][i .. i+7]; one thread emits an even/odd pair from five
+        // aligned 32-bit words (the odd entry is the even one funnel-shifted by one cell)
+        uint8_t* e_hi = base_ptr + p.off_e + ebuf * 2 * p.e_half_bytes;
+        uint8_t* e_lo = e_hi + p.e_half_bytes;
+        const int pairs_per_row = Pe / 2;
+        const int delta = (8 * cur.px - b) & 7;  // first needed cell inside the aligned window
+        const bool odd = delta & 1;
+        for (int pr = tg; pr < s.rows * pairs_per_row; pr += kGenThreads) {
+          const int r = pr / pairs_per_row, ip = pr - r * pairs_per_row;
+          const int wofs = (delta >> 1) + ip;  // 32-bit word holding the pair's first (even) cell
+          {
+            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(gs_hi + r * SP) + wofs;
+            const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
+            const uint4 al = odd ? make_uint4(w1, w2, w3, w4) : make_uint4(w0, w1, w2, w3);
+            const uint4 sh = make_uint4(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16), __funnelshift_r(w2, w3, 16),
+                                        __funnelshift_r(w3, w4, 16));
+            uint4* dst = reinterpret_cast<uint4*>(e_hi + 16u * (r * Pe + 2 * ip));
+            dst[0] = odd ? sh : al;
+            dst[1] = odd ? al : sh;
+          }
+          if (p.passes == 3) {
+            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(gs_lo + r * SP) + wofs;
+            const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
+            const uint4 al = odd ? make_uint4(w1, w2, w3, w4) : make_uint4(w0, w1, w2, w3);
+            const uint4 sh = make_uint4(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16), __funnelshift_r(w2, w3, 16),
+                                        __funnelshift_r(w3, w4, 16));
+            uint4* dst = reinterpret_cast<uint4*>(e_lo + 16u * (r * Pe + 2 * ip));
+            dst[0] = odd ? sh : al;
+            dst[1] = odd ? al : sh;
+          }
+        }
+        ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async reads
+        ptx::mbar_arrive(bar_efull(ebuf));
+        ptx::named_bar_sync(1, kGenThreads);  // everyone is done reading staging[sbuf]
+        cur = nxt;
+        advance(nxt);
+        ++es;
       }
     }
   }
@@ -287,7 +365,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
       const int nt = (int)(unit / per_tile);
       const long long rem = unit % per_tile;
-      const int g = (int)(rem / NP), pidx = (int)(rem % NP);
+      const int pidx = (int)(rem / p.G), g = (int)(rem % p.G);
       const int py = pidx / p.npx, px = pidx % p.npx;
       const int y = 16 * py + mh, x = 8 * px + ml;
       const bool valid = (y < p.Hp) && (x < p.Wp);
@@ -375,6 +453,30 @@ int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_
   }
   return SIR_OK;
 }
+// Packed gallery channels [planes][Hp][pitch] f16; box = one staging window (cols x rows), no
+// swizzle, out-of-bounds cells (the "same"-mode zero padding, negative coordinates included) read 0.
+int make_gallery_map(CUtensorMap* tm, const uint16_t* ptr, int planes, int Hp, int Wp, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SIR_E_CUDA;
+  }
+  const int pitch = gal_pitch(Wp);
+  // the logical width is Wp (pad cells are zero anyway, but keeping them out of bounds is free)
+  cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * (cuuint64_t)Hp};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(gallery) failed with CUresult %d (planes=%d Hp=%d Wp=%d box=%dx%d)", (int)r, planes, Hp,
+              Wp, box_cols, box_rows);
+    return SIR_E_CUDA;
+  }
+  return SIR_OK;
+}
 }  // namespace
 
 int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, int G, int C, int Hp, int Wp,
@@ -410,22 +512,26 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   const int Pe = 8 * p.nkc;
   const size_t limit = 227 * 1024 - 1024;  // alignment slack
   bool ok = false;
-  for (int nb = 4; nb >= 2 && !ok; --nb) {
-    for (int seg = p.nkstages; seg >= 1; --seg) {
-      // rows touched by a segment of `seg` stages: worst case over alignments
-      const int max_rows = 16 + (4 * seg - 1) / p.nkc + 1;
-      const size_t e_half = (size_t)(max_rows + 1) * Pe * 16;
-      const size_t gs_half = (size_t)(max_rows + 1) * Wp;
-      const size_t total = (size_t)nb * stage_bytes + 2 * halves * e_half + 2 * gs_half * 2 + 4 * kTileN * 4 + 256;
-      if (total <= limit) {
-        p.nbstages = nb;
-        p.seg_stages = seg;
-        p.e_half_bytes = (uint32_t)round_up((int)e_half, 128);
-        p.gs_half_elems = (uint32_t)round_up((int)gs_half, 8);
-        ok = true;
-        break;
+  for (int gsb = 2; gsb >= 1 && !ok; --gsb) {
+    for (int nb = 4; nb >= 2 && !ok; --nb) {
+      for (int seg = p.nkstages; seg >= 1; --seg) {
+        // rows touched by a segment of `seg` stages: worst case over alignments
+        const int max_rows = 16 + (4 * seg - 1) / p.nkc + 1;
+        const size_t e_half = (size_t)(max_rows + 1) * Pe * 16;
+        const size_t gs_half = (size_t)(max_rows + 1) * (Pe + 16);  // cells
+        const size_t total = (size_t)nb * stage_bytes + 2 * halves * e_half + (size_t)gsb * 2 * (gs_half * 2 + 128) + 4 * kTileN * 4 + 256;
+        if (total <= limit) {
+          p.nbstages = nb;
+          p.seg_stages = seg;
+          p.e_half_bytes = (uint32_t)round_up((int)e_half, 128);
+          p.gs_half_elems = (uint32_t)round_up((int)gs_half, 64);  // 128-byte aligned TMA destinations
+          p.gs_rows = max_rows + 1;
+          p.gs_bufs = gsb;
+          ok = true;
+          break;
+        }
+        if (seg > 64) seg -= seg / 8;  // coarse search for very long K
       }
-      if (seg > 64) seg -= seg / 8;  // coarse search for very long K
     }
   }
   SIR_CHECK_ARG(ok, "sir_ncc_scores: template %dx%d does not fit the shared-memory plan", Hm, Wm);
@@ -433,15 +539,22 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   p.off_b = 0;
   p.off_e = p.off_b + p.nbstages * stage_bytes;
   p.off_gs = p.off_e + 2 * 2 * p.e_half_bytes;
-  p.off_cm = (uint32_t)round_up((int)(p.off_gs + 2 * p.gs_half_elems * 2), 16);
+  p.off_cm = (uint32_t)round_up((int)(p.off_gs + p.gs_bufs * 2 * p.gs_half_elems * 2), 16);
   p.off_bar = p.off_cm + 4 * kTileN * 4;
   const size_t smem = 1024 + p.off_bar + 256;
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_scores: shared-memory plan overflow (%zu bytes)", smem);
 
-  CUtensorMap tm_hi, tm_lo;
+  SIR_CHECK_ARG(Pe + 16 <= 256 && p.gs_rows <= 256, "sir_ncc_scores: template %dx%d exceeds the staging TMA box", Hm, Wm);
+  SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ghi) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_glo) & 15) == 0,
+                "sir_ncc_scores: gallery operands must be 16-byte aligned");
+  CUtensorMap tm_hi, tm_lo, tm_ghi, tm_glo;
   int rc = make_template_map(&tm_hi, d_thi, Kpad, ncols_alloc, C);
   if (rc) return rc;
   rc = make_template_map(&tm_lo, d_tlo, Kpad, ncols_alloc, C);
+  if (rc) return rc;
+  rc = make_gallery_map(&tm_ghi, d_ghi, G * C, Hp, Wp, Pe + 16, p.gs_rows);
+  if (rc) return rc;
+  rc = make_gallery_map(&tm_glo, d_glo, G * C, Hp, Wp, Pe + 16, p.gs_rows);
   if (rc) return rc;
 
   static thread_local size_t configured = 0;
@@ -453,7 +566,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   SIR_CUDA(cudaGetDevice(&dev));
   SIR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned grid = (unsigned)std::min<long long>(p.nunits, sms);
-  ncc_tc_kernel<<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, p);
+  ncc_tc_kernel<<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_ghi, tm_glo, p);
   SIR_LAUNCH_CHECK("ncc_tc_kernel");
   return SIR_OK;
 }

@@ -43,15 +43,19 @@ __global__ void __launch_bounds__(256) gallery_pack_kernel(const float* __restri
   }
   if (threadIdx.x == 0) gexp[gc] = e;
 
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    const int y = i / Wp, x = i - y * Wp;
-    const float z = src[(y + kEdge) * wg + x + kEdge] - mean;
-    const float s = ldexpf(z, e);
-    const __half h = __float2half_rn(s);
-    const __half l = __float2half_rn(s - __half2float(h));
-    ghi[gc * M + i] = h;
-    glo[gc * M + i] = l;
-    if (gz) gz[gc * M + i] = z;
+  const int WP = gal_pitch(Wp);  // padded row pitch of the fp16 operands (pad cells are zero)
+  for (int i = threadIdx.x; i < Hp * WP; i += blockDim.x) {
+    const int y = i / WP, x = i - y * WP;
+    __half h = __ushort_as_half(0), l = __ushort_as_half(0);
+    if (x < Wp) {
+      const float z = src[(y + kEdge) * wg + x + kEdge] - mean;
+      const float s = ldexpf(z, e);
+      h = __float2half_rn(s);
+      l = __float2half_rn(s - __half2float(h));
+      if (gz) gz[gc * M + y * Wp + x] = z;
+    }
+    ghi[gc * Hp * WP + i] = h;
+    glo[gc * Hp * WP + i] = l;
   }
 }
 
@@ -72,7 +76,8 @@ __global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restr
     double v = 0.0;
     if (y > 0 && x > 0) {
       const size_t j = gc * M + (size_t)(y - 1) * Wp + (x - 1);
-      v = gz ? (double)gz[j] : (double)__half2float(ghi[j]) + (double)__half2float(glo[j]);
+      const size_t jp = (gc * Hp + (size_t)(y - 1)) * gal_pitch(Wp) + (x - 1);
+      v = gz ? (double)gz[j] : (double)__half2float(ghi[jp]) + (double)__half2float(glo[jp]);
     }
     s1[i] = v;
     s2[i] = v * v;
@@ -383,6 +388,8 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
   if (w2 != w) return run_pass(d_in, d_out, planes, h, w, h, w2, 1, st);
   return run_pass(d_in, d_out, planes, h, w, h2, w, 0, st);
 }
+
+extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }
 
 extern "C" int sir_template_kpad(int Hm, int Wm) { return (Hm > 0 && Wm > 0) ? tpl_kpad(Hm, Wm) : 0; }
 

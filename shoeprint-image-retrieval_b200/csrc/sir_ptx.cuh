@@ -52,7 +52,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+#ifdef SIR_DEBUG_BARRIERS
+      printf("sir: mbarrier timeout block %d thread %d bar_off %u parity %u\n", blockIdx.x, threadIdx.x, bar & 0xfff, parity);
+#endif
       __trap();
     }
   }

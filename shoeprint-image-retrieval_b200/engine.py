@@ -150,7 +150,7 @@ class GalleryOperands:
         n, c, h, w = (int(v) for v in group.maps.shape)
         hp, wp = h - 2 * EDGE, w - 2 * EDGE
         dev = group.maps.device
-        ghi = torch.empty((n, c, hp, wp), dtype=torch.float16, device=dev)
+        ghi = torch.empty((n, c, hp, int(nat.lib.sir_gallery_pitch(wp))), dtype=torch.float16, device=dev)
         glo = torch.empty_like(ghi)
         gexp = torch.empty((n, c), dtype=torch.int32, device=dev)
         gz = torch.empty((n, c, hp, wp), dtype=torch.float32, device=dev) if keep_fp32 else None

@@ -39,7 +39,7 @@ def test_gallery_pack_and_window_rnorm(eng):
     z = crop - crop.mean(axis=(2, 3), keepdims=True, dtype=np.float64).astype(np.float32)
     np.testing.assert_allclose(ops.gz.cpu().numpy(), z, rtol=0, atol=2e-6)
     e = ops.gexp.cpu().numpy()
-    packed = ops.ghi.float().cpu().numpy().astype(np.float64) + ops.glo.float().cpu().numpy()
+    packed = (ops.ghi.float().cpu().numpy().astype(np.float64) + ops.glo.float().cpu().numpy())[..., : maps.shape[3] - 4]
     scaled = ops.gz.cpu().numpy().astype(np.float64) * (2.0 ** e)[:, :, None, None]
     assert np.abs(scaled).max() < 1024 and np.abs(scaled).reshape(5, 3, -1).max(-1).min() >= 512
     np.testing.assert_allclose(packed, scaled, rtol=0, atol=1024 * 2.0**-21)

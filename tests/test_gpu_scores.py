@@ -38,6 +38,8 @@ CASES = [
     (4, (19, 14), 3, 3, 0.7, [-15, 9], [1.08]),      # both: 1 + (R+1)*S variants
     (2, (40, 9), 2, 2, 1.0, None, None),             # tall and thin
     (2, (9, 44), 2, 2, 1.0, None, None),             # short and wide (6 chunks per row)
+    (2, (70, 40), 2, 2, 1.0, None, None),            # large template: several E segments per channel
+    (2, (68, 132), 1, 1, 1.0, None, None),           # 1024x2048-input sized maps (config 5 shape), 16 chunks/row
 ]
 
 
