@@ -65,8 +65,8 @@ def merge_ranks(true_score, count_gt, count_ge, topk_val, topk_idx, group=None, 
             q = topk_val.shape[0]
             all_v = torch.empty((world, q, k), dtype=topk_val.dtype, device=topk_val.device)
             all_i = torch.empty((world, q, k), dtype=topk_idx.dtype, device=topk_idx.device)
-            dist.all_gather_into_tensor(all_v, topk_val.contiguous(), group=group)
-            dist.all_gather_into_tensor(all_i, topk_idx.contiguous(), group=group)
+            dist.all_gather(list(all_v.unbind(0)), topk_val.contiguous(), group=group)
+            dist.all_gather(list(all_i.unbind(0)), topk_idx.contiguous(), group=group)
             topk_val, topk_idx = (merge_fn or _merge_topk_cuda)(all_v, all_i, k)
     return count_gt + 1, torch.clamp(count_ge, min=1), topk_val, topk_idx
 
