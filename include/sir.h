@@ -115,6 +115,43 @@ int sir_rank_topk(const float* d_scores, int Q, int G, int score_ld, const float
 int sir_merge_topk(const float* d_vals, const int32_t* d_idx, int P, int Q, int k,
                    float* d_out_val, int32_t* d_out_idx, void* stream);
 
+/* ------------------------------------------------------------------ feature stage (K1-K3)
+ * The truncated backbone of network.py:185-186,234-235, operator by operator.  Activations are
+ * float32 NHWC [B][H][W][C] on the device.  Every producer maintains a running max |value| of its
+ * output in a device float (`d_amax_out`, zeroed by the caller before the forward pass); the next
+ * convolution reads it (`d_amax_in`) to pick the power-of-two scaling of its fp16 hi/lo operands.
+ * act: 0 none, 1 SiLU, 2 ReLU.
+ *
+ * sir_feat_image_to_nhwc: ToTensor + (grayscale repeat) + Normalize, network.py:51-87.
+ *   d_img uint8 [B][H][W] (in_ch 1) or [B][H][W][3]; h_mean/h_std: 3 host floats.
+ * sir_feat_im2col_split + sir_feat_gemm: Conv2d (groups 1, any kernel/stride/pad) with folded
+ *   BatchNorm, bias, activation and optional residual add (FusedMBConv/MBConv skip connection).
+ *   A [M = B*Ho*Wo][Kp] f16 hi/lo, k = (ky*kw + kx)*C + c, Kp a multiple of 32;  d_chan_scale
+ *   [B][C] or NULL multiplies the input per (image, channel) (squeeze-excitation scale).
+ *   Weights d_bhi/d_blo [n_rows_alloc][Kp] f16 = W * 2^w_exp split hi/lo, rows >= N zero.
+ *   out[m][n] = act(A.B^T * 2^-(e(amax_in)+w_exp) + bias[n]) + residual[m][n], row stride ldc.
+ * sir_feat_dwconv: depthwise k x k Conv2d + folded BN bias + activation; weights [k][k][C].
+ * sir_feat_se_scale: SqueezeExcitation._scale: global average (d_avg [B][C] scratch), fc1 [S][C] +
+ *   SiLU, fc2 [C][S] + sigmoid -> d_scale [B][C].
+ * sir_feat_maxpool: MaxPool2d (VGG).   sir_feat_nhwc_to_nchw: [B][HW][C] -> [B][C][HW]. */
+int sir_feat_image_to_nhwc(const uint8_t* d_img, int B, int H, int W, int in_ch, const float* h_mean, const float* h_std,
+                           float* d_out, float* d_amax_out, void* stream);
+int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int H, int W, int C, int kh, int kw, int stride,
+                          int pad, const float* d_chan_scale, int Kp, uint16_t* d_ahi, uint16_t* d_alo, void* stream);
+int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
+                  const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
+                  const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream);
+int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, const float* d_w,
+                    const float* d_bias, int act, float* d_out, float* d_amax_out, void* stream);
+int sir_feat_se_scale(const float* d_in, int B, int HW, int C, int S, const float* d_w1, const float* d_b1,
+                      const float* d_w2, const float* d_b2, float* d_avg, float* d_scale, void* stream);
+int sir_feat_maxpool(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, float* d_out,
+                     float* d_amax_out, void* stream);
+/* per-channel y = act(x * scale[c] + shift[c]) (scale/shift both NULL: activation only) */
+int sir_feat_affine_act(const float* d_in, long long total, int C, const float* d_scale, const float* d_shift, int act,
+                        float* d_out, float* d_amax_out, void* stream);
+int sir_feat_nhwc_to_nchw(const float* d_in, int B, int HW, int C, float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,14 @@ SIGNATURES = {
     "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
     "sir_rank_topk": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "sir_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "sir_feat_image_to_nhwc": (_i, [_p, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p]),
+    "sir_feat_im2col_split": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
+    "sir_feat_gemm": (_i, [_p, _p, _p, C.c_longlong, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p]),
+    "sir_feat_dwconv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
+    "sir_feat_se_scale": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "sir_feat_maxpool": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "sir_feat_affine_act": (_i, [_p, C.c_longlong, _i, _p, _p, _i, _p, _p, _p]),
+    "sir_feat_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _p, _p]),
 }
 
 

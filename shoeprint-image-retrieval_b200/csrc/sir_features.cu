@@ -1,0 +1,554 @@
+// Feature stage (K1-K3): the truncated CNN backbone of network.py:185-186,234-235 as hand-written
+// sm_100a kernels, operator by operator.  Activations are float32 NHWC in HBM.
+//
+//   K1  convolution (any kernel/stride/pad, groups=1) = im2col_split_kernel (gather + fp16 hi/lo
+//       split, per-tensor power-of-two scaling from a device-side running |max|) followed by
+//       gemm_tc_kernel: tcgen05.mma (kind::f16, fp32 accumulate in TMEM) fed by TMA through a
+//       4-stage mbarrier ring, three MMAs per K step (hi*hi + lo*hi + hi*lo) for fp32-grade
+//       results, epilogue fused: un-scale, + bias (folded BatchNorm), SiLU / ReLU, + residual.
+//   K2  depthwise k x k convolution + bias + activation (CUDA cores, HBM bound), global average
+//       pool for the squeeze.
+//   K3  squeeze-excitation MLP (two tiny FCs, SiLU, sigmoid); the channel scale is applied by the
+//       im2col/split pass of the following 1x1 projection, i.e. fused into its operand load.
+//
+// Reference semantics: torchvision Conv2d / BatchNorm2d(eval) / SiLU / SqueezeExcitation /
+// MaxPool2d as composed by torchvision.models.efficientnet / vgg (third party; the reference only
+// selects and truncates them, network.py:121-186).  ToTensor + Normalize (network.py:51-87) are
+// image_to_nhwc_kernel.
+#include <cuda.h>
+
+#include "sir_common.cuh"
+#include "sir_ptx.cuh"
+
+namespace sir {
+
+// ------------------------------------------------------------------------------------------ misc
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == 1) return v / (1.0f + expf(-v));  // SiLU
+  if (act == 2) return fmaxf(v, 0.0f);         // ReLU
+  return v;
+}
+// exponent e with amax * 2^e in [2^9, 2^10); 0 for an all-zero tensor
+__device__ __forceinline__ int scale_exp_from_amax(float amax) {
+  if (!(amax > 0.0f) || !isfinite(amax)) return 0;
+  int ex;
+  (void)frexpf(amax, &ex);
+  return kGalleryPeakLog2 - ex;
+}
+
+// uint8 image(s) -> normalised float32 NHWC with 3 channels (network.py:51-87: ToTensor, repeat to
+// 3 channels for grayscale, Normalize(mean, std)).
+__global__ void __launch_bounds__(256) image_to_nhwc_kernel(const uint8_t* __restrict__ img, int in_ch, size_t pixels,
+                                                            float m0, float m1, float m2, float s0, float s1, float s2,
+                                                            float* __restrict__ out, float* __restrict__ amax) {
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pixels; i += (size_t)gridDim.x * blockDim.x) {
+    float v[3];
+    if (in_ch == 1) {
+      const float x = __fdiv_rn((float)img[i], 255.0f);
+      v[0] = v[1] = v[2] = x;
+    } else {
+      v[0] = __fdiv_rn((float)img[3 * i], 255.0f);
+      v[1] = __fdiv_rn((float)img[3 * i + 1], 255.0f);
+      v[2] = __fdiv_rn((float)img[3 * i + 2], 255.0f);
+    }
+    v[0] = __fdiv_rn(v[0] - m0, s0);
+    v[1] = __fdiv_rn(v[1] - m1, s1);
+    v[2] = __fdiv_rn(v[2] - m2, s2);
+    out[3 * i] = v[0];
+    out[3 * i + 1] = v[1];
+    out[3 * i + 2] = v[2];
+    local = fmaxf(local, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(amax, local);
+}
+
+// ------------------------------------------------------------------------------------------ K1a
+// im2col + split: A[m][k] = in[b][oy*s - pad + ky][ox*s - pad + kx][c] * chan_scale[b][c], k = (ky*kw + kx)*C + c,
+// scaled by 2^e(amax_in) and split into fp16 hi/lo.  One thread produces 8 consecutive k (16 bytes).
+__global__ void __launch_bounds__(256) im2col_split_kernel(const float* __restrict__ in, const float* __restrict__ amax_in,
+                                                           int B, int H, int W, int C, int kh, int kw, int stride, int pad,
+                                                           int Ho, int Wo, const float* __restrict__ chan_scale, int Kp,
+                                                           __half* __restrict__ ahi, __half* __restrict__ alo) {
+  const int K = kh * kw * C;
+  const int e = scale_exp_from_amax(*amax_in);
+  const size_t M = (size_t)B * Ho * Wo;
+  const int k8s = Kp / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M * k8s; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / k8s;
+    const int k0 = (int)(i - m * k8s) * 8;
+    const int b = (int)(m / ((size_t)Ho * Wo));
+    const int r = (int)(m - (size_t)b * Ho * Wo);
+    const int oy = r / Wo, ox = r - oy * Wo;
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      float v = 0.0f;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+        const int ky = tap / kw, kx = tap - ky * kw;
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          v = in[(((size_t)b * H + iy) * W + ix) * C + c];
+          if (chan_scale) v *= chan_scale[(size_t)b * C + c];
+        }
+      }
+      const float s = ldexpf(v, e);
+      hi[j] = __float2half_rn(s);
+      lo[j] = __float2half_rn(s - __half2float(hi[j]));
+    }
+    *reinterpret_cast<uint4*>(ahi + m * Kp + k0) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(alo + m * Kp + k0) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K1b
+// C[m][n] = act((A_hi+A_lo)[m][:] . (B_hi+B_lo)[n][:] * 2^-(ea+ew) + bias[n]) (+ residual[m][n])
+constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
+constexpr int kGemmStages = 4;
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 32;
+constexpr uint32_t kGemmSub = 8192;  // one operand half of one stage (128 rows x 64 B)
+
+struct GemmParams {
+  int M, N, Kp, BN;
+  int w_exp;
+  const float* amax_in;
+  const float* bias;
+  const float* residual;
+  float* out;
+  float* amax_out;
+  int ldc, act;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+               const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = base + kGemmStages * 4 * kGemmSub;
+  auto bar_full = [&](int i) { return bar0 + 8u * i; };
+  auto bar_empty = [&](int i) { return bar0 + 8u * (kGemmStages + i); };
+  const uint32_t bar_acc = bar0 + 8u * (2 * kGemmStages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kGemmStages * 4 * kGemmSub + 8u * (2 * kGemmStages + 1));
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGemmStages; ++i) {
+      ptx::mbar_init(bar_full(i), 1);
+      ptx::mbar_init(bar_empty(i), 1);
+    }
+    ptx::mbar_init(bar_acc, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tm_ahi);
+    ptx::prefetch_tmap(&tm_alo);
+    ptx::prefetch_tmap(&tm_bhi);
+    ptx::prefetch_tmap(&tm_blo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot))),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * p.BN;
+  const int nk = p.Kp / kGemmBK;
+  const uint32_t stage_tx = 2 * kGemmSub + 2 * (uint32_t)p.BN * 64;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      for (int ks = 0; ks < nk; ++ks) {
+        const int slot = ks % kGemmStages;
+        ptx::mbar_wait(bar_empty(slot), ((ks / kGemmStages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar_full(slot), stage_tx);
+        const uint32_t dst = base + slot * 4 * kGemmSub;
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                     "l"(reinterpret_cast<uint64_t>(&tm_ahi)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(m0)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst + kGemmSub),
+                     "l"(reinterpret_cast<uint64_t>(&tm_alo)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(m0)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst + 2 * kGemmSub),
+                     "l"(reinterpret_cast<uint64_t>(&tm_bhi)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(n0)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst + 3 * kGemmSub),
+                     "l"(reinterpret_cast<uint64_t>(&tm_blo)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(n0)
+                     : "memory");
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_f16(kGemmBM, p.BN);
+      uint32_t accumulate = 0;
+      for (int ks = 0; ks < nk; ++ks) {
+        const int slot = ks % kGemmStages;
+        ptx::mbar_wait(bar_full(slot), (ks / kGemmStages) & 1);
+        ptx::tc_fence_after();
+        const uint32_t a_hi = base + slot * 4 * kGemmSub, a_lo = a_hi + kGemmSub, b_hi = a_hi + 2 * kGemmSub, b_lo = a_hi + 3 * kGemmSub;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {  // two K16 steps per 32-wide stage: +32 B inside the 64B-swizzle row
+          const uint64_t da_hi = ptx::make_smem_desc(a_hi + 32u * kk, 16, 512, 4);
+          const uint64_t da_lo = ptx::make_smem_desc(a_lo + 32u * kk, 16, 512, 4);
+          const uint64_t db_hi = ptx::make_smem_desc(b_hi + 32u * kk, 16, 512, 4);
+          const uint64_t db_lo = ptx::make_smem_desc(b_lo + 32u * kk, 16, 512, 4);
+          ptx::mma_f16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
+          ptx::mma_f16_ss(tmem_base, da_lo, db_hi, idesc, 1);
+          ptx::mma_f16_ss(tmem_base, da_hi, db_lo, idesc, 1);
+          accumulate = 1;
+        }
+        ptx::tc_commit(bar_empty(slot));
+      }
+      ptx::tc_commit(bar_acc);
+    }
+  } else {
+    // epilogue: warps 2..5 own TMEM lane quarters 2,3,0,1
+    const int q4 = warp & 3;
+    const int m = m0 + q4 * 32 + lane;
+    const int e_total = scale_exp_from_amax(*p.amax_in) + p.w_exp;
+    const float unscale = ldexpf(1.0f, -e_total);
+    ptx::mbar_wait(bar_acc, 0);
+    ptx::tc_fence_after();
+    float local_max = 0.0f;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + c0, v);
+      ptx::tmem_ld_wait();
+      if (m < p.M) {
+        float* orow = p.out + (size_t)m * p.ldc;
+        const float* rrow = p.residual ? p.residual + (size_t)m * p.ldc : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n + 3 < p.N) {
+            float4 o;
+            const float4 bb = *reinterpret_cast<const float4*>(p.bias + n);
+            o.x = act_apply(fmaf(__uint_as_float(v[j]), unscale, bb.x), p.act);
+            o.y = act_apply(fmaf(__uint_as_float(v[j + 1]), unscale, bb.y), p.act);
+            o.z = act_apply(fmaf(__uint_as_float(v[j + 2]), unscale, bb.z), p.act);
+            o.w = act_apply(fmaf(__uint_as_float(v[j + 3]), unscale, bb.w), p.act);
+            if (rrow) {
+              const float4 rr = *reinterpret_cast<const float4*>(rrow + n);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(orow + n) = o;
+            local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          } else {
+            for (int t = 0; t < 4; ++t) {
+              if (n + t < p.N) {
+                float o = act_apply(fmaf(__uint_as_float(v[j + t]), unscale, p.bias[n + t]), p.act);
+                if (rrow) o += rrow[n + t];
+                orow[n + t] = o;
+                local_max = fmaxf(local_max, fabsf(o));
+              }
+            }
+          }
+        }
+      }
+    }
+    local_max = warp_max(local_max);
+    if (lane == 0 && p.amax_out) atomic_max_nonneg(p.amax_out, local_max);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// depthwise k x k convolution, NHWC float32, weights [k][k][C], + bias, + activation
+__global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, int B, int H, int W, int C, int k, int stride,
+                                                     int pad, int Ho, int Wo, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, int act, float* __restrict__ out,
+                                                     float* __restrict__ amax) {
+  const size_t total = (size_t)B * Ho * Wo * C;
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float acc = 0.0f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        acc = fmaf(in[(((size_t)b * H + iy) * W + ix) * C + c], w[(ky * k + kx) * C + c], acc);
+      }
+    }
+    const float o = act_apply(acc + bias[c], act);
+    out[i] = o;
+    local = fmaxf(local, fabsf(o));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
+}
+
+// global average pool: [B][H*W][C] -> [B][C]; one CTA per (image, 64-channel slab)
+__global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ in, int HW, int C, float* __restrict__ out) {
+  __shared__ float part[4][64];
+  const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), sub = threadIdx.x >> 6;
+  float acc = 0.0f;
+  if (c < C)
+    for (int p = sub; p < HW; p += 4) acc += in[((size_t)b * HW + p) * C + c];
+  part[sub][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (sub == 0 && c < C) out[(size_t)b * C + c] = (part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]) / (float)HW;
+}
+
+// ------------------------------------------------------------------------------------------ K3
+// squeeze-excitation MLP, one CTA per image: scale = sigmoid(W2 . silu(W1 . avg + b1) + b2)
+__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ avg, int C, int S, const float* __restrict__ w1,
+                                                    const float* __restrict__ b1, const float* __restrict__ w2,
+                                                    const float* __restrict__ b2, float* __restrict__ scale) {
+  extern __shared__ float sh[];  // [C] avg, [S] hidden
+  float* savg = sh;
+  float* hid = sh + C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) savg[c] = avg[(size_t)b * C + c];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < S; j += nw) {
+    float acc = 0.0f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], savg[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) hid[j] = act_apply(acc + b1[j], 1);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = b2[c];
+    for (int j = 0; j < S; ++j) acc = fmaf(w2[(size_t)c * S + j], hid[j], acc);
+    scale[(size_t)b * C + c] = 1.0f / (1.0f + expf(-acc));
+  }
+}
+
+// max pooling, NHWC
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ in, int B, int H, int W, int C, int k, int stride,
+                                                      int pad, int Ho, int Wo, float* __restrict__ out, float* __restrict__ amax) {
+  const size_t total = (size_t)B * Ho * Wo * C;
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float best = -INFINITY;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        best = fmaxf(best, in[(((size_t)b * H + iy) * W + ix) * C + c]);
+      }
+    }
+    out[i] = best;
+    local = fmaxf(local, fabsf(best));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
+}
+
+// standalone per-channel affine + activation (BatchNorm2d / ReLU children that a block cut separates
+// from their convolution, e.g. VGG features[:n] ending between Conv2d and ReLU)
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ in, size_t total, int C, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, int act, float* __restrict__ out,
+                                                         float* __restrict__ amax) {
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float v = in[i];
+    if (scale) v = fmaf(v, scale[c], shift[c]);
+    v = act_apply(v, act);
+    out[i] = v;
+    local = fmaxf(local, fabsf(v));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
+}
+
+// NHWC -> NCHW (the reference returns [C,h,w] maps, network.py:238-244)
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, int HW, int C, float* __restrict__ out, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    size_t r = i / HW;
+    const int c = (int)(r % C);
+    const size_t b = r / C;
+    out[i] = in[(b * HW + p) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// row-major fp16 matrix [rows][Kp], box = [box_rows][32], 64-byte swizzle, OOB rows read as zero
+int make_matrix_map(CUtensorMap* tm, const void* ptr, long long rows, int Kp, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SIR_E_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(matrix %lld x %d) failed with CUresult %d", rows, Kp, (int)r);
+    return SIR_E_CUDA;
+  }
+  return SIR_OK;
+}
+unsigned grid_for(size_t work, int per_block = 256) { return (unsigned)std::min<size_t>((work + per_block - 1) / per_block, 148 * 32); }
+}  // namespace
+}  // namespace sir
+
+using namespace sir;
+
+extern "C" int sir_feat_image_to_nhwc(const uint8_t* d_img, int B, int H, int W, int in_ch, const float* h_mean, const float* h_std,
+                                      float* d_out, float* d_amax, void* stream) {
+  SIR_CHECK_ARG(d_img && d_out && d_amax && h_mean && h_std, "sir_feat_image_to_nhwc: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && (in_ch == 1 || in_ch == 3), "sir_feat_image_to_nhwc: bad shape");
+  const size_t pixels = (size_t)B * H * W;
+  image_to_nhwc_kernel<<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>(d_img, in_ch, pixels, h_mean[0], h_mean[1], h_mean[2],
+                                                                            h_std[0], h_std[1], h_std[2], d_out, d_amax);
+  SIR_LAUNCH_CHECK("image_to_nhwc_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int H, int W, int C, int kh, int kw, int stride,
+                                     int pad, const float* d_chan_scale, int Kp, uint16_t* d_ahi, uint16_t* d_alo, void* stream) {
+  SIR_CHECK_ARG(d_in && d_amax_in && d_ahi && d_alo, "sir_feat_im2col_split: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "sir_feat_im2col_split: bad shape");
+  SIR_CHECK_ARG(Kp % 32 == 0 && Kp >= kh * kw * C, "sir_feat_im2col_split: Kp=%d must be a multiple of 32 and >= %d", Kp, kh * kw * C);
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_im2col_split: empty output");
+  const size_t work = (size_t)B * Ho * Wo * (Kp / 8);
+  im2col_split_kernel<<<grid_for(work), 256, 0, (cudaStream_t)stream>>>(d_in, d_amax_in, B, H, W, C, kh, kw, stride, pad, Ho, Wo,
+                                                                         d_chan_scale, Kp, (__half*)d_ahi, (__half*)d_alo);
+  SIR_LAUNCH_CHECK("im2col_split_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
+                             const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
+                             const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream) {
+  SIR_CHECK_ARG(d_ahi && d_alo && d_bhi && d_blo && d_amax_in && d_bias && d_out, "sir_feat_gemm: null pointer");
+  SIR_CHECK_ARG(M > 0 && M < (1ll << 31) && N > 0 && Kp > 0 && Kp % 32 == 0 && ldc >= N, "sir_feat_gemm: bad shape M=%lld N=%d Kp=%d", M, N, Kp);
+  SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_gemm: unknown activation %d", act);
+  GemmParams p{};
+  p.M = (int)M;
+  p.N = N;
+  p.Kp = Kp;
+  p.BN = std::min(128, round_up(N, 32));
+  SIR_CHECK_ARG(n_rows_alloc >= round_up(N, p.BN), "sir_feat_gemm: weight matrix needs %d zero-padded rows, has %d", round_up(N, p.BN), n_rows_alloc);
+  p.w_exp = w_exp;
+  p.amax_in = d_amax_in;
+  p.bias = d_bias;
+  p.residual = d_residual;
+  p.out = d_out;
+  p.amax_out = d_amax_out;
+  p.ldc = ldc;
+  p.act = act;
+  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;
+  SIR_CHECK_ARG(((uintptr_t)d_bias & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ldc % 4 == 0 &&
+                    (!d_residual || ((uintptr_t)d_residual & 15) == 0),
+                "sir_feat_gemm: bias/out/residual must be 16-byte aligned and ldc a multiple of 4");
+  CUtensorMap ta, tb, tc, td;
+  int rc = make_matrix_map(&ta, d_ahi, M, Kp, kGemmBM);
+  if (rc) return rc;
+  rc = make_matrix_map(&tb, d_alo, M, Kp, kGemmBM);
+  if (rc) return rc;
+  rc = make_matrix_map(&tc, d_bhi, n_rows_alloc, Kp, p.BN);
+  if (rc) return rc;
+  rc = make_matrix_map(&td, d_blo, n_rows_alloc, Kp, p.BN);
+  if (rc) return rc;
+  const size_t smem = 1024 + kGemmStages * 4 * kGemmSub + 256;
+  static thread_local bool configured = false;
+  if (!configured) {
+    SIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div((int)M, kGemmBM), (unsigned)ceil_div(N, p.BN));
+  gemm_tc_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ta, tb, tc, td, p);
+  SIR_LAUNCH_CHECK("gemm_tc_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, const float* d_w,
+                               const float* d_bias, int act, float* d_out, float* d_amax_out, void* stream) {
+  SIR_CHECK_ARG(d_in && d_w && d_bias && d_out, "sir_feat_dwconv: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "sir_feat_dwconv: bad shape");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_dwconv: empty output");
+  dwconv_kernel<<<grid_for((size_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_w,
+                                                                                      d_bias, act, d_out, d_amax_out);
+  SIR_LAUNCH_CHECK("dwconv_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_se_scale(const float* d_in, int B, int HW, int C, int S, const float* d_w1, const float* d_b1,
+                                 const float* d_w2, const float* d_b2, float* d_avg, float* d_scale, void* stream) {
+  SIR_CHECK_ARG(d_in && d_w1 && d_b1 && d_w2 && d_b2 && d_avg && d_scale, "sir_feat_se_scale: null pointer");
+  SIR_CHECK_ARG(B > 0 && HW > 0 && C > 0 && S > 0 && (size_t)(C + S) * 4 <= 48 * 1024, "sir_feat_se_scale: bad shape");
+  avgpool_kernel<<<dim3((unsigned)ceil_div(C, 64), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(d_in, HW, C, d_avg);
+  SIR_LAUNCH_CHECK("avgpool_kernel");
+  se_fc_kernel<<<B, 256, (size_t)(C + S) * 4, (cudaStream_t)stream>>>(d_avg, C, S, d_w1, d_b1, d_w2, d_b2, d_scale);
+  SIR_LAUNCH_CHECK("se_fc_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_maxpool(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, float* d_out,
+                                float* d_amax_out, void* stream) {
+  SIR_CHECK_ARG(d_in && d_out, "sir_feat_maxpool: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "sir_feat_maxpool: bad shape");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_maxpool: empty output");
+  maxpool_kernel<<<grid_for((size_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_out,
+                                                                                       d_amax_out);
+  SIR_LAUNCH_CHECK("maxpool_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_affine_act(const float* d_in, long long total, int C, const float* d_scale, const float* d_shift, int act,
+                                   float* d_out, float* d_amax_out, void* stream) {
+  SIR_CHECK_ARG(d_in && d_out && total > 0 && C > 0 && (!d_scale == !d_shift), "sir_feat_affine_act: bad argument");
+  affine_act_kernel<<<grid_for((size_t)total), 256, 0, (cudaStream_t)stream>>>(d_in, (size_t)total, C, d_scale, d_shift, act, d_out, d_amax_out);
+  SIR_LAUNCH_CHECK("affine_act_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_nhwc_to_nchw(const float* d_in, int B, int HW, int C, float* d_out, void* stream) {
+  SIR_CHECK_ARG(d_in && d_out && B > 0 && HW > 0 && C > 0, "sir_feat_nhwc_to_nchw: bad argument");
+  const size_t total = (size_t)B * HW * C;
+  nhwc_to_nchw_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(d_in, HW, C, d_out, total);
+  SIR_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return SIR_OK;
+}

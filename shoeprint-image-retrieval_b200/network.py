@@ -1,0 +1,469 @@
+"""Feature extraction on B200: drop-in for the reference ``network.py``.
+
+Public surface follows the reference (``network.py:90-269``): ``Model(config, block)`` with
+``.get_feature_maps(img)`` and ``.get_multiple_feature_maps(images, *, progress=True)``, attributes
+``.config .clahe .device .model .transform .transform_rgb``, plus the helpers ``get_output_size``
+and ``printmodel``.
+
+What runs where:
+
+* CLAHE stays on the host in OpenCV (``network.py:108-111,197-208``): uint8 in, uint8 out, bit exact.
+* ToTensor / grayscale repeat / Normalize (``network.py:51-87``) and the truncated backbone
+  ``features[:block]`` (``network.py:185-186,234-235``) run through ``libsir.so``: torchvision only
+  *defines* the architecture and holds the weights (exactly its role in the reference); at build
+  time the module tree is compiled into a flat list of operators with BatchNorm folded, and the
+  forward pass is a sequence of ``sir_feat_*`` calls (tcgen05 GEMM convolutions with fused
+  bias/SiLU/residual epilogues, depthwise + squeeze-excitation kernels).  No torch operator runs on
+  activations.
+* Images of equal size are batched (the reference is batch 1, ``network.py:228``); results are
+  returned per image as ``[C, h, w]`` float32 numpy arrays like ``network.py:238-244``.
+
+Pretrained weights need torchvision's cached checkpoints (the reference downloads them).  Offline,
+pass ``random_init_seed=<int>`` (or set ``SIR_RANDOM_INIT_SEED``) to build the same architecture
+with seeded random weights -- what the benchmarks and tests do.
+
+Supported ``config["model"]["type"]``: the EfficientNet family (B1-B7, V2 S/M/L) and VGG16 /
+VGG19 / VGG19_BN.  ``DenseNet_201`` (concatenating blocks) is not compiled yet and raises
+``NotImplementedError``; unknown strings raise ``LookupError("Model string not found")`` like
+``network.py:181-182``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+import torch
+from torch import nn
+from tqdm import tqdm
+
+from . import _native as nat
+from .engine import _ptr, _require_cuda, _stream, launch_counter
+
+ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
+
+_IMAGENET = ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+_VGG16 = ((0.48235, 0.45882, 0.40784), (0.00392156862745098,) * 3)
+_HALF = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
+
+# model string -> (torchvision constructor, pretrained weights tag, (mean, std))   [network.py:121-177]
+_MODELS = {
+    "VGG19": ("vgg19", "IMAGENET1K_V1", _IMAGENET),
+    "VGG16": ("vgg16", "IMAGENET1K_FEATURES", _VGG16),
+    "VGG19_BN": ("vgg19_bn", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNet_B1": ("efficientnet_b1", "IMAGENET1K_V2", _IMAGENET),
+    "EfficientNet_B2": ("efficientnet_b2", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNet_B3": ("efficientnet_b3", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNet_B4": ("efficientnet_b4", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNet_B5": ("efficientnet_b5", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNet_B7": ("efficientnet_b7", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNetV2_S": ("efficientnet_v2_s", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNetV2_M": ("efficientnet_v2_m", "IMAGENET1K_V1", _IMAGENET),
+    "EfficientNetV2_L": ("efficientnet_v2_l", "IMAGENET1K_V1", _HALF),
+    "DenseNet_201": ("densenet201", "IMAGENET1K_V1", _IMAGENET),
+}
+
+
+# --------------------------------------------------------------------------- operator IR
+
+@dataclass
+class _Op:
+    kind: str            # conv | dwconv | se | affine | maxpool
+    src: int             # input tensor id
+    dst: int             # output tensor id
+    p: dict = field(default_factory=dict)
+
+
+def _act_code(m: nn.Module | None) -> int:
+    if m is None or isinstance(m, nn.Identity):
+        return ACT_NONE
+    if isinstance(m, nn.SiLU):
+        return ACT_SILU
+    if isinstance(m, nn.ReLU):
+        return ACT_RELU
+    raise NotImplementedError(f"activation {type(m).__name__} has no sm_100a kernel yet")
+
+
+def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d | None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Conv weight/bias with an eval-mode BatchNorm folded in (float64 arithmetic, float32 result)."""
+    w = conv.weight.detach().double()
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    if bn is not None:
+        g = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * g[:, None, None, None]
+        b = (b - bn.running_mean.detach().double()) * g + bn.bias.detach().double()
+    return w.float(), b.float()
+
+
+class _Compiler:
+    """Walks torchvision modules and emits the flat operator list."""
+
+    def __init__(self) -> None:
+        self.ops: list[_Op] = []
+        self.n_tensors = 1  # tensor 0 = normalised input image
+        self.cur = 0
+
+    def _new(self) -> int:
+        self.n_tensors += 1
+        return self.n_tensors - 1
+
+    def conv(self, conv: nn.Conv2d, bn, act: int, residual: int | None = None, chan_scale: int | None = None) -> None:
+        if conv.dilation != (1, 1) or conv.padding_mode != "zeros" or conv.padding[0] != conv.padding[1] or conv.stride[0] != conv.stride[1]:
+            raise NotImplementedError(f"unsupported convolution {conv}")
+        w, b = _fold_bn(conv, bn)
+        dst = self._new()
+        common = dict(k=conv.kernel_size[0], kw=conv.kernel_size[1], stride=conv.stride[0], pad=conv.padding[0], act=act, bias=b)
+        if conv.groups == 1:
+            self.ops.append(_Op("conv", self.cur, dst, dict(common, w=w, cin=conv.in_channels, cout=conv.out_channels,
+                                                            residual=residual, chan_scale=chan_scale)))
+        elif conv.groups == conv.in_channels == conv.out_channels and conv.kernel_size[0] == conv.kernel_size[1]:
+            self.ops.append(_Op("dwconv", self.cur, dst, dict(common, w=w, c=conv.in_channels)))
+        else:
+            raise NotImplementedError(f"grouped convolution {conv}")
+        self.cur = dst
+
+    def conv_norm_act(self, seq: nn.Sequential, residual: int | None = None, chan_scale: int | None = None) -> None:
+        mods = list(seq.children())
+        conv = mods[0]
+        bn = next((m for m in mods[1:] if isinstance(m, nn.BatchNorm2d)), None)
+        actm = next((m for m in mods[1:] if not isinstance(m, nn.BatchNorm2d)), None)
+        self.conv(conv, bn, _act_code(actm), residual, chan_scale)
+
+    def se(self, se: nn.Module) -> int:
+        sid = self._new()
+        if not isinstance(se.activation, nn.SiLU) or not isinstance(se.scale_activation, nn.Sigmoid):
+            raise NotImplementedError("squeeze-excitation with non SiLU/sigmoid activations")
+        self.ops.append(_Op("se", self.cur, sid, dict(
+            w1=se.fc1.weight.detach().float().flatten(1), b1=se.fc1.bias.detach().float(),
+            w2=se.fc2.weight.detach().float().flatten(1), b2=se.fc2.bias.detach().float())))
+        return sid
+
+    def module(self, m: nn.Module) -> None:  # noqa: C901, PLR0912
+        from torchvision.models.efficientnet import FusedMBConv, MBConv
+        from torchvision.ops.misc import Conv2dNormActivation, SqueezeExcitation
+
+        if isinstance(m, Conv2dNormActivation):
+            self.conv_norm_act(m)
+        elif isinstance(m, (FusedMBConv, MBConv)):
+            block_in = self.cur
+            res = block_in if m.use_res_connect else None
+            layers = list(m.block.children())
+            scale_id = None
+            for i, layer in enumerate(layers):
+                last = i == len(layers) - 1
+                if isinstance(layer, SqueezeExcitation):
+                    scale_id = self.se(layer)
+                else:
+                    self.conv_norm_act(layer, residual=res if last else None, chan_scale=scale_id if last else None)
+        elif isinstance(m, nn.Sequential):
+            for child in m.children():
+                self.module(child)
+        elif isinstance(m, nn.Conv2d):
+            self.conv(m, None, ACT_NONE)
+        elif isinstance(m, nn.BatchNorm2d):
+            g = m.weight.detach().double() / torch.sqrt(m.running_var.detach().double() + m.eps)
+            dst = self._new()
+            self.ops.append(_Op("affine", self.cur, dst, dict(scale=g.float(), shift=(m.bias.detach().double() - m.running_mean.detach().double() * g).float(), act=ACT_NONE)))
+            self.cur = dst
+        elif isinstance(m, (nn.ReLU, nn.SiLU)):
+            dst = self._new()
+            self.ops.append(_Op("affine", self.cur, dst, dict(scale=None, shift=None, act=_act_code(m))))
+            self.cur = dst
+        elif isinstance(m, nn.MaxPool2d):
+            k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+            s = m.stride if isinstance(m.stride, int) else m.stride[0]
+            pd = m.padding if isinstance(m.padding, int) else m.padding[0]
+            if m.ceil_mode or m.dilation not in (1, (1, 1)):
+                raise NotImplementedError(f"unsupported pooling {m}")
+            dst = self._new()
+            self.ops.append(_Op("maxpool", self.cur, dst, dict(k=k, stride=s, pad=pd)))
+            self.cur = dst
+        elif isinstance(m, (nn.Identity, nn.Dropout)):
+            pass
+        else:
+            raise NotImplementedError(f"module {type(m).__name__} has no sm_100a kernel yet")
+
+    def peephole(self) -> None:
+        """Fuse standalone BatchNorm / activation children into the convolution that feeds them
+        (VGG-style ``Conv2d, BatchNorm2d, ReLU`` sequences)."""
+        out: list[_Op] = []
+        for op in self.ops:
+            prev = out[-1] if out else None
+            if (op.kind == "affine" and prev is not None and prev.kind == "conv" and prev.dst == op.src
+                    and prev.p["act"] == ACT_NONE and prev.p["residual"] is None):
+                if op.p["scale"] is not None:
+                    prev.p["w"] = prev.p["w"] * op.p["scale"][:, None, None, None]
+                    prev.p["bias"] = prev.p["bias"] * op.p["scale"] + op.p["shift"]
+                prev.p["act"] = op.p["act"]
+                prev.dst = op.dst
+                continue
+            out.append(op)
+        self.ops = out
+
+
+def _split_fp16(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, int]:
+    """x * 2^e (peak in [2^9, 2^10)) as fp16 hi + lo; returns (hi, lo, e)."""
+    amax = float(x.abs().max())
+    e = 0 if amax == 0 else 10 - int(np.frexp(amax)[1])
+    xs = torch.ldexp(x.float(), torch.tensor(e))
+    hi = xs.half()
+    lo = (xs - hi.float()).half()
+    return hi.contiguous(), lo.contiguous(), e
+
+
+class _Program:
+    """Compiled backbone: device-resident weights + the executor."""
+
+    def __init__(self, modules: list[nn.Module], device: torch.device) -> None:
+        comp = _Compiler()
+        for m in modules:
+            comp.module(m)
+        comp.peephole()
+        self.ops = comp.ops
+        self.n_tensors = comp.n_tensors
+        self.out_id = comp.cur if not self.ops else self.ops[-1].dst
+        self.device = device
+        for op in self.ops:
+            p = op.p
+            if op.kind == "conv":
+                cout, cin, k, kw = p["cout"], p["cin"], p["k"], p["kw"]
+                kdim = k * kw * cin
+                kp = (kdim + 31) // 32 * 32
+                bn = min(128, (cout + 31) // 32 * 32)
+                rows = (cout + bn - 1) // bn * bn
+                wm = torch.zeros((rows, kp), dtype=torch.float32)
+                wm[:cout, :kdim] = p["w"].permute(0, 2, 3, 1).reshape(cout, kdim)
+                hi, lo, e = _split_fp16(wm)
+                bias = torch.zeros((cout + 3) // 4 * 4, dtype=torch.float32)
+                bias[:cout] = p["bias"]
+                p.update(whi=hi.to(device), wlo=lo.to(device), w_exp=e, kp=kp, rows=rows, bias_d=bias.to(device))
+                del p["w"]
+            elif op.kind == "dwconv":
+                p.update(w_d=p["w"][:, 0].permute(1, 2, 0).contiguous().to(device), bias_d=p["bias"].to(device))
+                del p["w"]
+            elif op.kind == "se":
+                for key in ("w1", "b1", "w2", "b2"):
+                    p[key] = p[key].contiguous().to(device)
+            elif op.kind == "affine" and p["scale"] is not None:
+                p["scale"], p["shift"] = p["scale"].to(device), p["shift"].to(device)
+
+    @staticmethod
+    def _out_hw(h: int, w: int, k: int, kw: int, s: int, pd: int) -> tuple[int, int]:
+        return (h + 2 * pd - k) // s + 1, (w + 2 * pd - kw) // s + 1
+
+    def run(self, x0: torch.Tensor, amax0: torch.Tensor) -> torch.Tensor:  # noqa: C901, PLR0915
+        """x0: normalised input [B,H,W,3] float32 NHWC; amax0: 1-element tensor with its max |x|."""
+        dev = self.device
+        st = _stream()
+        tensors: dict[int, torch.Tensor] = {0: x0}
+        amax = torch.zeros(self.n_tensors, dtype=torch.float32, device=dev)
+        amax[0:1] = amax0
+        last_use = {}
+        for i, op in enumerate(self.ops):
+            last_use[op.src] = i
+            for key in ("residual", "chan_scale"):
+                if op.p.get(key) is not None:
+                    last_use[op.p[key]] = i
+
+        def aptr(tid: int) -> C.c_void_p:
+            return C.c_void_p(amax.data_ptr() + 4 * tid)
+
+        for i, op in enumerate(self.ops):
+            p = op.p
+            src = tensors[op.src]
+            b, h, w, c = (int(v) for v in src.shape)
+            if op.kind == "conv":
+                ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
+                m = b * ho * wo
+                ahi = torch.empty((m, p["kp"]), dtype=torch.float16, device=dev)
+                alo = torch.empty_like(ahi)
+                cs = tensors[p["chan_scale"]] if p["chan_scale"] is not None else None
+                nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
+                                                        _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
+                out = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float32, device=dev)
+                res = tensors[p["residual"]] if p["residual"] is not None else None
+                nat.check(nat.lib.sir_feat_gemm(_ptr(ahi), _ptr(alo), aptr(op.src), m, p["kp"], _ptr(p["whi"]), _ptr(p["wlo"]),
+                                                p["cout"], p["rows"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
+                                                _ptr(out), p["cout"], aptr(op.dst), st), "sir_feat_gemm")
+                launch_counter.add(2)
+            elif op.kind == "dwconv":
+                ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
+                out = torch.empty((b, ho, wo, c), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.sir_feat_dwconv(_ptr(src), b, h, w, c, p["k"], p["stride"], p["pad"], _ptr(p["w_d"]),
+                                                  _ptr(p["bias_d"]), p["act"], _ptr(out), aptr(op.dst), st), "sir_feat_dwconv")
+                launch_counter.add()
+            elif op.kind == "se":
+                avg = torch.empty((b, c), dtype=torch.float32, device=dev)
+                out = torch.empty((b, c), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.sir_feat_se_scale(_ptr(src), b, h * w, c, int(p["w1"].shape[0]), _ptr(p["w1"]), _ptr(p["b1"]),
+                                                    _ptr(p["w2"]), _ptr(p["b2"]), _ptr(avg), _ptr(out), st), "sir_feat_se_scale")
+                launch_counter.add(2)
+            elif op.kind == "affine":
+                out = torch.empty_like(src)
+                nat.check(nat.lib.sir_feat_affine_act(_ptr(src), src.numel(), c, _ptr(p["scale"]), _ptr(p["shift"]), p["act"],
+                                                      _ptr(out), aptr(op.dst), st), "sir_feat_affine_act")
+                launch_counter.add()
+            elif op.kind == "maxpool":
+                ho, wo = self._out_hw(h, w, p["k"], p["k"], p["stride"], p["pad"])
+                out = torch.empty((b, ho, wo, c), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.sir_feat_maxpool(_ptr(src), b, h, w, c, p["k"], p["stride"], p["pad"], _ptr(out), aptr(op.dst), st),
+                          "sir_feat_maxpool")
+                launch_counter.add()
+            else:  # pragma: no cover
+                raise AssertionError(op.kind)
+            tensors[op.dst] = out
+            for tid in [t for t, lu in last_use.items() if lu == i and t != self.out_id]:
+                tensors.pop(tid, None)
+        return tensors[self.out_id]
+
+
+# --------------------------------------------------------------------------- public API
+
+def printmodel(model: nn.Module, input_shape: tuple[int, int, int, int] = (1, 3, 1968, 5872)) -> None:
+    """Print the architecture with torchinfo (``network.py:16-29``); debug helper."""
+    from torchinfo import summary
+
+    with torch.no_grad():
+        print(summary(model, input_shape))
+
+
+def get_output_size(model: "Model", input_shape: tuple[int, int, int, int]) -> torch.Size:
+    """Shape ``[1, C, h, w]`` of the feature maps for an input of ``input_shape`` (``network.py:32-48``),
+    computed from the compiled operator list without running the network."""
+    _, _, h, w = input_shape
+    c = 3
+    for op in model.program.ops:
+        p = op.p
+        if op.kind == "conv":
+            h, w = _Program._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
+            c = p["cout"]
+        elif op.kind == "dwconv":
+            h, w = _Program._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
+        elif op.kind == "maxpool":
+            h, w = _Program._out_hw(h, w, p["k"], p["k"], p["stride"], p["pad"])
+    return torch.Size((input_shape[0], c, h, w))
+
+
+class Model:
+    """Truncated pretrained backbone + pre-processing (reference ``network.py:90-269``)."""
+
+    def __init__(self, config: dict, block: int, *, random_init_seed: int | None = None) -> None:
+        import cv2
+        from torchvision import models
+
+        self.config = config
+        self.clahe = cv2.createCLAHE(
+            clipLimit=config["model"]["clahe_clip_limit"],
+            tileGridSize=tuple(config["model"]["clahe_tile_grid_size"]),
+        )
+        self.device = _require_cuda()
+        model_str = config["model"]["type"]
+        if model_str not in _MODELS:
+            raise LookupError("Model string not found")  # network.py:181-182
+        ctor, tag, (mean, std) = _MODELS[model_str]
+        if model_str == "DenseNet_201":
+            raise NotImplementedError("DenseNet_201 (concatenating dense blocks) is not compiled to sm_100a kernels yet")
+        if random_init_seed is None and os.environ.get("SIR_RANDOM_INIT_SEED"):
+            random_init_seed = int(os.environ["SIR_RANDOM_INIT_SEED"])
+        if random_init_seed is None:
+            net = getattr(models, ctor)(weights=tag)  # downloads / reads torchvision's cache like the reference
+        else:
+            gen_state = torch.random.get_rng_state()
+            torch.manual_seed(random_init_seed)
+            net = getattr(models, ctor)(weights=None)
+            torch.random.set_rng_state(gen_state)
+        net.eval()
+        layers = list(net.features.children())[:block]  # network.py:185
+        self.model = nn.Sequential(*layers).eval()       # kept for introspection (weights live here, on the host)
+        self.mean, self.std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
+        self.transform = self._host_transform(gray=True)
+        self.transform_rgb = self._host_transform(gray=False)
+        self.program = _Program(layers, self.device)
+        self.max_batch_bytes = 2 << 30  # cap on one im2col operand
+
+    def _host_transform(self, *, gray: bool):
+        mean, std = np.array(self.mean, np.float32), np.array(self.std, np.float32)
+
+        def apply(img: np.ndarray) -> torch.Tensor:
+            x = torch.from_numpy(np.ascontiguousarray(img)).float().div(255)
+            x = x[None].repeat(3, 1, 1) if gray else x.permute(2, 0, 1)
+            return (x - torch.from_numpy(mean)[:, None, None]) / torch.from_numpy(std)[:, None, None]
+
+        return apply
+
+    def _clahe(self, img: np.ndarray) -> np.ndarray:
+        """CLAHE on the luminance (``network.py:197-208``): RGB goes through LAB."""
+        import cv2
+
+        if img.ndim == 3:
+            lab = cv2.cvtColor(img, cv2.COLOR_RGB2LAB)
+            l_ch, a_ch, b_ch = cv2.split(lab)
+            return cv2.cvtColor(cv2.merge((self.clahe.apply(l_ch), a_ch, b_ch)), cv2.COLOR_LAB2RGB)
+        return self.clahe.apply(img)
+
+    # ---- device path -----------------------------------------------------------------------
+    def _forward_uint8(self, batch: np.ndarray) -> torch.Tensor:
+        """CLAHE'd uint8 images ``[B,H,W]`` or ``[B,H,W,3]`` -> feature maps ``[B,C,h,w]`` on the device."""
+        b, h, w = batch.shape[:3]
+        in_ch = 1 if batch.ndim == 3 else 3
+        d_img = torch.from_numpy(np.ascontiguousarray(batch)).to(self.device, non_blocking=True)
+        x0 = torch.empty((b, h, w, 3), dtype=torch.float32, device=self.device)
+        amax0 = torch.zeros(1, dtype=torch.float32, device=self.device)
+        mean = (C.c_float * 3)(*self.mean)
+        std = (C.c_float * 3)(*self.std)
+        nat.check(nat.lib.sir_feat_image_to_nhwc(_ptr(d_img), b, h, w, in_ch, mean, std, _ptr(x0), _ptr(amax0), _stream()),
+                  "sir_feat_image_to_nhwc")
+        launch_counter.add()
+        y = self.program.run(x0, amax0)
+        bo, ho, wo, co = (int(v) for v in y.shape)
+        out = torch.empty((bo, co, ho, wo), dtype=torch.float32, device=self.device)
+        nat.check(nat.lib.sir_feat_nhwc_to_nchw(_ptr(y), bo, ho * wo, co, _ptr(out), _stream()), "sir_feat_nhwc_to_nchw")
+        launch_counter.add()
+        return out
+
+    def _batch_limit(self, h: int, w: int) -> int:
+        worst = 1
+        hh, ww, c = h, w, 3
+        for op in self.program.ops:
+            p = op.p
+            if op.kind in ("conv", "dwconv"):
+                ho, wo = _Program._out_hw(hh, ww, p["k"], p["kw"], p["stride"], p["pad"])
+                if op.kind == "conv":
+                    worst = max(worst, ho * wo * p["kp"] * 4)
+                    c = p["cout"]
+                hh, ww = ho, wo
+            elif op.kind == "maxpool":
+                hh, ww = _Program._out_hw(hh, ww, p["k"], p["k"], p["stride"], p["pad"])
+        del c
+        return max(1, int(self.max_batch_bytes // worst))
+
+    def get_feature_maps(self, img: np.ndarray) -> np.ndarray:
+        """One image (uint8 ``[H,W]`` or ``[H,W,3]``) -> ``[C,h,w]`` float32 (``network.py:210-244``)."""
+        img = self._clahe(img)
+        out = self._forward_uint8(img[None])
+        return out.cpu().numpy().squeeze()  # squeeze like network.py:244
+
+    def get_multiple_feature_maps(self, images: list[np.ndarray], *, progress: bool = True) -> list[np.ndarray]:
+        """List of images -> list of feature maps, same order (``network.py:246-269``).  Images of
+        equal shape are pushed through the backbone as one batch."""
+        results: list[Any] = [None] * len(images)
+        by_shape: dict[tuple, list[int]] = {}
+        for i, im in enumerate(images):
+            by_shape.setdefault(tuple(im.shape), []).append(i)
+        bar = tqdm(total=len(images)) if progress else None
+        for shp, idx in by_shape.items():
+            limit = self._batch_limit(shp[0], shp[1])
+            for s in range(0, len(idx), limit):
+                chunk = idx[s : s + limit]
+                batch = np.stack([self._clahe(images[i]) for i in chunk])
+                maps = self._forward_uint8(batch).cpu().numpy()
+                for j, i in enumerate(chunk):
+                    results[i] = maps[j].squeeze()
+                if bar is not None:
+                    bar.update(len(chunk))
+        if bar is not None:
+            bar.close()
+        return results

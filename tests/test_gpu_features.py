@@ -1,0 +1,95 @@
+"""GPU parity of the feature stage (network.Model through libsir) against the same torchvision
+modules evaluated by PyTorch in float32 (TF32 off) -- the torch fp32 reference of a floating-point
+kernel.  Metric: relative L2 error of the feature maps (the feature stage has its own
+tolerance, 1e-4 relative L2, because 1e-4 on scores is defined on identical feature-map inputs)."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+FEATURE_REL_L2 = 1e-4
+
+
+def _config(model_type):
+    return {"model": {"type": model_type, "clahe_clip_limit": 2.0, "clahe_tile_grid_size": [8, 8]}}
+
+
+def _randomise_bn(seq, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in seq.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+
+
+def _torch_reference(model, img):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = model.transform_rgb(img) if img.ndim == 3 else model.transform(img)
+    net = model.model.to("cuda").double()
+    with torch.no_grad():
+        y = net(x[None].to("cuda").double())
+    model.model.to("cpu").float()
+    return y[0].float().cpu().numpy()
+
+
+def _image(seed, h, w, rgb=False):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, size=(h // 4 + 1, w // 4 + 1, 3 if rgb else 1)).astype(np.float32)
+    img = np.kron(base, np.ones((4, 4, 1), np.float32))[:h, :w]
+    img = np.clip(img + rng.normal(0, 12, img.shape), 0, 255).astype(np.uint8)
+    return img if rgb else img[..., 0]
+
+
+def _rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("model_type,block,hw,rgb", [
+    ("EfficientNetV2_M", 4, (150, 94), False),
+    ("EfficientNetV2_M", 6, (131, 77), False),
+    ("EfficientNetV2_S", 5, (96, 64), True),
+    ("EfficientNet_B1", 5, (90, 70), False),
+    ("VGG16", 9, (70, 50), False),
+    ("VGG19_BN", 12, (64, 48), True),
+])
+def test_feature_maps_match_torch_fp32(model_type, block, hw, rgb):
+    import __graft_entry__ as ge
+
+    ge.build()
+    from src.shoeprint_image_retrieval import network
+
+    model = network.Model(_config(model_type), block, random_init_seed=3)
+    _randomise_bn(model.model, 5)
+    model.program = network._Program(list(model.model.children()), model.device)
+    img = _image(7, *hw, rgb=rgb)
+    got = model.get_feature_maps(img)
+    want = _torch_reference(model, model._clahe(img))
+    assert got.shape == want.shape == tuple(network.get_output_size(model, (1, 3, *hw)))[1:]
+    assert got.dtype == np.float32
+    err = _rel_l2(got, want)
+    assert err < FEATURE_REL_L2, f"{model_type}[:{block}] relative L2 error {err:.3e}"
+
+
+def test_multiple_feature_maps_batches_and_keeps_order():
+    from src.shoeprint_image_retrieval import network
+
+    model = network.Model(_config("EfficientNetV2_M"), 4, random_init_seed=1)
+    imgs = [_image(1, 80, 56), _image(2, 64, 48), _image(3, 80, 56), _image(4, 80, 56)]
+    many = model.get_multiple_feature_maps(imgs, progress=False)
+    for im, fm in zip(imgs, many):
+        one = model.get_feature_maps(im)
+        assert fm.shape == one.shape == (80, (im.shape[0] + 7) // 8, (im.shape[1] + 7) // 8)
+        assert _rel_l2(fm, one) < 1e-6
+
+
+def test_unknown_model_string_raises_lookup_error():
+    from src.shoeprint_image_retrieval import network
+
+    with pytest.raises(LookupError, match="Model string not found"):
+        network.Model(_config("ResNet50"), 4, random_init_seed=0)
