@@ -144,6 +144,49 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- feature stage (side measurement)
+def feature_stage_numbers(args) -> dict:
+    """images/s of the backbone (EfficientNetV2-M cut at block 6, seeded random init, synthetic 800x300
+    uint8 prints): through ``Model.get_multiple_feature_maps`` (CLAHE on the host, H2D, kernels, D2H)
+    and device-only; plus the torch CPU forward of the same modules (the reference's path on a CPU box)."""
+    import numpy as np
+    import torch
+
+    from src.shoeprint_image_retrieval import network
+
+    cfg = {"model": {"type": "EfficientNetV2_M", "clahe_clip_limit": 2.0, "clahe_tile_grid_size": [8, 8]}}
+    model = network.Model(cfg, 6, random_init_seed=0)
+    rng = np.random.default_rng(0)
+    n = 32
+    imgs = [np.clip(np.kron(rng.integers(0, 256, size=(100, 38)), np.ones((8, 8))) + rng.normal(0, 10, (800, 304)), 0, 255).astype(np.uint8)[:, :300] for _ in range(n)]
+    imgs = [np.ascontiguousarray(im) for im in imgs]
+    model.get_multiple_feature_maps(imgs[:4], progress=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    maps = model.get_multiple_feature_maps(imgs, progress=False)
+    torch.cuda.synchronize()
+    e2e = n / (time.perf_counter() - t0)
+    batch = np.stack([model._clahe(im) for im in imgs[:16]])
+    model._forward_uint8(batch)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2):
+        model._forward_uint8(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    dev = 32 / (e0.elapsed_time(e1) * 1e-3)
+    out = {"unit": "images/s", "model": "EfficientNetV2_M[:6]", "input": "800x300 uint8", "map": list(maps[0].shape),
+           "e2e_images_per_s": e2e, "device_images_per_s": dev, "gflop_per_image": 34.72,
+           "device_tflops_algorithmic": dev * 34.72e-3}
+    if not args.no_cpu:
+        from oracle import features as ofeat
+
+        ips, threads = ofeat.images_per_second(model.model, [model._clahe(im) for im in imgs[:6]], model.mean, model.std)
+        out["cpu_images_per_s"] = ips
+        out["cpu_threads"] = threads
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_b200(args) -> None:
     import numpy as np
@@ -257,6 +300,7 @@ def run_b200(args) -> None:
     ms_e2e = t_e2e / max(1, min(args.steps, 3))
     ranks_host, h2d = out_e2e
 
+    feat = feature_stage_numbers(args) if (rank == 0 and not args.no_features) else None
     acc = float((ranks_dev == 1).float().mean().item())
     assert torch.equal(ranks_host.to(torch.int32), ranks_dev.cpu().to(torch.int32)), "e2e and device-resident ranks differ"
 
@@ -291,6 +335,7 @@ def run_b200(args) -> None:
                 "note": "achieved = algorithmic 2*C*M*K FLOPs per (column, gallery) / event time; the fp16x3 mode issues 3 MMAs per algorithmic MAC and tile padding adds ~19%, neither is counted",
             },
             "cpu_baseline": cb,
+            "feature_stage": feat,
             "clocks": clocks,
             "top1_accuracy": acc,
         }
@@ -307,6 +352,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16x1", "fp32_simt"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-features", action="store_true", help="skip the feature-stage side measurement")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 256 probes, no e2e / cpu legs, warm-up as given")
     args = ap.parse_args()
     if args.impl == "reference":
