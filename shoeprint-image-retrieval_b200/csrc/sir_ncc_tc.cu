@@ -49,7 +49,7 @@ constexpr int kTileN = 256;      // packed columns per tile
 constexpr int kStageK = 32;      // taps per B stage (64 bytes: one 64B-swizzle row)
 constexpr int kGenThreads = 64;
 constexpr int kEpiWarps = 8;
-constexpr int kMaxBStages = 6;
+constexpr int kMaxBStages = 16;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kBHalfBytes = kTileN * kStageK * 2;  // 16 KB
 
@@ -61,6 +61,7 @@ struct TcParams {
   float* scores;
   int score_ld, g0;
   int G, C, Hp, Wp, Hm, Wm;
+  int Gp;          // G rounded up to a multiple of the CTA group size (the extra unit repeats gallery G-1)
   int ncols;
   int nkc;         // 8-tap chunks per template row
   int nsteps;      // K16 steps per channel = ceil(Hm*nkc/2)
@@ -119,6 +120,11 @@ __device__ __forceinline__ Seg seg_geometry(const TcParams& p, const KRange& kr,
   return s;
 }
 
+// CG = 1: every CTA works alone.  CG = 2: the two CTAs of a cluster form a CTA pair -- each runs the
+// whole pipeline on its own work unit (same column tile and patch, neighbouring galleries) but the
+// leader issues one tcgen05.mma.cta_group::2 (M = 256) for both, and each CTA streams only its half
+// of the template columns: the B traffic per SM and the B footprint in shared memory halve.
+template <int CG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
               const __grid_constant__ CUtensorMap tm_ghi, const __grid_constant__ CUtensorMap tm_glo, const TcParams p) {
@@ -127,7 +133,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = kBHalfBytes * (p.passes == 3 ? 2 : 1);
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  constexpr uint32_t kBHalfCta = kBHalfBytes / CG;                         // this CTA's share of one operand half
+  const uint32_t stage_bytes = kBHalfCta * (p.passes == 3 ? 2 : 1);       // per CTA
   const uint32_t bar0 = base + p.off_bar;
   auto bar_full = [&](int i) { return bar0 + 8u * i; };
   auto bar_empty = [&](int i) { return bar0 + 8u * (kMaxBStages + i); };
@@ -144,10 +153,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       ptx::mbar_init(bar_empty(i), 1);
     }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(bar_efull(i), kGenThreads);
+      ptx::mbar_init(bar_efull(i), kGenThreads * CG);   // the leader also collects the peer's arrivals
       ptx::mbar_init(bar_eempty(i), 1);
       ptx::mbar_init(bar_accfull(i), 1);
-      ptx::mbar_init(bar_accempty(i), kEpiWarps);
+      ptx::mbar_init(bar_accempty(i), kEpiWarps * CG);
       ptx::mbar_init(bar_gsfull(i), 1);
     }
     ptx::fence_barrier_init();
@@ -156,9 +165,13 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     ptx::prefetch_tmap(&tm_ghi);
     ptx::prefetch_tmap(&tm_glo);
   }
-  if (warp == 1) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 1) {
+    if constexpr (CG == 2) ptx::tmem_alloc_2cta(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+    else ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync();  // the peer's barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -166,7 +179,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   // (column tile, patch, gallery): at any moment all CTAs work on the same column tile (one B stream
   // shared through L2) and on the same patch row (equal cost once zero rows are skipped).
   const int NP = p.npy * p.npx;
-  const long long per_tile = (long long)p.G * NP;
+  const long long per_tile = (long long)p.Gp * NP;
   const int Pe = 8 * p.nkc;  // entries per E row
   const int a = p.Hm / 2, b = p.Wm / 2;
   const int M = p.Hp * p.Wp;
@@ -180,27 +193,43 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       uint32_t bs = 0;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const int nt = (int)(unit / per_tile);
-        const KRange kr = k_range(p, (int)((unit % per_tile) / p.G) / p.npx);
+        const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx);
         for (int c = 0; c < p.C; ++c) {
           for (int st = kr.st_lo; st < kr.st_hi; ++st, ++bs) {
             const int slot = bs % p.nbstages;
             const uint32_t par = (bs / p.nbstages) & 1;
             ptx::mbar_wait(bar_empty(slot), par ^ 1);
-            ptx::mbar_arrive_expect_tx(bar_full(slot), stage_bytes);
             const uint32_t dst = base + p.off_b + slot * stage_bytes;
-            ptx::tma_load_3d(dst, &tm_hi, bar_full(slot), st * kStageK, nt * kTileN, c);
-            if (p.passes == 3) ptx::tma_load_3d(dst + kBHalfBytes, &tm_lo, bar_full(slot), st * kStageK, nt * kTileN, c);
+            if constexpr (CG == 2) {
+              // both CTAs' loads complete on the leader's barrier; only the leader arms it
+              if (leader) ptx::mbar_arrive_expect_tx(bar_full(slot), 2 * stage_bytes);
+              const int col = nt * kTileN + (int)cta_rank * (kTileN / 2);
+              ptx::tma_load_3d_2sm(dst, &tm_hi, bar_full(slot), st * kStageK, col, c);
+              if (p.passes == 3) ptx::tma_load_3d_2sm(dst + kBHalfCta, &tm_lo, bar_full(slot), st * kStageK, col, c);
+            } else {
+              ptx::mbar_arrive_expect_tx(bar_full(slot), stage_bytes);
+              ptx::tma_load_3d(dst, &tm_hi, bar_full(slot), st * kStageK, nt * kTileN, c);
+              if (p.passes == 3) ptx::tma_load_3d(dst + kBHalfCta, &tm_lo, bar_full(slot), st * kStageK, nt * kTileN, c);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kTileN);
+    if (leader && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM * CG, kTileN);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if constexpr (CG == 2) ptx::mma_f16_ss_2cta(d, da, db, idesc, acc);
+        else ptx::mma_f16_ss(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) {
+        if constexpr (CG == 2) ptx::tc_commit_2cta(bar, 0b11);
+        else ptx::tc_commit(bar);
+      };
       uint32_t bs = 0, es = 0, cs = 0;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-        const KRange kr = k_range(p, (int)((unit % per_tile) / p.G) / p.npx);
+        const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx);
         for (int c = 0; c < p.C; ++c, ++cs) {
           const int buf = cs & 1;
           ptx::mbar_wait(bar_accempty(buf), ((cs >> 1) & 1) ^ 1);
@@ -220,7 +249,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
               ptx::mbar_wait(bar_full(slot), (bs / p.nbstages) & 1);
               ptx::tc_fence_after();
               const uint32_t b_hi = base + p.off_b + slot * stage_bytes;
-              const uint32_t b_lo = b_hi + kBHalfBytes;
+              const uint32_t b_lo = b_hi + kBHalfCta;
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const int ks = 2 * st + kk;
@@ -231,21 +260,21 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                   const uint64_t da_hi = ptx::make_smem_desc(e_hi + a_off, 128, 16u * Pe, 0);
                   // B: 64B swizzle, 8-row groups 512 B apart; K16 sub-step = +32 B inside the swizzle row.
                   const uint64_t db_hi = ptx::make_smem_desc(b_hi + 32u * kk, 16, 512, 4);
-                  ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
+                  mma(tmem_d, da_hi, db_hi, accumulate);
                   accumulate = 1;
                   if (p.passes == 3) {
                     const uint64_t da_lo = ptx::make_smem_desc(e_lo + a_off, 128, 16u * Pe, 0);
                     const uint64_t db_lo = ptx::make_smem_desc(b_lo + 32u * kk, 16, 512, 4);
-                    ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, 1);
-                    ptx::mma_f16_ss(tmem_d, da_hi, db_lo, idesc, 1);
+                    mma(tmem_d, da_lo, db_hi, 1);
+                    mma(tmem_d, da_hi, db_lo, 1);
                   }
                 }
               }
-              ptx::tc_commit(bar_empty(slot));
+              commit(bar_empty(slot));
             }
-            ptx::tc_commit(bar_eempty(ebuf));
+            commit(bar_eempty(ebuf));
           }
-          ptx::tc_commit(bar_accfull(buf));
+          commit(bar_accfull(buf));
         }
       }
     }
@@ -268,8 +297,8 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     };
     auto decode = [&](Cursor& cu) {
       const long long rem = cu.unit % per_tile;
-      const int pidx = (int)(rem / p.G);
-      cu.g = (int)(rem % p.G);
+      const int pidx = (int)(rem / p.Gp);
+      cu.g = min((int)(rem % p.Gp), p.G - 1);
       cu.py = pidx / p.npx;
       cu.px = pidx % p.npx;
       cu.kr = k_range(p, cu.py);
@@ -344,7 +373,8 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
           }
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async reads
-        ptx::mbar_arrive(bar_efull(ebuf));
+        if constexpr (CG == 2) ptx::mbar_arrive_leader(bar_efull(ebuf));
+        else ptx::mbar_arrive(bar_efull(ebuf));
         ptx::named_bar_sync(1, kGenThreads);  // everyone is done reading staging[sbuf]
         cur = nxt;
         advance(nxt);
@@ -365,7 +395,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
       const int nt = (int)(unit / per_tile);
       const long long rem = unit % per_tile;
-      const int pidx = (int)(rem / p.G), g = (int)(rem % p.G);
+      const int pidx = (int)(rem / p.Gp), g = min((int)(rem % p.Gp), p.G - 1);
       const int py = pidx / p.npx, px = pidx % p.npx;
       const int y = 16 * py + mh, x = 8 * px + ml;
       const bool valid = (y < p.Hp) && (x < p.Wp);
@@ -391,7 +421,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_accempty(buf));
+        if (lane == 0) {
+          if constexpr (CG == 2) ptx::mbar_arrive_leader(bar_accempty(buf));
+          else ptx::mbar_arrive(bar_accempty(buf));
+        }
         r_cur = r_next;
       }
       // max over the tile's valid positions, then over the 4 lane quarters, then into scores
@@ -413,7 +446,11 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  if constexpr (CG == 2) ptx::cluster_sync();  // nobody frees TMEM or exits while the peer still uses this CTA's memory
+  if (warp == 1) {
+    if constexpr (CG == 2) ptx::tmem_dealloc_2cta(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -434,7 +471,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_alloc, int C) {
+int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_alloc, int C, int box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -442,7 +479,7 @@ int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_
   }
   cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)ncols_alloc, (cuuint64_t)C};
   cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Kpad * 2 * (cuuint64_t)ncols_alloc};
-  cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)kTileN, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)box_cols, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -502,24 +539,30 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   p.npy = ceil_div(Hp, 16);
   p.npx = ceil_div(Wp, 8);
   p.ntiles_n = ceil_div(ncols, kTileN);
-  p.nunits = (long long)p.ntiles_n * G * p.npy * p.npx;
+  // CTA pairs (cta_group::2) whenever there are at least two galleries; SIR_CTA_GROUP=1 forces single CTAs
+  int cg = G >= 2 ? 2 : 1;
+  if (const char* env = getenv("SIR_CTA_GROUP")) cg = atoi(env) == 1 ? 1 : cg;
+  p.Gp = round_up(G, cg);
+  p.nunits = (long long)p.ntiles_n * p.Gp * p.npy * p.npx;
   p.passes = passes;
   p.out_scale = 1.0f / ((float)C * (float)(1 << kTemplateScaleLog2));
 
   // shared memory plan: B ring, 2 E buffers (x halves), row staging, column maxima, barriers
   const int halves = passes == 3 ? 2 : 1;
-  const uint32_t stage_bytes = kBHalfBytes * halves;
+  const uint32_t stage_bytes = kBHalfBytes / cg * halves;  // per CTA
   const int Pe = 8 * p.nkc;
   const size_t limit = 227 * 1024 - 1024;  // alignment slack
   bool ok = false;
   for (int gsb = 2; gsb >= 1 && !ok; --gsb) {
-    for (int nb = 4; nb >= 2 && !ok; --nb) {
+    // ring depth: enough stages in flight to cover the TMA round trip (a stage is 768 MMA cycles in
+    // fp16x3 but only 256 in fp16x1)
+    for (int nb = (passes == 1 ? 12 : (cg == 2 ? 6 : 4)); nb >= 2 && !ok; --nb) {
       for (int seg = p.nkstages; seg >= 1; --seg) {
         // rows touched by a segment of `seg` stages: worst case over alignments
         const int max_rows = 16 + (4 * seg - 1) / p.nkc + 1;
         const size_t e_half = (size_t)(max_rows + 1) * Pe * 16;
         const size_t gs_half = (size_t)(max_rows + 1) * (Pe + 16);  // cells
-        const size_t total = (size_t)nb * stage_bytes + 2 * halves * e_half + (size_t)gsb * 2 * (gs_half * 2 + 128) + 4 * kTileN * 4 + 256;
+        const size_t total = (size_t)nb * stage_bytes + 2 * halves * e_half + (size_t)gsb * 2 * (gs_half * 2 + 128) + 4 * kTileN * 4 + 512;
         if (total <= limit) {
           p.nbstages = nb;
           p.seg_stages = seg;
@@ -541,32 +584,50 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   p.off_gs = p.off_e + 2 * 2 * p.e_half_bytes;
   p.off_cm = (uint32_t)round_up((int)(p.off_gs + p.gs_bufs * 2 * p.gs_half_elems * 2), 16);
   p.off_bar = p.off_cm + 4 * kTileN * 4;
-  const size_t smem = 1024 + p.off_bar + 256;
+  const size_t smem = 1024 + p.off_bar + 512;
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_scores: shared-memory plan overflow (%zu bytes)", smem);
 
   SIR_CHECK_ARG(Pe + 16 <= 256 && p.gs_rows <= 256, "sir_ncc_scores: template %dx%d exceeds the staging TMA box", Hm, Wm);
   SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ghi) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_glo) & 15) == 0,
                 "sir_ncc_scores: gallery operands must be 16-byte aligned");
   CUtensorMap tm_hi, tm_lo, tm_ghi, tm_glo;
-  int rc = make_template_map(&tm_hi, d_thi, Kpad, ncols_alloc, C);
+  int rc = make_template_map(&tm_hi, d_thi, Kpad, ncols_alloc, C, kTileN / cg);
   if (rc) return rc;
-  rc = make_template_map(&tm_lo, d_tlo, Kpad, ncols_alloc, C);
+  rc = make_template_map(&tm_lo, d_tlo, Kpad, ncols_alloc, C, kTileN / cg);
   if (rc) return rc;
   rc = make_gallery_map(&tm_ghi, d_ghi, G * C, Hp, Wp, Pe + 16, p.gs_rows);
   if (rc) return rc;
   rc = make_gallery_map(&tm_glo, d_glo, G * C, Hp, Wp, Pe + 16, p.gs_rows);
   if (rc) return rc;
 
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    SIR_CUDA(cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  static thread_local size_t configured[3] = {0, 0, 0};
+  if (smem > configured[cg]) {
+    if (cg == 2) SIR_CUDA(cudaFuncSetAttribute(ncc_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else SIR_CUDA(cudaFuncSetAttribute(ncc_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[cg] = smem;
   }
   int dev = 0, sms = 0;
   SIR_CUDA(cudaGetDevice(&dev));
   SIR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const unsigned grid = (unsigned)std::min<long long>(p.nunits, sms);
-  ncc_tc_kernel<<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_ghi, tm_glo, p);
+  unsigned grid = (unsigned)std::min<long long>(p.nunits, sms);
+  if (cg == 2) {
+    grid &= ~1u;  // whole pairs only (nunits is even)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SIR_CUDA(cudaLaunchKernelEx(&cfg, ncc_tc_kernel<2>, tm_hi, tm_lo, tm_ghi, tm_glo, p));
+  } else {
+    ncc_tc_kernel<1><<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_ghi, tm_glo, p);
+  }
   SIR_LAUNCH_CHECK("ncc_tc_kernel");
   return SIR_OK;
 }
