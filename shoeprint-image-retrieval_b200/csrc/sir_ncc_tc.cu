@@ -190,14 +190,12 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   if (warp == 0) {
     // ================================================================== TMA producer (B ring)
     if (ptx::elect_one()) {
-      uint32_t bs = 0;
+      uint32_t slot = 0, par = 0;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const int nt = (int)(unit / per_tile);
         const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx);
         for (int c = 0; c < p.C; ++c) {
-          for (int st = kr.st_lo; st < kr.st_hi; ++st, ++bs) {
-            const int slot = bs % p.nbstages;
-            const uint32_t par = (bs / p.nbstages) & 1;
+          for (int st = kr.st_lo; st < kr.st_hi; ++st) {
             ptx::mbar_wait(bar_empty(slot), par ^ 1);
             const uint32_t dst = base + p.off_b + slot * stage_bytes;
             if constexpr (CG == 2) {
@@ -210,6 +208,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
               ptx::mbar_arrive_expect_tx(bar_full(slot), stage_bytes);
               ptx::tma_load_3d(dst, &tm_hi, bar_full(slot), st * kStageK, nt * kTileN, c);
               if (p.passes == 3) ptx::tma_load_3d(dst + kBHalfCta, &tm_lo, bar_full(slot), st * kStageK, nt * kTileN, c);
+            }
+            if (++slot == (uint32_t)p.nbstages) {
+              slot = 0;
+              par ^= 1;
             }
           }
         }
@@ -227,7 +229,20 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
         if constexpr (CG == 2) ptx::tc_commit_2cta(bar, 0b11);
         else ptx::tc_commit(bar);
       };
-      uint32_t bs = 0, es = 0, cs = 0;
+      // The issuing thread is a single scalar instruction stream: everything it needs per MMA is kept
+      // as a running 32-bit descriptor word (start address >> 4 in the low 14 bits) so that one stage
+      // costs a barrier wait, a few adds and the MMAs themselves.
+      //   A: no swizzle, rows of a core matrix 16 B apart (consecutive entries = consecutive x), 8-row
+      //      groups one E row apart (SBO), the two K chunks of a step 8 entries apart (LBO = 128 B).
+      //   B: 64B swizzle, 8-row groups 512 B apart; a K16 sub-step is +32 B inside the swizzle row.
+      const uint64_t a_desc_hi = ((uint64_t)((16u * Pe) >> 4) | (1ull << 14)) << 32;                 // SBO | version
+      const uint64_t b_desc_hi = ((uint64_t)(512u >> 4) | (1ull << 14) | (4ull << 29)) << 32;        // SBO | version | SW64
+      constexpr uint32_t a_lbo = (128u >> 4) << 16, b_lbo = (16u >> 4) << 16;
+      auto a_desc = [&](uint32_t addr) { return a_desc_hi | a_lbo | ((addr >> 4) & 0x3FFFu); };
+      auto b_desc = [&](uint32_t addr) { return b_desc_hi | b_lbo | ((addr >> 4) & 0x3FFFu); };
+      uint32_t slot = 0, bphase = 0, es = 0, cs = 0;
+      uint32_t b_addr = base + p.off_b;
+      const uint32_t b_end = b_addr + p.nbstages * stage_bytes;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx);
         for (int c = 0; c < p.C; ++c, ++cs) {
@@ -242,35 +257,32 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             ptx::mbar_wait(bar_efull(ebuf), (es >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t e_hi = base + p.off_e + ebuf * 2 * p.e_half_bytes;
-            const uint32_t e_lo = e_hi + p.e_half_bytes;
-            const uint32_t e_shift = 16u * s.u_first * Pe;  // bytes of E rows before this segment
-            for (int st = s.st0; st < s.st1; ++st, ++bs) {
-              const int slot = bs % p.nbstages;
-              ptx::mbar_wait(bar_full(slot), (bs / p.nbstages) & 1);
+            // E row 0 of this segment is template row u_first: K step ks starts 256*ks - 16*u_first*Pe bytes in
+            uint32_t a_hi = e_hi + 512u * s.st0 - 16u * s.u_first * Pe;
+            for (int st = s.st0; st < s.st1; ++st, a_hi += 512u) {
+              ptx::mbar_wait(bar_full(slot), bphase);
               ptx::tc_fence_after();
-              const uint32_t b_hi = base + p.off_b + slot * stage_bytes;
-              const uint32_t b_lo = b_hi + kBHalfCta;
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const int ks = 2 * st + kk;
                 if (ks >= kr.ks_lo && ks < kr.ks_hi) {
-                  // A: no swizzle, rows of a core matrix 16 B apart (consecutive entries = consecutive x),
-                  // 8-row groups one E row apart (consecutive y), the two K chunks 8 entries apart.
-                  const uint32_t a_off = 256u * ks - e_shift;
-                  const uint64_t da_hi = ptx::make_smem_desc(e_hi + a_off, 128, 16u * Pe, 0);
-                  // B: 64B swizzle, 8-row groups 512 B apart; K16 sub-step = +32 B inside the swizzle row.
-                  const uint64_t db_hi = ptx::make_smem_desc(b_hi + 32u * kk, 16, 512, 4);
+                  const uint64_t da_hi = a_desc(a_hi + 256u * kk);
+                  const uint64_t db_hi = b_desc(b_addr + 32u * kk);
                   mma(tmem_d, da_hi, db_hi, accumulate);
                   accumulate = 1;
                   if (p.passes == 3) {
-                    const uint64_t da_lo = ptx::make_smem_desc(e_lo + a_off, 128, 16u * Pe, 0);
-                    const uint64_t db_lo = ptx::make_smem_desc(b_lo + 32u * kk, 16, 512, 4);
-                    mma(tmem_d, da_lo, db_hi, 1);
-                    mma(tmem_d, da_hi, db_lo, 1);
+                    mma(tmem_d, a_desc(a_hi + p.e_half_bytes + 256u * kk), db_hi, 1);
+                    mma(tmem_d, da_hi, b_desc(b_addr + kBHalfCta + 32u * kk), 1);
                   }
                 }
               }
               commit(bar_empty(slot));
+              b_addr += stage_bytes;
+              if (++slot == (uint32_t)p.nbstages) {
+                slot = 0;
+                bphase ^= 1;
+                b_addr = b_end - p.nbstages * stage_bytes;
+              }
             }
             commit(bar_eempty(ebuf));
           }
