@@ -109,6 +109,10 @@ __device__ __forceinline__ KRange k_range(const TcParams& p, int py) {
   return r;
 }
 
+// Columns the MMA of column tile `nt` really needs (the last tile of a block is usually narrower):
+// a multiple of 32 so that a CTA pair splits it into two 16-row aligned halves.
+__device__ __forceinline__ int tile_cols(const TcParams& p, int nt) { return min(kTileN, round_up(p.ncols - nt * kTileN, 32)); }
+
 __device__ __forceinline__ Seg seg_geometry(const TcParams& p, const KRange& kr, int sg) {
   Seg s;
   s.st0 = kr.st_lo + sg * p.seg_stages;
@@ -201,7 +205,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             if constexpr (CG == 2) {
               // both CTAs' loads complete on the leader's barrier; only the leader arms it
               if (leader) ptx::mbar_arrive_expect_tx(bar_full(slot), 2 * stage_bytes);
-              const int col = nt * kTileN + (int)cta_rank * (kTileN / 2);
+              const int col = nt * kTileN + (int)cta_rank * (tile_cols(p, nt) / 2);
               ptx::tma_load_3d_2sm(dst, &tm_hi, bar_full(slot), st * kStageK, col, c);
               if (p.passes == 3) ptx::tma_load_3d_2sm(dst + kBHalfCta, &tm_lo, bar_full(slot), st * kStageK, col, c);
             } else {
@@ -220,7 +224,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   } else if (warp == 1) {
     // ================================================================== MMA issuer
     if (leader && ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM * CG, kTileN);
+      uint32_t idesc = 0;
       auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
         if constexpr (CG == 2) ptx::mma_f16_ss_2cta(d, da, db, idesc, acc);
         else ptx::mma_f16_ss(d, da, db, idesc, acc);
@@ -245,6 +249,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       const uint32_t b_end = b_addr + p.nbstages * stage_bytes;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx);
+        idesc = ptx::make_idesc_f16(kTileM * CG, tile_cols(p, (int)(unit / per_tile)));
         for (int c = 0; c < p.C; ++c, ++cs) {
           const int buf = cs & 1;
           ptx::mbar_wait(bar_accempty(buf), ((cs >> 1) & 1) ^ 1);
@@ -411,6 +416,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       const int py = pidx / p.npx, px = pidx % p.npx;
       const int y = 16 * py + mh, x = 8 * px + ml;
       const bool valid = (y < p.Hp) && (x < p.Wp);
+      const int ncol_half = tile_cols(p, nt) - half * 128;  // columns of this warp's half that exist
       const float* rrow = p.rnorm + (size_t)g * p.C * M + (valid ? y * p.Wp + x : 0);
 
       float total[128];
@@ -425,6 +431,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
         const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * kTileN + half * 128;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
+          if (j4 * 32 >= ncol_half) break;  // warp-uniform
           uint32_t v[32];
           ptx::tmem_ld_32x32(taddr + j4 * 32, v);
           ptx::tmem_ld_wait();
