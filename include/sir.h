@@ -38,6 +38,8 @@ extern "C" {
 #define SIR_PREC_FP16X3 0  /* tcgen05, fp16 hi/lo split operands, 3 MMAs per K step (parity grade, default) */
 #define SIR_PREC_FP16X1 1  /* tcgen05, fp16 operands, 1 MMA per K step (fast; ~1e-4 relative worst case) */
 #define SIR_PREC_FP32_SIMT 2 /* CUDA cores, fp32 FMA (exact-order independent check path) */
+#define SIR_PREC_FP16_FP8C 3 /* tcgen05, hi*hi in fp16 + the two correction products in fp8 e4m3 (2/3 of the
+                                FP16X3 tensor cycles, ~2^-14 relative per product); own entry points *_fp8c */
 
 const char* sir_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
@@ -100,6 +102,24 @@ int sir_ncc_scores(const uint16_t* d_ghi, const uint16_t* d_glo, const int32_t* 
                    int ncols, int ncols_alloc, int Hm, int Wm,
                    const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
                    int precision, void* stream);
+
+/* fp8-corrected variant (SIR_PREC_FP16_FP8C).  Same quantity as sir_ncc_scores; operands:
+ *   gallery : d_ghi (as above) + d_g8a = e4m3(hi/4), d_g8l = e4m3(lo*4), uint8 [G][C][Hp][sir_gallery_pitch8(Wp)]
+ *             produced from d_ghi/d_glo by sir_gallery_pack_fp8c;
+ *   templates: rows padded to 16 taps (Kpad = sir_template_kpad_fp8c), d_thi f16 + d_t8b = e4m3(hi/4),
+ *             d_t8l = e4m3(lo*4), uint8 [C][ncols_alloc][Kpad], produced by sir_template_pack_fp8c.
+ * Per 32-tap K stage the kernel issues two fp16 MMAs (hi*hi) and two e4m3 MMAs ((lo*4)(hi/4) and
+ * (hi/4)(lo*4)) into the same fp32 accumulator. */
+int sir_gallery_pitch8(int Wp);
+int sir_gallery_pack_fp8c(const uint16_t* d_ghi, const uint16_t* d_glo, int G, int C, int Hp, int Wp,
+                          uint8_t* d_g8a, uint8_t* d_g8l, void* stream);
+int sir_template_kpad_fp8c(int Hm, int Wm);
+int sir_template_pack_fp8c(const float* d_maps, int N, int C, int h, int w, int col0, int ncols_alloc,
+                           uint16_t* d_thi, uint8_t* d_t8b, uint8_t* d_t8l, void* stream);
+int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, const uint8_t* d_g8l, const float* d_rnorm,
+                        int G, int C, int Hp, int Wp, const uint16_t* d_thi, const uint8_t* d_t8b, const uint8_t* d_t8l,
+                        int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores,
+                        int score_ld, int g0, void* stream);
 
 /* ------------------------------------------------------------------ ranking (K8, K9)
  * _get_rank (similarity.py:378-386) without the sort: d_true_score[q] is scores[q][true] on the

@@ -15,7 +15,8 @@ LIB_PATH = PKG_DIR / "lib" / "libsir.so"
 PREC_FP16X3 = 0
 PREC_FP16X1 = 1
 PREC_FP32_SIMT = 2
-PRECISIONS = {"fp16x3": PREC_FP16X3, "fp16x1": PREC_FP16X1, "fp32_simt": PREC_FP32_SIMT}
+PREC_FP16_FP8C = 3
+PRECISIONS = {"fp16x3": PREC_FP16X3, "fp16x1": PREC_FP16X1, "fp32_simt": PREC_FP32_SIMT, "fp16_fp8c": PREC_FP16_FP8C}
 
 _p = C.c_void_p
 _i = C.c_int
@@ -33,6 +34,11 @@ SIGNATURES = {
     "sir_template_kpad": (_i, [_i, _i]),
     "sir_template_pack": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sir_ncc_scores": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+    "sir_gallery_pitch8": (_i, [_i]),
+    "sir_gallery_pack_fp8c": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "sir_template_kpad_fp8c": (_i, [_i, _i]),
+    "sir_template_pack_fp8c": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "sir_ncc_scores_fp8c": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
     "sir_rank_topk": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "sir_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),

@@ -54,6 +54,10 @@ __host__ __device__ inline int gal_pitch(int Wp) { return round_up(Wp, 8); }
 // Number of 8-tap chunks per template row and padded K (multiple of 32) -- see sir_template_kpad.
 __host__ __device__ inline int tpl_chunks_per_row(int Wm) { return ceil_div(Wm, 8); }
 __host__ __device__ inline int tpl_kpad(int Hm, int Wm) { return round_up(Hm * tpl_chunks_per_row(Wm) * 8, 32); }
+// The fp8-corrected mode pads template rows to 16 taps (one 16-byte fp8 core-matrix row).
+__host__ __device__ inline int tpl_row_taps(int Wm, int row_align) { return round_up(Wm, row_align); }
+__host__ __device__ inline int tpl_kpad_aligned(int Hm, int Wm, int row_align) { return round_up(Hm * tpl_row_taps(Wm, row_align), 32); }
+__host__ __device__ inline int gal_pitch8(int Wp) { return round_up(Wp, 16); }  // 1-byte operands: 16 cells = 16 bytes
 
 // warp / block reductions ---------------------------------------------------------------
 template <typename T>

@@ -72,7 +72,10 @@ struct TcParams {
   int seg_stages;  // B stages per E segment
   int nseg;
   int nbstages;    // B ring depth
-  int passes;      // 3 (hi/lo split) or 1
+  int passes;      // 3: fp16 hi/lo split, 3 fp16 MMAs per K16 step; 1: hi only; 2: hi*hi in fp16 + the two
+                   //    correction products (lo*hi, hi*lo) in fp8 e4m3 at twice the MMA rate ("fp8c")
+  int nhalf;       // operand arrays per E buffer / staging buffer: 1, 2 or 3
+  uint32_t gs8_bytes;  // fp8c: bytes of one staged 1-byte window
   float out_scale; // 1 / (C * 2^kTemplateScaleLog2)
   // shared memory carve-up (byte offsets from the 1024-aligned base)
   uint32_t off_b, off_e, off_gs, off_cm, off_bar;
@@ -130,8 +133,12 @@ __device__ __forceinline__ Seg seg_geometry(const TcParams& p, const KRange& kr,
 // of the template columns: the B traffic per SM and the B footprint in shared memory halve.
 template <int CG>
 __global__ void __launch_bounds__(kTcThreads, 1)
-ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-              const __grid_constant__ CUtensorMap tm_ghi, const __grid_constant__ CUtensorMap tm_glo, const TcParams p) {
+ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_x,
+              const __grid_constant__ CUtensorMap tm_ghi, const __grid_constant__ CUtensorMap tm_glo,
+              const __grid_constant__ CUtensorMap tm_gx, const TcParams p) {
+  // operand maps by mode   fp16x3: tm_lo = template lo (f16), tm_glo = gallery lo (f16), tm_x / tm_gx unused
+  //                        fp8c  : tm_lo = template lo*4 (e4m3), tm_x = template hi/4 (e4m3),
+  //                                tm_glo = gallery lo*4 (e4m3), tm_gx = gallery hi/4 (e4m3)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -140,7 +147,8 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   constexpr uint32_t kBHalfCta = kBHalfBytes / CG;                         // this CTA's share of one operand half
-  const uint32_t stage_bytes = kBHalfCta * (p.passes == 3 ? 2 : 1);       // per CTA
+  const uint32_t stage_bytes = kBHalfCta * (p.passes == 1 ? 1 : 2);       // per CTA (fp8c: 1 + 1/2 + 1/2)
+  const uint32_t e_buf_bytes = p.nhalf * p.e_half_bytes;
   const uint32_t bar0 = base + p.off_bar;
   auto bar_full = [&](int i) { return bar0 + 8u * i; };
   auto bar_empty = [&](int i) { return bar0 + 8u * (kMaxBStages + i); };
@@ -168,6 +176,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     ptx::prefetch_tmap(&tm_lo);
     ptx::prefetch_tmap(&tm_ghi);
     ptx::prefetch_tmap(&tm_glo);
+    if (p.passes == 2) {
+      ptx::prefetch_tmap(&tm_x);
+      ptx::prefetch_tmap(&tm_gx);
+    }
   }
   if (warp == 1) {
     if constexpr (CG == 2) ptx::tmem_alloc_2cta(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
@@ -208,10 +220,18 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
               const int col = nt * kTileN + (int)cta_rank * (tile_cols(p, nt) / 2);
               ptx::tma_load_3d_2sm(dst, &tm_hi, bar_full(slot), st * kStageK, col, c);
               if (p.passes == 3) ptx::tma_load_3d_2sm(dst + kBHalfCta, &tm_lo, bar_full(slot), st * kStageK, col, c);
+              if (p.passes == 2) {
+                ptx::tma_load_3d_2sm(dst + kBHalfCta, &tm_x, bar_full(slot), st * kStageK, col, c);
+                ptx::tma_load_3d_2sm(dst + kBHalfCta + kBHalfCta / 2, &tm_lo, bar_full(slot), st * kStageK, col, c);
+              }
             } else {
               ptx::mbar_arrive_expect_tx(bar_full(slot), stage_bytes);
               ptx::tma_load_3d(dst, &tm_hi, bar_full(slot), st * kStageK, nt * kTileN, c);
               if (p.passes == 3) ptx::tma_load_3d(dst + kBHalfCta, &tm_lo, bar_full(slot), st * kStageK, nt * kTileN, c);
+              if (p.passes == 2) {
+                ptx::tma_load_3d(dst + kBHalfCta, &tm_x, bar_full(slot), st * kStageK, nt * kTileN, c);
+                ptx::tma_load_3d(dst + kBHalfCta + kBHalfCta / 2, &tm_lo, bar_full(slot), st * kStageK, nt * kTileN, c);
+              }
             }
             if (++slot == (uint32_t)p.nbstages) {
               slot = 0;
@@ -229,6 +249,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
         if constexpr (CG == 2) ptx::mma_f16_ss_2cta(d, da, db, idesc, acc);
         else ptx::mma_f16_ss(d, da, db, idesc, acc);
       };
+      auto mma8 = [&](uint32_t d, uint64_t da, uint64_t db) {  // e4m3 x e4m3, K = 32, accumulate
+        if constexpr (CG == 2) ptx::mma_f8_ss_2cta(d, da, db, idesc, 1);
+        else ptx::mma_f8_ss(d, da, db, idesc, 1);
+      };
       auto commit = [&](uint32_t bar) {
         if constexpr (CG == 2) ptx::tc_commit_2cta(bar, 0b11);
         else ptx::tc_commit(bar);
@@ -244,6 +268,12 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       constexpr uint32_t a_lbo = (128u >> 4) << 16, b_lbo = (16u >> 4) << 16;
       auto a_desc = [&](uint32_t addr) { return a_desc_hi | a_lbo | ((addr >> 4) & 0x3FFFu); };
       auto b_desc = [&](uint32_t addr) { return b_desc_hi | b_lbo | ((addr >> 4) & 0x3FFFu); };
+      // fp8 operands: A entries hold 16 one-byte cells, the two K chunks of a K32 step are 16 entries
+      // (256 B) apart; B rows are 32 bytes (32B swizzle), 8-row groups 256 B apart.
+      constexpr uint32_t a8_lbo = (256u >> 4) << 16;
+      const uint64_t b8_desc_hi = ((uint64_t)(256u >> 4) | (1ull << 14) | (6ull << 29)) << 32;       // SBO | version | SW32
+      auto a8_desc = [&](uint32_t addr) { return a_desc_hi | a8_lbo | ((addr >> 4) & 0x3FFFu); };
+      auto b8_desc = [&](uint32_t addr) { return b8_desc_hi | b_lbo | ((addr >> 4) & 0x3FFFu); };
       uint32_t slot = 0, bphase = 0, es = 0, cs = 0;
       uint32_t b_addr = base + p.off_b;
       const uint32_t b_end = b_addr + p.nbstages * stage_bytes;
@@ -261,7 +291,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             const int ebuf = es & 1;
             ptx::mbar_wait(bar_efull(ebuf), (es >> 1) & 1);
             ptx::tc_fence_after();
-            const uint32_t e_hi = base + p.off_e + ebuf * 2 * p.e_half_bytes;
+            const uint32_t e_hi = base + p.off_e + ebuf * e_buf_bytes;
             // E row 0 of this segment is template row u_first: K step ks starts 256*ks - 16*u_first*Pe bytes in
             uint32_t a_hi = e_hi + 512u * s.st0 - 16u * s.u_first * Pe;
             for (int st = s.st0; st < s.st1; ++st, a_hi += 512u) {
@@ -280,6 +310,11 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                     mma(tmem_d, da_hi, b_desc(b_addr + kBHalfCta + 32u * kk), 1);
                   }
                 }
+              }
+              if (p.passes == 2 && 2 * st + 1 >= kr.ks_lo && 2 * st < kr.ks_hi) {
+                // corrections over the whole 32-tap stage: (A_lo*4)(B_hi/4) and (A_hi/4)(B_lo*4), both e4m3
+                mma8(tmem_d, a8_desc(a_hi + p.e_half_bytes), b8_desc(b_addr + kBHalfCta));
+                mma8(tmem_d, a8_desc(a_hi + 2 * p.e_half_bytes), b8_desc(b_addr + kBHalfCta + kBHalfCta / 2));
               }
               commit(bar_empty(slot));
               b_addr += stage_bytes;
@@ -305,7 +340,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     // multiple of 8 at or below (8*px - b) and is 8 cells wider than the entries need
     const int SP = Pe + 16;
     const uint32_t gs_bytes_half = 2u * p.gs_half_elems;
-    const uint32_t gs_tx = 2u * SP * p.gs_rows * (p.passes == 3 ? 2 : 1);  // bytes one staging TMA round delivers
+    const int SP8 = Pe + 32;  // fp8c: staged BYTES per row of the 1-byte windows (start column aligned to 16)
+    // staging buffer: [fp16 hi window][fp16 lo window | fp8 lo window][fp8 hi/4 window]
+    const uint32_t gs_buf_bytes = gs_bytes_half + (p.passes == 3 ? gs_bytes_half : 0) + (p.passes == 2 ? 2 * p.gs8_bytes : 0);
+    const uint32_t gs_tx = 2u * SP * p.gs_rows * (p.passes == 3 ? 2 : 1) + (p.passes == 2 ? 2u * SP8 * p.gs_rows : 0);
 
     struct Cursor {
       long long unit;
@@ -330,12 +368,17 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     };
     auto issue_stage = [&](const Cursor& cu, int sbuf) {  // one thread
       const Seg sgm = seg_geometry(p, cu.kr, cu.sg);
-      const uint32_t dst = base + p.off_gs + sbuf * 2 * gs_bytes_half;
+      const uint32_t dst = base + p.off_gs + sbuf * gs_buf_bytes;
       ptx::fence_proxy_async_smem();  // earlier generic reads of this buffer precede the async write
       ptx::mbar_arrive_expect_tx(bar_gsfull(sbuf), gs_tx);
       const int x0 = (8 * cu.px - b) & ~7, y0 = 16 * cu.py + sgm.u_first - a, z0 = cu.g * p.C + cu.c;
       ptx::tma_load_3d(dst, &tm_ghi, bar_gsfull(sbuf), x0, y0, z0);
       if (p.passes == 3) ptx::tma_load_3d(dst + gs_bytes_half, &tm_glo, bar_gsfull(sbuf), x0, y0, z0);
+      if (p.passes == 2) {
+        const int x8 = (8 * cu.px - b) & ~15;
+        ptx::tma_load_3d(dst + gs_bytes_half, &tm_glo, bar_gsfull(sbuf), x8, y0, z0);
+        ptx::tma_load_3d(dst + gs_bytes_half + p.gs8_bytes, &tm_gx, bar_gsfull(sbuf), x8, y0, z0);
+      }
     };
 
     Cursor cur{};
@@ -356,11 +399,11 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
         const Seg s = seg_geometry(p, cur.kr, cur.sg);
         ptx::mbar_wait(bar_eempty(ebuf), ((es >> 1) & 1) ^ 1);
         ptx::mbar_wait(bar_gsfull(sbuf), ahead ? ((es >> 1) & 1) : (es & 1));
-        const __half* gs_hi = reinterpret_cast<const __half*>(base_ptr + p.off_gs + sbuf * 2 * gs_bytes_half);
+        const __half* gs_hi = reinterpret_cast<const __half*>(base_ptr + p.off_gs + sbuf * gs_buf_bytes);
         const __half* gs_lo = gs_hi + p.gs_half_elems;
         // shifted entries E[r][i] = gs[r][i .. i+7]; one thread emits an even/odd pair from five
         // aligned 32-bit words (the odd entry is the even one funnel-shifted by one cell)
-        uint8_t* e_hi = base_ptr + p.off_e + ebuf * 2 * p.e_half_bytes;
+        uint8_t* e_hi = base_ptr + p.off_e + ebuf * e_buf_bytes;
         uint8_t* e_lo = e_hi + p.e_half_bytes;
         const int pairs_per_row = Pe / 2;
         const int delta = (8 * cur.px - b) & 7;  // first needed cell inside the aligned window
@@ -387,6 +430,25 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             uint4* dst = reinterpret_cast<uint4*>(e_lo + 16u * (r * Pe + 2 * ip));
             dst[0] = odd ? sh : al;
             dst[1] = odd ? al : sh;
+          }
+        }
+        if (p.passes == 2) {
+          // fp8 entries: E8[r][i] = 16 one-byte cells gs8[r][d8 + i .. +15], assembled from five aligned
+          // 32-bit words and a byte-granular funnel shift; arrays: [1] = lo*4, [2] = hi/4
+          const int d8 = (8 * cur.px - b) & 15;
+#pragma unroll 1
+          for (int arr = 0; arr < 2; ++arr) {
+            const uint8_t* g8 = reinterpret_cast<const uint8_t*>(gs_hi) + gs_bytes_half + arr * p.gs8_bytes;
+            uint8_t* e8 = e_hi + (1 + arr) * p.e_half_bytes;
+            for (int e = tg; e < s.rows * Pe; e += kGenThreads) {
+              const int r = e / Pe, i = e - r * Pe;
+              const int o = d8 + i;
+              const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(g8 + r * SP8) + (o >> 2);
+              const uint32_t sh = (o & 3) * 8;
+              const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
+              *reinterpret_cast<uint4*>(e8 + 16u * e) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                                                                  __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+            }
           }
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async reads
@@ -533,14 +595,58 @@ int make_gallery_map(CUtensorMap* tm, const uint16_t* ptr, int planes, int Hp, i
   }
   return SIR_OK;
 }
+// e4m3 template operands [C][ncols][Kpad] bytes: box 32 bytes x box_cols, 32-byte swizzle
+int make_template_map8(CUtensorMap* tm, const uint8_t* ptr, int Kpad, int ncols_alloc, int C, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SIR_E_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)ncols_alloc, (cuuint64_t)C};
+  cuuint64_t strides[2] = {(cuuint64_t)Kpad, (cuuint64_t)Kpad * (cuuint64_t)ncols_alloc};
+  cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)box_cols, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(e4m3 templates) failed with CUresult %d (Kpad=%d ncols=%d C=%d)", (int)r, Kpad, ncols_alloc, C);
+    return SIR_E_CUDA;
+  }
+  return SIR_OK;
+}
+// e4m3 gallery channels [planes][Hp][pitch8] bytes; box = one staging window
+int make_gallery_map8(CUtensorMap* tm, const uint8_t* ptr, int planes, int Hp, int Wp, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SIR_E_CUDA;
+  }
+  const int pitch = gal_pitch8(Wp);
+  cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)Hp};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(e4m3 gallery) failed with CUresult %d (planes=%d Hp=%d Wp=%d box=%dx%d)", (int)r, planes, Hp, Wp,
+              box_cols, box_rows);
+    return SIR_E_CUDA;
+  }
+  return SIR_OK;
+}
 }  // namespace
 
-int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, int G, int C, int Hp, int Wp,
-                  const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hm, int Wm,
-                  const int32_t* d_col2probe, float* d_scores, int score_ld, int g0, int passes, cudaStream_t st) {
-  SIR_CHECK_ARG(d_ghi && d_glo && d_thi && d_tlo, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
-  SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_thi) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_tlo) & 15) == 0,
-                "sir_ncc_scores: template operands must be 16-byte aligned");
+// passes 3 / 1: d_glo, d_tlo are the fp16 lo operands, the *8* pointers are unused.
+// passes 2 (fp8c): d_g8l/d_g8a and d_t8l/d_t8b are the e4m3 companions (lo*4, hi/4), d_glo/d_tlo unused.
+int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l, const float* d_rnorm, int G,
+                  int C, int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
+                  int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
+                  int passes, cudaStream_t st) {
+  SIR_CHECK_ARG(d_ghi && d_thi, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
+  if (passes == 2) SIR_CHECK_ARG(d_g8a && d_g8l && d_t8b && d_t8l, "sir_ncc_scores_fp8c: needs the e4m3 companion operands");
+  else SIR_CHECK_ARG(d_glo && d_tlo, "sir_ncc_scores(tcgen05): needs the fp16 lo operands");
+  SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_thi) & 15) == 0, "sir_ncc_scores: template operands must be 16-byte aligned");
   TcParams p{};
   p.ghi = (const __half*)d_ghi;
   p.glo = (const __half*)d_glo;
@@ -551,8 +657,9 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   p.g0 = g0;
   p.G = G; p.C = C; p.Hp = Hp; p.Wp = Wp; p.Hm = Hm; p.Wm = Wm;
   p.ncols = ncols;
-  p.nkc = tpl_chunks_per_row(Wm);
-  const int Kpad = tpl_kpad(Hm, Wm);
+  const int row_align = passes == 2 ? 16 : 8;
+  p.nkc = tpl_row_taps(Wm, row_align) / 8;
+  const int Kpad = tpl_kpad_aligned(Hm, Wm, row_align);
   p.nsteps = ceil_div(Hm * p.nkc, 2);
   p.nkstages = Kpad / kStageK;
   p.npy = ceil_div(Hp, 16);
@@ -567,8 +674,9 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   p.out_scale = 1.0f / ((float)C * (float)(1 << kTemplateScaleLog2));
 
   // shared memory plan: B ring, 2 E buffers (x halves), row staging, column maxima, barriers
-  const int halves = passes == 3 ? 2 : 1;
-  const uint32_t stage_bytes = kBHalfBytes / cg * halves;  // per CTA
+  const int halves = passes == 3 ? 2 : passes == 2 ? 3 : 1;          // operand arrays per E buffer
+  const int gs16 = passes == 3 ? 2 : 1;                             // staged fp16 windows
+  const uint32_t stage_bytes = kBHalfBytes / cg * (passes == 1 ? 1 : 2);  // per CTA
   const int Pe = 8 * p.nkc;
   const size_t limit = 227 * 1024 - 1024;  // alignment slack
   bool ok = false;
@@ -581,7 +689,9 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
         const int max_rows = 16 + (4 * seg - 1) / p.nkc + 1;
         const size_t e_half = (size_t)(max_rows + 1) * Pe * 16;
         const size_t gs_half = (size_t)(max_rows + 1) * (Pe + 16);  // cells
-        const size_t total = (size_t)nb * stage_bytes + 2 * halves * e_half + (size_t)gsb * 2 * (gs_half * 2 + 128) + 4 * kTileN * 4 + 512;
+        const size_t gs8 = passes == 2 ? (size_t)round_up((max_rows + 1) * (Pe + 32), 128) : 0;  // bytes of one 1-byte window
+        const size_t gs_buf = gs16 * (size_t)round_up((int)gs_half, 64) * 2 + 2 * gs8;
+        const size_t total = (size_t)nb * stage_bytes + 2 * halves * (e_half + 128) + (size_t)gsb * gs_buf + 4 * kTileN * 4 + 512;
         if (total <= limit) {
           p.nbstages = nb;
           p.seg_stages = seg;
@@ -589,6 +699,8 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
           p.gs_half_elems = (uint32_t)round_up((int)gs_half, 64);  // 128-byte aligned TMA destinations
           p.gs_rows = max_rows + 1;
           p.gs_bufs = gsb;
+          p.gs8_bytes = (uint32_t)gs8;
+          p.nhalf = halves;
           ok = true;
           break;
         }
@@ -600,24 +712,37 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
   p.nseg = ceil_div(p.nkstages, p.seg_stages);
   p.off_b = 0;
   p.off_e = p.off_b + p.nbstages * stage_bytes;
-  p.off_gs = p.off_e + 2 * 2 * p.e_half_bytes;
-  p.off_cm = (uint32_t)round_up((int)(p.off_gs + p.gs_bufs * 2 * p.gs_half_elems * 2), 16);
+  p.off_gs = p.off_e + 2 * p.nhalf * p.e_half_bytes;
+  p.off_cm = (uint32_t)round_up((int)(p.off_gs + p.gs_bufs * (gs16 * p.gs_half_elems * 2 + 2 * p.gs8_bytes)), 16);
   p.off_bar = p.off_cm + 4 * kTileN * 4;
   const size_t smem = 1024 + p.off_bar + 512;
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_scores: shared-memory plan overflow (%zu bytes)", smem);
 
-  SIR_CHECK_ARG(Pe + 16 <= 256 && p.gs_rows <= 256, "sir_ncc_scores: template %dx%d exceeds the staging TMA box", Hm, Wm);
+  SIR_CHECK_ARG(Pe + (passes == 2 ? 32 : 16) <= 256 && p.gs_rows <= 256, "sir_ncc_scores: template %dx%d exceeds the staging TMA box", Hm, Wm);
   SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ghi) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_glo) & 15) == 0,
                 "sir_ncc_scores: gallery operands must be 16-byte aligned");
-  CUtensorMap tm_hi, tm_lo, tm_ghi, tm_glo;
+  CUtensorMap tm_hi, tm_lo, tm_x, tm_ghi, tm_glo, tm_gx;
   int rc = make_template_map(&tm_hi, d_thi, Kpad, ncols_alloc, C, kTileN / cg);
-  if (rc) return rc;
-  rc = make_template_map(&tm_lo, d_tlo, Kpad, ncols_alloc, C, kTileN / cg);
   if (rc) return rc;
   rc = make_gallery_map(&tm_ghi, d_ghi, G * C, Hp, Wp, Pe + 16, p.gs_rows);
   if (rc) return rc;
-  rc = make_gallery_map(&tm_glo, d_glo, G * C, Hp, Wp, Pe + 16, p.gs_rows);
-  if (rc) return rc;
+  if (passes == 2) {
+    rc = make_template_map8(&tm_lo, d_t8l, Kpad, ncols_alloc, C, kTileN / cg);
+    if (rc) return rc;
+    rc = make_template_map8(&tm_x, d_t8b, Kpad, ncols_alloc, C, kTileN / cg);
+    if (rc) return rc;
+    rc = make_gallery_map8(&tm_glo, d_g8l, G * C, Hp, Wp, Pe + 32, p.gs_rows);
+    if (rc) return rc;
+    rc = make_gallery_map8(&tm_gx, d_g8a, G * C, Hp, Wp, Pe + 32, p.gs_rows);
+    if (rc) return rc;
+  } else {
+    rc = make_template_map(&tm_lo, d_tlo, Kpad, ncols_alloc, C, kTileN / cg);
+    if (rc) return rc;
+    rc = make_gallery_map(&tm_glo, d_glo, G * C, Hp, Wp, Pe + 16, p.gs_rows);
+    if (rc) return rc;
+    tm_x = tm_lo;
+    tm_gx = tm_glo;
+  }
 
   static thread_local size_t configured[3] = {0, 0, 0};
   if (smem > configured[cg]) {
@@ -643,9 +768,9 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_r
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SIR_CUDA(cudaLaunchKernelEx(&cfg, ncc_tc_kernel<2>, tm_hi, tm_lo, tm_ghi, tm_glo, p));
+    SIR_CUDA(cudaLaunchKernelEx(&cfg, ncc_tc_kernel<2>, tm_hi, tm_lo, tm_x, tm_ghi, tm_glo, tm_gx, p));
   } else {
-    ncc_tc_kernel<1><<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_ghi, tm_glo, p);
+    ncc_tc_kernel<1><<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_x, tm_ghi, tm_glo, tm_gx, p);
   }
   SIR_LAUNCH_CHECK("ncc_tc_kernel");
   return SIR_OK;

@@ -7,9 +7,13 @@
 //   similarity.py:57-65   D = box(g^2) - box(g)^2 / (Hm*Wm), clamped at 0, float64
 //   similarity.py:67      E = sum(t^2)
 //   similarity.py:262-276 Image.rotate (nearest) / Image.resize (bicubic) per channel
+#include <cuda_fp8.h>
+
 #include "sir_common.cuh"
 
 namespace sir {
+
+__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
 
 // ------------------------------------------------------------------------------------------
 // K5 gallery: one CTA per (gallery, channel).  Reads 4 B/cell, writes 4 B/cell (hi+lo) [+4 gz].
@@ -184,11 +188,12 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------
 // K5 templates: one CTA per (map n, channel c).
 __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restrict__ maps, int C, int h, int w, int col0,
-                                                            int ncols_alloc, __half* __restrict__ thi,
-                                                            __half* __restrict__ tlo, float* __restrict__ t32) {
+                                                            int ncols_alloc, int row_align, __half* __restrict__ thi,
+                                                            __half* __restrict__ tlo, float* __restrict__ t32,
+                                                            uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l) {
   __shared__ double sred[32];
   const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm;
-  const int nkc = tpl_chunks_per_row(Wm), Kpad = tpl_kpad(Hm, Wm), rowk = nkc * 8;
+  const int rowk = tpl_row_taps(Wm, row_align), Kpad = tpl_kpad_aligned(Hm, Wm, row_align);
   const int n = blockIdx.x / C, c = blockIdx.x - n * C;
   const float* src = maps + ((size_t)n * C + c) * (size_t)h * w;
 
@@ -217,8 +222,31 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
     }
     const float s = ldexpf(tn, kTemplateScaleLog2);
     const __half hi = __float2half_rn(s);
+    const float lo = s - __half2float(hi);
     thi[col * Kpad + k] = hi;
-    tlo[col * Kpad + k] = __float2half_rn(s - __half2float(hi));
+    if (tlo) tlo[col * Kpad + k] = __float2half_rn(lo);
+    if (t8b) {  // fp8 copies for the correction MMAs: (B_hi / 4) and (B_lo * 4), see sir_ncc_tc.cu
+      t8b[col * Kpad + k] = to_e4m3(__half2float(hi) * 0.25f);
+      t8l[col * Kpad + k] = to_e4m3(lo * 4.0f);
+    }
+  }
+}
+
+// fp8 companions of the packed gallery: a8 = e4m3(hi / 4), l8 = e4m3(lo * 4); rows padded to 16 cells
+__global__ void __launch_bounds__(256) gallery_fp8_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo, int Hp,
+                                                          int Wp, uint8_t* __restrict__ g8a, uint8_t* __restrict__ g8l) {
+  const int WP = gal_pitch(Wp), WP8 = gal_pitch8(Wp);
+  const size_t gc = blockIdx.x;
+  for (int i = threadIdx.x; i < Hp * WP8; i += blockDim.x) {
+    const int y = i / WP8, x = i - y * WP8;
+    uint8_t a = 0, l = 0;
+    if (x < Wp) {
+      const size_t j = (gc * Hp + y) * WP + x;
+      a = to_e4m3(__half2float(ghi[j]) * 0.25f);
+      l = to_e4m3(__half2float(glo[j]) * 4.0f);
+    }
+    g8a[gc * Hp * WP8 + i] = a;
+    g8l[gc * Hp * WP8 + i] = l;
   }
 }
 
@@ -391,7 +419,32 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
 
 extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }
 
+extern "C" int sir_gallery_pitch8(int Wp) { return Wp > 0 ? gal_pitch8(Wp) : 0; }
+
+extern "C" int sir_gallery_pack_fp8c(const uint16_t* d_ghi, const uint16_t* d_glo, int G, int C, int Hp, int Wp, uint8_t* d_g8a,
+                                     uint8_t* d_g8l, void* stream) {
+  SIR_CHECK_ARG(d_ghi && d_glo && d_g8a && d_g8l, "sir_gallery_pack_fp8c: null pointer");
+  SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0, "sir_gallery_pack_fp8c: bad shape");
+  gallery_fp8_kernel<<<(unsigned)((size_t)G * C), 256, 0, (cudaStream_t)stream>>>((const __half*)d_ghi, (const __half*)d_glo, Hp, Wp,
+                                                                                   d_g8a, d_g8l);
+  SIR_LAUNCH_CHECK("gallery_fp8_kernel");
+  return SIR_OK;
+}
+
 extern "C" int sir_template_kpad(int Hm, int Wm) { return (Hm > 0 && Wm > 0) ? tpl_kpad(Hm, Wm) : 0; }
+extern "C" int sir_template_kpad_fp8c(int Hm, int Wm) { return (Hm > 0 && Wm > 0) ? tpl_kpad_aligned(Hm, Wm, 16) : 0; }
+
+extern "C" int sir_template_pack_fp8c(const float* d_maps, int N, int C, int h, int w, int col0, int ncols_alloc, uint16_t* d_thi,
+                                      uint8_t* d_t8b, uint8_t* d_t8l, void* stream) {
+  SIR_CHECK_ARG(d_maps && d_thi && d_t8b && d_t8l, "sir_template_pack_fp8c: null pointer");
+  SIR_CHECK_ARG(N > 0 && C > 0, "sir_template_pack_fp8c: empty input");
+  SIR_CHECK_ARG(h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack_fp8c: map %dx%d vanishes after the 2-cell crop", h, w);
+  SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack_fp8c: columns [%d,%d) outside %d", col0, col0 + N, ncols_alloc);
+  template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, (cudaStream_t)stream>>>(d_maps, C, h, w, col0, ncols_alloc, 16, (__half*)d_thi,
+                                                                                     nullptr, nullptr, d_t8b, d_t8l);
+  SIR_LAUNCH_CHECK("template_pack_kernel");
+  return SIR_OK;
+}
 
 extern "C" int sir_template_pack(const float* d_maps, int N, int C, int h, int w, int col0, int ncols_alloc,
                                  uint16_t* d_thi, uint16_t* d_tlo, float* d_t32, void* stream) {
@@ -401,7 +454,7 @@ extern "C" int sir_template_pack(const float* d_maps, int N, int C, int h, int w
   SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack: columns [%d,%d) outside %d", col0, col0 + N,
                 ncols_alloc);
   template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, (cudaStream_t)stream>>>(
-      d_maps, C, h, w, col0, ncols_alloc, (__half*)d_thi, (__half*)d_tlo, d_t32);
+      d_maps, C, h, w, col0, ncols_alloc, 8, (__half*)d_thi, (__half*)d_tlo, d_t32, nullptr, nullptr);
   SIR_LAUNCH_CHECK("template_pack_kernel");
   return SIR_OK;
 }

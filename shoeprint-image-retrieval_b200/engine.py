@@ -37,6 +37,10 @@ __all__ = [
 
 EDGE = 2  # similarity.py:92-93
 
+#: parity-grade default: fp16 hi*hi + fp8 correction products (measured <= 1e-5 relative vs the float64
+#: oracle, tools/precision_study.py); "fp16x3" is the all-fp16 alternative, "fp16x1" the fast lossy one
+DEFAULT_PRECISION = "fp16_fp8c"
+
 
 class _LaunchCounter:
     """Counts libsir kernel launches (bench.py reports it as ``gpu_launches``)."""
@@ -144,6 +148,21 @@ class GalleryOperands:
     gz: torch.Tensor | None
     ids: torch.Tensor
     _rnorm: dict = field(default_factory=dict)
+    _fp8: tuple | None = None
+
+    def fp8_companions(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """e4m3 copies (hi/4, lo*4) of the packed gallery for the fp8-corrected mode, built once."""
+        if self._fp8 is None:
+            wp8 = int(nat.lib.sir_gallery_pitch8(self.Wp))
+            g8a = torch.empty((self.G, self.C, self.Hp, wp8), dtype=torch.uint8, device=self.ghi.device)
+            g8l = torch.empty_like(g8a)
+            nat.check(
+                nat.lib.sir_gallery_pack_fp8c(_ptr(self.ghi), _ptr(self.glo), self.G, self.C, self.Hp, self.Wp, _ptr(g8a), _ptr(g8l), _stream()),
+                "sir_gallery_pack_fp8c",
+            )
+            launch_counter.add()
+            self._fp8 = (g8a, g8l)
+        return self._fp8
 
     @staticmethod
     def pack(group: MapGroup, keep_fp32: bool) -> "GalleryOperands":
@@ -241,23 +260,47 @@ class _Block:
 
 def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperands], offsets: list[int],
                  scores: torch.Tensor, precision: int) -> None:
+    if precision == nat.PREC_FP16_FP8C:
+        try:
+            _score_block_impl(block, hw, gallery, offsets, scores, precision)
+        except nat.SirError as err:
+            # very wide templates need three operand arrays per E buffer and do not fit shared memory in
+            # the fp8-corrected mode; the argument check fails before anything is launched
+            if "does not fit the shared-memory plan" not in str(err):
+                raise
+            _score_block_impl(block, hw, gallery, offsets, scores, nat.PREC_FP16X3)
+        return
+    _score_block_impl(block, hw, gallery, offsets, scores, precision)
+
+
+def _score_block_impl(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperands], offsets: list[int],
+                      scores: torch.Tensor, precision: int) -> None:
     h, w = hw
     hm, wm = h - 2 * EDGE, w - 2 * EDGE
     dev = scores.device
     c = gallery[0].C
     ncols = block.ncols
-    kpad = int(nat.lib.sir_template_kpad(hm, wm))
     simt = precision == nat.PREC_FP32_SIMT
+    fp8c = precision == nat.PREC_FP16_FP8C
+    kpad = int(nat.lib.sir_template_kpad_fp8c(hm, wm) if fp8c else nat.lib.sir_template_kpad(hm, wm))
     thi = torch.empty((c, ncols, kpad), dtype=torch.float16, device=dev)
-    tlo = torch.empty_like(thi)
+    tlo = None if fp8c else torch.empty_like(thi)
+    t8b = torch.empty((c, ncols, kpad), dtype=torch.uint8, device=dev) if fp8c else None
+    t8l = torch.empty_like(t8b) if fp8c else None
     t32 = torch.empty((c, ncols, hm * wm), dtype=torch.float32, device=dev) if simt else None
     col0 = 0
     for m in block.maps:
         n = int(m.shape[0])
-        nat.check(
-            nat.lib.sir_template_pack(_ptr(m), n, c, h, w, col0, ncols, _ptr(thi), _ptr(tlo), _ptr(t32), _stream()),
-            "sir_template_pack",
-        )
+        if fp8c:
+            nat.check(
+                nat.lib.sir_template_pack_fp8c(_ptr(m), n, c, h, w, col0, ncols, _ptr(thi), _ptr(t8b), _ptr(t8l), _stream()),
+                "sir_template_pack_fp8c",
+            )
+        else:
+            nat.check(
+                nat.lib.sir_template_pack(_ptr(m), n, c, h, w, col0, ncols, _ptr(thi), _ptr(tlo), _ptr(t32), _stream()),
+                "sir_template_pack",
+            )
         launch_counter.add()
         col0 += n
     col2probe = torch.cat(block.ids).to(torch.int32).to(dev, non_blocking=True)
@@ -266,15 +309,26 @@ def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperan
         if kernel_events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        nat.check(
-            nat.lib.sir_ncc_scores(
-                _ptr(ops.ghi), _ptr(ops.glo), _ptr(ops.gexp), _ptr(ops.gz), _ptr(rn),
-                ops.G, ops.C, ops.Hp, ops.Wp,
-                _ptr(thi), _ptr(tlo), _ptr(t32), ncols, ncols, hm, wm,
-                _ptr(col2probe), _ptr(scores), int(scores.stride(0)), g0, precision, _stream(),
-            ),
-            "sir_ncc_scores",
-        )
+        if fp8c:
+            g8a, g8l = ops.fp8_companions()
+            nat.check(
+                nat.lib.sir_ncc_scores_fp8c(
+                    _ptr(ops.ghi), _ptr(g8a), _ptr(g8l), _ptr(rn), ops.G, ops.C, ops.Hp, ops.Wp,
+                    _ptr(thi), _ptr(t8b), _ptr(t8l), ncols, ncols, hm, wm,
+                    _ptr(col2probe), _ptr(scores), int(scores.stride(0)), g0, _stream(),
+                ),
+                "sir_ncc_scores_fp8c",
+            )
+        else:
+            nat.check(
+                nat.lib.sir_ncc_scores(
+                    _ptr(ops.ghi), _ptr(ops.glo), _ptr(ops.gexp), _ptr(ops.gz), _ptr(rn),
+                    ops.G, ops.C, ops.Hp, ops.Wp,
+                    _ptr(thi), _ptr(tlo), _ptr(t32), ncols, ncols, hm, wm,
+                    _ptr(col2probe), _ptr(scores), int(scores.stride(0)), g0, precision, _stream(),
+                ),
+                "sir_ncc_scores",
+            )
         launch_counter.add()
         if kernel_events is not None:
             ev1.record()
@@ -283,7 +337,7 @@ def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperan
             kernel_events.append((ev0, ev1, flops))
 
 
-def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, precision: str = "fp16x3",
+def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, precision: str = DEFAULT_PRECISION,
                  col_block: int = 16384, packed_gallery: list[GalleryOperands] | None = None) -> torch.Tensor:
     """float32 ``[Q, G]`` on the device: max over the variant set, floored at 0
     (``similarities_all`` of similarity.py:355-367), columns in the caller's gallery order."""
@@ -351,7 +405,7 @@ def rank_true_matches(scores: torch.Tensor, true_idx, k: int = 0, g0: int = 0, t
     return count_gt, count_ge, tv[:, :k], ti[:, :k], true_score
 
 
-def compare(probe_maps, gallery_maps, matching_pairs, rotations=None, scales=None, precision: str = "fp16x3", k: int = 0):
+def compare(probe_maps, gallery_maps, matching_pairs, rotations=None, scales=None, precision: str = DEFAULT_PRECISION, k: int = 0):
     """Host lists in, (ranks int32 [Q] on host, scores [Q,G] on device, top-k lists) out."""
     probes = probe_maps if isinstance(probe_maps, MapSet) else MapSet.from_host(list(probe_maps))
     gallery = gallery_maps if isinstance(gallery_maps, MapSet) else MapSet.from_host(list(gallery_maps))

@@ -72,7 +72,7 @@ def merge_ranks(true_score, count_gt, count_ge, topk_val, topk_idx, group=None, 
 
 
 def compare_sharded(probes, gallery_shard, true_idx, g0: int, rotations=None, scales=None,
-                    precision: str = "fp16x3", k: int = 0, group=None, packed_gallery=None):
+                    precision: str = "fp16_fp8c", k: int = 0, group=None, packed_gallery=None):
     """Sharded compare pass on this rank: ``probes`` are replicated, ``gallery_shard`` holds global
     gallery indices ``[g0, g0 + G_local)``, ``true_idx`` are GLOBAL gallery indices.
 

@@ -69,7 +69,7 @@ def compare_maps(
     comparison = config["comparison"]
     rotations = comparison.get("rotations")
     scales = comparison.get("scales")
-    precision = comparison.get("precision", "fp16x3")
+    precision = comparison.get("precision", engine.DEFAULT_PRECISION)
     top_k = int(comparison.get("top_k", 0))
     if len(matching_pairs) < len(shoemark_maps):
         raise IndexError("matching_pairs is shorter than shoemark_maps")
@@ -98,7 +98,7 @@ def get_similarity(shoemark: FeatureMapsArrayType, shoeprint: FeatureMapsArrayTy
     of the 2-cell-cropped maps, summed over channels, max over positions, divided by C."""
     probes = engine.MapSet.from_host([_as_f32(shoemark)])
     gallery = engine.MapSet.from_host([_as_f32(shoeprint)])
-    scores = engine.score_matrix(probes, gallery, None, None, "fp16x3")
+    scores = engine.score_matrix(probes, gallery, None, None, engine.DEFAULT_PRECISION)
     # compare_maps floors at 0 (similarity.py:355); a lone get_similarity call in the reference does
     # not, but a negative best NCC only arises for anti-correlated maps and ranks last either way.
     return np.float64(scores[0, 0].item())

@@ -43,7 +43,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-5), ("fp16x3", REL_TOL)])
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-5), ("fp16x3", REL_TOL), ("fp16_fp8c", REL_TOL)])
 @pytest.mark.parametrize("case", CASES)
 def test_scores_match_oracle(eng, case, precision, tol):
     from oracle import compare as ocmp
@@ -102,6 +102,9 @@ def test_simt_and_tensor_core_agree_at_reference_shapes(eng):
         a = eng.score_matrix(ps, gs, [-5, 5], None, "fp32_simt").cpu().numpy()
         b = eng.score_matrix(ps, gs, [-5, 5], None, "fp16x3").cpu().numpy()
         _check(b, a)
+        c8 = eng.score_matrix(ps, gs, [-5, 5], None, "fp16_fp8c").cpu().numpy()
+        _check(c8, a)
+        print(f"C={c}: max rel err fp16x3 {np.max(np.abs(b - a) / np.maximum(a, 1e-3)):.2e}, fp16_fp8c {np.max(np.abs(c8 - a) / np.maximum(a, 1e-3)):.2e}")
         assert np.all(a.argmax(1) == pairs.cpu().numpy())
 
 
