@@ -105,10 +105,56 @@ __global__ void __launch_bounds__(256) im2col_split_kernel(const float* __restri
   }
 }
 
+// Fast path for C % 8 == 0: the 8 values of a thread are 8 consecutive channels of ONE tap, i.e. 32
+// contiguous bytes of the NHWC activation -> two 16-byte loads, no per-element index arithmetic.
+__global__ void __launch_bounds__(256) im2col_split_c8_kernel(const float* __restrict__ in, const float* __restrict__ amax_in,
+                                                              int B, int H, int W, int C, int kh, int kw, int stride, int pad,
+                                                              int Ho, int Wo, const float* __restrict__ chan_scale, int Kp,
+                                                              __half* __restrict__ ahi, __half* __restrict__ alo) {
+  const int K = kh * kw * C;
+  const int e = scale_exp_from_amax(*amax_in);
+  const size_t M = (size_t)B * Ho * Wo;
+  const int k8s = Kp / 8, c8s = C / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M * k8s; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / k8s;
+    const int k8 = (int)(i - m * k8s);
+    const int k0 = k8 * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (k0 < K) {
+      const int tap = k8 / c8s, c0 = (k8 - tap * c8s) * 8;
+      const int ky = tap / kw, kx = tap - ky * kw;
+      const int b = (int)(m / ((size_t)Ho * Wo));
+      const int r = (int)(m - (size_t)b * Ho * Wo);
+      const int oy = r / Wo, ox = r - oy * Wo;
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const float4* src = reinterpret_cast<const float4*>(in + (((size_t)b * H + iy) * W + ix) * C + c0);
+        const float4 a = __ldg(src), d = __ldg(src + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+        if (chan_scale) {
+          const float4* sc = reinterpret_cast<const float4*>(chan_scale + (size_t)b * C + c0);
+          const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1);
+          v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+        }
+      }
+    }
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sv = ldexpf(v[j], e);
+      hi[j] = __float2half_rn(sv);
+      lo[j] = __float2half_rn(sv - __half2float(hi[j]));
+    }
+    *reinterpret_cast<uint4*>(ahi + m * Kp + k0) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(alo + m * Kp + k0) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ K1b
 // C[m][n] = act((A_hi+A_lo)[m][:] . (B_hi+B_lo)[n][:] * 2^-(ea+ew) + bias[n]) (+ residual[m][n])
 constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
-constexpr int kGemmStages = 4;
+constexpr int kGemmStages = 3;  // 96 KB of operand stages: two CTAs fit one SM and overlap epilogue with mainloop
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 32;
 constexpr uint32_t kGemmSub = 8192;  // one operand half of one stage (128 rows x 64 B)
@@ -125,7 +171,7 @@ struct GemmParams {
   uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -296,6 +342,43 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ i
   if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
 }
 
+// 4 channels per thread (C % 4 == 0): 16-byte loads of activations and weights
+__global__ void __launch_bounds__(256) dwconv_c4_kernel(const float* __restrict__ in, int B, int H, int W, int C, int k, int stride,
+                                                        int pad, int Ho, int Wo, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int act, float* __restrict__ out,
+                                                        float* __restrict__ amax) {
+  const int C4 = C / 4;
+  const size_t total = (size_t)B * Ho * Wo * C4;
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    size_t r = i / C4;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + iy) * W + ix) * C + c));
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * k + kx) * C + c));
+        acc.x = fmaf(x.x, ww.x, acc.x); acc.y = fmaf(x.y, ww.y, acc.y); acc.z = fmaf(x.z, ww.z, acc.z); acc.w = fmaf(x.w, ww.w, acc.w);
+      }
+    }
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float4 o;
+    o.x = act_apply(acc.x + bb.x, act); o.y = act_apply(acc.y + bb.y, act); o.z = act_apply(acc.z + bb.z, act); o.w = act_apply(acc.w + bb.w, act);
+    *reinterpret_cast<float4*>(out + i * 4) = o;
+    local = fmaxf(local, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
+}
+
 // global average pool: [B][H*W][C] -> [B][C]; one CTA per (image, 64-channel slab)
 __global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ in, int HW, int C, float* __restrict__ out) {
   __shared__ float part[4][64];
@@ -451,8 +534,12 @@ extern "C" int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, 
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_im2col_split: empty output");
   const size_t work = (size_t)B * Ho * Wo * (Kp / 8);
-  im2col_split_kernel<<<grid_for(work), 256, 0, (cudaStream_t)stream>>>(d_in, d_amax_in, B, H, W, C, kh, kw, stride, pad, Ho, Wo,
-                                                                         d_chan_scale, Kp, (__half*)d_ahi, (__half*)d_alo);
+  if (C % 8 == 0 && ((uintptr_t)d_in & 15) == 0 && (!d_chan_scale || ((uintptr_t)d_chan_scale & 15) == 0))
+    im2col_split_c8_kernel<<<grid_for(work), 256, 0, (cudaStream_t)stream>>>(d_in, d_amax_in, B, H, W, C, kh, kw, stride, pad, Ho, Wo,
+                                                                              d_chan_scale, Kp, (__half*)d_ahi, (__half*)d_alo);
+  else
+    im2col_split_kernel<<<grid_for(work), 256, 0, (cudaStream_t)stream>>>(d_in, d_amax_in, B, H, W, C, kh, kw, stride, pad, Ho, Wo,
+                                                                           d_chan_scale, Kp, (__half*)d_ahi, (__half*)d_alo);
   SIR_LAUNCH_CHECK("im2col_split_kernel");
   return SIR_OK;
 }
@@ -508,8 +595,12 @@ extern "C" int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, in
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "sir_feat_dwconv: bad shape");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_dwconv: empty output");
-  dwconv_kernel<<<grid_for((size_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_w,
-                                                                                      d_bias, act, d_out, d_amax_out);
+  if (C % 4 == 0 && (((uintptr_t)d_in | (uintptr_t)d_w | (uintptr_t)d_bias | (uintptr_t)d_out) & 15) == 0)
+    dwconv_c4_kernel<<<grid_for((size_t)B * Ho * Wo * (C / 4)), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo,
+                                                                                              d_w, d_bias, act, d_out, d_amax_out);
+  else
+    dwconv_kernel<<<grid_for((size_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_w,
+                                                                                        d_bias, act, d_out, d_amax_out);
   SIR_LAUNCH_CHECK("dwconv_kernel");
   return SIR_OK;
 }
