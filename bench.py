@@ -52,6 +52,21 @@ WORKLOAD = {
 CPU_SAMPLE = {"Q": 16, "G": 16}  # bounded CPU sample: 16 x 16 pairs x 13 variants at the full map shape (~15-20 s on 8 cores)
 
 
+def _ncu_traffic() -> tuple[float | None, str | None]:
+    """DRAM bytes of one ncc_tc_kernel launch from the committed `ncu --set full` capture (profiles/)."""
+    f = ROOT / "profiles" / "r01_ncu_full_ncc_tc_kernel_final.txt"
+    if not f.exists():
+        return None, None
+    total = 0.0
+    for line in f.read_text().splitlines():
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if line.startswith(key + " ["):
+                unit = line.split("[")[1].split("]")[0]
+                val = float(line.split("=")[1])
+                total += val * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+    return total, "ncu --set full capture of the bench --profile launch (3,328 columns x 150 gallery; the bench's own launches are 16,384 and 3,116 columns wide and move proportionally more)"
+
+
 def _peaks() -> dict:
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -328,7 +343,7 @@ def run_b200(args) -> None:
             "roofline": {
                 "kernel": "ncc_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                 "frac": (achieved / peaks["bf16"]) if achieved else None,
-                "traffic": None,
+                "traffic": _ncu_traffic()[0], "traffic_source": _ncu_traffic()[1],
                 "peak_source": peaks["src"],
                 "launches": len(k_ms), "mean_launch_ms": (sum(k_ms) / len(k_ms)) if k_ms else None,
                 "share_of_step": (sum(k_ms) / ms_total) if k_ms else None,
