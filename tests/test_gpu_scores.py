@@ -157,3 +157,27 @@ def test_idempotent_and_gallery_permutation_invariant(eng):
     perm = torch.randperm(40, device="cuda")
     c = eng.score_matrix(ps, eng.MapSet.from_device(gal[perm].contiguous()), [7], None, "fp16x3")
     assert torch.equal(c, a[:, perm])
+
+
+def test_full_bench_size_properties(eng):
+    """BASELINE configs[1] at full size (1,500 probes x 150 gallery x 13 variants, 176x50x19): too big for
+    the CPU oracle, so size-independent properties are checked: every probe is a noisy copy of its
+    true match and must rank it first with a score near 1; the default precision mode must agree
+    with fp16x3 to 1e-4; the score of an (unrotated) probe against itself-as-gallery is exactly the
+    max over variants, so adding variants can only raise scores (monotonicity)."""
+    from src.shoeprint_image_retrieval import synth
+
+    gal = synth.device_gallery(61, 150, 176, 50, 19)
+    prb, pairs = synth.device_probes(62, gal, 1500)
+    ps, gs = eng.MapSet.from_device(prb), eng.MapSet.from_device(gal)
+    rot = [a for a in range(-30, 31, 5) if a != 0]
+    full = eng.score_matrix(ps, gs, rot, None)
+    gt, ge, tv, ti, ts = eng.rank_true_matches(full, pairs, 5)
+    assert int((gt == 0).sum()) == 1500
+    assert torch.equal(ti[:, 0].long(), pairs.long())
+    assert float(ts.min()) > 0.8
+    x3 = eng.score_matrix(ps, gs, rot, None, "fp16x3")
+    err = ((full - x3).abs() / x3.abs().clamp_min(1e-3)).max().item()
+    assert err < REL_TOL, err
+    base = eng.score_matrix(ps, gs, None, None)
+    assert bool((full >= base).all())
