@@ -167,9 +167,13 @@ int sir_feat_se_scale(const float* d_in, int B, int HW, int C, int S, const floa
                       const float* d_w2, const float* d_b2, float* d_avg, float* d_scale, void* stream);
 int sir_feat_maxpool(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, float* d_out,
                      float* d_amax_out, void* stream);
-/* per-channel y = act(x * scale[c] + shift[c]) (scale/shift both NULL: activation only) */
-int sir_feat_affine_act(const float* d_in, long long total, int C, const float* d_scale, const float* d_shift, int act,
-                        float* d_out, float* d_amax_out, void* stream);
+/* per-channel y = act(x * scale[c] + shift[c]) (scale/shift both NULL: activation only) over `rows`
+ * pixels of C channels; row strides ld_in / ld_out let it read or write a channel slice of a wider
+ * NHWC buffer (DenseNet concatenation).  sir_feat_avgpool2d: AvgPool2d(k, stride), no padding. */
+int sir_feat_affine_act(const float* d_in, long long rows, int C, int ld_in, int ld_out, const float* d_scale,
+                        const float* d_shift, int act, float* d_out, float* d_amax_out, void* stream);
+int sir_feat_avgpool2d(const float* d_in, int B, int H, int W, int C, int k, int stride, float* d_out, float* d_amax_out,
+                       void* stream);
 int sir_feat_nhwc_to_nchw(const float* d_in, int B, int HW, int C, float* d_out, void* stream);
 
 #ifdef __cplusplus

@@ -48,7 +48,8 @@ SIGNATURES = {
     "sir_feat_dwconv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
     "sir_feat_se_scale": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "sir_feat_maxpool": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "sir_feat_affine_act": (_i, [_p, C.c_longlong, _i, _p, _p, _i, _p, _p, _p]),
+    "sir_feat_affine_act": (_i, [_p, C.c_longlong, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
+    "sir_feat_avgpool2d": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "sir_feat_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _p, _p]),
 }
 

@@ -448,17 +448,42 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
 
 // standalone per-channel affine + activation (BatchNorm2d / ReLU children that a block cut separates
 // from their convolution, e.g. VGG features[:n] ending between Conv2d and ReLU)
-__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ in, size_t total, int C, const float* __restrict__ scale,
-                                                         const float* __restrict__ shift, int act, float* __restrict__ out,
-                                                         float* __restrict__ amax) {
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ in, size_t total, int C, int ld_in, int ld_out,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                         float* __restrict__ out, float* __restrict__ amax) {
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / C;
+    const int c = (int)(i - row * C);
+    float v = in[row * ld_in + c];
+    if (scale) v = fmaf(v, scale[c], shift[c]);
+    v = act_apply(v, act);
+    out[row * ld_out + c] = v;
+    local = fmaxf(local, fabsf(v));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
+}
+
+// average pooling (DenseNet transitions: AvgPool2d(2, 2)), NHWC, no padding
+__global__ void __launch_bounds__(256) avgpool2d_kernel(const float* __restrict__ in, int B, int H, int W, int C, int k, int stride,
+                                                        int Ho, int Wo, float* __restrict__ out, float* __restrict__ amax) {
+  const size_t total = (size_t)B * Ho * Wo * C;
+  const float inv = 1.0f / (float)(k * k);
   float local = 0.0f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
-    float v = in[i];
-    if (scale) v = fmaf(v, scale[c], shift[c]);
-    v = act_apply(v, act);
-    out[i] = v;
-    local = fmaxf(local, fabsf(v));
+    size_t r = i / C;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float acc = 0.0f;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) acc += in[(((size_t)b * H + oy * stride + ky) * W + ox * stride + kx) * C + c];
+    const float o = acc * inv;
+    out[i] = o;
+    local = fmaxf(local, fabsf(o));
   }
   local = warp_max(local);
   if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
@@ -628,11 +653,21 @@ extern "C" int sir_feat_maxpool(const float* d_in, int B, int H, int W, int C, i
   return SIR_OK;
 }
 
-extern "C" int sir_feat_affine_act(const float* d_in, long long total, int C, const float* d_scale, const float* d_shift, int act,
-                                   float* d_out, float* d_amax_out, void* stream) {
-  SIR_CHECK_ARG(d_in && d_out && total > 0 && C > 0 && (!d_scale == !d_shift), "sir_feat_affine_act: bad argument");
-  affine_act_kernel<<<grid_for((size_t)total), 256, 0, (cudaStream_t)stream>>>(d_in, (size_t)total, C, d_scale, d_shift, act, d_out, d_amax_out);
+extern "C" int sir_feat_affine_act(const float* d_in, long long rows, int C, int ld_in, int ld_out, const float* d_scale,
+                                   const float* d_shift, int act, float* d_out, float* d_amax_out, void* stream) {
+  SIR_CHECK_ARG(d_in && d_out && rows > 0 && C > 0 && ld_in >= C && ld_out >= C && (!d_scale == !d_shift), "sir_feat_affine_act: bad argument");
+  const size_t total = (size_t)rows * C;
+  affine_act_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(d_in, total, C, ld_in, ld_out, d_scale, d_shift, act, d_out, d_amax_out);
   SIR_LAUNCH_CHECK("affine_act_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_avgpool2d(const float* d_in, int B, int H, int W, int C, int k, int stride, float* d_out, float* d_amax_out,
+                                  void* stream) {
+  SIR_CHECK_ARG(d_in && d_out && B > 0 && H >= k && W >= k && C > 0 && k > 0 && stride > 0, "sir_feat_avgpool2d: bad argument");
+  const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+  avgpool2d_kernel<<<grid_for((size_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, Ho, Wo, d_out, d_amax_out);
+  SIR_LAUNCH_CHECK("avgpool2d_kernel");
   return SIR_OK;
 }
 

@@ -22,10 +22,10 @@ Pretrained weights need torchvision's cached checkpoints (the reference download
 pass ``random_init_seed=<int>`` (or set ``SIR_RANDOM_INIT_SEED``) to build the same architecture
 with seeded random weights -- what the benchmarks and tests do.
 
-Supported ``config["model"]["type"]``: the EfficientNet family (B1-B7, V2 S/M/L) and VGG16 /
-VGG19 / VGG19_BN.  ``DenseNet_201`` (concatenating blocks) is not compiled yet and raises
-``NotImplementedError``; unknown strings raise ``LookupError("Model string not found")`` like
-``network.py:181-182``.
+Supported ``config["model"]["type"]``: all 13 strings of the reference -- the EfficientNet family
+(B1-B7, V2 S/M/L), VGG16 / VGG19 / VGG19_BN and DenseNet_201 (dense blocks write their growth
+channels straight into a shared NHWC buffer, so the concatenation costs nothing).  Unknown strings
+raise ``LookupError("Model string not found")`` like ``network.py:181-182``.
 """
 
 from __future__ import annotations
@@ -71,7 +71,7 @@ _MODELS = {
 
 @dataclass
 class _Op:
-    kind: str            # conv | dwconv | se | affine | maxpool
+    kind: str            # conv | dwconv | se | affine | maxpool | avgpool | alloc
     src: int             # input tensor id
     dst: int             # output tensor id
     p: dict = field(default_factory=dict)
@@ -110,15 +110,19 @@ class _Compiler:
         self.n_tensors += 1
         return self.n_tensors - 1
 
-    def conv(self, conv: nn.Conv2d, bn, act: int, residual: int | None = None, chan_scale: int | None = None) -> None:
+    def conv(self, conv: nn.Conv2d, bn, act: int, residual: int | None = None, chan_scale: int | None = None,
+             into: tuple[int, int] | None = None) -> None:
+        """``into = (buffer tensor id, channel offset)``: write the result into a channel slice of an
+        existing wider NHWC buffer instead of a fresh tensor (DenseNet concatenation)."""
         if conv.dilation != (1, 1) or conv.padding_mode != "zeros" or conv.padding[0] != conv.padding[1] or conv.stride[0] != conv.stride[1]:
             raise NotImplementedError(f"unsupported convolution {conv}")
         w, b = _fold_bn(conv, bn)
-        dst = self._new()
+        dst = into[0] if into is not None else self._new()
         common = dict(k=conv.kernel_size[0], kw=conv.kernel_size[1], stride=conv.stride[0], pad=conv.padding[0], act=act, bias=b)
         if conv.groups == 1:
             self.ops.append(_Op("conv", self.cur, dst, dict(common, w=w, cin=conv.in_channels, cout=conv.out_channels,
-                                                            residual=residual, chan_scale=chan_scale)))
+                                                            residual=residual, chan_scale=chan_scale,
+                                                            c_off=None if into is None else into[1])))
         elif conv.groups == conv.in_channels == conv.out_channels and conv.kernel_size[0] == conv.kernel_size[1]:
             self.ops.append(_Op("dwconv", self.cur, dst, dict(common, w=w, c=conv.in_channels)))
         else:
@@ -131,6 +135,35 @@ class _Compiler:
         bn = next((m for m in mods[1:] if isinstance(m, nn.BatchNorm2d)), None)
         actm = next((m for m in mods[1:] if not isinstance(m, nn.BatchNorm2d)), None)
         self.conv(conv, bn, _act_code(actm), residual, chan_scale)
+
+    def affine(self, bn: nn.BatchNorm2d | None, act: int, src_channels: int | None = None) -> None:
+        """Standalone BatchNorm (eval) and/or activation; ``src_channels`` = read only the first n channels
+        of the (wider) source buffer."""
+        scale = shift = None
+        if bn is not None:
+            g = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+            scale, shift = g.float(), (bn.bias.detach().double() - bn.running_mean.detach().double() * g).float()
+        dst = self._new()
+        self.ops.append(_Op("affine", self.cur, dst, dict(scale=scale, shift=shift, act=act, src_channels=src_channels)))
+        self.cur = dst
+
+    def dense_block(self, block: nn.Module) -> None:
+        """torchvision ``_DenseBlock``: every layer reads the concatenation of all earlier features
+        (BN-ReLU-1x1 conv-BN-ReLU-3x3 conv) and appends ``growth_rate`` channels."""
+        layers = list(block.children())
+        c0 = layers[0].norm1.num_features
+        growth = layers[0].conv2.out_channels
+        c_total = c0 + growth * len(layers)
+        buf = self._new()
+        self.ops.append(_Op("alloc", self.cur, buf, dict(channels=c_total, copy=c0)))
+        c_in = c0
+        for layer in layers:
+            self.cur = buf
+            self.affine(layer.norm1, _act_code(layer.relu1), src_channels=c_in)
+            self.conv(layer.conv1, layer.norm2, _act_code(layer.relu2))
+            self.conv(layer.conv2, None, ACT_NONE, into=(buf, c_in))
+            c_in += growth
+        self.cur = buf
 
     def se(self, se: nn.Module) -> int:
         sid = self._new()
@@ -158,20 +191,30 @@ class _Compiler:
                     scale_id = self.se(layer)
                 else:
                     self.conv_norm_act(layer, residual=res if last else None, chan_scale=scale_id if last else None)
+        elif type(m).__name__ == "_DenseBlock":
+            self.dense_block(m)
+        elif type(m).__name__ == "_Transition":
+            self.affine(m.norm, _act_code(m.relu))
+            self.conv(m.conv, None, ACT_NONE)
+            self.module(m.pool)
+        elif isinstance(m, nn.AvgPool2d):
+            k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+            st = m.stride if isinstance(m.stride, int) else m.stride[0]
+            pd = m.padding if isinstance(m.padding, int) else m.padding[0]
+            if pd != 0 or m.ceil_mode:
+                raise NotImplementedError(f"unsupported pooling {m}")
+            dst = self._new()
+            self.ops.append(_Op("avgpool", self.cur, dst, dict(k=k, stride=st)))
+            self.cur = dst
         elif isinstance(m, nn.Sequential):
             for child in m.children():
                 self.module(child)
         elif isinstance(m, nn.Conv2d):
             self.conv(m, None, ACT_NONE)
         elif isinstance(m, nn.BatchNorm2d):
-            g = m.weight.detach().double() / torch.sqrt(m.running_var.detach().double() + m.eps)
-            dst = self._new()
-            self.ops.append(_Op("affine", self.cur, dst, dict(scale=g.float(), shift=(m.bias.detach().double() - m.running_mean.detach().double() * g).float(), act=ACT_NONE)))
-            self.cur = dst
+            self.affine(m, ACT_NONE)
         elif isinstance(m, (nn.ReLU, nn.SiLU)):
-            dst = self._new()
-            self.ops.append(_Op("affine", self.cur, dst, dict(scale=None, shift=None, act=_act_code(m))))
-            self.cur = dst
+            self.affine(None, _act_code(m))
         elif isinstance(m, nn.MaxPool2d):
             k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
             s = m.stride if isinstance(m.stride, int) else m.stride[0]
@@ -193,11 +236,17 @@ class _Compiler:
         for op in self.ops:
             prev = out[-1] if out else None
             if (op.kind == "affine" and prev is not None and prev.kind == "conv" and prev.dst == op.src
-                    and prev.p["act"] == ACT_NONE and prev.p["residual"] is None):
+                    and prev.p["act"] == ACT_NONE and prev.p["residual"] is None and prev.p["c_off"] is None
+                    and op.p["src_channels"] is None):
                 if op.p["scale"] is not None:
                     prev.p["w"] = prev.p["w"] * op.p["scale"][:, None, None, None]
                     prev.p["bias"] = prev.p["bias"] * op.p["scale"] + op.p["shift"]
                 prev.p["act"] = op.p["act"]
+                prev.dst = op.dst
+                continue
+            if (op.kind == "affine" and prev is not None and prev.kind == "affine" and prev.dst == op.src
+                    and prev.p["act"] == ACT_NONE and op.p["scale"] is None and op.p["src_channels"] is None):
+                prev.p["act"] = op.p["act"]  # BatchNorm followed by its activation: one pass
                 prev.dst = op.dst
                 continue
             out.append(op)
@@ -264,6 +313,8 @@ class _Program:
         last_use = {}
         for i, op in enumerate(self.ops):
             last_use[op.src] = i
+            if op.p.get("c_off") is not None:
+                last_use[op.dst] = i  # the dense block's buffer stays alive while layers write into it
             for key in ("residual", "chan_scale"):
                 if op.p.get(key) is not None:
                     last_use[op.p[key]] = i
@@ -283,11 +334,16 @@ class _Program:
                 cs = tensors[p["chan_scale"]] if p["chan_scale"] is not None else None
                 nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
                                                         _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
-                out = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float32, device=dev)
                 res = tensors[p["residual"]] if p["residual"] is not None else None
+                if p["c_off"] is None:
+                    out = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float32, device=dev)
+                    out_ptr, ldc = _ptr(out), p["cout"]
+                else:  # growth channels of a dense layer go straight into the block's buffer
+                    out = tensors[op.dst]
+                    out_ptr, ldc = C.c_void_p(out.data_ptr() + 4 * p["c_off"]), int(out.shape[3])
                 nat.check(nat.lib.sir_feat_gemm(_ptr(ahi), _ptr(alo), aptr(op.src), m, p["kp"], _ptr(p["whi"]), _ptr(p["wlo"]),
                                                 p["cout"], p["rows"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
-                                                _ptr(out), p["cout"], aptr(op.dst), st), "sir_feat_gemm")
+                                                out_ptr, ldc, aptr(op.dst), st), "sir_feat_gemm")
                 launch_counter.add(2)
             elif op.kind == "dwconv":
                 ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
@@ -302,9 +358,21 @@ class _Program:
                                                     _ptr(p["w2"]), _ptr(p["b2"]), _ptr(avg), _ptr(out), st), "sir_feat_se_scale")
                 launch_counter.add(2)
             elif op.kind == "affine":
-                out = torch.empty_like(src)
-                nat.check(nat.lib.sir_feat_affine_act(_ptr(src), src.numel(), c, _ptr(p["scale"]), _ptr(p["shift"]), p["act"],
+                cs_ = p["src_channels"] or c
+                out = torch.empty((b, h, w, cs_), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.sir_feat_affine_act(_ptr(src), b * h * w, cs_, c, cs_, _ptr(p["scale"]), _ptr(p["shift"]), p["act"],
                                                       _ptr(out), aptr(op.dst), st), "sir_feat_affine_act")
+                launch_counter.add()
+            elif op.kind == "alloc":
+                out = torch.empty((b, h, w, p["channels"]), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.sir_feat_affine_act(_ptr(src), b * h * w, p["copy"], c, p["channels"], None, None, ACT_NONE,
+                                                      _ptr(out), aptr(op.dst), st), "sir_feat_affine_act")
+                launch_counter.add()
+            elif op.kind == "avgpool":
+                ho, wo = (h - p["k"]) // p["stride"] + 1, (w - p["k"]) // p["stride"] + 1
+                out = torch.empty((b, ho, wo, c), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.sir_feat_avgpool2d(_ptr(src), b, h, w, c, p["k"], p["stride"], _ptr(out), aptr(op.dst), st),
+                          "sir_feat_avgpool2d")
                 launch_counter.add()
             elif op.kind == "maxpool":
                 ho, wo = self._out_hw(h, w, p["k"], p["k"], p["stride"], p["pad"])
@@ -334,7 +402,8 @@ def get_output_size(model: "Model", input_shape: tuple[int, int, int, int]) -> t
     """Shape ``[1, C, h, w]`` of the feature maps for an input of ``input_shape`` (``network.py:32-48``),
     computed from the compiled operator list without running the network."""
     _, _, h, w = input_shape
-    c = 3
+    c: int | None = 3
+    block_channels = 0
     for op in model.program.ops:
         p = op.p
         if op.kind == "conv":
@@ -344,6 +413,14 @@ def get_output_size(model: "Model", input_shape: tuple[int, int, int, int]) -> t
             h, w = _Program._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
         elif op.kind == "maxpool":
             h, w = _Program._out_hw(h, w, p["k"], p["k"], p["stride"], p["pad"])
+        elif op.kind == "avgpool":
+            h, w = (h - p["k"]) // p["stride"] + 1, (w - p["k"]) // p["stride"] + 1
+        if op.kind == "conv" and p["c_off"] is not None:
+            c = None  # channel count of a dense block comes from its buffer
+        if op.kind == "alloc":
+            block_channels = p["channels"]
+        if c is None:
+            c = block_channels
     return torch.Size((input_shape[0], c, h, w))
 
 
@@ -364,8 +441,6 @@ class Model:
         if model_str not in _MODELS:
             raise LookupError("Model string not found")  # network.py:181-182
         ctor, tag, (mean, std) = _MODELS[model_str]
-        if model_str == "DenseNet_201":
-            raise NotImplementedError("DenseNet_201 (concatenating dense blocks) is not compiled to sm_100a kernels yet")
         if random_init_seed is None and os.environ.get("SIR_RANDOM_INIT_SEED"):
             random_init_seed = int(os.environ["SIR_RANDOM_INIT_SEED"])
         if random_init_seed is None:
@@ -437,6 +512,8 @@ class Model:
                 hh, ww = ho, wo
             elif op.kind == "maxpool":
                 hh, ww = _Program._out_hw(hh, ww, p["k"], p["k"], p["stride"], p["pad"])
+            elif op.kind == "avgpool":
+                hh, ww = (hh - p["k"]) // p["stride"] + 1, (ww - p["k"]) // p["stride"] + 1
         del c
         return max(1, int(self.max_batch_bytes // worst))
 

@@ -57,6 +57,9 @@ def _rel_l2(a, b):
     ("EfficientNet_B1", 5, (90, 70), False),
     ("VGG16", 9, (70, 50), False),
     ("VGG19_BN", 12, (64, 48), True),
+    ("DenseNet_201", 5, (96, 64), False),
+    ("DenseNet_201", 7, (128, 96), False),
+    ("DenseNet_201", 12, (96, 96), True),
 ])
 def test_feature_maps_match_torch_fp32(model_type, block, hw, rgb):
     import __graft_entry__ as ge
