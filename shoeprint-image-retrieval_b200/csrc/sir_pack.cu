@@ -63,6 +63,71 @@ __global__ void __launch_bounds__(256) gallery_pack_kernel(const float* __restri
   }
 }
 
+// Warp-per-channel version for maps that fit shared memory (all but the high-resolution configs): the
+// channel is read once with coalesced loads into the warp's smem slab, reductions are warp shuffles
+// (no block barriers); every loop walks the PADDED cropped rows in chunks of 8 cells (one division per
+// 8 cells) and the operands leave as 16-byte stores.
+__global__ void __launch_bounds__(256) gallery_pack_warp_kernel(const float* __restrict__ gal, long long planes, int hg, int wg,
+                                                                __half* __restrict__ ghi, __half* __restrict__ glo,
+                                                                int32_t* __restrict__ gexp, float* __restrict__ gz) {
+  extern __shared__ float slab[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int Hp = hg - 2 * kEdge, Wp = wg - 2 * kEdge, M = Hp * Wp, HW = hg * wg, WP = gal_pitch(Wp);
+  float* ch = slab + (size_t)wid * HW;
+  const int c8 = WP / 8, n8 = Hp * c8;
+  for (long long gc = (long long)blockIdx.x * nw + wid; gc < planes; gc += (long long)gridDim.x * nw) {
+    const float* src = gal + gc * HW;
+    for (int i = lane; i < HW; i += 32) ch[i] = __ldg(src + i);
+    __syncwarp();
+    double acc = 0.0;
+    for (int o = lane; o < n8; o += 32) {
+      const int y = o / c8, x0 = (o - y * c8) * 8;
+      const float* row = ch + (y + kEdge) * wg + kEdge + x0;
+      float part = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part += (x0 + j < Wp) ? row[j] : 0.0f;
+      acc += (double)part;
+    }
+    const float mean = (float)(warp_sum(acc) / (double)M);
+    float amax = 0.0f;
+    for (int o = lane; o < n8; o += 32) {
+      const int y = o / c8, x0 = (o - y * c8) * 8;
+      const float* row = ch + (y + kEdge) * wg + kEdge + x0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (x0 + j < Wp) amax = fmaxf(amax, fabsf(row[j] - mean));
+    }
+    amax = warp_max(amax);
+    int e = 0;
+    if (amax > 0.0f && isfinite(amax)) {
+      int ex;
+      (void)frexpf(amax, &ex);
+      e = kGalleryPeakLog2 - ex;
+    }
+    if (lane == 0) gexp[gc] = e;
+    for (int o = lane; o < n8; o += 32) {
+      const int y = o / c8, x0 = (o - y * c8) * 8;
+      const float* row = ch + (y + kEdge) * wg + kEdge + x0;
+      __align__(16) __half h8[8];
+      __align__(16) __half l8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float sc = 0.0f;
+        if (x0 + j < Wp) {
+          const float z = row[j] - mean;
+          sc = ldexpf(z, e);
+          if (gz) gz[gc * M + y * Wp + x0 + j] = z;
+        }
+        h8[j] = __float2half_rn(sc);
+        l8[j] = __float2half_rn(sc - __half2float(h8[j]));
+      }
+      *reinterpret_cast<uint4*>(ghi + gc * Hp * WP + (size_t)o * 8) = *reinterpret_cast<const uint4*>(h8);
+      *reinterpret_cast<uint4*>(glo + gc * Hp * WP + (size_t)o * 8) = *reinterpret_cast<const uint4*>(l8);
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K6: window inverse norm through float64 summed-area tables held in shared memory.
 // One CTA per (gallery, channel); dynamic smem = 2 * (Hp+1)*(Wp+1) doubles.
@@ -120,7 +185,8 @@ __global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restr
       const double d = t2 - t1 * t1 * inv_n;
       // A window that is flat up to SAT round-off is the reference's "division by ~0" case
       // (similarity.py:69-70 zeroes the non-finite results; FFT noise decides the rest): call it 0.
-      if (d > 1e-10 * t2) r = (float)(1.0 / sqrt(d));
+      // the table is float32: an IEEE float sqrt + divide of the float64 window energy is exact enough
+      if (d > 1e-10 * t2) r = __fdiv_rn(1.0f, __fsqrt_rn((float)d));
     }
     rnorm[gc * M + i] = r;
   }
@@ -135,28 +201,32 @@ struct RotateCoeffs {
 };
 
 __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
-                                                     size_t total, RotateCoeffs rc) {
-  const size_t hw = (size_t)h * w;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t plane = i / hw;
-    const int p = (int)(i - plane * hw);
-    const int y = p / w, x = p - y * w;
-    int sy, sx;
-    bool ok = true;
-    switch (rc.mode) {
-      case 0: sy = y; sx = x; break;
-      case 1: sy = h - 1 - y; sx = w - 1 - x; break;
-      case 2: sy = x; sx = w - 1 - y; break;
-      case 3: sy = h - 1 - x; sx = y; break;
-      default: {
-        const long long xs = (rc.a2 + rc.a1 * y + rc.a0 * x) >> 16;
-        const long long ys = (rc.a5 + rc.a4 * y + rc.a3 * x) >> 16;
-        ok = xs >= 0 && xs < w && ys >= 0 && ys < h;
-        sx = (int)xs;
-        sy = (int)ys;
-      }
+                                                     long long planes, RotateCoeffs rc) {
+  // The source index depends only on (y, x): compute it once per thread, then walk the planes
+  // (channels x maps) with it -- the gather is shared by all channels and all probes of that shape.
+  const int hw = h * w;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hw) return;
+  const int y = p / w, x = p - y * w;
+  int sy, sx;
+  bool ok = true;
+  switch (rc.mode) {
+    case 0: sy = y; sx = x; break;
+    case 1: sy = h - 1 - y; sx = w - 1 - x; break;
+    case 2: sy = x; sx = w - 1 - y; break;
+    case 3: sy = h - 1 - x; sx = y; break;
+    default: {
+      const long long xs = (rc.a2 + rc.a1 * y + rc.a0 * x) >> 16;
+      const long long ys = (rc.a5 + rc.a4 * y + rc.a3 * x) >> 16;
+      ok = xs >= 0 && xs < w && ys >= 0 && ys < h;
+      sx = (int)xs;
+      sy = (int)ys;
     }
-    out[i] = ok ? in[plane * hw + (size_t)sy * w + sx] : 0.0f;
+  }
+  const int src = ok ? sy * w + sx : 0;
+  for (long long plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+    const float v = ok ? __ldg(in + plane * hw + src) : 0.0f;
+    out[plane * hw + p] = v;
   }
 }
 
@@ -232,6 +302,77 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
   }
 }
 
+// Warp-per-(map, channel) version of the template pack, same idea as gallery_pack_warp_kernel.
+__global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __restrict__ maps, long long planes, int C, int h, int w,
+                                                                 int col0, int ncols_alloc, int row_align, __half* __restrict__ thi,
+                                                                 __half* __restrict__ tlo, float* __restrict__ t32,
+                                                                 uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l) {
+  extern __shared__ float slab[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm, HW = h * w;
+  const int rowk = tpl_row_taps(Wm, row_align), Kpad = tpl_kpad_aligned(Hm, Wm, row_align);
+  float* ch = slab + (size_t)wid * HW;
+  const int c8 = rowk / 8, n8 = Kpad / 8;
+  for (long long pc = (long long)blockIdx.x * nw + wid; pc < planes; pc += (long long)gridDim.x * nw) {
+    const int n = (int)(pc / C), c = (int)(pc - (long long)n * C);
+    const float* src = maps + pc * HW;
+    for (int i = lane; i < HW; i += 32) ch[i] = __ldg(src + i);
+    __syncwarp();
+    double acc = 0.0;
+    for (int o = lane; o < Hm * c8; o += 32) {
+      const int u = o / c8, v0 = (o - u * c8) * 8;
+      const float* row = ch + (u + kEdge) * w + kEdge + v0;
+      float part = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part += (v0 + j < Wm) ? row[j] : 0.0f;
+      acc += (double)part;
+    }
+    const float mean = (float)(warp_sum(acc) / (double)K);
+    double e = 0.0;
+    for (int o = lane; o < Hm * c8; o += 32) {
+      const int u = o / c8, v0 = (o - u * c8) * 8;
+      const float* row = ch + (u + kEdge) * w + kEdge + v0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double z = (v0 + j < Wm) ? (double)(row[j] - mean) : 0.0;
+        e += z * z;
+      }
+    }
+    e = warp_sum(e);
+    const double inv = e > 0.0 ? 1.0 / sqrt(e) : 0.0;
+    const size_t col = (size_t)c * ncols_alloc + col0 + n;
+    for (int o = lane; o < n8; o += 32) {
+      const int u = o / c8, v0 = (o - u * c8) * 8;
+      const float* row = ch + (u + kEdge) * w + kEdge + v0;
+      __align__(16) __half h8[8];
+      __align__(16) __half l8[8];
+      __align__(8) uint8_t b8[8];
+      __align__(8) uint8_t q8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float tn = 0.0f;
+        if (u < Hm && v0 + j < Wm) {
+          tn = (float)((double)(row[j] - mean) * inv);
+          if (t32) t32[col * K + u * Wm + v0 + j] = tn;
+        }
+        const float sc = ldexpf(tn, kTemplateScaleLog2);
+        h8[j] = __float2half_rn(sc);
+        const float lo = sc - __half2float(h8[j]);
+        l8[j] = __float2half_rn(lo);
+        b8[j] = to_e4m3(__half2float(h8[j]) * 0.25f);
+        q8[j] = to_e4m3(lo * 4.0f);
+      }
+      *reinterpret_cast<uint4*>(thi + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(h8);
+      if (tlo) *reinterpret_cast<uint4*>(tlo + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(l8);
+      if (t8b) {
+        *reinterpret_cast<uint2*>(t8b + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint2*>(b8);
+        *reinterpret_cast<uint2*>(t8l + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint2*>(q8);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // fp8 companions of the packed gallery: a8 = e4m3(hi / 4), l8 = e4m3(lo * 4); rows padded to 16 cells
 __global__ void __launch_bounds__(256) gallery_fp8_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo, int Hp,
                                                           int Wp, uint8_t* __restrict__ g8a, uint8_t* __restrict__ g8l) {
@@ -264,8 +405,16 @@ extern "C" int sir_gallery_pack(const float* d_gallery, int G, int C, int hg, in
   SIR_CHECK_ARG(d_gallery && d_ghi && d_glo && d_gexp, "sir_gallery_pack: null pointer");
   SIR_CHECK_ARG(G > 0 && C > 0, "sir_gallery_pack: empty gallery (G=%d C=%d)", G, C);
   SIR_CHECK_ARG(hg > 2 * kEdge && wg > 2 * kEdge, "sir_gallery_pack: map %dx%d vanishes after the 2-cell crop", hg, wg);
-  gallery_pack_kernel<<<(unsigned)((size_t)G * C), 256, 0, (cudaStream_t)stream>>>(
-      d_gallery, C, hg, wg, (__half*)d_ghi, (__half*)d_glo, d_gexp, d_gz);
+  const size_t slab = (size_t)hg * wg * sizeof(float);
+  if (8 * slab <= 48 * 1024) {
+    const long long planes = (long long)G * C;
+    const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 148 * 8);
+    gallery_pack_warp_kernel<<<blocks, 256, 8 * slab, (cudaStream_t)stream>>>(d_gallery, planes, hg, wg, (__half*)d_ghi, (__half*)d_glo,
+                                                                               d_gexp, d_gz);
+  } else {
+    gallery_pack_kernel<<<(unsigned)((size_t)G * C), 256, 0, (cudaStream_t)stream>>>(
+        d_gallery, C, hg, wg, (__half*)d_ghi, (__half*)d_glo, d_gexp, d_gz);
+  }
   SIR_LAUNCH_CHECK("gallery_pack_kernel");
   return SIR_OK;
 }
@@ -320,9 +469,10 @@ extern "C" int sir_variant_rotate(const float* d_in, int N, int C, int h, int w,
     rc.a2 = fix16(m2 + m0 * 0.5 + m1 * 0.5);
     rc.a5 = fix16(m5 + m3 * 0.5 + m4 * 0.5);
   }
-  const size_t total = (size_t)N * C * h * w;
-  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
-  rotate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, h, w, total, rc);
+  const long long planes = (long long)N * C;
+  const unsigned bx = (unsigned)ceil_div(h * w, 256);
+  const unsigned by = (unsigned)std::min<long long>(planes, std::max(1u, 148u * 16u / bx));
+  rotate_kernel<<<dim3(bx, by), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, h, w, planes, rc);
   SIR_LAUNCH_CHECK("rotate_kernel");
   return SIR_OK;
 }
@@ -419,6 +569,18 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
 
 extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }
 
+static void launch_template_pack(const float* d_maps, int N, int C, int h, int w, int col0, int ncols_alloc, int row_align, __half* thi,
+                                 __half* tlo, float* t32, uint8_t* t8b, uint8_t* t8l, cudaStream_t st) {
+  const size_t slab = (size_t)h * w * sizeof(float);
+  if (8 * slab <= 48 * 1024) {
+    const long long planes = (long long)N * C;
+    const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 148 * 8);
+    template_pack_warp_kernel<<<blocks, 256, 8 * slab, st>>>(d_maps, planes, C, h, w, col0, ncols_alloc, row_align, thi, tlo, t32, t8b, t8l);
+  } else {
+    template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, st>>>(d_maps, C, h, w, col0, ncols_alloc, row_align, thi, tlo, t32, t8b, t8l);
+  }
+}
+
 extern "C" int sir_gallery_pitch8(int Wp) { return Wp > 0 ? gal_pitch8(Wp) : 0; }
 
 extern "C" int sir_gallery_pack_fp8c(const uint16_t* d_ghi, const uint16_t* d_glo, int G, int C, int Hp, int Wp, uint8_t* d_g8a,
@@ -440,8 +602,7 @@ extern "C" int sir_template_pack_fp8c(const float* d_maps, int N, int C, int h, 
   SIR_CHECK_ARG(N > 0 && C > 0, "sir_template_pack_fp8c: empty input");
   SIR_CHECK_ARG(h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack_fp8c: map %dx%d vanishes after the 2-cell crop", h, w);
   SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack_fp8c: columns [%d,%d) outside %d", col0, col0 + N, ncols_alloc);
-  template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, (cudaStream_t)stream>>>(d_maps, C, h, w, col0, ncols_alloc, 16, (__half*)d_thi,
-                                                                                     nullptr, nullptr, d_t8b, d_t8l);
+  launch_template_pack(d_maps, N, C, h, w, col0, ncols_alloc, 16, (__half*)d_thi, nullptr, nullptr, d_t8b, d_t8l, (cudaStream_t)stream);
   SIR_LAUNCH_CHECK("template_pack_kernel");
   return SIR_OK;
 }
@@ -453,8 +614,7 @@ extern "C" int sir_template_pack(const float* d_maps, int N, int C, int h, int w
   SIR_CHECK_ARG(h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack: map %dx%d vanishes after the 2-cell crop", h, w);
   SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack: columns [%d,%d) outside %d", col0, col0 + N,
                 ncols_alloc);
-  template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, (cudaStream_t)stream>>>(
-      d_maps, C, h, w, col0, ncols_alloc, 8, (__half*)d_thi, (__half*)d_tlo, d_t32, nullptr, nullptr);
+  launch_template_pack(d_maps, N, C, h, w, col0, ncols_alloc, 8, (__half*)d_thi, (__half*)d_tlo, d_t32, nullptr, nullptr, (cudaStream_t)stream);
   SIR_LAUNCH_CHECK("template_pack_kernel");
   return SIR_OK;
 }

@@ -24,27 +24,30 @@ __global__ void true_scores_kernel(const float* __restrict__ scores, int Q, int 
 // (value desc, index asc) strict order
 __device__ __forceinline__ bool beats(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
 
-// Sorted insertion of (v, idx) into a warp-owned list of length k held in shared memory.
-// Called by all 32 lanes with the same (v, idx).  Returns the new k-th value (threshold).
-__device__ __forceinline__ float warp_insert(float* lv, int* li, int k, float v, int idx, int lane) {
-  // position = number of entries that stay ahead of the newcomer
-  int pos = 0;
-  for (int j = lane; j < k; j += 32) pos += beats(lv[j], li[j], v, idx) ? 1 : 0;
-  pos = warp_sum(pos);
-  // shift [pos, k-1) down by one, highest index first (chunks of 32 from the tail)
-  for (int base = ((k - 2 - pos) / 32) * 32 + pos; base >= pos; base -= 32) {
-    const int j = base + lane;
-    float tv = 0.f;
-    int ti = 0;
-    const bool act = j <= k - 2;
-    if (act) { tv = lv[j]; ti = li[j]; }
-    __syncwarp();
-    if (act) { lv[j + 1] = tv; li[j + 1] = ti; }
-    __syncwarp();
+// Warp-select: each warp keeps an UNSORTED list of its k best (value, index) pairs in shared memory
+// together with the current worst entry (value `thr`, slot `wslot`).  A candidate that beats the worst
+// replaces it and the worst is recomputed by a warp reduction -- O(k/32) per insertion, no shifting.
+// Ordering (value desc, index asc) is only established once, by the final merge.
+struct Worst {
+  float v;
+  int idx;
+  int slot;
+};
+__device__ __forceinline__ Worst warp_find_worst(const float* lv, const int* li, int k, int lane) {
+  Worst w{INFINITY, -1, 0};
+  for (int j = lane; j < k; j += 32) {
+    const float v = lv[j];
+    const int id = li[j];
+    if (v < w.v || (v == w.v && id > w.idx)) w = Worst{v, id, j};
   }
-  if (lane == 0) { lv[pos] = v; li[pos] = idx; }
-  __syncwarp();
-  return lv[k - 1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, w.v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, w.idx, o);
+    const int os = __shfl_xor_sync(0xffffffffu, w.slot, o);
+    if (ov < w.v || (ov == w.v && oi > w.idx)) w = Worst{ov, oi, os};
+  }
+  return w;
 }
 
 __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __restrict__ scores, int Q, int G, int ld,
@@ -60,24 +63,29 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
 
   for (int j = lane; j < k; j += 32) { lv[wid][j] = -INFINITY; li[wid][j] = INT_MAX; }
   __syncwarp();
-  float thr = -INFINITY;  // current k-th best of this warp
+  Worst worst{-INFINITY, INT_MAX, 0};  // every slot is empty: any finite value beats it
   int gt = 0, ge = 0;
 
   auto consider = [&](float v, int g, bool valid) {
     if (valid) { gt += v > ts; ge += v >= ts; }
     if (k > 0) {
-      unsigned m = __ballot_sync(0xffffffffu, valid && v > thr);
+      // indices arrive in increasing order, so an equal value never displaces an earlier one
+      unsigned m = __ballot_sync(0xffffffffu, valid && v > worst.v);
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const float cv = __shfl_sync(0xffffffffu, v, src);
         const int ci = __shfl_sync(0xffffffffu, g, src);
-        if (cv > thr) thr = warp_insert(lv[wid], li[wid], k, cv, ci, lane);
+        if (cv > worst.v) {
+          if (lane == 0) { lv[wid][worst.slot] = cv; li[wid][worst.slot] = ci; }
+          __syncwarp();
+          worst = warp_find_worst(lv[wid], li[wid], k, lane);
+        }
       }
     }
   };
 
-  // each warp owns a contiguous slice; 16-byte loads when the row is aligned
+  // each warp owns a contiguous slice; 16-byte loads, four in flight per lane, when the row is aligned
   const int per = ceil_div(G, kRankWarps);
   const int beg = wid * per, end = min(G, beg + per);
   const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
@@ -88,13 +96,20 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
     g = head;
     const int nvec = (end - g) / 4;
     const float4* rv = reinterpret_cast<const float4*>(row + g);
-    for (int base = 0; base < nvec; base += 32) {
-      const int i = base + lane;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool ok = i < nvec;
-      if (ok) v = __ldg(rv + i);
-      const int gi = g0 + g + 4 * i;
-      consider(v.x, gi, ok); consider(v.y, gi + 1, ok); consider(v.z, gi + 2, ok); consider(v.w, gi + 3, ok);
+    for (int base = 0; base < nvec; base += 128) {
+      float4 v[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * 32 + lane;
+        ok[u] = i < nvec;
+        v[u] = ok[u] ? __ldg(rv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int gi = g0 + g + 4 * (base + u * 32 + lane);
+        consider(v[u].x, gi, ok[u]); consider(v[u].y, gi + 1, ok[u]); consider(v[u].z, gi + 2, ok[u]); consider(v[u].w, gi + 3, ok[u]);
+      }
     }
     g += nvec * 4;
   }
@@ -120,7 +135,8 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
     const float v = lv[i / k][i % k];
     const int id = li[i / k][i % k];
     int r = 0;
-    for (int j = 0; j < ncand; ++j) r += beats(lv[j / k][j % k], li[j / k][j % k], v, id) ? 1 : 0;
+    for (int w = 0; w < kRankWarps; ++w)
+      for (int j = 0; j < k; ++j) r += beats(lv[w][j], li[w][j], v, id) ? 1 : 0;
     if (r < k) {
       topk_val[(size_t)q * k + r] = v;
       topk_idx[(size_t)q * k + r] = (id == INT_MAX) ? -1 : id;
