@@ -103,6 +103,12 @@ int sir_ncc_scores(const uint16_t* d_ghi, const uint16_t* d_glo, const int32_t* 
                    const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
                    int precision, void* stream);
 
+/* normxcorr (similarity.py:26-72) for one channel pair, surface written out (debug/helper path only):
+ * d_gz [Hp][Wp] zero-meaned image, d_rnorm its window inverse norm for Hm x Wm, d_t32 [Hm][Wm] the packed
+ * template (t - mean)/sqrt(E);  d_out [Hp][Wp] f32. */
+int sir_ncc_surface(const float* d_gz, const float* d_rnorm, int Hp, int Wp, const float* d_t32, int Hm, int Wm,
+                    float* d_out, void* stream);
+
 /* fp8-corrected variant (SIR_PREC_FP16_FP8C).  Same quantity as sir_ncc_scores; operands:
  *   gallery : d_ghi (as above) + d_g8a = e4m3(hi/4), d_g8l = e4m3(lo*4), uint8 [G][C][Hp][sir_gallery_pitch8(Wp)]
  *             produced from d_ghi/d_glo by sir_gallery_pack_fp8c;

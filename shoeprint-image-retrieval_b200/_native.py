@@ -34,6 +34,7 @@ SIGNATURES = {
     "sir_template_kpad": (_i, [_i, _i]),
     "sir_template_pack": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sir_ncc_scores": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+    "sir_ncc_surface": (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _p]),
     "sir_gallery_pitch8": (_i, [_i]),
     "sir_gallery_pack_fp8c": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "sir_template_kpad_fp8c": (_i, [_i, _i]),

@@ -66,6 +66,27 @@ __global__ void __launch_bounds__(kSimtThreads) ncc_simt_kernel(const float* __r
   if (threadIdx.x == 0) atomic_max_nonneg(&scores[(size_t)col2probe[n] * score_ld + g0 + g], best / (float)C);
 }
 
+// Full correlation surface of ONE (template, image) channel pair: out[y][x] = rnorm[y][x] * sum t*g.
+// Serves the public helper normxcorr() (similarity.py:26-72); never used by the matching path, which
+// keeps the surface on chip.
+__global__ void __launch_bounds__(256) ncc_surface_kernel(const float* __restrict__ gz, const float* __restrict__ rnorm, int Hp, int Wp,
+                                                          const float* __restrict__ t32, int Hm, int Wm, float* __restrict__ out) {
+  const int a = Hm / 2, b = Wm / 2;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < Hp * Wp; m += gridDim.x * blockDim.x) {
+    const int y = m / Wp, x = m - y * Wp;
+    float acc = 0.0f;
+    for (int u = 0; u < Hm; ++u) {
+      const int iy = y + u - a;
+      if (iy < 0 || iy >= Hp) continue;
+      for (int v = 0; v < Wm; ++v) {
+        const int ix = x + v - b;
+        if (ix >= 0 && ix < Wp) acc = fmaf(t32[u * Wm + v], gz[iy * Wp + ix], acc);
+      }
+    }
+    out[m] = acc * rnorm[m];
+  }
+}
+
 int launch_ncc_simt(const float* d_gz, const float* d_rnorm, int G, int C, int Hp, int Wp, const float* d_t32, int ncols,
                     int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
                     cudaStream_t st) {
@@ -86,3 +107,12 @@ int launch_ncc_simt(const float* d_gz, const float* d_rnorm, int G, int C, int H
 }
 
 }  // namespace sir
+
+extern "C" int sir_ncc_surface(const float* d_gz, const float* d_rnorm, int Hp, int Wp, const float* d_t32, int Hm, int Wm, float* d_out,
+                               void* stream) {
+  SIR_CHECK_ARG(d_gz && d_rnorm && d_t32 && d_out, "sir_ncc_surface: null pointer");
+  SIR_CHECK_ARG(Hp > 0 && Wp > 0 && Hm > 0 && Wm > 0, "sir_ncc_surface: bad shape");
+  sir::ncc_surface_kernel<<<sir::ceil_div(Hp * Wp, 256), 256, 0, (cudaStream_t)stream>>>(d_gz, d_rnorm, Hp, Wp, d_t32, Hm, Wm, d_out);
+  SIR_LAUNCH_CHECK("ncc_surface_kernel");
+  return SIR_OK;
+}

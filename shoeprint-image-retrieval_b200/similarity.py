@@ -111,38 +111,40 @@ def normxcorr(
 ) -> ImageArrayType:
     """Normalised cross-correlation surface of ``template`` over ``image`` (``similarity.py:26-72``).
 
-    Debug helper, not on the matching path: the fused GPU kernel never materialises the surface
+    Helper, not on the matching path: the fused kernel never materialises the surface
     (``compare_maps`` / ``get_similarity`` go through ``sir_ncc_scores``).  Here the zero-meaned
-    operands and the window norm come from the library's pack kernels (``sir_gallery_pack``,
-    ``sir_gallery_window_rnorm``) and only the numerator of this one surface is a plain
-    ``torch.nn.functional.conv2d`` on the device.  Only ``mode="same"`` -- the only mode the
-    reference uses (``similarity.py:104``) -- is supported.
+    operands and the window norm come from the library's pack kernels and the surface from
+    ``sir_ncc_surface`` (fp32 CUDA cores).  Only ``mode="same"`` -- the only mode the reference uses
+    (``similarity.py:104``) -- is supported.
     """
     if mode != "same":
         raise NotImplementedError("only mode='same' is used by the matching path (similarity.py:104)")
+    import ctypes as C
+
     import torch
+
+    from . import _native as nat
 
     t = _as_f32(template)
     g = _as_f32(image)
     hm, wm = t.shape
     hp, wp = g.shape
     # frame both so the library's 2-cell crop removes exactly the frame
-    tpad = np.pad(t, _PAD)[None]
-    gpad = np.pad(g, _PAD)[None]
-    probes = engine.MapSet.from_host([tpad])
-    gal = engine.MapSet.from_host([gpad])
+    gal = engine.MapSet.from_host([np.pad(g, _PAD)[None]])
     ops = engine.GalleryOperands.pack(gal.groups[0], keep_fp32=True)
-    rn = ops.rnorm(hm, wm, simt=True).reshape(hp, wp)
-    # numerator: correlate on the device with the packed fp32 operands
-    gz = ops.gz.reshape(1, 1, hp, wp)
-    tz = torch.from_numpy(t - t.mean(dtype=np.float32)).to(gz.device)
-    e = float((tz.double() ** 2).sum())
-    a, b = hm // 2, wm // 2
-    padded = torch.nn.functional.pad(gz, (b, wm - 1 - b, a, hm - 1 - a))
-    num = torch.nn.functional.conv2d(padded.double(), tz.double().reshape(1, 1, hm, wm)).reshape(hp, wp)
-    out = num * rn.double() / np.sqrt(e) if e > 0 else torch.zeros_like(num)
-    out = torch.nan_to_num(out, nan=0.0, posinf=0.0, neginf=0.0)
-    return out.cpu().numpy()
+    rn = ops.rnorm(hm, wm, simt=True)
+    tmap = torch.from_numpy(np.pad(t, _PAD)[None, None]).to(rn.device)
+    kpad = int(nat.lib.sir_template_kpad(hm, wm))
+    thi = torch.empty((1, 1, kpad), dtype=torch.float16, device=rn.device)
+    tlo = torch.empty_like(thi)
+    t32 = torch.empty((1, 1, hm * wm), dtype=torch.float32, device=rn.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nat.check(nat.lib.sir_template_pack(C.c_void_p(tmap.data_ptr()), 1, 1, hm + 2 * _PAD, wm + 2 * _PAD, 0, 1, C.c_void_p(thi.data_ptr()),
+                                        C.c_void_p(tlo.data_ptr()), C.c_void_p(t32.data_ptr()), st), "sir_template_pack")
+    out = torch.empty((hp, wp), dtype=torch.float32, device=rn.device)
+    nat.check(nat.lib.sir_ncc_surface(C.c_void_p(ops.gz.data_ptr()), C.c_void_p(rn.data_ptr()), hp, wp, C.c_void_p(t32.data_ptr()), hm, wm,
+                                      C.c_void_p(out.data_ptr()), st), "sir_ncc_surface")
+    return out.cpu().numpy().astype(np.float64)
 
 
 def _get_rank(similarities, matching_pairs: list[int], print_id: int) -> int:
