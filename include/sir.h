@@ -77,6 +77,10 @@ int sir_variant_rotate(const float* d_in, int N, int C, int h, int w, double ang
 int sir_variant_resize(const float* d_in, int N, int C, int h, int w, int h2, int w2,
                        float* d_out, float* d_tmp, void* stream);
 
+/* [N][C][h][w] -> [N][C][w][h].  Scores are invariant under transposing probe and gallery maps alike; the
+ * host uses this to present the correlation kernel with the orientation that pads less. */
+int sir_maps_transpose(const float* d_in, int N, int C, int h, int w, float* d_out, void* stream);
+
 /* K-padded length of a packed template of cropped shape Hm x Wm: taps are ordered row by row,
  * each row padded to a multiple of 8 taps, the total to a multiple of 32 (one TMA box). */
 int sir_template_kpad(int Hm, int Wm);
@@ -126,6 +130,12 @@ int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, const uint8
                         int G, int C, int Hp, int Wp, const uint16_t* d_thi, const uint8_t* d_t8b, const uint8_t* d_t8l,
                         int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores,
                         int score_ld, int g0, void* stream);
+
+/* Planning aid (host only, nothing is launched): estimated SM cycles per (gallery, 256-column tile, channel)
+ * of the tensor-core kernel for this shape and precision mode -- the larger of the MMA time of the
+ * non-skipped K stages and the shifted-entry generation time under the shared-memory plan the launch
+ * would use.  The host uses it to choose map orientation and between FP16_FP8C and FP16X3. */
+int sir_ncc_cost(int precision, int G, int Hp, int Wp, int Hm, int Wm, double* h_cost);
 
 /* ------------------------------------------------------------------ ranking (K8, K9)
  * _get_rank (similarity.py:378-386) without the sort: d_true_score[q] is scores[q][true] on the

@@ -31,6 +31,7 @@ SIGNATURES = {
     "sir_gallery_window_rnorm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "sir_variant_rotate": (_i, [_p, _i, _i, _i, _i, C.c_double, _p, _p]),
     "sir_variant_resize": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "sir_maps_transpose": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "sir_template_kpad": (_i, [_i, _i]),
     "sir_template_pack": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sir_ncc_scores": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
@@ -40,6 +41,7 @@ SIGNATURES = {
     "sir_template_kpad_fp8c": (_i, [_i, _i]),
     "sir_template_pack_fp8c": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sir_ncc_scores_fp8c": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
+    "sir_ncc_cost": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
     "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
     "sir_rank_topk": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "sir_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),

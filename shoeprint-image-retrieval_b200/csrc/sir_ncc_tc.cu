@@ -642,7 +642,9 @@ int make_gallery_map8(CUtensorMap* tm, const uint8_t* ptr, int planes, int Hp, i
 int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l, const float* d_rnorm, int G,
                   int C, int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
                   int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
-                  int passes, cudaStream_t st) {
+                  int passes, cudaStream_t st, double* cost_out) {
+  // cost_out != NULL: dry run -- plan only, report the estimated SM cycles per (gallery, 256-column tile,
+  // channel) and return without touching any pointer (sir_ncc_cost)
   SIR_CHECK_ARG(d_ghi && d_thi, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
   if (passes == 2) SIR_CHECK_ARG(d_g8a && d_g8l && d_t8b && d_t8l, "sir_ncc_scores_fp8c: needs the e4m3 companion operands");
   else SIR_CHECK_ARG(d_glo && d_tlo, "sir_ncc_scores(tcgen05): needs the fp16 lo operands");
@@ -679,11 +681,13 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   const uint32_t stage_bytes = kBHalfBytes / cg * (passes == 1 ? 1 : 2);  // per CTA
   const int Pe = 8 * p.nkc;
   const size_t limit = 227 * 1024 - 1024;  // alignment slack
+  // Plan: long E segments first (every segment rebuilds 16 + rows-in-segment E rows, so short segments
+  // make the generators the bottleneck), then as deep a B ring as the remaining shared memory allows
+  // (at least 3 stages; 2 as a last resort), staging double-buffered unless that is what does not fit.
   bool ok = false;
-  for (int gsb = 2; gsb >= 1 && !ok; --gsb) {
-    // ring depth: enough stages in flight to cover the TMA round trip (a stage is 768 MMA cycles in
-    // fp16x3 but only 256 in fp16x1)
-    for (int nb = (passes == 1 ? 12 : (cg == 2 ? 6 : 4)); nb >= 2 && !ok; --nb) {
+  const int nb_max = passes == 1 ? 12 : (cg == 2 ? 6 : 4);
+  for (int nb_min = 3; nb_min >= 2 && !ok; --nb_min) {
+    for (int gsb = 2; gsb >= 1 && !ok; --gsb) {
       for (int seg = p.nkstages; seg >= 1; --seg) {
         // rows touched by a segment of `seg` stages: worst case over alignments
         const int max_rows = 16 + (4 * seg - 1) / p.nkc + 1;
@@ -691,9 +695,9 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
         const size_t gs_half = (size_t)(max_rows + 1) * (Pe + 16);  // cells
         const size_t gs8 = passes == 2 ? (size_t)round_up((max_rows + 1) * (Pe + 32), 128) : 0;  // bytes of one 1-byte window
         const size_t gs_buf = gs16 * (size_t)round_up((int)gs_half, 64) * 2 + 2 * gs8;
-        const size_t total = (size_t)nb * stage_bytes + 2 * halves * (e_half + 128) + (size_t)gsb * gs_buf + 4 * kTileN * 4 + 512;
-        if (total <= limit) {
-          p.nbstages = nb;
+        const size_t fixed = 2 * halves * (e_half + 128) + (size_t)gsb * gs_buf + 4 * kTileN * 4 + 512;
+        if (fixed + (size_t)nb_min * stage_bytes <= limit) {
+          p.nbstages = (int)std::min<size_t>(nb_max, (limit - fixed) / stage_bytes);
           p.seg_stages = seg;
           p.e_half_bytes = (uint32_t)round_up((int)e_half, 128);
           p.gs_half_elems = (uint32_t)round_up((int)gs_half, 64);  // 128-byte aligned TMA destinations
@@ -710,6 +714,27 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   }
   SIR_CHECK_ARG(ok, "sir_ncc_scores: template %dx%d does not fit the shared-memory plan", Hm, Wm);
   p.nseg = ceil_div(p.nkstages, p.seg_stages);
+  if (cost_out) {
+    // MMA cycles of the non-skipped stages vs generator cycles (calibrated on B200 with 64 generator
+    // threads: ~1.3 cycles per fp16 entry, built in pairs, ~2.5 per fp8 entry); whichever is larger paces
+    // a (unit, channel)
+    const double cyc_stage = passes == 3 ? 768.0 : passes == 2 ? 512.0 : 256.0;
+    const int a = Hm / 2;
+    double total = 0.0;
+    for (int py = 0; py < p.npy; ++py) {
+      const int u_lo = std::max(0, a - 16 * py - 15), u_hi = std::min(Hm, Hp + a - 16 * py);
+      const int ks_lo = (u_lo * p.nkc) / 2, ks_hi = std::min(p.nsteps, (u_hi * p.nkc + 1) / 2);
+      const int stages = (ks_hi + 1) / 2 - ks_lo / 2;
+      const int nseg_u = ceil_div(stages, p.seg_stages);
+      const int rows_seg = 16 + (4 * std::min(stages, p.seg_stages) - 1) / p.nkc + 2;
+      const double mma = stages * cyc_stage;
+      const double per_entry = passes == 2 ? 1.3 + 2 * 2.5 : 1.3 * p.nhalf;
+      const double gen = per_entry * nseg_u * (double)rows_seg * Pe;
+      total += p.npx * std::max(mma, gen);
+    }
+    *cost_out = total;
+    return SIR_OK;
+  }
   p.off_b = 0;
   p.off_e = p.off_b + p.nbstages * stage_bytes;
   p.off_gs = p.off_e + 2 * p.nhalf * p.e_half_bytes;
@@ -777,3 +802,13 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
 }
 
 }  // namespace sir
+
+extern "C" int sir_ncc_cost(int precision, int G, int Hp, int Wp, int Hm, int Wm, double* h_cost) {
+  SIR_CHECK_ARG(h_cost && G > 0 && Hp > 0 && Wp > 0 && Hm > 0 && Wm > 0, "sir_ncc_cost: bad argument");
+  const int passes = precision == SIR_PREC_FP16X3 ? 3 : precision == SIR_PREC_FP16_FP8C ? 2 : precision == SIR_PREC_FP16X1 ? 1 : 0;
+  SIR_CHECK_ARG(passes != 0, "sir_ncc_cost: precision %d has no tensor-core plan", precision);
+  alignas(16) static const uint16_t dummy16[8] = {0};
+  alignas(16) static const uint8_t dummy8[16] = {0};
+  return sir::launch_ncc_tc(dummy16, dummy16, dummy8, dummy8, nullptr, G, 1, Hp, Wp, dummy16, dummy16, dummy8, dummy8, 256, 256, Hm, Wm,
+                            nullptr, nullptr, 0, 0, passes, nullptr, h_cost);
+}

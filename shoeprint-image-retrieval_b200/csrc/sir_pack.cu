@@ -230,6 +230,19 @@ __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ i
   }
 }
 
+// Plane transpose [P][h][w] -> [P][w][h].  Correlation scores are invariant under transposing both
+// maps, and the correlation kernel tiles positions 16 x 8 and template rows by 8/16 taps, so the host
+// picks the orientation with less padding (engine.py); planes are a few KB, the strided reads stay in L1.
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                        long long planes) {
+  const int hw = h * w;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;  // output cell: (x, y) of the h x w input
+  if (p >= hw) return;
+  const int x = p / h, y = p - x * h;
+  const int src = y * w + x;
+  for (long long plane = blockIdx.y; plane < planes; plane += gridDim.y) out[plane * hw + p] = __ldg(in + plane * hw + src);
+}
+
 // K4 resize: one separable bicubic pass (Pillow Resample.c, 32bpc float path): sequential double
 // accumulation of float32 pixel * double weight, no FMA contraction, cast to float32.
 // axis 1: along w (in [P][h][n_in] -> out [P][h][n_out]); axis 0: along h.
@@ -474,6 +487,16 @@ extern "C" int sir_variant_rotate(const float* d_in, int N, int C, int h, int w,
   const unsigned by = (unsigned)std::min<long long>(planes, std::max(1u, 148u * 16u / bx));
   rotate_kernel<<<dim3(bx, by), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, h, w, planes, rc);
   SIR_LAUNCH_CHECK("rotate_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_maps_transpose(const float* d_in, int N, int C, int h, int w, float* d_out, void* stream) {
+  SIR_CHECK_ARG(d_in && d_out && N > 0 && C > 0 && h > 0 && w > 0, "sir_maps_transpose: bad argument");
+  const long long planes = (long long)N * C;
+  const unsigned bx = (unsigned)ceil_div(h * w, 256);
+  const unsigned by = (unsigned)std::min<long long>(planes, std::max(1u, 148u * 16u / bx));
+  transpose_kernel<<<dim3(bx, by), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, h, w, planes);
+  SIR_LAUNCH_CHECK("transpose_kernel");
   return SIR_OK;
 }
 

@@ -88,6 +88,23 @@ class MapGroup:
         return int(self.maps.shape[2]), int(self.maps.shape[3])
 
 
+def transpose_maps(maps: torch.Tensor) -> torch.Tensor:
+    """``[n,C,h,w] -> [n,C,w,h]`` through ``sir_maps_transpose``."""
+    n, c, h, w = (int(v) for v in maps.shape)
+    out = torch.empty((n, c, w, h), dtype=torch.float32, device=maps.device)
+    nat.check(nat.lib.sir_maps_transpose(_ptr(maps), n, c, h, w, _ptr(out), _stream()), "sir_maps_transpose")
+    launch_counter.add()
+    return out
+
+
+def plan_cost(precision: int, g: int, hp: int, wp: int, hm: int, wm: int) -> float:
+    """Estimated SM cycles per (gallery, 256-column tile, channel) from the library's own planner
+    (``sir_ncc_cost``); ``inf`` when the shape does not fit that mode's shared-memory plan."""
+    cost = C.c_double(0.0)
+    rc = nat.lib.sir_ncc_cost(precision, g, hp, wp, hm, wm, C.byref(cost))
+    return cost.value if rc == 0 else float("inf")
+
+
 @dataclass
 class MapSet:
     groups: list[MapGroup]
@@ -149,6 +166,19 @@ class GalleryOperands:
     ids: torch.Tensor
     _rnorm: dict = field(default_factory=dict)
     _fp8: tuple | None = None
+    _source: MapGroup | None = None       # kept so the other orientation can be packed on demand
+    _keep_fp32: bool = False
+    _transposed: "GalleryOperands | None" = None
+
+    def transposed(self) -> "GalleryOperands":
+        """The same gallery group packed from transposed maps (built on first use)."""
+        if self._transposed is None:
+            if self._source is None:
+                raise RuntimeError("this gallery pack does not hold its source maps")
+            grp = MapGroup(transpose_maps(self._source.maps), self._source.ids)
+            self._transposed = GalleryOperands.pack(grp, self._keep_fp32)
+            self._transposed._source = None
+        return self._transposed
 
     def fp8_companions(self) -> tuple[torch.Tensor, torch.Tensor]:
         """e4m3 copies (hi/4, lo*4) of the packed gallery for the fp8-corrected mode, built once."""
@@ -178,7 +208,9 @@ class GalleryOperands:
             "sir_gallery_pack",
         )
         launch_counter.add()
-        return GalleryOperands(n, c, hp, wp, ghi, glo, gexp, gz, group.ids)
+        ops = GalleryOperands(n, c, hp, wp, ghi, glo, gexp, gz, group.ids)
+        ops._source, ops._keep_fp32 = group, keep_fp32
+        return ops
 
     def rnorm(self, hm: int, wm: int, simt: bool) -> torch.Tensor:
         key = (hm, wm, simt)
@@ -260,21 +292,41 @@ class _Block:
 
 def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperands], offsets: list[int],
                  scores: torch.Tensor, precision: int) -> None:
-    if precision == nat.PREC_FP16_FP8C:
-        try:
-            _score_block_impl(block, hw, gallery, offsets, scores, precision)
-        except nat.SirError as err:
-            # very wide templates need three operand arrays per E buffer and do not fit shared memory in
-            # the fp8-corrected mode; the argument check fails before anything is launched
-            if "does not fit the shared-memory plan" not in str(err):
-                raise
-            _score_block_impl(block, hw, gallery, offsets, scores, nat.PREC_FP16X3)
-        return
-    _score_block_impl(block, hw, gallery, offsets, scores, precision)
+    """Scores one column block against every gallery group.
+
+    Scores are invariant under transposing probe and gallery maps alike, and ``fp16_fp8c`` and
+    ``fp16x3`` are both parity grade, so each (block, gallery group) runs in the cheapest of those
+    configurations according to the library's planner: the kernel tiles positions 16 x 8 and template
+    rows by 8 / 16 taps, and wide templates make the fp8-corrected mode generator bound."""
+    h, w = hw
+    hm, wm = h - 2 * EDGE, w - 2 * EDGE
+    plans: dict[tuple[int, bool], list[tuple[GalleryOperands, int]]] = {}
+    for ops, g0 in zip(gallery, offsets):
+        if precision == nat.PREC_FP32_SIMT:
+            plans.setdefault((precision, False), []).append((ops, g0))
+            continue
+        modes = [precision, nat.PREC_FP16X3] if precision == nat.PREC_FP16_FP8C else [precision]
+        best, best_cost = (modes[-1], False), float("inf")
+        for mode in modes:
+            for flip in ((False, True) if ops._source is not None else (False,)):
+                cost = plan_cost(mode, ops.G, *((ops.Wp, ops.Hp, wm, hm) if flip else (ops.Hp, ops.Wp, hm, wm)))
+                if cost < best_cost * (0.97 if (mode, flip) != (modes[0], False) else 1.0):
+                    best, best_cost = (mode, flip), cost
+        if best_cost == float("inf"):
+            raise nat.SirError(f"template {hm}x{wm} does not fit any shared-memory plan of the correlation kernel")
+        plans.setdefault(best, []).append((ops, g0))
+    tblock = None
+    for (mode, flip), members in plans.items():
+        if flip:
+            if tblock is None:
+                tblock = _Block([transpose_maps(m) for m in block.maps], block.ids, block.ncols)
+            _score_block_oriented(tblock, (w, h), [o.transposed() for o, _ in members], [g for _, g in members], scores, mode)
+        else:
+            _score_block_oriented(block, (h, w), [o for o, _ in members], [g for _, g in members], scores, mode)
 
 
-def _score_block_impl(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperands], offsets: list[int],
-                      scores: torch.Tensor, precision: int) -> None:
+def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperands], offsets: list[int],
+                          scores: torch.Tensor, precision: int) -> None:
     h, w = hw
     hm, wm = h - 2 * EDGE, w - 2 * EDGE
     dev = scores.device
