@@ -26,8 +26,6 @@ import os
 from concurrent.futures import ThreadPoolExecutor
 from math import floor
 from pathlib import Path
-from typing import Any
-
 import numpy as np
 from PIL import Image
 
@@ -172,7 +170,3 @@ class Dataloader:
                 blocks.append(block)
                 groups.append(list(files))
         return scales, blocks, groups
-
-
-def _unused(*_: Any) -> None:  # pragma: no cover - keeps `Any` imported for type checkers
-    return None

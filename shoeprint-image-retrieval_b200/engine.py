@@ -390,20 +390,42 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[Gall
 
 
 def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, precision: str = DEFAULT_PRECISION,
-                 col_block: int = 16384, packed_gallery: list[GalleryOperands] | None = None) -> torch.Tensor:
+                 col_block: int = 16384, packed_gallery: list[GalleryOperands] | None = None,
+                 gallery_chunk_bytes: int = 8 << 30) -> torch.Tensor:
     """float32 ``[Q, G]`` on the device: max over the variant set, floored at 0
     (``similarities_all`` of similarity.py:355-367), columns in the caller's gallery order."""
     dev = _require_cuda()
     if probes.channels != gallery.channels:
         raise ValueError(f"probe maps have {probes.channels} channels, gallery maps {gallery.channels}")
     prec = nat.PRECISIONS[precision]
-    ops = packed_gallery or [GalleryOperands.pack(g, keep_fp32=(prec == nat.PREC_FP32_SIMT)) for g in gallery.groups]
+    keep32 = prec == nat.PREC_FP32_SIMT
+    # gallery groups are cut into chunks so that the per-chunk operands (packs, transposed copy, window
+    # norms: ~3x the chunk's float32 bytes) stay bounded; small galleries are packed once up front,
+    # large ones chunk by chunk inside every column block (packing is ~2 % of the correlation time)
+    chunks: list[MapGroup] = []
+    for grp in gallery.groups:
+        n = int(grp.maps.shape[0])
+        per_map = grp.maps[0].numel() * 4
+        step = max(1, min(n, gallery_chunk_bytes // max(per_map, 1)))
+        for s0 in range(0, n, step):
+            chunks.append(MapGroup(grp.maps[s0 : s0 + step], grp.ids[s0 : s0 + step]))
     offsets, g0 = [], 0
-    for o in ops:
+    for ch in chunks:
         offsets.append(g0)
-        g0 += o.G
+        g0 += int(ch.maps.shape[0])
+    total_bytes = sum(ch.maps.numel() * 4 for ch in chunks)
+    prepacked = packed_gallery
+    if prepacked is None and total_bytes <= gallery_chunk_bytes:
+        prepacked = [GalleryOperands.pack(ch, keep_fp32=keep32) for ch in chunks]
     ld = (gallery.count + 3) // 4 * 4  # 16-byte aligned rows for the vectorised rank kernel
     grouped = torch.zeros((probes.count, ld), dtype=torch.float32, device=dev)
+
+    def flush(blk: _Block, key: tuple[int, int]) -> None:
+        if prepacked is not None:
+            _score_block(blk, key, prepacked, offsets, grouped, prec)
+            return
+        for ch, off in zip(chunks, offsets):
+            _score_block(blk, key, [GalleryOperands.pack(ch, keep_fp32=keep32)], [off], grouped, prec)
 
     pending: dict[tuple[int, int], _Block] = {}
     for rot, scale in variant_plan(rotations, scales):
@@ -415,13 +437,13 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
             blk.ids.append(grp.ids)
             blk.ncols += int(v.shape[0])
             if blk.ncols >= col_block:
-                _score_block(blk, key, ops, offsets, grouped, prec)
+                flush(blk, key)
                 del pending[key]
     for key, blk in pending.items():
-        _score_block(blk, key, ops, offsets, grouped, prec)
+        flush(blk, key)
 
     # un-group the gallery axis back to the caller's order
-    order = torch.cat([o.ids for o in ops])
+    order = torch.cat([ch.ids for ch in chunks])
     if torch.equal(order, torch.arange(gallery.count)):
         return grouped[:, : gallery.count]
     out = torch.empty((probes.count, gallery.count), dtype=torch.float32, device=dev)

@@ -181,3 +181,17 @@ def test_full_bench_size_properties(eng):
     assert err < REL_TOL, err
     base = eng.score_matrix(ps, gs, None, None)
     assert bool((full >= base).all())
+
+
+def test_gallery_chunking_does_not_change_scores(eng):
+    """Large galleries are scored chunk by chunk (engine.score_matrix gallery_chunk_bytes); chunking
+    must be invisible: bit-identical scores, caller's gallery order."""
+    from src.shoeprint_image_retrieval import synth
+
+    gal = synth.device_gallery(71, 37, 8, 24, 16)
+    prb, _ = synth.device_probes(72, gal, 9)
+    ps, gs = eng.MapSet.from_device(prb), eng.MapSet.from_device(gal)
+    whole = eng.score_matrix(ps, gs, [5], [1.1])
+    per_map = gal[0].numel() * 4
+    pieces = eng.score_matrix(ps, gs, [5], [1.1], gallery_chunk_bytes=5 * per_map)
+    assert torch.equal(whole, pieces)
