@@ -114,12 +114,12 @@ int sir_ncc_surface(const float* d_gz, const float* d_rnorm, int Hp, int Wp, con
                     float* d_out, void* stream);
 
 /* fp8-corrected variant (SIR_PREC_FP16_FP8C).  Same quantity as sir_ncc_scores; operands:
- *   gallery : d_ghi (as above) + d_g8a = e4m3(hi/4), d_g8l = e4m3(lo*4), uint8 [G][C][Hp][sir_gallery_pitch8(Wp)]
+ *   gallery : d_ghi (as above) + d_g8a = e4m3(hi/64), d_g8l = e4m3(lo*64), uint8 [G][C][Hp][sir_gallery_pitch8(Wp)]
  *             produced from d_ghi/d_glo by sir_gallery_pack_fp8c;
- *   templates: rows padded to 16 taps (Kpad = sir_template_kpad_fp8c), d_thi f16 + d_t8b = e4m3(hi/4),
- *             d_t8l = e4m3(lo*4), uint8 [C][ncols_alloc][Kpad], produced by sir_template_pack_fp8c.
- * Per 32-tap K stage the kernel issues two fp16 MMAs (hi*hi) and two e4m3 MMAs ((lo*4)(hi/4) and
- * (hi/4)(lo*4)) into the same fp32 accumulator. */
+ *   templates: rows padded to 16 taps (Kpad = sir_template_kpad_fp8c), d_thi f16 + d_t8b = e4m3(hi/64),
+ *             d_t8l = e4m3(lo*64), uint8 [C][ncols_alloc][Kpad], produced by sir_template_pack_fp8c.
+ * Per 32-tap K stage the kernel issues two fp16 MMAs (hi*hi) and two e4m3 MMAs ((lo*64)(hi/64) and
+ * (hi/64)(lo*64)) into the same fp32 accumulator. */
 int sir_gallery_pitch8(int Wp);
 int sir_gallery_pack_fp8c(const uint16_t* d_ghi, const uint16_t* d_glo, int G, int C, int Hp, int Wp,
                           uint8_t* d_g8a, uint8_t* d_g8l, void* stream);

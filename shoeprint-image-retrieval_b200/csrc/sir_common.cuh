@@ -43,6 +43,11 @@ void set_error(const char* fmt, ...);
 constexpr int kEdge = 2;           // similarity.py:92-93 crop
 constexpr int kTemplateScaleLog2 = 10;  // packed templates are (t-mean)/sqrt(E) * 2^10
 constexpr int kGalleryPeakLog2 = 10;    // packed gallery channels have max|v| in [2^9, 2^10)
+// fp8 (e4m3: 2^-9 .. 448) companions of the fp16 operands for the correction MMAs: hi / 64 (peak 16) and
+// lo * 64 (|lo| <= 0.5 -> 32).  The two factors cancel in every product; 64 centres both parts in the
+// e4m3 range so that cells down to ~1/8000 of the channel peak still get their correction term.
+constexpr float kFp8HiScale = 1.0f / 64.0f;
+constexpr float kFp8LoScale = 64.0f;
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -308,9 +308,9 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
     const float lo = s - __half2float(hi);
     thi[col * Kpad + k] = hi;
     if (tlo) tlo[col * Kpad + k] = __float2half_rn(lo);
-    if (t8b) {  // fp8 copies for the correction MMAs: (B_hi / 4) and (B_lo * 4), see sir_ncc_tc.cu
-      t8b[col * Kpad + k] = to_e4m3(__half2float(hi) * 0.25f);
-      t8l[col * Kpad + k] = to_e4m3(lo * 4.0f);
+    if (t8b) {  // fp8 copies for the correction MMAs: (B_hi / 64) and (B_lo * 64), see sir_ncc_tc.cu
+      t8b[col * Kpad + k] = to_e4m3(__half2float(hi) * kFp8HiScale);
+      t8l[col * Kpad + k] = to_e4m3(lo * kFp8LoScale);
     }
   }
 }
@@ -372,8 +372,8 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
         h8[j] = __float2half_rn(sc);
         const float lo = sc - __half2float(h8[j]);
         l8[j] = __float2half_rn(lo);
-        b8[j] = to_e4m3(__half2float(h8[j]) * 0.25f);
-        q8[j] = to_e4m3(lo * 4.0f);
+        b8[j] = to_e4m3(__half2float(h8[j]) * kFp8HiScale);
+        q8[j] = to_e4m3(lo * kFp8LoScale);
       }
       *reinterpret_cast<uint4*>(thi + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(h8);
       if (tlo) *reinterpret_cast<uint4*>(tlo + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(l8);
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
   }
 }
 
-// fp8 companions of the packed gallery: a8 = e4m3(hi / 4), l8 = e4m3(lo * 4); rows padded to 16 cells
+// fp8 companions of the packed gallery: a8 = e4m3(hi / 64), l8 = e4m3(lo * 64); rows padded to 16 cells
 __global__ void __launch_bounds__(256) gallery_fp8_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo, int Hp,
                                                           int Wp, uint8_t* __restrict__ g8a, uint8_t* __restrict__ g8l) {
   const int WP = gal_pitch(Wp), WP8 = gal_pitch8(Wp);
@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(256) gallery_fp8_kernel(const __half* __restri
     uint8_t a = 0, l = 0;
     if (x < Wp) {
       const size_t j = (gc * Hp + y) * WP + x;
-      a = to_e4m3(__half2float(ghi[j]) * 0.25f);
-      l = to_e4m3(__half2float(glo[j]) * 4.0f);
+      a = to_e4m3(__half2float(ghi[j]) * kFp8HiScale);
+      l = to_e4m3(__half2float(glo[j]) * kFp8LoScale);
     }
     g8a[gc * Hp * WP8 + i] = a;
     g8l[gc * Hp * WP8 + i] = l;
