@@ -131,6 +131,20 @@ int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, const uint8
                         int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores,
                         int score_ld, int g0, void* stream);
 
+/* Multi-shape column tiles (ragged probe sets: every probe / scale variant its own template shape).
+ * Templates of different true shapes are packed into the K layout of one BUCKET shape Hb x Wb, anchor on
+ * anchor, zeros elsewhere (the numerator is unchanged); each 32-column chunk of the block holds templates
+ * of one true shape and d_rnorm_tab[chunk] points at that shape's window-norm table (similarity.py:57-65
+ * depends on the TRUE template size).  d_rnorm_tab: device array of device pointers, 8 per 256-column
+ * tile, every entry valid.  precision: SIR_PREC_FP16X3 (d_glo, d_tlo) or SIR_PREC_FP16_FP8C (e4m3 operands). */
+int sir_template_pack_embed(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
+                            int precision, uint16_t* d_thi, uint16_t* d_tlo, uint8_t* d_t8b, uint8_t* d_t8l, void* stream);
+int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l,
+                         const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
+                         const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
+                         int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe, float* d_scores,
+                         int score_ld, int g0, int precision, void* stream);
+
 /* Planning aid (host only, nothing is launched): estimated SM cycles per (gallery, 256-column tile, channel)
  * of the tensor-core kernel for this shape and precision mode -- the larger of the MMA time of the
  * non-skipped K stages and the shifted-entry generation time under the shared-memory plan the launch

@@ -41,6 +41,8 @@ SIGNATURES = {
     "sir_template_kpad_fp8c": (_i, [_i, _i]),
     "sir_template_pack_fp8c": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sir_ncc_scores_fp8c": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
+    "sir_template_pack_embed": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "sir_ncc_scores_multi": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
     "sir_ncc_cost": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
     "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
     "sir_rank_topk": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),

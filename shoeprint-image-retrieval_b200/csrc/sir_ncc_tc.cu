@@ -57,6 +57,9 @@ struct TcParams {
   const __half* ghi;
   const __half* glo;
   const float* rnorm;
+  // multi-shape column tiles: one window-norm table per 32-column chunk (8 per 256-column tile), NULL
+  // when every column of the launch has the same true template shape
+  const float* const* rnorm_tab;
   const int32_t* col2probe;
   float* scores;
   int score_ld, g0;
@@ -479,14 +482,24 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       const int y = 16 * py + mh, x = 8 * px + ml;
       const bool valid = (y < p.Hp) && (x < p.Wp);
       const int ncol_half = tile_cols(p, nt) - half * 128;  // columns of this warp's half that exist
-      const float* rrow = p.rnorm + (size_t)g * p.C * M + (valid ? y * p.Wp + x : 0);
+      // window-norm rows of this thread's position, one per 32-column chunk of its column half: with
+      // multi-shape tiles the chunks of a tile may belong to templates of different true shapes
+      const size_t roff = (size_t)g * p.C * M + (valid ? y * p.Wp + x : 0);
+      const float* rrow[4];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4)
+        rrow[j4] = (p.rnorm_tab ? p.rnorm_tab[(size_t)nt * 8 + half * 4 + j4] : p.rnorm) + roff;
 
       float total[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) total[j] = 0.0f;
-      float r_cur = valid ? __ldg(rrow) : 0.0f;
+      float r_cur[4], r_next[4];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) r_cur[j4] = (valid && j4 * 32 < ncol_half) ? __ldg(rrow[j4]) : 0.0f;
       for (int c = 0; c < p.C; ++c, ++cs) {
-        const float r_next = (valid && c + 1 < p.C) ? __ldg(rrow + (size_t)(c + 1) * M) : 0.0f;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          r_next[j4] = (valid && c + 1 < p.C && j4 * 32 < ncol_half) ? __ldg(rrow[j4] + (size_t)(c + 1) * M) : 0.0f;
         const int buf = cs & 1;
         ptx::mbar_wait(bar_accfull(buf), (cs >> 1) & 1);
         ptx::tc_fence_after();
@@ -498,7 +511,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
           ptx::tmem_ld_32x32(taddr + j4 * 32, v);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) total[j4 * 32 + j] = fmaf(r_cur, __uint_as_float(v[j]), total[j4 * 32 + j]);
+          for (int j = 0; j < 32; ++j) total[j4 * 32 + j] = fmaf(r_cur[j4], __uint_as_float(v[j]), total[j4 * 32 + j]);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -506,7 +519,8 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
           if constexpr (CG == 2) ptx::mbar_arrive_leader(bar_accempty(buf));
           else ptx::mbar_arrive(bar_accempty(buf));
         }
-        r_cur = r_next;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) r_cur[j4] = r_next[j4];
       }
       // max over the tile's valid positions, then over the 4 lane quarters, then into scores
 #pragma unroll
@@ -642,7 +656,7 @@ int make_gallery_map8(CUtensorMap* tm, const uint8_t* ptr, int planes, int Hp, i
 int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l, const float* d_rnorm, int G,
                   int C, int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
                   int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
-                  int passes, cudaStream_t st, double* cost_out) {
+                  int passes, cudaStream_t st, double* cost_out, const float* const* d_rnorm_tab) {
   // cost_out != NULL: dry run -- plan only, report the estimated SM cycles per (gallery, 256-column tile,
   // channel) and return without touching any pointer (sir_ncc_cost)
   SIR_CHECK_ARG(d_ghi && d_thi, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
@@ -653,6 +667,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   p.ghi = (const __half*)d_ghi;
   p.glo = (const __half*)d_glo;
   p.rnorm = d_rnorm;
+  p.rnorm_tab = d_rnorm_tab;
   p.col2probe = d_col2probe;
   p.scores = d_scores;
   p.score_ld = score_ld;
@@ -810,5 +825,5 @@ extern "C" int sir_ncc_cost(int precision, int G, int Hp, int Wp, int Hm, int Wm
   alignas(16) static const uint16_t dummy16[8] = {0};
   alignas(16) static const uint8_t dummy8[16] = {0};
   return sir::launch_ncc_tc(dummy16, dummy16, dummy8, dummy8, nullptr, G, 1, Hp, Wp, dummy16, dummy16, dummy8, dummy8, 256, 256, Hm, Wm,
-                            nullptr, nullptr, 0, 0, passes, nullptr, h_cost);
+                            nullptr, nullptr, 0, 0, passes, nullptr, h_cost, nullptr);
 }

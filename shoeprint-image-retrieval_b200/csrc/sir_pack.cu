@@ -270,13 +270,14 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------------------------------
 // K5 templates: one CTA per (map n, channel c).
-__global__ void __launch_bounds__(128) template_pack_kernel(const float* __restrict__ maps, int C, int h, int w, int col0,
+__global__ void __launch_bounds__(128) template_pack_kernel(const float* __restrict__ maps, int C, int h, int w, int Hb, int Wb, int col0,
                                                             int ncols_alloc, int row_align, __half* __restrict__ thi,
                                                             __half* __restrict__ tlo, float* __restrict__ t32,
                                                             uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l) {
   __shared__ double sred[32];
   const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm;
-  const int rowk = tpl_row_taps(Wm, row_align), Kpad = tpl_kpad_aligned(Hm, Wm, row_align);
+  const int rowk = tpl_row_taps(Wb, row_align), Kpad = tpl_kpad_aligned(Hb, Wb, row_align);
+  const int oy = Hb / 2 - Hm / 2, ox = Wb / 2 - Wm / 2;
   const int n = blockIdx.x / C, c = blockIdx.x - n * C;
   const float* src = maps + ((size_t)n * C + c) * (size_t)h * w;
 
@@ -297,9 +298,9 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
 
   const size_t col = (size_t)c * ncols_alloc + col0 + n;
   for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
-    const int u = k / rowk, v = k - u * rowk;
+    const int ub = k / rowk, u = ub - oy, v = k - ub * rowk - ox;
     float tn = 0.0f;
-    if (u < Hm && v < Wm) {
+    if (u >= 0 && u < Hm && v >= 0 && v < Wm) {
       tn = (float)((double)(src[(u + kEdge) * w + v + kEdge] - mean) * inv);
       if (t32) t32[col * K + u * Wm + v] = tn;
     }
@@ -317,23 +318,27 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
 
 // Warp-per-(map, channel) version of the template pack, same idea as gallery_pack_warp_kernel.
 __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __restrict__ maps, long long planes, int C, int h, int w,
-                                                                 int col0, int ncols_alloc, int row_align, __half* __restrict__ thi,
+                                                                 int Hb, int Wb, int col0, int ncols_alloc, int row_align,
+                                                                 __half* __restrict__ thi,
                                                                  __half* __restrict__ tlo, float* __restrict__ t32,
                                                                  uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l) {
   extern __shared__ float slab[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm, HW = h * w;
-  const int rowk = tpl_row_taps(Wm, row_align), Kpad = tpl_kpad_aligned(Hm, Wm, row_align);
+  // K layout of the BUCKET shape Hb x Wb (== Hm x Wm for single-shape blocks); the true template sits
+  // inside it so that its anchor (Hm/2, Wm/2) lands on the bucket's anchor (Hb/2, Wb/2)
+  const int rowk = tpl_row_taps(Wb, row_align), Kpad = tpl_kpad_aligned(Hb, Wb, row_align);
+  const int oy = Hb / 2 - Hm / 2, ox = Wb / 2 - Wm / 2;
   float* ch = slab + (size_t)wid * HW;
-  const int c8 = rowk / 8, n8 = Kpad / 8;
+  const int c8 = rowk / 8, n8 = Kpad / 8, m8 = (Wm + 7) / 8;
   for (long long pc = (long long)blockIdx.x * nw + wid; pc < planes; pc += (long long)gridDim.x * nw) {
     const int n = (int)(pc / C), c = (int)(pc - (long long)n * C);
     const float* src = maps + pc * HW;
     for (int i = lane; i < HW; i += 32) ch[i] = __ldg(src + i);
     __syncwarp();
     double acc = 0.0;
-    for (int o = lane; o < Hm * c8; o += 32) {
-      const int u = o / c8, v0 = (o - u * c8) * 8;
+    for (int o = lane; o < Hm * m8; o += 32) {
+      const int u = o / m8, v0 = (o - u * m8) * 8;
       const float* row = ch + (u + kEdge) * w + kEdge + v0;
       float part = 0.0f;
 #pragma unroll
@@ -342,8 +347,8 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
     }
     const float mean = (float)(warp_sum(acc) / (double)K);
     double e = 0.0;
-    for (int o = lane; o < Hm * c8; o += 32) {
-      const int u = o / c8, v0 = (o - u * c8) * 8;
+    for (int o = lane; o < Hm * m8; o += 32) {
+      const int u = o / m8, v0 = (o - u * m8) * 8;
       const float* row = ch + (u + kEdge) * w + kEdge + v0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -355,18 +360,19 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
     const double inv = e > 0.0 ? 1.0 / sqrt(e) : 0.0;
     const size_t col = (size_t)c * ncols_alloc + col0 + n;
     for (int o = lane; o < n8; o += 32) {
-      const int u = o / c8, v0 = (o - u * c8) * 8;
-      const float* row = ch + (u + kEdge) * w + kEdge + v0;
+      const int ub = o / c8, vb0 = (o - ub * c8) * 8;  // bucket coordinates of this 8-tap chunk
+      const int u = ub - oy;
       __align__(16) __half h8[8];
       __align__(16) __half l8[8];
       __align__(8) uint8_t b8[8];
       __align__(8) uint8_t q8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const int v = vb0 + j - ox;
         float tn = 0.0f;
-        if (u < Hm && v0 + j < Wm) {
-          tn = (float)((double)(row[j] - mean) * inv);
-          if (t32) t32[col * K + u * Wm + v0 + j] = tn;
+        if (u >= 0 && u < Hm && v >= 0 && v < Wm) {
+          tn = (float)((double)(ch[(u + kEdge) * w + kEdge + v] - mean) * inv);
+          if (t32) t32[col * K + u * Wm + v] = tn;
         }
         const float sc = ldexpf(tn, kTemplateScaleLog2);
         h8[j] = __float2half_rn(sc);
@@ -592,15 +598,17 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
 
 extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }
 
-static void launch_template_pack(const float* d_maps, int N, int C, int h, int w, int col0, int ncols_alloc, int row_align, __half* thi,
-                                 __half* tlo, float* t32, uint8_t* t8b, uint8_t* t8l, cudaStream_t st) {
+static void launch_template_pack(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc, int row_align,
+                                 __half* thi, __half* tlo, float* t32, uint8_t* t8b, uint8_t* t8l, cudaStream_t st) {
   const size_t slab = (size_t)h * w * sizeof(float);
   if (8 * slab <= 48 * 1024) {
     const long long planes = (long long)N * C;
     const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 148 * 8);
-    template_pack_warp_kernel<<<blocks, 256, 8 * slab, st>>>(d_maps, planes, C, h, w, col0, ncols_alloc, row_align, thi, tlo, t32, t8b, t8l);
+    template_pack_warp_kernel<<<blocks, 256, 8 * slab, st>>>(d_maps, planes, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32,
+                                                             t8b, t8l);
   } else {
-    template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, st>>>(d_maps, C, h, w, col0, ncols_alloc, row_align, thi, tlo, t32, t8b, t8l);
+    template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, st>>>(d_maps, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32, t8b,
+                                                                    t8l);
   }
 }
 
@@ -625,7 +633,8 @@ extern "C" int sir_template_pack_fp8c(const float* d_maps, int N, int C, int h, 
   SIR_CHECK_ARG(N > 0 && C > 0, "sir_template_pack_fp8c: empty input");
   SIR_CHECK_ARG(h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack_fp8c: map %dx%d vanishes after the 2-cell crop", h, w);
   SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack_fp8c: columns [%d,%d) outside %d", col0, col0 + N, ncols_alloc);
-  launch_template_pack(d_maps, N, C, h, w, col0, ncols_alloc, 16, (__half*)d_thi, nullptr, nullptr, d_t8b, d_t8l, (cudaStream_t)stream);
+  launch_template_pack(d_maps, N, C, h, w, h - 2 * kEdge, w - 2 * kEdge, col0, ncols_alloc, 16, (__half*)d_thi, nullptr, nullptr, d_t8b, d_t8l,
+                       (cudaStream_t)stream);
   SIR_LAUNCH_CHECK("template_pack_kernel");
   return SIR_OK;
 }
@@ -637,7 +646,26 @@ extern "C" int sir_template_pack(const float* d_maps, int N, int C, int h, int w
   SIR_CHECK_ARG(h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack: map %dx%d vanishes after the 2-cell crop", h, w);
   SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack: columns [%d,%d) outside %d", col0, col0 + N,
                 ncols_alloc);
-  launch_template_pack(d_maps, N, C, h, w, col0, ncols_alloc, 8, (__half*)d_thi, (__half*)d_tlo, d_t32, nullptr, nullptr, (cudaStream_t)stream);
+  launch_template_pack(d_maps, N, C, h, w, h - 2 * kEdge, w - 2 * kEdge, col0, ncols_alloc, 8, (__half*)d_thi, (__half*)d_tlo, d_t32, nullptr,
+                       nullptr, (cudaStream_t)stream);
+  SIR_LAUNCH_CHECK("template_pack_kernel");
+  return SIR_OK;
+}
+
+// Multi-shape column tiles: pack templates of true shape (h-4) x (w-4) into the K layout of a BUCKET shape
+// Hb x Wb (>= the true shape), anchor on anchor, zeros elsewhere.  precision selects the row alignment and
+// which companion operands are written (FP16X3: d_tlo; FP16_FP8C: d_t8b, d_t8l).
+extern "C" int sir_template_pack_embed(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
+                                       int precision, uint16_t* d_thi, uint16_t* d_tlo, uint8_t* d_t8b, uint8_t* d_t8l, void* stream) {
+  SIR_CHECK_ARG(d_maps && d_thi, "sir_template_pack_embed: null pointer");
+  SIR_CHECK_ARG(N > 0 && C > 0 && h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack_embed: bad input shape");
+  SIR_CHECK_ARG(Hb >= h - 2 * kEdge && Wb >= w - 2 * kEdge, "sir_template_pack_embed: bucket %dx%d smaller than template %dx%d", Hb, Wb,
+                h - 2 * kEdge, w - 2 * kEdge);
+  SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack_embed: columns [%d,%d) outside %d", col0, col0 + N, ncols_alloc);
+  const bool fp8c = precision == SIR_PREC_FP16_FP8C;
+  SIR_CHECK_ARG(fp8c ? (d_t8b && d_t8l) : (d_tlo != nullptr), "sir_template_pack_embed: missing companion operands for precision %d", precision);
+  launch_template_pack(d_maps, N, C, h, w, Hb, Wb, col0, ncols_alloc, fp8c ? 16 : 8, (__half*)d_thi, fp8c ? nullptr : (__half*)d_tlo, nullptr,
+                       fp8c ? d_t8b : nullptr, fp8c ? d_t8l : nullptr, (cudaStream_t)stream);
   SIR_LAUNCH_CHECK("template_pack_kernel");
   return SIR_OK;
 }

@@ -389,9 +389,108 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[Gall
             kernel_events.append((ev0, ev1, flops))
 
 
+def _best_plan(ops: GalleryOperands, hm: int, wm: int, precision: int) -> tuple[int, bool, float]:
+    """(mode, transposed, cost) of the cheapest parity-grade configuration for this shape (see _score_block)."""
+    modes = [precision, nat.PREC_FP16X3] if precision == nat.PREC_FP16_FP8C else [precision]
+    best, best_cost = (modes[-1], False), float("inf")
+    for mode in modes:
+        for flip in ((False, True) if ops._source is not None else (False,)):
+            cost = plan_cost(mode, ops.G, *((ops.Wp, ops.Hp, wm, hm) if flip else (ops.Hp, ops.Wp, hm, wm)))
+            if cost < best_cost * (0.97 if (mode, flip) != (modes[0], False) else 1.0):
+                best, best_cost = (mode, flip), cost
+    return best[0], best[1], best_cost
+
+
+def _score_buckets(blocks: dict[tuple[int, int], _Block], gallery: list[GalleryOperands], offsets: list[int],
+                   scores: torch.Tensor, precision: int, max_cols: int = 8192, table_budget: int = 12 << 30) -> None:
+    """Multi-shape column tiles (``sir_template_pack_embed`` + ``sir_ncc_scores_multi``).
+
+    Template shapes that round to the same bucket (rows to 8, columns to the mode's row alignment, in
+    the orientation the planner prefers) are packed into one K layout, anchor on anchor; each shape's
+    columns are padded to a multiple of 32 so that every 32-column chunk has one true shape and hence
+    one window-norm table."""
+    dev = scores.device
+    for ops, g0 in zip(gallery, offsets):
+        buckets: dict[tuple, list] = {}
+        for (h, w), blk in blocks.items():
+            hm, wm = h - 2 * EDGE, w - 2 * EDGE
+            mode, flip, cost = _best_plan(ops, hm, wm, precision)
+            if cost == float("inf"):
+                raise nat.SirError(f"template {hm}x{wm} does not fit any shared-memory plan of the correlation kernel")
+            oh, ow = (wm, hm) if flip else (hm, wm)
+            align = 16 if mode == nat.PREC_FP16_FP8C else 8
+            buckets.setdefault((mode, flip, -(-oh // 8) * 8, -(-ow // align) * align), []).append(((h, w), blk))
+        table_bytes = ops.G * ops.C * ops.Hp * ops.Wp * 4
+        for (mode, flip, _, _), members in buckets.items():
+            gops = ops.transposed() if flip else ops
+            batch: list = []
+            cols = 0
+            for item in members:
+                n32 = -(-item[1].ncols // 32) * 32
+                if batch and (cols + n32 > max_cols or (len(batch) + 1) * table_bytes > table_budget):
+                    _score_one_bucket(batch, gops, g0, scores, mode, flip, dev)
+                    batch, cols = [], 0
+                batch.append(item)
+                cols += n32
+            if batch:
+                _score_one_bucket(batch, gops, g0, scores, mode, flip, dev)
+
+
+def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: torch.Tensor, mode: int, flip: bool, dev) -> None:
+    fp8c = mode == nat.PREC_FP16_FP8C
+    c = gops.C
+    oriented = []
+    for (h, w), blk in members:
+        maps = [transpose_maps(m) for m in blk.maps] if flip else blk.maps
+        oriented.append(((w, h) if flip else (h, w), maps, blk))
+    hb = max(hw[0] for hw, _, _ in oriented) - 2 * EDGE
+    wb = max(hw[1] for hw, _, _ in oriented) - 2 * EDGE
+    ncols = sum(-(-blk.ncols // 32) * 32 for _, _, blk in oriented)
+    kpad = int(nat.lib.sir_template_kpad_fp8c(hb, wb) if fp8c else nat.lib.sir_template_kpad(hb, wb))
+    thi = torch.zeros((c, ncols, kpad), dtype=torch.float16, device=dev)
+    tlo = None if fp8c else torch.zeros_like(thi)
+    t8b = torch.zeros((c, ncols, kpad), dtype=torch.uint8, device=dev) if fp8c else None
+    t8l = torch.zeros_like(t8b) if fp8c else None
+    col2probe = torch.zeros(ncols, dtype=torch.int32)
+    ntiles = -(-ncols // 256)
+    tab = torch.zeros(ntiles * 8, dtype=torch.int64)
+    tables = []  # keeps every window-norm table alive until the launch is queued
+    col0 = 0
+    for (h, w), maps, blk in oriented:
+        hm, wm = h - 2 * EDGE, w - 2 * EDGE
+        rn = torch.empty((gops.G, gops.C, gops.Hp * gops.Wp), dtype=torch.float32, device=dev)
+        nat.check(nat.lib.sir_gallery_window_rnorm(_ptr(gops.ghi), _ptr(gops.glo), None, gops.G, gops.C, gops.Hp, gops.Wp, hm, wm,
+                                                   _ptr(rn), _stream()), "sir_gallery_window_rnorm")
+        launch_counter.add()
+        tables.append(rn)
+        start = col0
+        for m in maps:
+            n = int(m.shape[0])
+            nat.check(nat.lib.sir_template_pack_embed(_ptr(m), n, c, h, w, hb, wb, col0, ncols, mode, _ptr(thi), _ptr(tlo), _ptr(t8b),
+                                                      _ptr(t8l), _stream()), "sir_template_pack_embed")
+            launch_counter.add()
+            col0 += n
+        col2probe[start:col0] = torch.cat(blk.ids).to(torch.int32)
+        col0 = start + -(-blk.ncols // 32) * 32
+        tab[start // 32 : col0 // 32] = rn.data_ptr()
+    tab[col0 // 32 :] = tables[-1].data_ptr()
+    d_tab = tab.to(dev, non_blocking=True)
+    d_c2p = col2probe.to(dev, non_blocking=True)
+    g8a, g8l = gops.fp8_companions() if fp8c else (None, None)
+    nat.check(
+        nat.lib.sir_ncc_scores_multi(
+            _ptr(gops.ghi), _ptr(None if fp8c else gops.glo), _ptr(g8a), _ptr(g8l), _ptr(d_tab), gops.G, gops.C, gops.Hp, gops.Wp,
+            _ptr(thi), _ptr(tlo), _ptr(t8b), _ptr(t8l), ncols, ncols, hb, wb, _ptr(d_c2p), _ptr(scores), int(scores.stride(0)), g0,
+            mode, _stream(),
+        ),
+        "sir_ncc_scores_multi",
+    )
+    launch_counter.add()
+
+
 def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, precision: str = DEFAULT_PRECISION,
                  col_block: int = 16384, packed_gallery: list[GalleryOperands] | None = None,
-                 gallery_chunk_bytes: int = 8 << 30) -> torch.Tensor:
+                 gallery_chunk_bytes: int = 8 << 30, bucket_below: int = 192) -> torch.Tensor:
     """float32 ``[Q, G]`` on the device: max over the variant set, floored at 0
     (``similarities_all`` of similarity.py:355-367), columns in the caller's gallery order."""
     dev = _require_cuda()
@@ -439,8 +538,18 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
             if blk.ncols >= col_block:
                 flush(blk, key)
                 del pending[key]
+    # ragged probe sets leave many narrow blocks (a handful of columns per template shape): those share
+    # column tiles through shape buckets instead of running one narrow launch each
+    small = {k: b for k, b in pending.items() if b.ncols < bucket_below}
     for key, blk in pending.items():
-        flush(blk, key)
+        if key not in small or len(small) < 2 or prec in (nat.PREC_FP32_SIMT, nat.PREC_FP16X1):
+            flush(blk, key)
+    if len(small) >= 2 and prec not in (nat.PREC_FP32_SIMT, nat.PREC_FP16X1):
+        if prepacked is not None:
+            _score_buckets(small, prepacked, offsets, grouped, prec)
+        else:
+            for ch, off in zip(chunks, offsets):
+                _score_buckets(small, [GalleryOperands.pack(ch, keep_fp32=False)], [off], grouped, prec)
 
     # un-group the gallery axis back to the caller's order
     order = torch.cat([ch.ids for ch in chunks])
