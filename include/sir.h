@@ -67,6 +67,11 @@ int sir_gallery_pack(const float* d_gallery, int G, int C, int hg, int wg,
 int sir_gallery_window_rnorm(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_gz,
                              int G, int C, int Hp, int Wp, int Hm, int Wm, float* d_rnorm, void* stream);
 
+/* The same for `nshapes` template shapes in one pass over the gallery (the summed-area tables are built
+ * once per channel): h_hm/h_wm host arrays of shapes, h_out host array of DEVICE pointers to the tables. */
+int sir_gallery_window_rnorm_multi(const uint16_t* d_ghi, const uint16_t* d_glo, int G, int C, int Hp, int Wp, int nshapes,
+                                   const int* h_hm, const int* h_wm, float* const* h_out, void* stream);
+
 /* ------------------------------------------------------------------ probe side (K4 + K5)
  * Variant generation, similarity.py:262-276 (Pillow rotate nearest / resize bicubic on mode "F").
  * d_in [N][C][h][w] f32 -> d_out [N][C][h2][w2] f32.

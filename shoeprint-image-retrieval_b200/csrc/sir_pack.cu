@@ -192,6 +192,75 @@ __global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restr
   }
 }
 
+// Several template shapes at once: the float64 summed-area tables of a channel are built once and every
+// shape's window norm is read off them (ragged probe sets need one table per distinct template shape).
+constexpr int kMaxRnormShapes = 24;
+struct RnormShapes {
+  int n;
+  int hm[kMaxRnormShapes], wm[kMaxRnormShapes];
+  float* out[kMaxRnormShapes];
+};
+__global__ void __launch_bounds__(256) window_rnorm_multi_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo,
+                                                                 const float* __restrict__ gz, int Hp, int Wp, RnormShapes sh) {
+  extern __shared__ double sat[];
+  const int W1 = Wp + 1, M = Hp * Wp;
+  double* s1 = sat;
+  double* s2 = sat + (size_t)(Hp + 1) * W1;
+  const size_t gc = blockIdx.x;
+
+  for (int i = threadIdx.x; i < (Hp + 1) * W1; i += blockDim.x) {
+    const int y = i / W1, x = i - y * W1;
+    double v = 0.0;
+    if (y > 0 && x > 0) {
+      const size_t j = gc * M + (size_t)(y - 1) * Wp + (x - 1);
+      const size_t jp = (gc * Hp + (size_t)(y - 1)) * gal_pitch(Wp) + (x - 1);
+      v = gz ? (double)gz[j] : (double)__half2float(ghi[jp]) + (double)__half2float(glo[jp]);
+    }
+    s1[i] = v;
+    s2[i] = v * v;
+  }
+  __syncthreads();
+  for (int y = 1 + threadIdx.x; y <= Hp; y += blockDim.x) {  // prefix along x
+    double a = 0.0, b = 0.0;
+    for (int x = 1; x <= Wp; ++x) {
+      a += s1[y * W1 + x];
+      b += s2[y * W1 + x];
+      s1[y * W1 + x] = a;
+      s2[y * W1 + x] = b;
+    }
+  }
+  __syncthreads();
+  for (int x = 1 + threadIdx.x; x <= Wp; x += blockDim.x) {  // prefix along y
+    double a = 0.0, b = 0.0;
+    for (int y = 1; y <= Hp; ++y) {
+      a += s1[y * W1 + x];
+      b += s2[y * W1 + x];
+      s1[y * W1 + x] = a;
+      s2[y * W1 + x] = b;
+    }
+  }
+  __syncthreads();
+  for (int si = 0; si < sh.n; ++si) {
+    const int Hm = sh.hm[si], Wm = sh.wm[si];
+    float* __restrict__ rnorm = sh.out[si];
+    const int a = Hm / 2, b = Wm / 2;
+    const double inv_n = 1.0 / ((double)Hm * (double)Wm);
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      const int y = i / Wp, x = i - y * Wp;
+      const int r0 = max(y - a, 0), r1 = min(y - a + Hm, Hp);
+      const int c0 = max(x - b, 0), c1 = min(x - b + Wm, Wp);
+      float r = 0.0f;
+      if (r1 > r0 && c1 > c0) {
+        const double t1 = s1[r1 * W1 + c1] - s1[r0 * W1 + c1] - s1[r1 * W1 + c0] + s1[r0 * W1 + c0];
+        const double t2 = s2[r1 * W1 + c1] - s2[r0 * W1 + c1] - s2[r1 * W1 + c0] + s2[r0 * W1 + c0];
+        const double d = t2 - t1 * t1 * inv_n;
+        if (d > 1e-10 * t2) r = __fdiv_rn(1.0f, __fsqrt_rn((float)d));
+      }
+      rnorm[gc * M + i] = r;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K4 rotate: Pillow affine_fixed (Geometry.c) nearest neighbour.  mode 0 copy, 1 flip (180),
 // 2 transpose-90, 3 transpose-270 (square maps only), 4 general 16.16 fixed point.
@@ -452,6 +521,33 @@ extern "C" int sir_gallery_window_rnorm(const uint16_t* d_ghi, const uint16_t* d
   window_rnorm_kernel<<<(unsigned)((size_t)G * C), 256, smem, (cudaStream_t)stream>>>(
       (const __half*)d_ghi, (const __half*)d_glo, d_gz, Hp, Wp, Hm, Wm, d_rnorm);
   SIR_LAUNCH_CHECK("window_rnorm_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_gallery_window_rnorm_multi(const uint16_t* d_ghi, const uint16_t* d_glo, int G, int C, int Hp, int Wp, int nshapes,
+                                              const int* h_hm, const int* h_wm, float* const* h_out, void* stream) {
+  SIR_CHECK_ARG(d_ghi && d_glo && h_hm && h_wm && h_out, "sir_gallery_window_rnorm_multi: null pointer");
+  SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0 && nshapes > 0, "sir_gallery_window_rnorm_multi: bad shape");
+  const size_t smem = 2 * (size_t)(Hp + 1) * (Wp + 1) * sizeof(double);
+  SIR_CHECK_ARG(smem <= 227 * 1024, "sir_gallery_window_rnorm_multi: map %dx%d too large for the smem SAT", Hp, Wp);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SIR_CUDA(cudaFuncSetAttribute(window_rnorm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  for (int s0 = 0; s0 < nshapes; s0 += kMaxRnormShapes) {
+    RnormShapes sh{};
+    sh.n = std::min(kMaxRnormShapes, nshapes - s0);
+    for (int i = 0; i < sh.n; ++i) {
+      SIR_CHECK_ARG(h_hm[s0 + i] > 0 && h_wm[s0 + i] > 0 && h_out[s0 + i], "sir_gallery_window_rnorm_multi: bad shape entry %d", s0 + i);
+      sh.hm[i] = h_hm[s0 + i];
+      sh.wm[i] = h_wm[s0 + i];
+      sh.out[i] = h_out[s0 + i];
+    }
+    window_rnorm_multi_kernel<<<(unsigned)((size_t)G * C), 256, smem, (cudaStream_t)stream>>>((const __half*)d_ghi, (const __half*)d_glo,
+                                                                                              nullptr, Hp, Wp, sh);
+    SIR_LAUNCH_CHECK("window_rnorm_multi_kernel");
+  }
   return SIR_OK;
 }
 

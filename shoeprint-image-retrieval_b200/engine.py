@@ -454,15 +454,18 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
     col2probe = torch.zeros(ncols, dtype=torch.int32)
     ntiles = -(-ncols // 256)
     tab = torch.zeros(ntiles * 8, dtype=torch.int64)
-    tables = []  # keeps every window-norm table alive until the launch is queued
+    # one pass over the gallery builds the window-norm tables of every member shape
+    tables = [torch.empty((gops.G, gops.C, gops.Hp * gops.Wp), dtype=torch.float32, device=dev) for _ in oriented]
+    ns = len(oriented)
+    hms = (C.c_int * ns)(*[hw[0] - 2 * EDGE for hw, _, _ in oriented])
+    wms = (C.c_int * ns)(*[hw[1] - 2 * EDGE for hw, _, _ in oriented])
+    outs = (C.c_void_p * ns)(*[t.data_ptr() for t in tables])
+    nat.check(nat.lib.sir_gallery_window_rnorm_multi(_ptr(gops.ghi), _ptr(gops.glo), gops.G, gops.C, gops.Hp, gops.Wp, ns, hms, wms, outs,
+                                                     _stream()), "sir_gallery_window_rnorm_multi")
+    launch_counter.add(-(-ns // 24))
     col0 = 0
-    for (h, w), maps, blk in oriented:
+    for ((h, w), maps, blk), rn in zip(oriented, tables):
         hm, wm = h - 2 * EDGE, w - 2 * EDGE
-        rn = torch.empty((gops.G, gops.C, gops.Hp * gops.Wp), dtype=torch.float32, device=dev)
-        nat.check(nat.lib.sir_gallery_window_rnorm(_ptr(gops.ghi), _ptr(gops.glo), None, gops.G, gops.C, gops.Hp, gops.Wp, hm, wm,
-                                                   _ptr(rn), _stream()), "sir_gallery_window_rnorm")
-        launch_counter.add()
-        tables.append(rn)
         start = col0
         for m in maps:
             n = int(m.shape[0])
