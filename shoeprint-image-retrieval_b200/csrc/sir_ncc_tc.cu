@@ -57,7 +57,7 @@ struct TcParams {
   const __half* ghi;
   const __half* glo;
   const float* rnorm;
-  // multi-shape column tiles: one window-norm table per 32-column chunk (8 per 256-column tile), NULL
+  // multi-shape column tiles: one window-norm table per 16-column chunk (16 per 256-column tile), NULL
   // when every column of the launch has the same true template shape
   const float* const* rnorm_tab;
   const int32_t* col2probe;
@@ -482,24 +482,24 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       const int y = 16 * py + mh, x = 8 * px + ml;
       const bool valid = (y < p.Hp) && (x < p.Wp);
       const int ncol_half = tile_cols(p, nt) - half * 128;  // columns of this warp's half that exist
-      // window-norm rows of this thread's position, one per 32-column chunk of its column half: with
+      // window-norm rows of this thread's position, one per 16-column chunk of its column half: with
       // multi-shape tiles the chunks of a tile may belong to templates of different true shapes
       const size_t roff = (size_t)g * p.C * M + (valid ? y * p.Wp + x : 0);
-      const float* rrow[4];
+      const float* rrow[8];
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4)
-        rrow[j4] = (p.rnorm_tab ? p.rnorm_tab[(size_t)nt * 8 + half * 4 + j4] : p.rnorm) + roff;
+      for (int j8 = 0; j8 < 8; ++j8)
+        rrow[j8] = (p.rnorm_tab ? p.rnorm_tab[(size_t)nt * 16 + half * 8 + j8] : p.rnorm) + roff;
 
       float total[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) total[j] = 0.0f;
-      float r_cur[4], r_next[4];
+      float r_cur[8], r_next[8];
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) r_cur[j4] = (valid && j4 * 32 < ncol_half) ? __ldg(rrow[j4]) : 0.0f;
+      for (int j8 = 0; j8 < 8; ++j8) r_cur[j8] = (valid && j8 * 16 < ncol_half) ? __ldg(rrow[j8]) : 0.0f;
       for (int c = 0; c < p.C; ++c, ++cs) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          r_next[j4] = (valid && c + 1 < p.C && j4 * 32 < ncol_half) ? __ldg(rrow[j4] + (size_t)(c + 1) * M) : 0.0f;
+        for (int j8 = 0; j8 < 8; ++j8)
+          r_next[j8] = (valid && c + 1 < p.C && j8 * 16 < ncol_half) ? __ldg(rrow[j8] + (size_t)(c + 1) * M) : 0.0f;
         const int buf = cs & 1;
         ptx::mbar_wait(bar_accfull(buf), (cs >> 1) & 1);
         ptx::tc_fence_after();
@@ -511,7 +511,8 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
           ptx::tmem_ld_32x32(taddr + j4 * 32, v);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) total[j4 * 32 + j] = fmaf(r_cur[j4], __uint_as_float(v[j]), total[j4 * 32 + j]);
+          for (int j = 0; j < 32; ++j)
+            total[j4 * 32 + j] = fmaf(r_cur[2 * j4 + (j >> 4)], __uint_as_float(v[j]), total[j4 * 32 + j]);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -520,7 +521,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
           else ptx::mbar_arrive(bar_accempty(buf));
         }
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) r_cur[j4] = r_next[j4];
+        for (int j8 = 0; j8 < 8; ++j8) r_cur[j8] = r_next[j8];
       }
       // max over the tile's valid positions, then over the 4 lane quarters, then into scores
 #pragma unroll

@@ -407,7 +407,7 @@ def _score_buckets(blocks: dict[tuple[int, int], _Block], gallery: list[GalleryO
 
     Template shapes that round to the same bucket (rows to 8, columns to the mode's row alignment, in
     the orientation the planner prefers) are packed into one K layout, anchor on anchor; each shape's
-    columns are padded to a multiple of 32 so that every 32-column chunk has one true shape and hence
+    columns are padded to a multiple of 16 so that every 16-column chunk has one true shape and hence
     one window-norm table."""
     dev = scores.device
     for ops, g0 in zip(gallery, offsets):
@@ -426,7 +426,7 @@ def _score_buckets(blocks: dict[tuple[int, int], _Block], gallery: list[GalleryO
             batch: list = []
             cols = 0
             for item in members:
-                n32 = -(-item[1].ncols // 32) * 32
+                n32 = -(-item[1].ncols // 16) * 16
                 if batch and (cols + n32 > max_cols or (len(batch) + 1) * table_bytes > table_budget):
                     _score_one_bucket(batch, gops, g0, scores, mode, flip, dev)
                     batch, cols = [], 0
@@ -445,7 +445,7 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
         oriented.append(((w, h) if flip else (h, w), maps, blk))
     hb = max(hw[0] for hw, _, _ in oriented) - 2 * EDGE
     wb = max(hw[1] for hw, _, _ in oriented) - 2 * EDGE
-    ncols = sum(-(-blk.ncols // 32) * 32 for _, _, blk in oriented)
+    ncols = sum(-(-blk.ncols // 16) * 16 for _, _, blk in oriented)
     kpad = int(nat.lib.sir_template_kpad_fp8c(hb, wb) if fp8c else nat.lib.sir_template_kpad(hb, wb))
     thi = torch.zeros((c, ncols, kpad), dtype=torch.float16, device=dev)
     tlo = None if fp8c else torch.zeros_like(thi)
@@ -453,7 +453,7 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
     t8l = torch.zeros_like(t8b) if fp8c else None
     col2probe = torch.zeros(ncols, dtype=torch.int32)
     ntiles = -(-ncols // 256)
-    tab = torch.zeros(ntiles * 8, dtype=torch.int64)
+    tab = torch.zeros(ntiles * 16, dtype=torch.int64)
     # one pass over the gallery builds the window-norm tables of every member shape
     tables = [torch.empty((gops.G, gops.C, gops.Hp * gops.Wp), dtype=torch.float32, device=dev) for _ in oriented]
     ns = len(oriented)
@@ -474,9 +474,9 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
             launch_counter.add()
             col0 += n
         col2probe[start:col0] = torch.cat(blk.ids).to(torch.int32)
-        col0 = start + -(-blk.ncols // 32) * 32
-        tab[start // 32 : col0 // 32] = rn.data_ptr()
-    tab[col0 // 32 :] = tables[-1].data_ptr()
+        col0 = start + -(-blk.ncols // 16) * 16
+        tab[start // 16 : col0 // 16] = rn.data_ptr()
+    tab[col0 // 16 :] = tables[-1].data_ptr()
     d_tab = tab.to(dev, non_blocking=True)
     d_c2p = col2probe.to(dev, non_blocking=True)
     g8a, g8l = gops.fp8_companions() if fp8c else (None, None)
