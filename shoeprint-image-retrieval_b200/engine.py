@@ -38,7 +38,7 @@ __all__ = [
 EDGE = 2  # similarity.py:92-93
 
 #: parity-grade default: fp16 hi*hi + fp8 correction products (measured <= 1e-5 relative vs the float64
-#: oracle, tools/precision_study.py); "fp16x3" is the all-fp16 alternative, "fp16x1" the fast lossy one
+#: oracle, tests/precision_study.py); "fp16x3" is the all-fp16 alternative, "fp16x1" the fast lossy one
 DEFAULT_PRECISION = "fp16_fp8c"
 
 
