@@ -189,6 +189,12 @@ int sir_merge_topk(const float* d_vals, const int32_t* d_idx, int P, int Q, int 
  * sir_feat_se_scale: SqueezeExcitation._scale: global average (d_avg [B][C] scratch), fc1 [S][C] +
  *   SiLU, fc2 [C][S] + sigmoid -> d_scale [B][C].
  * sir_feat_maxpool: MaxPool2d (VGG).   sir_feat_nhwc_to_nchw: [B][HW][C] -> [B][C][HW]. */
+/* sir_feat_clahe_to_nhwc: cv2.createCLAHE(clip_limit, (tiles_x, tiles_y)).apply (network.py:108-111,197-208) on
+ * uint8 grayscale [B][H][W], bit exact, fused with ToTensor / repeat / Normalize.  d_lut: scratch of
+ * B*tiles_x*tiles_y*256 bytes; d_clahe_u8 [B][H][W] or NULL receives the equalised uint8 image. */
+int sir_feat_clahe_to_nhwc(const uint8_t* d_img, int B, int H, int W, double clip_limit, int tiles_x, int tiles_y,
+                           const float* h_mean, const float* h_std, uint8_t* d_lut, uint8_t* d_clahe_u8, float* d_out,
+                           float* d_amax_out, void* stream);
 int sir_feat_image_to_nhwc(const uint8_t* d_img, int B, int H, int W, int in_ch, const float* h_mean, const float* h_std,
                            float* d_out, float* d_amax_out, void* stream);
 int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int H, int W, int C, int kh, int kw, int stride,

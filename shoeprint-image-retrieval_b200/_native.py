@@ -48,6 +48,7 @@ SIGNATURES = {
     "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
     "sir_rank_topk": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "sir_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "sir_feat_clahe_to_nhwc": (_i, [_p, _i, _i, _i, C.c_double, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p, _p, _p]),
     "sir_feat_image_to_nhwc": (_i, [_p, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p]),
     "sir_feat_im2col_split": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     "sir_feat_gemm": (_i, [_p, _p, _p, C.c_longlong, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p]),

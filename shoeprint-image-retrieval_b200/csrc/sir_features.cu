@@ -64,6 +64,96 @@ __global__ void __launch_bounds__(256) image_to_nhwc_kernel(const uint8_t* __res
   if ((threadIdx.x & 31) == 0) atomic_max_nonneg(amax, local);
 }
 
+// ------------------------------------------------------------------------------------------ CLAHE
+// OpenCV CLAHE (modules/imgproc/src/clahe.cpp; network.py:108-111,197-208) for uint8 grayscale, bit exact:
+// per tile a 256-bin histogram of the (REFLECT_101 extended) image, clipped and redistributed, its
+// cumulative sum scaled to 0..255 is the tile's LUT; every pixel is the bilinear blend (float32, products
+// and sums rounded separately, round half to even) of the LUT values of the four nearest tile centres.
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ img, int H, int W, int tiles_x, int th, int tw,
+                                                        int clip, float lut_scale, uint8_t* __restrict__ lut) {
+  __shared__ int hist[256];
+  __shared__ int scan[256];
+  __shared__ int red[8];
+  const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const uint8_t* src = img + (size_t)b * H * W;
+  hist[t] = 0;
+  __syncthreads();
+  for (int i = t; i < th * tw; i += 256) {
+    int y = ty * th + i / tw, x = tx * tw + i % tw;
+    if (y >= H) y = 2 * H - 2 - y;  // BORDER_REFLECT_101 extension to a multiple of the grid
+    if (x >= W) x = 2 * W - 2 - x;
+    atomicAdd(&hist[src[(size_t)y * W + x]], 1);
+  }
+  __syncthreads();
+  int hv = hist[t];
+  if (clip > 0) {
+    int over = max(hv - clip, 0);
+    hv = min(hv, clip);
+    over = warp_sum(over);
+    if ((t & 31) == 0) red[t >> 5] = over;
+    __syncthreads();
+    int clipped = 0;
+    for (int i = 0; i < 8; ++i) clipped += red[i];
+    const int batch = clipped / 256, residual = clipped - batch * 256;
+    hv += batch;
+    if (residual != 0) {
+      const int step = max(256 / residual, 1);
+      if (t % step == 0 && t / step < residual) hv += 1;
+    }
+  }
+  // inclusive scan over the 256 bins
+  scan[t] = hv;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const int add = t >= o ? scan[t - o] : 0;
+    __syncthreads();
+    scan[t] += add;
+    __syncthreads();
+  }
+  const int v = __float2int_rn(__fmul_rn((float)scan[t], lut_scale));
+  lut[((size_t)b * gridDim.x + tile) * 256 + t] = (uint8_t)min(max(v, 0), 255);
+}
+
+// CLAHE interpolation fused with ToTensor / grayscale repeat / Normalize: uint8 in, float32 NHWC(3) out.
+__global__ void __launch_bounds__(256) clahe_apply_to_nhwc_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int tiles_x,
+                                                                  int tiles_y, float inv_tw, float inv_th, const uint8_t* __restrict__ lut,
+                                                                  float m0, float m1, float m2, float s0, float s1, float s2,
+                                                                  uint8_t* __restrict__ clahe_out, float* __restrict__ out,
+                                                                  float* __restrict__ amax) {
+  const size_t total = (size_t)B * H * W;
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const size_t r = i / W;
+    const int y = (int)(r % H), b = (int)(r / H);
+    const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+    const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+    const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+    const int tx2 = min(tx1 + 1, tiles_x - 1), ty2 = min(ty1 + 1, tiles_y - 1);
+    tx1 = max(tx1, 0);
+    ty1 = max(ty1, 0);
+    const int v = img[i];
+    const uint8_t* lb = lut + (size_t)b * tiles_x * tiles_y * 256 + v;
+    const float l11 = lb[(ty1 * tiles_x + tx1) * 256], l12 = lb[(ty1 * tiles_x + tx2) * 256];
+    const float l21 = lb[(ty2 * tiles_x + tx1) * 256], l22 = lb[(ty2 * tiles_x + tx2) * 256];
+    const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+    const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+    const int q = min(max(__float2int_rn(res), 0), 255);
+    if (clahe_out) clahe_out[i] = (uint8_t)q;
+    const float g = __fdiv_rn((float)q, 255.0f);
+    const float o0 = __fdiv_rn(g - m0, s0), o1 = __fdiv_rn(g - m1, s1), o2 = __fdiv_rn(g - m2, s2);
+    out[3 * i] = o0;
+    out[3 * i + 1] = o1;
+    out[3 * i + 2] = o2;
+    local = fmaxf(local, fmaxf(fabsf(o0), fmaxf(fabsf(o1), fabsf(o2))));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(amax, local);
+}
+
 // ------------------------------------------------------------------------------------------ K1a
 // im2col + split: A[m][k] = in[b][oy*s - pad + ky][ox*s - pad + kx][c] * chan_scale[b][c], k = (ky*kw + kx)*C + c,
 // scaled by 2^e(amax_in) and split into fp16 hi/lo.  One thread produces 8 consecutive k (16 bytes).
@@ -548,6 +638,30 @@ extern "C" int sir_feat_image_to_nhwc(const uint8_t* d_img, int B, int H, int W,
   image_to_nhwc_kernel<<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>(d_img, in_ch, pixels, h_mean[0], h_mean[1], h_mean[2],
                                                                             h_std[0], h_std[1], h_std[2], d_out, d_amax);
   SIR_LAUNCH_CHECK("image_to_nhwc_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_clahe_to_nhwc(const uint8_t* d_img, int B, int H, int W, double clip_limit, int tiles_x, int tiles_y,
+                                      const float* h_mean, const float* h_std, uint8_t* d_lut, uint8_t* d_clahe_u8, float* d_out,
+                                      float* d_amax, void* stream) {
+  SIR_CHECK_ARG(d_img && d_lut && d_out && d_amax && h_mean && h_std, "sir_feat_clahe_to_nhwc: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 1 && W > 1 && tiles_x > 0 && tiles_y > 0 && tiles_x * tiles_y <= 65535, "sir_feat_clahe_to_nhwc: bad shape");
+  const int eh = H % tiles_y == 0 && W % tiles_x == 0 ? H : H + (tiles_y - H % tiles_y);
+  const int ew = H % tiles_y == 0 && W % tiles_x == 0 ? W : W + (tiles_x - W % tiles_x);
+  const int th = eh / tiles_y, tw = ew / tiles_x;
+  SIR_CHECK_ARG(eh - H < H && ew - W < W, "sir_feat_clahe_to_nhwc: image %dx%d too small for a %dx%d tile grid", H, W, tiles_y, tiles_x);
+  const int area = th * tw;
+  const float lut_scale = 255.0f / (float)area;
+  int clip = 0;
+  if (clip_limit > 0.0) clip = std::max((int)(clip_limit * area / 256), 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  clahe_lut_kernel<<<dim3((unsigned)(tiles_x * tiles_y), (unsigned)B), 256, 0, st>>>(d_img, H, W, tiles_x, th, tw, clip, lut_scale, d_lut);
+  SIR_LAUNCH_CHECK("clahe_lut_kernel");
+  const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+  clahe_apply_to_nhwc_kernel<<<grid_for((size_t)B * H * W), 256, 0, st>>>(d_img, B, H, W, tiles_x, tiles_y, inv_tw, inv_th, d_lut, h_mean[0],
+                                                                          h_mean[1], h_mean[2], h_std[0], h_std[1], h_std[2], d_clahe_u8,
+                                                                          d_out, d_amax);
+  SIR_LAUNCH_CHECK("clahe_apply_to_nhwc_kernel");
   return SIR_OK;
 }
 

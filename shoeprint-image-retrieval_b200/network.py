@@ -7,7 +7,10 @@ and ``printmodel``.
 
 What runs where:
 
-* CLAHE stays on the host in OpenCV (``network.py:108-111,197-208``): uint8 in, uint8 out, bit exact.
+* CLAHE (``network.py:108-111,197-208``): grayscale images are equalised on the GPU by
+  ``sir_feat_clahe_to_nhwc`` (bit exact with ``cv2.createCLAHE(...).apply``, fused with the
+  normalisation); RGB images take the reference's LAB round trip in OpenCV on the host.
+  ``SIR_HOST_CLAHE=1`` forces the OpenCV path for grayscale too.
 * ToTensor / grayscale repeat / Normalize (``network.py:51-87``) and the truncated backbone
   ``features[:block]`` (``network.py:185-186,234-235``) run through ``libsir.so``: torchvision only
   *defines* the architecture and holds the weights (exactly its role in the reference); at build
@@ -458,6 +461,7 @@ class Model:
         self.transform_rgb = self._host_transform(gray=False)
         self.program = _Program(layers, self.device)
         self.max_batch_bytes = 2 << 30  # cap on one im2col operand
+        self._host_clahe = os.environ.get("SIR_HOST_CLAHE", "") == "1"
 
     def _host_transform(self, *, gray: bool):
         mean, std = np.array(self.mean, np.float32), np.array(self.std, np.float32)
@@ -480,8 +484,9 @@ class Model:
         return self.clahe.apply(img)
 
     # ---- device path -----------------------------------------------------------------------
-    def _forward_uint8(self, batch: np.ndarray) -> torch.Tensor:
-        """CLAHE'd uint8 images ``[B,H,W]`` or ``[B,H,W,3]`` -> feature maps ``[B,C,h,w]`` on the device."""
+    def _forward_uint8(self, batch: np.ndarray, *, apply_clahe: bool = False) -> torch.Tensor:
+        """uint8 images ``[B,H,W]`` or ``[B,H,W,3]`` -> feature maps ``[B,C,h,w]`` on the device.
+        ``apply_clahe``: the (grayscale) batch is raw and CLAHE runs on the GPU; otherwise it is already equalised."""
         b, h, w = batch.shape[:3]
         in_ch = 1 if batch.ndim == 3 else 3
         d_img = torch.from_numpy(np.ascontiguousarray(batch)).to(self.device, non_blocking=True)
@@ -489,9 +494,17 @@ class Model:
         amax0 = torch.zeros(1, dtype=torch.float32, device=self.device)
         mean = (C.c_float * 3)(*self.mean)
         std = (C.c_float * 3)(*self.std)
-        nat.check(nat.lib.sir_feat_image_to_nhwc(_ptr(d_img), b, h, w, in_ch, mean, std, _ptr(x0), _ptr(amax0), _stream()),
-                  "sir_feat_image_to_nhwc")
-        launch_counter.add()
+        if apply_clahe:
+            assert in_ch == 1
+            tx, ty = (int(v) for v in self.config["model"]["clahe_tile_grid_size"])
+            lut = torch.empty((b, tx * ty, 256), dtype=torch.uint8, device=self.device)
+            nat.check(nat.lib.sir_feat_clahe_to_nhwc(_ptr(d_img), b, h, w, float(self.config["model"]["clahe_clip_limit"]), tx, ty, mean, std,
+                                                     _ptr(lut), None, _ptr(x0), _ptr(amax0), _stream()), "sir_feat_clahe_to_nhwc")
+            launch_counter.add(2)
+        else:
+            nat.check(nat.lib.sir_feat_image_to_nhwc(_ptr(d_img), b, h, w, in_ch, mean, std, _ptr(x0), _ptr(amax0), _stream()),
+                      "sir_feat_image_to_nhwc")
+            launch_counter.add()
         y = self.program.run(x0, amax0)
         bo, ho, wo, co = (int(v) for v in y.shape)
         out = torch.empty((bo, co, ho, wo), dtype=torch.float32, device=self.device)
@@ -519,8 +532,10 @@ class Model:
 
     def get_feature_maps(self, img: np.ndarray) -> np.ndarray:
         """One image (uint8 ``[H,W]`` or ``[H,W,3]``) -> ``[C,h,w]`` float32 (``network.py:210-244``)."""
-        img = self._clahe(img)
-        out = self._forward_uint8(img[None])
+        if img.ndim == 2 and not self._host_clahe:
+            out = self._forward_uint8(img[None], apply_clahe=True)
+        else:
+            out = self._forward_uint8(self._clahe(img)[None])
         return out.cpu().numpy().squeeze()  # squeeze like network.py:244
 
     def get_multiple_feature_maps(self, images: list[np.ndarray], *, progress: bool = True) -> list[np.ndarray]:
@@ -535,8 +550,10 @@ class Model:
             limit = self._batch_limit(shp[0], shp[1])
             for s in range(0, len(idx), limit):
                 chunk = idx[s : s + limit]
-                batch = np.stack([self._clahe(images[i]) for i in chunk])
-                maps = self._forward_uint8(batch).cpu().numpy()
+                if len(shp) == 2 and not self._host_clahe:
+                    maps = self._forward_uint8(np.stack([images[i] for i in chunk]), apply_clahe=True).cpu().numpy()
+                else:
+                    maps = self._forward_uint8(np.stack([self._clahe(images[i]) for i in chunk])).cpu().numpy()
                 for j, i in enumerate(chunk):
                     results[i] = maps[j].squeeze()
                 if bar is not None:

@@ -96,3 +96,44 @@ def test_unknown_model_string_raises_lookup_error():
 
     with pytest.raises(LookupError, match="Model string not found"):
         network.Model(_config("ResNet50"), 4, random_init_seed=0)
+
+
+def test_gpu_clahe_bit_exact_vs_opencv():
+    """sir_feat_clahe_to_nhwc against cv2.createCLAHE(...).apply: the equalised uint8 image must be
+    identical, and the fused normalised output must equal ToTensor + repeat + Normalize of it."""
+    import ctypes as C
+
+    import cv2
+
+    from src.shoeprint_image_retrieval import _native as nat
+
+    rng = np.random.default_rng(9)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    for (h, w), clip, tiles in [((470, 162), 2.0, (8, 8)), ((800, 300), 2.0, (8, 8)), ((123, 77), 4.0, (4, 6)), ((64, 64), 0.0, (8, 8)), ((97, 45), 40.0, (2, 2))]:
+        imgs = np.stack([_image(int(rng.integers(1 << 30)), h, w) for _ in range(3)])
+        d = torch.from_numpy(imgs).cuda()
+        lut = torch.empty((3, tiles[0] * tiles[1], 256), dtype=torch.uint8, device="cuda")
+        u8 = torch.empty_like(d)
+        out = torch.empty((3, h, w, 3), dtype=torch.float32, device="cuda")
+        amax = torch.zeros(1, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nat.check(nat.lib.sir_feat_clahe_to_nhwc(C.c_void_p(d.data_ptr()), 3, h, w, clip, tiles[0], tiles[1], (C.c_float * 3)(*mean), (C.c_float * 3)(*std),
+                                                 C.c_void_p(lut.data_ptr()), C.c_void_p(u8.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(amax.data_ptr()), st))
+        cl = cv2.createCLAHE(clipLimit=clip, tileGridSize=tiles)
+        want = np.stack([cl.apply(im) for im in imgs])
+        np.testing.assert_array_equal(u8.cpu().numpy(), want, err_msg=f"{h}x{w} clip {clip} tiles {tiles}")
+        x = torch.from_numpy(want).float().div(255)[..., None].repeat(1, 1, 1, 3)
+        ref = (x - torch.tensor(mean)) / torch.tensor(std)
+        np.testing.assert_array_equal(out.cpu().numpy(), ref.numpy())
+        assert abs(float(amax) - float(ref.abs().max())) < 1e-6
+
+
+def test_model_gpu_clahe_path_matches_host_clahe_path(monkeypatch):
+    from src.shoeprint_image_retrieval import network
+
+    img = _image(21, 300, 130)
+    model = network.Model(_config("EfficientNetV2_M"), 4, random_init_seed=2)
+    a = model.get_feature_maps(img)
+    model._host_clahe = True
+    b = model.get_feature_maps(img)
+    np.testing.assert_array_equal(a, b)
