@@ -162,8 +162,8 @@ def run_reference(args) -> None:
 # ----------------------------------------------------------------------------- feature stage (side measurement)
 def feature_stage_numbers(args) -> dict:
     """images/s of the backbone (EfficientNetV2-M cut at block 6, seeded random init, synthetic 800x300
-    uint8 prints): through ``Model.get_multiple_feature_maps`` (CLAHE on the host, H2D, kernels, D2H)
-    and device-only; plus the torch CPU forward of the same modules (the reference's path on a CPU box)."""
+    uint8 prints): through ``Model.get_multiple_feature_maps`` (H2D, GPU CLAHE, kernels, D2H) and
+    device-only (CLAHE included); plus the torch CPU forward of the same modules (the reference's path on a CPU box)."""
     import numpy as np
     import torch
 
@@ -181,12 +181,12 @@ def feature_stage_numbers(args) -> dict:
     maps = model.get_multiple_feature_maps(imgs, progress=False)
     torch.cuda.synchronize()
     e2e = n / (time.perf_counter() - t0)
-    batch = np.stack([model._clahe(im) for im in imgs[:16]])
-    model._forward_uint8(batch)
+    batch = np.stack(imgs[:16])
+    model._forward_uint8(batch, apply_clahe=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(2):
-        model._forward_uint8(batch)
+        model._forward_uint8(batch, apply_clahe=True)
     e1.record()
     torch.cuda.synchronize()
     dev = 32 / (e0.elapsed_time(e1) * 1e-3)
