@@ -199,6 +199,17 @@ int sir_feat_image_to_nhwc(const uint8_t* d_img, int B, int H, int W, int in_ch,
                            float* d_out, float* d_amax_out, void* stream);
 int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int H, int W, int C, int kh, int kw, int stride,
                           int pad, const float* d_chan_scale, int Kp, uint16_t* d_ahi, uint16_t* d_alo, void* stream);
+/* sir_feat_conv: Conv2d (groups 1, stride 1, square zero padding) + folded BN bias + activation (+ residual) as an
+ * implicit GEMM: no im2col matrix.  d_xhi/d_xlo: the input split into fp16 hi/lo NHWC planes [B][H][W][C]
+ * (sir_feat_im2col_split with a 1x1 kernel and Kp = C), C % 8 == 0.  Weights [n_rows_alloc][taps*Cp] fp16 hi/lo with
+ * k = (ky*kw + kx)*Cp + c, Cp = C rounded up to bk (16 or 32), rows zero padded to a multiple of
+ * sir_feat_conv_tile_n(N).  A GEMM over an explicit [M][K] matrix is the call with B=H=1, W=M, C=K, kh=kw=1.
+ * Replaces the torch Conv2d/BatchNorm/SiLU modules the reference runs at network.py:234-235. */
+int sir_feat_conv_tile_n(int N);
+int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
+                  int kw, int pad, int bk, const uint16_t* d_whi, const uint16_t* d_wlo, int N, int n_rows_alloc, int w_exp,
+                  const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
+                  void* stream);
 int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
                   const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
                   const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream);

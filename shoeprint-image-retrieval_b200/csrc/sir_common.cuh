@@ -64,6 +64,14 @@ __host__ __device__ inline int tpl_row_taps(int Wm, int row_align) { return roun
 __host__ __device__ inline int tpl_kpad_aligned(int Hm, int Wm, int row_align) { return round_up(Hm * tpl_row_taps(Wm, row_align), 32); }
 __host__ __device__ inline int gal_pitch8(int Wp) { return round_up(Wp, 16); }  // 1-byte operands: 16 cells = 16 bytes
 
+// Feature stage: exponent e with amax * 2^e in [2^9, 2^10); 0 for an all-zero tensor.
+__device__ __forceinline__ int scale_exp_from_amax(float amax) {
+  if (!(amax > 0.0f) || !isfinite(amax)) return 0;
+  int ex;
+  (void)frexpf(amax, &ex);
+  return kGalleryPeakLog2 - ex;
+}
+
 // warp / block reductions ---------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

@@ -1,0 +1,410 @@
+// Feature stage K1: Conv2d (groups 1, stride 1) as an implicit GEMM on the tcgen05 tensor cores.
+//
+//   out[b][oy][ox][n] = act( sum_{ky,kx,c} x[b][oy+ky-pad][ox+kx-pad][c] * w[n][ky][kx][c] + bias[n] ) (+ residual)
+//
+// (torchvision Conv2d + folded BatchNorm + SiLU/ReLU as composed by network.py:121-186.)  The
+// activation arrives as two fp16 NHWC planes (hi + lo = the float32 value times a power of two,
+// written by the split pass), the weights as two fp16 [N][taps*Cp] matrices.  No im2col matrix
+// exists anywhere: the A operand of output patch (TH x TW pixels = 128 rows) and tap (ky,kx) is the
+// same patch of the input shifted by (ky-pad, kx-pad), which one 4-D TMA box fetches straight into
+// the swizzled K-major layout tcgen05.mma reads; rows outside the image are zero filled by the TMA
+// unit, which is the convolution's zero padding.  A 1x1 convolution (and a plain GEMM over an
+// explicit [M][K] matrix) is the same kernel with a 128 x 1 "patch" over a 1 x M image.
+//
+// Persistent, warp specialised, one CTA per SM:
+//   warp 0      TMA producer: per K step (tap, 16/32-channel chunk) A_hi, A_lo, B_hi, B_lo into a ring
+//   warp 1      TMEM owner + MMA issuer: hi*hi + lo*hi + hi*lo (fp32-grade), accumulators double
+//               buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of i+1
+//   warps 2-9   epilogue: tcgen05.ld 16 columns, transpose through shared memory so that global
+//               stores / residual loads are row contiguous, un-scale + bias + activation + residual,
+//               running max |out| for the next layer's scaling
+// Bound: tensor pipe for wide layers (three MMAs per algorithmic MAC), L2->smem operand feed otherwise.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "sir_common.cuh"
+#include "sir_ptx.cuh"
+
+namespace sir {
+
+constexpr int kConvThreads = 320;
+constexpr int kConvBM = 128;
+constexpr int kConvMaxStages = 8;
+constexpr uint32_t kConvAccStride = 256;  // TMEM columns between the two accumulator buffers
+
+struct ConvParams {
+  int Ho, Wo;             // output grid of one image (1 x M for flat GEMMs)
+  int N, BN, n_tiles_n;
+  int taps, kw, pad;
+  int chunks, bk;         // K step = bk channels of one tap; chunks = Cp / bk
+  int tw_log2, TH;        // patch = TH x (1 << tw_log2) pixels = 128 rows
+  int tiles_x, tiles_y;
+  int total_tiles;
+  int stages;
+  int w_exp;
+  const float* amax_in;
+  const float* bias;
+  const float* residual;
+  float* out;
+  float* amax_out;
+  int ldc;
+};
+
+template <int ACT>
+__device__ __forceinline__ float conv_act(float v) {
+  if (ACT == 1) return __fdividef(v, 1.0f + __expf(-v));  // SiLU
+  if (ACT == 2) return fmaxf(v, 0.0f);                    // ReLU
+  return v;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+               const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t a_bytes = (uint32_t)kConvBM * p.bk * 2, b_bytes = (uint32_t)p.BN * p.bk * 2;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t ring_bytes = stage_bytes * p.stages;
+  const uint32_t bar0 = base + ring_bytes;
+  auto bar_full = [&](int i) { return bar0 + 8u * i; };
+  auto bar_empty = [&](int i) { return bar0 + 8u * (kConvMaxStages + i); };
+  auto bar_acc_full = [&](int i) { return bar0 + 8u * (2 * kConvMaxStages + i); };
+  auto bar_acc_empty = [&](int i) { return bar0 + 8u * (2 * kConvMaxStages + 2 + i); };
+  const uint32_t slot_off = ring_bytes + 8u * (2 * kConvMaxStages + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + slot_off);
+  float* xpose = reinterpret_cast<float*>(base_ptr + slot_off + 16);  // 8 warps x 32 rows x 16 floats
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(bar_full(i), 1);
+      ptx::mbar_init(bar_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_acc_full(i), 1);
+      ptx::mbar_init(bar_acc_empty(i), 8);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tm_xhi);
+    ptx::prefetch_tmap(&tm_xlo);
+    ptx::prefetch_tmap(&tm_whi);
+    ptx::prefetch_tmap(&tm_wlo);
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int TW = 1 << p.tw_log2;
+  const int k_iters = p.taps * p.chunks;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+        const int px = mt % p.tiles_x, r1 = mt / p.tiles_x;
+        const int py = r1 % p.tiles_y, b = r1 / p.tiles_y;
+        const int x0 = px * TW - p.pad, y0 = py * p.TH - p.pad, n0 = nt * p.BN;
+        int tap_y = 0, tap_x = 0, chunk = 0;
+        for (int ks = 0; ks < k_iters; ++ks, ++it) {
+          const uint32_t slot = it % p.stages;
+          ptx::mbar_wait(bar_empty(slot), ((it / p.stages) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full(slot), stage_bytes);
+          const uint32_t dst = base + slot * stage_bytes;
+          const int c0 = chunk * p.bk;
+          ptx::tma_load_4d(dst, &tm_xhi, bar_full(slot), c0, x0 + tap_x, y0 + tap_y, b);
+          ptx::tma_load_4d(dst + a_bytes, &tm_xlo, bar_full(slot), c0, x0 + tap_x, y0 + tap_y, b);
+          ptx::tma_load_2d(dst + 2 * a_bytes, &tm_whi, bar_full(slot), ks * p.bk, n0);
+          ptx::tma_load_2d(dst + 2 * a_bytes + b_bytes, &tm_wlo, bar_full(slot), ks * p.bk, n0);
+          if (++chunk == p.chunks) {
+            chunk = 0;
+            if (++tap_x == p.kw) {
+              tap_x = 0;
+              ++tap_y;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_f16(kConvBM, p.BN);
+      const uint32_t sbo = (uint32_t)p.bk * 16, layout = p.bk == 32 ? 4u : 6u;  // 8 rows of 64 B / 32 B
+      const int k16s = p.bk / 16;
+      uint32_t it = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        ptx::mbar_wait(bar_acc_empty(buf), ((lt >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * kConvAccStride;
+        uint32_t accumulate = 0;
+        for (int ks = 0; ks < k_iters; ++ks, ++it) {
+          const uint32_t slot = it % p.stages;
+          ptx::mbar_wait(bar_full(slot), (it / p.stages) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = base + slot * stage_bytes, a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+          for (int kk = 0; kk < k16s; ++kk) {
+            const uint64_t da_hi = ptx::make_smem_desc(a_hi + 32u * kk, 16, sbo, layout);
+            const uint64_t da_lo = ptx::make_smem_desc(a_lo + 32u * kk, 16, sbo, layout);
+            const uint64_t db_hi = ptx::make_smem_desc(b_hi + 32u * kk, 16, sbo, layout);
+            const uint64_t db_lo = ptx::make_smem_desc(b_lo + 32u * kk, 16, sbo, layout);
+            ptx::mma_f16_ss(acc, da_hi, db_hi, idesc, accumulate);
+            ptx::mma_f16_ss(acc, da_lo, db_hi, idesc, 1);
+            ptx::mma_f16_ss(acc, da_hi, db_lo, idesc, 1);
+            accumulate = 1;
+          }
+          ptx::tc_commit(bar_empty(slot));
+        }
+        ptx::tc_commit(bar_acc_full(buf));
+      }
+    }
+  } else {
+    // epilogue warps 2..9: TMEM lane quarter = warp % 4, the two warps of a quarter take alternate 16-column chunks
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* xp = xpose + (warp - 2) * (32 * 16);
+    const int rs = lane >> 2, c4 = lane & 3;
+    const int e_total = scale_exp_from_amax(*p.amax_in) + p.w_exp;
+    const float unscale = ldexpf(1.0f, -e_total);
+    const int n_chunks = p.BN >> 4;
+    float local_max = 0.0f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+      const int px = mt % p.tiles_x, r1 = mt / p.tiles_x;
+      const int py = r1 % p.tiles_y, b = r1 / p.tiles_y;
+      long long row_off[4];  // element offset of the 4 rows this lane stores per chunk; -1 = outside the image
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int r = q * 32 + ps * 8 + rs;
+        const int oy = py * p.TH + (r >> p.tw_log2), ox = px * TW + (r & (TW - 1));
+        row_off[ps] = (oy < p.Ho && ox < p.Wo) ? (((long long)b * p.Ho + oy) * p.Wo + ox) * p.ldc : -1;
+      }
+      ptx::mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * kConvAccStride + ((uint32_t)(q * 32) << 16);
+      for (int ci = half; ci < n_chunks; ci += 2) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tacc + ci * 16, v);
+        ptx::tmem_ld_wait();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(xp + lane * 16 + 4 * (j ^ ((lane >> 1) & 3))) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int n = nt * p.BN + ci * 16 + c4 * 4;
+        if (n < p.N) {
+          const bool full4 = n + 3 < p.N;
+          float bb[4] = {0.f, 0.f, 0.f, 0.f};
+          if (full4) {
+            const float4 t = *reinterpret_cast<const float4*>(p.bias + n);
+            bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
+          } else {
+            for (int t = 0; n + t < p.N; ++t) bb[t] = p.bias[n + t];
+          }
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            if (row_off[ps] < 0) continue;
+            const int row = ps * 8 + rs;
+            const float4 a = *reinterpret_cast<const float4*>(xp + row * 16 + 4 * (c4 ^ ((row >> 1) & 3)));
+            float o[4] = {conv_act<ACT>(fmaf(a.x, unscale, bb[0])), conv_act<ACT>(fmaf(a.y, unscale, bb[1])),
+                          conv_act<ACT>(fmaf(a.z, unscale, bb[2])), conv_act<ACT>(fmaf(a.w, unscale, bb[3]))};
+            float* dst = p.out + row_off[ps] + n;
+            if (full4) {
+              if (p.residual) {
+                const float4 rr = *reinterpret_cast<const float4*>(p.residual + row_off[ps] + n);
+                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+              }
+              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+              local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+            } else {
+              for (int t = 0; n + t < p.N; ++t) {
+                float ov = o[t];
+                if (p.residual) ov += p.residual[row_off[ps] + n + t];
+                dst[t] = ov;
+                local_max = fmaxf(local_max, fabsf(ov));
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_acc_empty(buf));
+    }
+    local_max = warp_max(local_max);
+    if (lane == 0 && p.amax_out) atomic_max_nonneg(p.amax_out, local_max);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn conv_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, int bk,
+           const char* what) {
+  EncodeTiledFn fn = conv_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SIR_E_CUDA;
+  }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return SIR_E_CUDA;
+  }
+  return SIR_OK;
+}
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+}  // namespace
+
+// Column tile: multiple of 16 up to 256 that wastes the fewest padded columns (ties -> the wider tile).
+int conv_tile_n(int N) {
+  int best = 16;
+  long best_cols = -1;
+  for (int bn = 16; bn <= 256; bn += 16) {
+    const long cols = (long)ceil_div(N, bn) * bn;
+    if (best_cols < 0 || cols < best_cols || (cols == best_cols && bn > best)) {
+      best = bn;
+      best_cols = cols;
+    }
+  }
+  return best;
+}
+
+}  // namespace sir
+
+using namespace sir;
+
+extern "C" int sir_feat_conv_tile_n(int N) { return N > 0 ? conv_tile_n(N) : 0; }
+
+extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
+                             int kw, int pad, int bk, const uint16_t* d_whi, const uint16_t* d_wlo, int N, int n_rows_alloc, int w_exp,
+                             const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
+                             void* stream) {
+  SIR_CHECK_ARG(d_xhi && d_xlo && d_whi && d_wlo && d_amax_in && d_bias && d_out, "sir_feat_conv: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && kh > 0 && kw > 0 && pad >= 0 && N > 0 && ldc >= N,
+                "sir_feat_conv: bad shape B=%d H=%d W=%d C=%d (C must be a multiple of 8) k=%dx%d N=%d ldc=%d", B, H, W, C, kh, kw, N, ldc);
+  SIR_CHECK_ARG(bk == 16 || bk == 32, "sir_feat_conv: bk must be 16 or 32, got %d", bk);
+  SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_conv: unknown activation %d", act);
+  const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
+  SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_conv: empty output");
+  SIR_CHECK_ARG((long long)B * Ho * Wo * (long long)ldc < (1ll << 40), "sir_feat_conv: output too large");
+  ConvParams p{};
+  p.N = N;
+  p.BN = conv_tile_n(N);
+  p.n_tiles_n = ceil_div(N, p.BN);
+  SIR_CHECK_ARG(n_rows_alloc >= p.n_tiles_n * p.BN, "sir_feat_conv: weight matrix needs %d zero-padded rows, has %d", p.n_tiles_n * p.BN,
+                n_rows_alloc);
+  SIR_CHECK_ARG(((uintptr_t)d_bias & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ldc % 4 == 0 && (!d_residual || ((uintptr_t)d_residual & 15) == 0) &&
+                    ((uintptr_t)d_xhi & 15) == 0 && ((uintptr_t)d_xlo & 15) == 0 && ((uintptr_t)d_whi & 15) == 0 && ((uintptr_t)d_wlo & 15) == 0,
+                "sir_feat_conv: operands must be 16-byte aligned and ldc a multiple of 4");
+  p.taps = kh * kw;
+  p.kw = kw;
+  p.pad = pad;
+  p.bk = bk;
+  p.chunks = ceil_div(C, bk);
+  const int Kp = p.taps * p.chunks * bk;
+  // image geometry seen by the kernel; a 1x1 convolution is flattened to one 1 x M row so that no patch is ragged
+  int gB = B, gH = H, gW = W;
+  if (p.taps == 1 && pad == 0) {
+    SIR_CHECK_ARG((long long)B * H * W < (1ll << 31), "sir_feat_conv: too many rows");
+    gW = B * H * W;
+    gH = 1;
+    gB = 1;
+  }
+  p.Ho = gH + 2 * pad - kh + 1;
+  p.Wo = gW + 2 * pad - kw + 1;
+  long long best_tiles = -1;
+  for (int l2 = 7; l2 >= 0; --l2) {  // patch = (128 >> l2) rows x (1 << l2) columns; prefer wide patches on ties
+    const int tw = 1 << l2, th = kConvBM >> l2;
+    const long long tiles = (long long)ceil_div(p.Ho, th) * ceil_div(p.Wo, tw);
+    if (best_tiles < 0 || tiles < best_tiles) {
+      best_tiles = tiles;
+      p.tw_log2 = l2;
+      p.TH = th;
+    }
+  }
+  p.tiles_x = ceil_div(p.Wo, 1 << p.tw_log2);
+  p.tiles_y = ceil_div(p.Ho, p.TH);
+  const long long total = (long long)gB * p.tiles_x * p.tiles_y * p.n_tiles_n;
+  SIR_CHECK_ARG(total < (1ll << 31), "sir_feat_conv: too many tiles");
+  p.total_tiles = (int)total;
+  p.w_exp = w_exp;
+  p.amax_in = d_amax_in;
+  p.bias = d_bias;
+  p.residual = d_residual;
+  p.out = d_out;
+  p.amax_out = d_amax_out;
+  p.ldc = ldc;
+  const uint32_t stage_bytes = (uint32_t)(2 * kConvBM + 2 * p.BN) * bk * 2;
+  const uint32_t tail = 8u * (2 * kConvMaxStages + 4) + 16 + 8 * 32 * 16 * 4;
+  p.stages = std::min<int>(kConvMaxStages, (int)((220u * 1024 - 1024 - tail) / stage_bytes));
+  SIR_CHECK_ARG(p.stages >= 2, "sir_feat_conv: tile does not fit shared memory");
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail;
+
+  CUtensorMap txh, txl, twh, twl;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gB};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)gW * C * 2, (cuuint64_t)gH * gW * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(1 << p.tw_log2), (cuuint32_t)p.TH, 1};
+    int rc = encode(&txh, d_xhi, 4, dims, strides, box, bk, "activation hi");
+    if (rc) return rc;
+    rc = encode(&txl, d_xlo, 4, dims, strides, box, bk, "activation lo");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)n_rows_alloc};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.BN};
+    int rc = encode(&twh, d_whi, 2, dims, strides, box, bk, "weights hi");
+    if (rc) return rc;
+    rc = encode(&twl, d_wlo, 2, dims, strides, box, bk, "weights lo");
+    if (rc) return rc;
+  }
+  static thread_local size_t configured[3] = {0, 0, 0};
+  const void* fn = act == 0 ? (const void*)conv_tc_kernel<0> : act == 1 ? (const void*)conv_tc_kernel<1> : (const void*)conv_tc_kernel<2>;
+  if (smem > configured[act]) {
+    SIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024)));
+    configured[act] = 221 * 1024;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(total, sm_count());
+  if (act == 0)
+    conv_tc_kernel<0><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(txh, txl, twh, twl, p);
+  else if (act == 1)
+    conv_tc_kernel<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(txh, txl, twh, twl, p);
+  else
+    conv_tc_kernel<2><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(txh, txl, twh, twl, p);
+  SIR_LAUNCH_CHECK("conv_tc_kernel");
+  return SIR_OK;
+}

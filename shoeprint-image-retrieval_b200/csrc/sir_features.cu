@@ -28,13 +28,6 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == 2) return fmaxf(v, 0.0f);         // ReLU
   return v;
 }
-// exponent e with amax * 2^e in [2^9, 2^10); 0 for an all-zero tensor
-__device__ __forceinline__ int scale_exp_from_amax(float amax) {
-  if (!(amax > 0.0f) || !isfinite(amax)) return 0;
-  int ex;
-  (void)frexpf(amax, &ex);
-  return kGalleryPeakLog2 - ex;
-}
 
 // uint8 image(s) -> normalised float32 NHWC with 3 channels (network.py:51-87: ToTensor, repeat to
 // 3 channels for grayscale, Normalize(mean, std)).
@@ -669,7 +662,7 @@ extern "C" int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, 
                                      int pad, const float* d_chan_scale, int Kp, uint16_t* d_ahi, uint16_t* d_alo, void* stream) {
   SIR_CHECK_ARG(d_in && d_amax_in && d_ahi && d_alo, "sir_feat_im2col_split: null pointer");
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "sir_feat_im2col_split: bad shape");
-  SIR_CHECK_ARG(Kp % 32 == 0 && Kp >= kh * kw * C, "sir_feat_im2col_split: Kp=%d must be a multiple of 32 and >= %d", Kp, kh * kw * C);
+  SIR_CHECK_ARG(Kp % 8 == 0 && Kp >= kh * kw * C, "sir_feat_im2col_split: Kp=%d must be a multiple of 8 and >= %d", Kp, kh * kw * C);
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_im2col_split: empty output");
   const size_t work = (size_t)B * Ho * Wo * (Kp / 8);

@@ -282,16 +282,26 @@ class _Program:
             p = op.p
             if op.kind == "conv":
                 cout, cin, k, kw = p["cout"], p["cin"], p["k"], p["kw"]
-                kdim = k * kw * cin
-                kp = (kdim + 31) // 32 * 32
-                bn = min(128, (cout + 31) // 32 * 32)
+                bn = int(nat.lib.sir_feat_conv_tile_n(cout))
                 rows = (cout + bn - 1) // bn * bn
-                wm = torch.zeros((rows, kp), dtype=torch.float32)
-                wm[:cout, :kdim] = p["w"].permute(0, 2, 3, 1).reshape(cout, kdim)
+                w = p["w"].permute(0, 2, 3, 1)  # [cout][ky][kx][cin]
+                implicit = p["stride"] == 1 and cin % 8 == 0
+                if implicit:  # K = (tap, channel) with the channels of a tap padded to the K step
+                    bk = 32 if cin % 32 == 0 else 16 if cin % 16 == 0 else 32
+                    cp = (cin + bk - 1) // bk * bk
+                    wm = torch.zeros((rows, k * kw, cp), dtype=torch.float32)
+                    wm[:cout, :, :cin] = w.reshape(cout, k * kw, cin)
+                    wm = wm.reshape(rows, k * kw * cp)
+                else:  # explicit im2col matrix, K = (tap, channel) packed and padded to 32
+                    bk = 32
+                    kdim = k * kw * cin
+                    wm = torch.zeros((rows, (kdim + 31) // 32 * 32), dtype=torch.float32)
+                    wm[:cout, :kdim] = w.reshape(cout, kdim)
                 hi, lo, e = _split_fp16(wm)
                 bias = torch.zeros((cout + 3) // 4 * 4, dtype=torch.float32)
                 bias[:cout] = p["bias"]
-                p.update(whi=hi.to(device), wlo=lo.to(device), w_exp=e, kp=kp, rows=rows, bias_d=bias.to(device))
+                p.update(whi=hi.to(device), wlo=lo.to(device), w_exp=e, kp=int(wm.shape[1]), rows=rows, bias_d=bias.to(device),
+                         implicit=implicit, bk=bk)
                 del p["w"]
             elif op.kind == "dwconv":
                 p.update(w_d=p["w"][:, 0].permute(1, 2, 0).contiguous().to(device), bias_d=p["bias"].to(device))
@@ -332,11 +342,7 @@ class _Program:
             if op.kind == "conv":
                 ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
                 m = b * ho * wo
-                ahi = torch.empty((m, p["kp"]), dtype=torch.float16, device=dev)
-                alo = torch.empty_like(ahi)
                 cs = tensors[p["chan_scale"]] if p["chan_scale"] is not None else None
-                nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
-                                                        _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
                 res = tensors[p["residual"]] if p["residual"] is not None else None
                 if p["c_off"] is None:
                     out = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float32, device=dev)
@@ -344,9 +350,21 @@ class _Program:
                 else:  # growth channels of a dense layer go straight into the block's buffer
                     out = tensors[op.dst]
                     out_ptr, ldc = C.c_void_p(out.data_ptr() + 4 * p["c_off"]), int(out.shape[3])
-                nat.check(nat.lib.sir_feat_gemm(_ptr(ahi), _ptr(alo), aptr(op.src), m, p["kp"], _ptr(p["whi"]), _ptr(p["wlo"]),
+                if p["implicit"]:  # split once into fp16 hi/lo NHWC planes; the kernel gathers the taps itself
+                    ahi = torch.empty((b, h, w, c), dtype=torch.float16, device=dev)
+                    alo = torch.empty_like(ahi)
+                    nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, 1, 1, 1, 0, _ptr(cs), c, _ptr(ahi), _ptr(alo), st),
+                              "sir_feat_im2col_split")
+                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"])
+                else:
+                    ahi = torch.empty((m, p["kp"]), dtype=torch.float16, device=dev)
+                    alo = torch.empty_like(ahi)
+                    nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
+                                                            _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
+                    geom = (1, 1, m, p["kp"], 1, 1, 0)
+                nat.check(nat.lib.sir_feat_conv(_ptr(ahi), _ptr(alo), aptr(op.src), *geom, p["bk"], _ptr(p["whi"]), _ptr(p["wlo"]),
                                                 p["cout"], p["rows"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
-                                                out_ptr, ldc, aptr(op.dst), st), "sir_feat_gemm")
+                                                out_ptr, ldc, aptr(op.dst), st), "sir_feat_conv")
                 launch_counter.add(2)
             elif op.kind == "dwconv":
                 ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Per-kernel time split of one batched feature-stage forward (CUPTI through torch.profiler; not a bench number)."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np, torch
+import __graft_entry__ as ge
+ge.build()
+from src.shoeprint_image_retrieval import network
+from torch.profiler import profile, ProfilerActivity
+block = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+b = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+mtype = sys.argv[3] if len(sys.argv) > 3 else "EfficientNetV2_M"
+cfg = {"model": {"type": mtype, "clahe_clip_limit": 2.0, "clahe_tile_grid_size": [8, 8]}}
+model = network.Model(cfg, block, random_init_seed=0)
+batch = np.random.default_rng(0).integers(0, 256, size=(b, 800, 300), dtype=np.uint8)
+model._forward_uint8(batch, apply_clahe=True); torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    model._forward_uint8(batch, apply_clahe=True); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+# per-launch list in launch order, with the program's op shapes beside it
+evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "sir::" in e.name], key=lambda e: e.time_range.start)
+desc = []
+for op in model.program.ops:
+    p = op.p
+    if op.kind == "conv":
+        d = f"conv k{p['k']} s{p['stride']} {p['cin']}->{p['cout']} kp{p['kp']}"
+        desc += [d, d]
+    elif op.kind == "dwconv":
+        desc += [f"dw k{p['k']} s{p['stride']}"]
+    elif op.kind == "se":
+        desc += ["se", "se"]
+    else:
+        desc += [op.kind]
+body = [e for e in evs if "clahe" not in e.name and "nhwc_to_nchw" not in e.name]
+for e, d in zip(body, desc):
+    short = e.name.split("(")[0].replace("sir::", "")
+    print(f"{short:24s} {e.device_time:8.1f} us  {d}")
