@@ -185,9 +185,12 @@ int sir_merge_topk(const float* d_vals, const int32_t* d_idx, int P, int Q, int 
  *   [B][C] or NULL multiplies the input per (image, channel) (squeeze-excitation scale).
  *   Weights d_bhi/d_blo [n_rows_alloc][Kp] f16 = W * 2^w_exp split hi/lo, rows >= N zero.
  *   out[m][n] = act(A.B^T * 2^-(e(amax_in)+w_exp) + bias[n]) + residual[m][n], row stride ldc.
- * sir_feat_dwconv: depthwise k x k Conv2d + folded BN bias + activation; weights [k][k][C].
- * sir_feat_se_scale: SqueezeExcitation._scale: global average (d_avg [B][C] scratch), fc1 [S][C] +
- *   SiLU, fc2 [C][S] + sigmoid -> d_scale [B][C].
+ * sir_feat_dwconv: depthwise k x k Conv2d + folded BN bias + activation; weights [k][k][C].  If d_pool_part is
+ *   not NULL it also receives the squeeze of a following SqueezeExcitation as partial sums over pixels,
+ *   [B][parts][C] with parts = sir_feat_dwconv_pool_parts(k, stride, C, Ho, Wo) (fused into the 3x3 fast path).
+ * sir_feat_pool_sum: the same squeeze for any other producer, one part: [B][HW][C] -> [B][1][C].
+ * sir_feat_se_scale: SqueezeExcitation._scale: avg = sum of parts / HW (d_avg [B][C] scratch), fc1 [S][C] + SiLU, fc2 given
+ *   transposed as [S][C] + sigmoid -> d_scale [B][C].
  * sir_feat_maxpool: MaxPool2d (VGG).   sir_feat_nhwc_to_nchw: [B][HW][C] -> [B][C][HW]. */
 /* sir_feat_clahe_to_nhwc: cv2.createCLAHE(clip_limit, (tiles_x, tiles_y)).apply (network.py:108-111,197-208) on
  * uint8 grayscale [B][H][W], bit exact, fused with ToTensor / repeat / Normalize.  d_lut: scratch of
@@ -213,10 +216,12 @@ int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_a
 int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
                   const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
                   const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream);
+int sir_feat_dwconv_pool_parts(int k, int stride, int C, int Ho, int Wo);
 int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, const float* d_w,
-                    const float* d_bias, int act, float* d_out, float* d_amax_out, void* stream);
-int sir_feat_se_scale(const float* d_in, int B, int HW, int C, int S, const float* d_w1, const float* d_b1,
-                      const float* d_w2, const float* d_b2, float* d_avg, float* d_scale, void* stream);
+                    const float* d_bias, int act, float* d_out, float* d_amax_out, float* d_pool_part, void* stream);
+int sir_feat_pool_sum(const float* d_in, int B, int HW, int C, float* d_pool_part, void* stream);
+int sir_feat_se_scale(const float* d_pool_part, int B, int parts, int HW, int C, int S, const float* d_w1, const float* d_b1,
+                      const float* d_w2t, const float* d_b2, float* d_avg, float* d_scale, void* stream);
 int sir_feat_maxpool(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, float* d_out,
                      float* d_amax_out, void* stream);
 /* per-channel y = act(x * scale[c] + shift[c]) (scale/shift both NULL: activation only) over `rows`

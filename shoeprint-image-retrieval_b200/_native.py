@@ -54,8 +54,10 @@ SIGNATURES = {
     "sir_feat_conv_tile_n": (_i, [_i]),
     "sir_feat_conv": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p]),
     "sir_feat_gemm": (_i, [_p, _p, _p, C.c_longlong, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p]),
-    "sir_feat_dwconv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
-    "sir_feat_se_scale": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "sir_feat_dwconv_pool_parts": (_i, [_i, _i, _i, _i, _i]),
+    "sir_feat_dwconv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p]),
+    "sir_feat_pool_sum": (_i, [_p, _i, _i, _i, _p, _p]),
+    "sir_feat_se_scale": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "sir_feat_maxpool": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "sir_feat_affine_act": (_i, [_p, C.c_longlong, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
     "sir_feat_avgpool2d": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

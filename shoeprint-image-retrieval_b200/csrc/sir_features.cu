@@ -462,8 +462,86 @@ __global__ void __launch_bounds__(256) dwconv_c4_kernel(const float* __restrict_
   if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
 }
 
-// global average pool: [B][H*W][C] -> [B][C]; one CTA per (image, 64-channel slab)
-__global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ in, int HW, int C, float* __restrict__ out) {
+// Depthwise 3x3 fast path (C % 4 == 0, pad 1, stride S): one thread owns 4 channels of one output column over a
+// strip of kDwRows output rows and slides a 3-row register window down the strip, so every input value is
+// fetched 3 times (its column neighbours) instead of 9, and the 9 weight vectors live in registers.  The
+// squeeze of the following SqueezeExcitation (sum over all pixels) is fused: each thread writes the sum of its
+// strip to pool_part[b][strip*Wo + ox][c]; the SE kernel adds the parts in a fixed order (deterministic).
+constexpr int kDwRows = 8;
+__device__ __forceinline__ float4 f4_fma(float4 x, float4 w, float4 a) {
+  return make_float4(fmaf(x.x, w.x, a.x), fmaf(x.y, w.y, a.y), fmaf(x.z, w.z, a.z), fmaf(x.w, w.w, a.w));
+}
+template <int S, int ACT>
+__global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restrict__ in, int B, int H, int W, int C, int Ho, int Wo,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           float* __restrict__ out, float* __restrict__ amax,
+                                                           float* __restrict__ pool_part) {
+  const int C4 = C >> 2, strips = (Ho + kDwRows - 1) / kDwRows;
+  const size_t total = (size_t)B * strips * Wo * C4;
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    size_t r = i / C4;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int strip = (int)(r % strips), b = (int)(r / strips);
+    float4 wv[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const float* img = in + (size_t)b * H * W * C + c;
+    const int ix0 = ox * S - 1;
+    auto load_row = [&](int iy, float4 (&row)[3]) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ix0 + kx;
+        row[kx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const float4*>(img + ((size_t)iy * W + ix) * C))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    const int oy0 = strip * kDwRows, oy1 = min(Ho, oy0 + kDwRows);
+    float4 r0[3], r1[3], r2[3];
+    load_row(oy0 * S - 1, r0);
+    load_row(oy0 * S, r1);
+    float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oy = oy0; oy < oy1; ++oy) {
+      load_row(oy * S + 1, r2);
+      float4 acc = bb;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        acc = f4_fma(r0[kx], wv[kx], acc);
+        acc = f4_fma(r1[kx], wv[3 + kx], acc);
+        acc = f4_fma(r2[kx], wv[6 + kx], acc);
+      }
+      float4 o;
+      if (ACT == 1) {
+        o = make_float4(__fdividef(acc.x, 1.0f + __expf(-acc.x)), __fdividef(acc.y, 1.0f + __expf(-acc.y)),
+                        __fdividef(acc.z, 1.0f + __expf(-acc.z)), __fdividef(acc.w, 1.0f + __expf(-acc.w)));
+      } else if (ACT == 2) {
+        o = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+      } else {
+        o = acc;
+      }
+      *reinterpret_cast<float4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
+      pool.x += o.x; pool.y += o.y; pool.z += o.z; pool.w += o.w;
+      local = fmaxf(local, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+      if (S == 1) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) { r0[kx] = r1[kx]; r1[kx] = r2[kx]; }
+      } else {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) r0[kx] = r2[kx];
+        if (oy + 1 < oy1) load_row((oy + 1) * S, r1);
+      }
+    }
+    if (pool_part) *reinterpret_cast<float4*>(pool_part + ((size_t)b * strips * Wo + (size_t)strip * Wo + ox) * C + c) = pool;
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0 && amax) atomic_max_nonneg(amax, local);
+}
+
+// sum over all pixels: [B][HW][C] -> part[B][1][C] (the one-part squeeze for producers without a fused pool)
+__global__ void __launch_bounds__(256) pool_sum_kernel(const float* __restrict__ in, int HW, int C, float* __restrict__ out) {
   __shared__ float part[4][64];
   const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), sub = threadIdx.x >> 6;
   float acc = 0.0f;
@@ -471,14 +549,36 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ 
     for (int p = sub; p < HW; p += 4) acc += in[((size_t)b * HW + p) * C + c];
   part[sub][threadIdx.x & 63] = acc;
   __syncthreads();
-  if (sub == 0 && c < C) out[(size_t)b * C + c] = (part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]) / (float)HW;
+  if (sub == 0 && c < C) out[(size_t)b * C + c] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------ K3
-// squeeze-excitation MLP, one CTA per image: scale = sigmoid(W2 . silu(W1 . avg + b1) + b2)
-__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ avg, int C, int S, const float* __restrict__ w1,
-                                                    const float* __restrict__ b1, const float* __restrict__ w2,
-                                                    const float* __restrict__ b2, float* __restrict__ scale) {
+// squeeze-excitation, one CTA per image: avg = sum of the pooled parts / HW (fixed order), then
+// scale = sigmoid(W2 . silu(W1 . avg + b1) + b2).  w1 [S][C], w2t [S][C] (fc2 transposed: coalesced over c).
+// avg[b][c] = (sum over parts, fixed order) / HW; one CTA per (image, 64-channel slab), 4 threads per channel
+__global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restrict__ pool_part, int parts, float inv_hw, int C,
+                                                          float* __restrict__ avg) {
+  __shared__ float part[4][64];
+  const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), sub = threadIdx.x >> 6;
+  const float* src = pool_part + (size_t)b * parts * C;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    int q = sub;
+    for (; q + 28 < parts; q += 32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += src[(size_t)(q + 4 * u) * C + c];
+    }
+    for (; q < parts; q += 4) a[0] += src[(size_t)q * C + c];
+  }
+  part[sub][threadIdx.x & 63] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (sub == 0 && c < C)
+    avg[(size_t)b * C + c] = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x])) * inv_hw;
+}
+__global__ void __launch_bounds__(1024) se_fc_kernel(const float* __restrict__ avg, int C, int S,
+                                                     const float* __restrict__ w1, const float* __restrict__ b1,
+                                                     const float* __restrict__ w2t, const float* __restrict__ b2,
+                                                     float* __restrict__ scale) {
   extern __shared__ float sh[];  // [C] avg, [S] hidden
   float* savg = sh;
   float* hid = sh + C;
@@ -495,7 +595,7 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ av
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = b2[c];
-    for (int j = 0; j < S; ++j) acc = fmaf(w2[(size_t)c * S + j], hid[j], acc);
+    for (int j = 0; j < S; ++j) acc = fmaf(w2t[(size_t)j * C + c], hid[j], acc);
     scale[(size_t)b * C + c] = 1.0f / (1.0f + expf(-acc));
   }
 }
@@ -721,29 +821,59 @@ extern "C" int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const
   return SIR_OK;
 }
 
+extern "C" int sir_feat_dwconv_pool_parts(int k, int stride, int C, int Ho, int Wo) {
+  return (k == 3 && (stride == 1 || stride == 2) && C % 4 == 0) ? ceil_div(Ho, kDwRows) * Wo : 1;
+}
+
 extern "C" int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, const float* d_w,
-                               const float* d_bias, int act, float* d_out, float* d_amax_out, void* stream) {
+                               const float* d_bias, int act, float* d_out, float* d_amax_out, float* d_pool_part, void* stream) {
   SIR_CHECK_ARG(d_in && d_w && d_bias && d_out, "sir_feat_dwconv: null pointer");
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "sir_feat_dwconv: bad shape");
+  SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_dwconv: unknown activation %d", act);
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_dwconv: empty output");
-  if (C % 4 == 0 && (((uintptr_t)d_in | (uintptr_t)d_w | (uintptr_t)d_bias | (uintptr_t)d_out) & 15) == 0)
-    dwconv_c4_kernel<<<grid_for((size_t)B * Ho * Wo * (C / 4)), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo,
-                                                                                              d_w, d_bias, act, d_out, d_amax_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool aligned = C % 4 == 0 && (((uintptr_t)d_in | (uintptr_t)d_w | (uintptr_t)d_bias | (uintptr_t)d_out | (uintptr_t)d_pool_part) & 15) == 0;
+  if (aligned && k == 3 && pad == 1 && (stride == 1 || stride == 2)) {
+    const unsigned grid = grid_for((size_t)B * ceil_div(Ho, kDwRows) * Wo * (C / 4));
+#define SIR_DW3(S_, A_) dwconv3_rows_kernel<S_, A_><<<grid, 256, 0, st>>>(d_in, B, H, W, C, Ho, Wo, d_w, d_bias, d_out, d_amax_out, d_pool_part)
+    if (stride == 1) {
+      if (act == 0) SIR_DW3(1, 0); else if (act == 1) SIR_DW3(1, 1); else SIR_DW3(1, 2);
+    } else {
+      if (act == 0) SIR_DW3(2, 0); else if (act == 1) SIR_DW3(2, 1); else SIR_DW3(2, 2);
+    }
+#undef SIR_DW3
+    SIR_LAUNCH_CHECK("dwconv3_rows_kernel");
+    return SIR_OK;
+  }
+  if (aligned)
+    dwconv_c4_kernel<<<grid_for((size_t)B * Ho * Wo * (C / 4)), 256, 0, st>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_w, d_bias, act, d_out,
+                                                                             d_amax_out);
   else
-    dwconv_kernel<<<grid_for((size_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_w,
-                                                                                        d_bias, act, d_out, d_amax_out);
+    dwconv_kernel<<<grid_for((size_t)B * Ho * Wo * C), 256, 0, st>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_w, d_bias, act, d_out, d_amax_out);
   SIR_LAUNCH_CHECK("dwconv_kernel");
+  if (d_pool_part) {  // one part per image
+    pool_sum_kernel<<<dim3((unsigned)ceil_div(C, 64), (unsigned)B), 256, 0, st>>>(d_out, Ho * Wo, C, d_pool_part);
+    SIR_LAUNCH_CHECK("pool_sum_kernel");
+  }
   return SIR_OK;
 }
 
-extern "C" int sir_feat_se_scale(const float* d_in, int B, int HW, int C, int S, const float* d_w1, const float* d_b1,
-                                 const float* d_w2, const float* d_b2, float* d_avg, float* d_scale, void* stream) {
-  SIR_CHECK_ARG(d_in && d_w1 && d_b1 && d_w2 && d_b2 && d_avg && d_scale, "sir_feat_se_scale: null pointer");
-  SIR_CHECK_ARG(B > 0 && HW > 0 && C > 0 && S > 0 && (size_t)(C + S) * 4 <= 48 * 1024, "sir_feat_se_scale: bad shape");
-  avgpool_kernel<<<dim3((unsigned)ceil_div(C, 64), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(d_in, HW, C, d_avg);
-  SIR_LAUNCH_CHECK("avgpool_kernel");
-  se_fc_kernel<<<B, 256, (size_t)(C + S) * 4, (cudaStream_t)stream>>>(d_avg, C, S, d_w1, d_b1, d_w2, d_b2, d_scale);
+extern "C" int sir_feat_pool_sum(const float* d_in, int B, int HW, int C, float* d_pool_part, void* stream) {
+  SIR_CHECK_ARG(d_in && d_pool_part && B > 0 && HW > 0 && C > 0, "sir_feat_pool_sum: bad argument");
+  pool_sum_kernel<<<dim3((unsigned)ceil_div(C, 64), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(d_in, HW, C, d_pool_part);
+  SIR_LAUNCH_CHECK("pool_sum_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_se_scale(const float* d_pool_part, int B, int parts, int HW, int C, int S, const float* d_w1, const float* d_b1,
+                                 const float* d_w2t, const float* d_b2, float* d_avg, float* d_scale, void* stream) {
+  SIR_CHECK_ARG(d_pool_part && d_w1 && d_b1 && d_w2t && d_b2 && d_avg && d_scale, "sir_feat_se_scale: null pointer");
+  const size_t se_smem = (size_t)(C + S) * 4;
+  SIR_CHECK_ARG(B > 0 && parts > 0 && HW > 0 && C > 0 && S > 0 && se_smem <= 48 * 1024, "sir_feat_se_scale: bad shape");
+  pool_reduce_kernel<<<dim3((unsigned)ceil_div(C, 64), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(d_pool_part, parts, 1.0f / (float)HW, C, d_avg);
+  SIR_LAUNCH_CHECK("pool_reduce_kernel");
+  se_fc_kernel<<<B, 1024, se_smem, (cudaStream_t)stream>>>(d_avg, C, S, d_w1, d_b1, d_w2t, d_b2, d_scale);
   SIR_LAUNCH_CHECK("se_fc_kernel");
   return SIR_OK;
 }

@@ -307,6 +307,7 @@ class _Program:
                 p.update(w_d=p["w"][:, 0].permute(1, 2, 0).contiguous().to(device), bias_d=p["bias"].to(device))
                 del p["w"]
             elif op.kind == "se":
+                p["w2"] = p["w2"].t()  # fc2 as [S][C]: coalesced over channels
                 for key in ("w1", "b1", "w2", "b2"):
                     p[key] = p[key].contiguous().to(device)
             elif op.kind == "affine" and p["scale"] is not None:
@@ -331,6 +332,9 @@ class _Program:
             for key in ("residual", "chan_scale"):
                 if op.p.get(key) is not None:
                     last_use[op.p[key]] = i
+
+        squeezed = {op.src for op in self.ops if op.kind == "se"}
+        pooled: dict[int, tuple[torch.Tensor, int]] = {}
 
         def aptr(tid: int) -> C.c_void_p:
             return C.c_void_p(amax.data_ptr() + 4 * tid)
@@ -369,13 +373,24 @@ class _Program:
             elif op.kind == "dwconv":
                 ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
                 out = torch.empty((b, ho, wo, c), dtype=torch.float32, device=dev)
+                part = None
+                if op.dst in squeezed:  # a SqueezeExcitation follows: its global sum is produced here
+                    parts = int(nat.lib.sir_feat_dwconv_pool_parts(p["k"], p["stride"], c, ho, wo))
+                    part = torch.empty((b, parts, c), dtype=torch.float32, device=dev)
+                    pooled[op.dst] = (part, parts)
                 nat.check(nat.lib.sir_feat_dwconv(_ptr(src), b, h, w, c, p["k"], p["stride"], p["pad"], _ptr(p["w_d"]),
-                                                  _ptr(p["bias_d"]), p["act"], _ptr(out), aptr(op.dst), st), "sir_feat_dwconv")
+                                                  _ptr(p["bias_d"]), p["act"], _ptr(out), aptr(op.dst), _ptr(part), st), "sir_feat_dwconv")
                 launch_counter.add()
             elif op.kind == "se":
+                if op.src in pooled:
+                    part, parts = pooled.pop(op.src)
+                else:
+                    part, parts = torch.empty((b, 1, c), dtype=torch.float32, device=dev), 1
+                    nat.check(nat.lib.sir_feat_pool_sum(_ptr(src), b, h * w, c, _ptr(part), st), "sir_feat_pool_sum")
+                    launch_counter.add()
                 avg = torch.empty((b, c), dtype=torch.float32, device=dev)
                 out = torch.empty((b, c), dtype=torch.float32, device=dev)
-                nat.check(nat.lib.sir_feat_se_scale(_ptr(src), b, h * w, c, int(p["w1"].shape[0]), _ptr(p["w1"]), _ptr(p["b1"]),
+                nat.check(nat.lib.sir_feat_se_scale(_ptr(part), b, parts, h * w, c, int(p["w1"].shape[0]), _ptr(p["w1"]), _ptr(p["b1"]),
                                                     _ptr(p["w2"]), _ptr(p["b2"]), _ptr(avg), _ptr(out), st), "sir_feat_se_scale")
                 launch_counter.add(2)
             elif op.kind == "affine":
@@ -478,7 +493,8 @@ class Model:
         self.transform = self._host_transform(gray=True)
         self.transform_rgb = self._host_transform(gray=False)
         self.program = _Program(layers, self.device)
-        self.max_batch_bytes = 2 << 30  # cap on one im2col operand
+        self.max_batch_bytes = 4 << 30  # cap on the live tensors of one layer
+        self.max_batch = 64
         self._host_clahe = os.environ.get("SIR_HOST_CLAHE", "") == "1"
 
     def _host_transform(self, *, gray: bool):
@@ -531,6 +547,8 @@ class Model:
         return out
 
     def _batch_limit(self, h: int, w: int) -> int:
+        """Images per forward pass: the largest (input + fp16 operand planes + output) of any layer within
+        ``max_batch_bytes``, at most ``max_batch`` (late layers need ~64 images to fill 148 SMs)."""
         worst = 1
         hh, ww, c = h, w, 3
         for op in self.program.ops:
@@ -538,15 +556,20 @@ class Model:
             if op.kind in ("conv", "dwconv"):
                 ho, wo = _Program._out_hw(hh, ww, p["k"], p["kw"], p["stride"], p["pad"])
                 if op.kind == "conv":
-                    worst = max(worst, ho * wo * p["kp"] * 4)
+                    operand = hh * ww * c * 4 if p["implicit"] else ho * wo * p["kp"] * 4
+                    worst = max(worst, hh * ww * c * 4 + operand + ho * wo * p["cout"] * 4)
                     c = p["cout"]
+                else:
+                    worst = max(worst, (hh * ww + ho * wo) * c * 4)
                 hh, ww = ho, wo
             elif op.kind == "maxpool":
                 hh, ww = _Program._out_hw(hh, ww, p["k"], p["k"], p["stride"], p["pad"])
             elif op.kind == "avgpool":
                 hh, ww = (hh - p["k"]) // p["stride"] + 1, (ww - p["k"]) // p["stride"] + 1
-        del c
-        return max(1, int(self.max_batch_bytes // worst))
+            elif op.kind == "alloc":
+                c = p["channels"]
+                worst = max(worst, hh * ww * c * 8)
+        return max(1, min(self.max_batch, int(self.max_batch_bytes // worst)))
 
     def get_feature_maps(self, img: np.ndarray) -> np.ndarray:
         """One image (uint8 ``[H,W]`` or ``[H,W,3]``) -> ``[C,h,w]`` float32 (``network.py:210-244``)."""

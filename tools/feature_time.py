@@ -12,7 +12,7 @@ b = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 cfg = {"model": {"type": "EfficientNetV2_M", "clahe_clip_limit": 2.0, "clahe_tile_grid_size": [8, 8]}}
 model = network.Model(cfg, block, random_init_seed=0)
 batch = np.random.default_rng(0).integers(0, 256, size=(b, 800, 300), dtype=np.uint8)
-model._forward_uint8(batch); torch.cuda.synchronize()
+model._forward_uint8(batch, apply_clahe=True); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); model._forward_uint8(batch); e1.record(); torch.cuda.synchronize()
+e0.record(); model._forward_uint8(batch, apply_clahe=True); e1.record(); torch.cuda.synchronize()
 print(f"block {block} batch {b}: {e0.elapsed_time(e1):.1f} ms -> {b / e0.elapsed_time(e1) * 1e3:.0f} images/s")
