@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "sir_common.cuh"
 #include "sir_ptx.cuh"
@@ -56,6 +57,60 @@ __device__ __forceinline__ float conv_act(float v) {
   if (ACT == 1) return __fdividef(v, 1.0f + __expf(-v));  // SiLU
   if (ACT == 2) return fmaxf(v, 0.0f);                    // ReLU
   return v;
+}
+
+// Epilogue of one 128 x BN accumulator tile: this warp owns 32 TMEM lanes (rows) and every second 16-column chunk.
+// row_off[ps]: element offset of output row (ps*8 + lane/4) of the warp's 32 rows, or -1 if outside the image.
+template <int ACT>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t tacc, float* xp, int lane, int half, int nt,
+                                                   const long long (&row_off)[4], float unscale, float& local_max) {
+  const int rs = lane >> 2, c4 = lane & 3;
+  const int n_chunks = p.BN >> 4;
+  for (int ci = half; ci < n_chunks; ci += 2) {
+    uint32_t v[16];
+    ptx::tmem_ld_32x16(tacc + ci * 16, v);
+    ptx::tmem_ld_wait();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(xp + lane * 16 + 4 * (j ^ ((lane >> 1) & 3))) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int n = nt * p.BN + ci * 16 + c4 * 4;
+    if (n < p.N) {
+      const bool full4 = n + 3 < p.N;
+      float bb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (full4) {
+        const float4 t = *reinterpret_cast<const float4*>(p.bias + n);
+        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
+      } else {
+        for (int t = 0; n + t < p.N; ++t) bb[t] = p.bias[n + t];
+      }
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        if (row_off[ps] < 0) continue;
+        const int row = ps * 8 + rs;
+        const float4 a = *reinterpret_cast<const float4*>(xp + row * 16 + 4 * (c4 ^ ((row >> 1) & 3)));
+        float o[4] = {conv_act<ACT>(fmaf(a.x, unscale, bb[0])), conv_act<ACT>(fmaf(a.y, unscale, bb[1])),
+                      conv_act<ACT>(fmaf(a.z, unscale, bb[2])), conv_act<ACT>(fmaf(a.w, unscale, bb[3]))};
+        float* dst = p.out + row_off[ps] + n;
+        if (full4) {
+          if (p.residual) {
+            const float4 rr = *reinterpret_cast<const float4*>(p.residual + row_off[ps] + n);
+            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+          }
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+        } else {
+          for (int t = 0; n + t < p.N; ++t) {
+            float ov = o[t];
+            if (p.residual) ov += p.residual[row_off[ps] + n + t];
+            dst[t] = ov;
+            local_max = fmaxf(local_max, fabsf(ov));
+          }
+        }
+      }
+    }
+  }
 }
 
 template <int ACT>
@@ -169,10 +224,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     // epilogue warps 2..9: TMEM lane quarter = warp % 4, the two warps of a quarter take alternate 16-column chunks
     const int q = warp & 3, half = (warp - 2) >> 2;
     float* xp = xpose + (warp - 2) * (32 * 16);
-    const int rs = lane >> 2, c4 = lane & 3;
+    const int rs = lane >> 2;
     const int e_total = scale_exp_from_amax(*p.amax_in) + p.w_exp;
     const float unscale = ldexpf(1.0f, -e_total);
-    const int n_chunks = p.BN >> 4;
     float local_max = 0.0f;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -190,50 +244,216 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       ptx::mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + buf * kConvAccStride + ((uint32_t)(q * 32) << 16);
-      for (int ci = half; ci < n_chunks; ci += 2) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(tacc + ci * 16, v);
-        ptx::tmem_ld_wait();
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(xp + lane * 16 + 4 * (j ^ ((lane >> 1) & 3))) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int n = nt * p.BN + ci * 16 + c4 * 4;
-        if (n < p.N) {
-          const bool full4 = n + 3 < p.N;
-          float bb[4] = {0.f, 0.f, 0.f, 0.f};
-          if (full4) {
-            const float4 t = *reinterpret_cast<const float4*>(p.bias + n);
-            bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
-          } else {
-            for (int t = 0; n + t < p.N; ++t) bb[t] = p.bias[n + t];
-          }
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            if (row_off[ps] < 0) continue;
-            const int row = ps * 8 + rs;
-            const float4 a = *reinterpret_cast<const float4*>(xp + row * 16 + 4 * (c4 ^ ((row >> 1) & 3)));
-            float o[4] = {conv_act<ACT>(fmaf(a.x, unscale, bb[0])), conv_act<ACT>(fmaf(a.y, unscale, bb[1])),
-                          conv_act<ACT>(fmaf(a.z, unscale, bb[2])), conv_act<ACT>(fmaf(a.w, unscale, bb[3]))};
-            float* dst = p.out + row_off[ps] + n;
-            if (full4) {
-              if (p.residual) {
-                const float4 rr = *reinterpret_cast<const float4*>(p.residual + row_off[ps] + n);
-                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-              }
-              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-              local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
-            } else {
-              for (int t = 0; n + t < p.N; ++t) {
-                float ov = o[t];
-                if (p.residual) ov += p.residual[row_off[ps] + n + t];
-                dst[t] = ov;
-                local_max = fmaxf(local_max, fabsf(ov));
-              }
+      conv_epilogue_tile<ACT>(p, tacc, xp, lane, half, nt, row_off, unscale, local_max);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_acc_empty(buf));
+    }
+    local_max = warp_max(local_max);
+    if (lane == 0 && p.amax_out) atomic_max_nonneg(p.amax_out, local_max);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Halo variant for k x k kernels (stride 1): the A operand of ALL taps comes from one shared-memory copy of the
+// patch plus its halo.  conv_tc_kernel fetches the shifted patch once per tap, i.e. kh*kw times, and is bound by
+// the L2 -> shared-memory feed; here one 5-D TMA box per 32-channel chunk lands the (16+kh-1) x (8+kw-1) pixel
+// halo as [slab of 8 channels][y][x][8 ch], which is the un-swizzled K-major core-matrix layout: 8 consecutive
+// pixels of a patch row are the 8 rows of a core matrix (16 B apart), the next patch row is SBO = one halo row
+// further, the next 8 channels LBO = one slab further, and tap (ky,kx) is nothing but a different start address.
+// Two patches (32 x 8 pixels) share every weight stage, which halves the weight traffic per output.
+constexpr int kHaloTW = 8, kHaloTH = 16;  // patch = 16 rows x 8 columns of output pixels
+constexpr int kHaloAStages = 3;
+constexpr int kHaloMaxBStages = 12;
+
+struct HaloParams {
+  ConvParams c;          // Ho, Wo, N, BN, n_tiles_n, taps, kw, pad, w_exp, pointers, ldc; tiles_x/tiles_y in super-tiles
+  int np;                // patches per tile (1 or 2), stacked in y
+  int hw, hh;            // halo width / height in pixels
+  int chunks32;          // 32-channel chunks of the (16-padded) input channels
+  int cp16;              // input channels padded to 16
+  int b_stages;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                 const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const HaloParams hp) {
+  const ConvParams& p = hp.c;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t slab_bytes = (uint32_t)hp.hw * hp.hh * 16;           // one 8-channel slab of one halo
+  const uint32_t plane_bytes = 4 * slab_bytes;                        // 32 channels
+  const uint32_t a_stage = (uint32_t)hp.np * 2 * plane_bytes;         // np halos x (hi, lo)
+  const uint32_t a_stage_al = (a_stage + 1023u) & ~1023u;
+  const uint32_t b_half = (uint32_t)p.BN * 32, b_stage = 2 * b_half;  // BN rows x 16 channels x 2 B, hi + lo
+  const uint32_t b_base = base + kHaloAStages * a_stage_al;
+  const uint32_t bar0 = b_base + hp.b_stages * b_stage;
+  auto bar_a_full = [&](int i) { return bar0 + 8u * i; };
+  auto bar_a_empty = [&](int i) { return bar0 + 8u * (kHaloAStages + i); };
+  auto bar_b_full = [&](int i) { return bar0 + 8u * (2 * kHaloAStages + i); };
+  auto bar_b_empty = [&](int i) { return bar0 + 8u * (2 * kHaloAStages + kHaloMaxBStages + i); };
+  auto bar_acc_full = [&](int i) { return bar0 + 8u * (2 * kHaloAStages + 2 * kHaloMaxBStages + i); };
+  auto bar_acc_empty = [&](int i) { return bar0 + 8u * (2 * kHaloAStages + 2 * kHaloMaxBStages + 2 + i); };
+  const uint32_t slot_off = (bar0 - base) + 8u * (2 * kHaloAStages + 2 * kHaloMaxBStages + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + slot_off);
+  float* xpose = reinterpret_cast<float*>(base_ptr + slot_off + 16);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kHaloAStages; ++i) {
+      ptx::mbar_init(bar_a_full(i), 1);
+      ptx::mbar_init(bar_a_empty(i), 1);
+    }
+    for (int i = 0; i < hp.b_stages; ++i) {
+      ptx::mbar_init(bar_b_full(i), 1);
+      ptx::mbar_init(bar_b_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_acc_full(i), 1);
+      ptx::mbar_init(bar_acc_empty(i), 8);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tm_xhi);
+    ptx::prefetch_tmap(&tm_xlo);
+    ptx::prefetch_tmap(&tm_whi);
+    ptx::prefetch_tmap(&tm_wlo);
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int& nt, int& px, int& py, int& b) {
+    nt = tile % p.n_tiles_n;
+    const int mt = tile / p.n_tiles_n;
+    px = mt % p.tiles_x;
+    const int r1 = mt / p.tiles_x;
+    py = r1 % p.tiles_y;
+    b = r1 / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // items = (tile, chunk) in order; the halo of item i+1 is requested before the weight stages of item i
+      uint32_t a_it = 0, b_it = 0;
+      auto load_halo = [&](int tile, int chunk) {
+        int nt, px, py, b;
+        decode(tile, nt, px, py, b);
+        const uint32_t slot = a_it % kHaloAStages;
+        ptx::mbar_wait(bar_a_empty(slot), ((a_it / kHaloAStages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar_a_full(slot), a_stage);
+        const uint32_t dst = base + slot * a_stage_al;
+        for (int q = 0; q < hp.np; ++q) {
+          const int x0 = px * kHaloTW - p.pad, y0 = (py * hp.np + q) * kHaloTH - p.pad;
+          ptx::tma_load_5d(dst + q * 2 * plane_bytes, &tm_xhi, bar_a_full(slot), 0, x0, y0, chunk * 4, b);
+          ptx::tma_load_5d(dst + q * 2 * plane_bytes + plane_bytes, &tm_xlo, bar_a_full(slot), 0, x0, y0, chunk * 4, b);
+        }
+        ++a_it;
+      };
+      int tile = blockIdx.x;
+      if (tile < p.total_tiles) load_halo(tile, 0);
+      for (; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles_n) * p.BN;
+        for (int chunk = 0; chunk < hp.chunks32; ++chunk) {
+          if (chunk + 1 < hp.chunks32)
+            load_halo(tile, chunk + 1);
+          else if (tile + (int)gridDim.x < p.total_tiles)
+            load_halo(tile + gridDim.x, 0);
+          const int k16s = min(2, (hp.cp16 - chunk * 32) >> 4);
+          for (int tap = 0; tap < p.taps; ++tap) {
+            for (int kk = 0; kk < k16s; ++kk, ++b_it) {
+              const uint32_t slot = b_it % hp.b_stages;
+              ptx::mbar_wait(bar_b_empty(slot), ((b_it / hp.b_stages) & 1) ^ 1);
+              ptx::mbar_arrive_expect_tx(bar_b_full(slot), b_stage);
+              const int k0 = tap * hp.cp16 + chunk * 32 + kk * 16;
+              ptx::tma_load_2d(b_base + slot * b_stage, &tm_whi, bar_b_full(slot), k0, n0);
+              ptx::tma_load_2d(b_base + slot * b_stage + b_half, &tm_wlo, bar_b_full(slot), k0, n0);
             }
           }
         }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_f16(kConvBM, p.BN);
+      const uint32_t a_sbo = (uint32_t)hp.hw * 16, a_lbo = slab_bytes;
+      uint32_t a_it = 0, b_it = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        ptx::mbar_wait(bar_acc_empty(buf), ((lt >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * kConvAccStride;
+        uint32_t accumulate = 0;
+        for (int chunk = 0; chunk < hp.chunks32; ++chunk, ++a_it) {
+          const uint32_t aslot = a_it % kHaloAStages;
+          ptx::mbar_wait(bar_a_full(aslot), (a_it / kHaloAStages) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a0 = base + aslot * a_stage_al;
+          const int k16s = min(2, (hp.cp16 - chunk * 32) >> 4);
+          int ky = 0, kx = 0;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const uint32_t tap_off = (uint32_t)(ky * hp.hw + kx) * 16;
+            for (int kk = 0; kk < k16s; ++kk, ++b_it) {
+              const uint32_t slot = b_it % hp.b_stages;
+              ptx::mbar_wait(bar_b_full(slot), (b_it / hp.b_stages) & 1);
+              ptx::tc_fence_after();
+              const uint32_t b_hi = b_base + slot * b_stage;
+              const uint64_t db_hi = ptx::make_smem_desc(b_hi, 16, 256, 6);
+              const uint64_t db_lo = ptx::make_smem_desc(b_hi + b_half, 16, 256, 6);
+              for (int q = 0; q < hp.np; ++q) {
+                const uint32_t a_hi = a0 + q * 2 * plane_bytes + tap_off + (uint32_t)kk * 2 * slab_bytes;
+                const uint64_t da_hi = ptx::make_smem_desc(a_hi, a_lbo, a_sbo, 0);
+                const uint64_t da_lo = ptx::make_smem_desc(a_hi + plane_bytes, a_lbo, a_sbo, 0);
+                const uint32_t d = acc + q * p.BN;
+                ptx::mma_f16_ss(d, da_hi, db_hi, idesc, accumulate);
+                ptx::mma_f16_ss(d, da_lo, db_hi, idesc, 1);
+                ptx::mma_f16_ss(d, da_hi, db_lo, idesc, 1);
+              }
+              accumulate = 1;
+              ptx::tc_commit(bar_b_empty(slot));
+            }
+            if (++kx == p.kw) {
+              kx = 0;
+              ++ky;
+            }
+          }
+          ptx::tc_commit(bar_a_empty(aslot));
+        }
+        ptx::tc_commit(bar_acc_full(buf));
+      }
+    }
+  } else {
+    const int q4 = warp & 3, half = (warp - 2) >> 2;
+    float* xp = xpose + (warp - 2) * (32 * 16);
+    const int rs = lane >> 2;
+    const int e_total = scale_exp_from_amax(*p.amax_in) + p.w_exp;
+    const float unscale = ldexpf(1.0f, -e_total);
+    float local_max = 0.0f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      int nt, px, py, b;
+      decode(tile, nt, px, py, b);
+      ptx::mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int q = 0; q < hp.np; ++q) {
+        long long row_off[4];
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const int r = q4 * 32 + ps * 8 + rs;
+          const int oy = (py * hp.np + q) * kHaloTH + (r >> 3), ox = px * kHaloTW + (r & 7);
+          row_off[ps] = (oy < p.Ho && ox < p.Wo) ? (((long long)b * p.Ho + oy) * p.Wo + ox) * p.ldc : -1;
+        }
+        const uint32_t tacc = tmem_base + buf * kConvAccStride + q * p.BN + ((uint32_t)(q4 * 32) << 16);
+        conv_epilogue_tile<ACT>(p, tacc, xp, lane, half, nt, row_off, unscale, local_max);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -261,6 +481,7 @@ EncodeTiledFn conv_encode_fn() {
   }
   return fn;
 }
+// bk: 32 -> 64-byte swizzle, 16 -> 32-byte swizzle, 0 -> no swizzle
 int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, int bk,
            const char* what) {
   EncodeTiledFn fn = conv_encode_fn();
@@ -268,9 +489,10 @@ int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, c
     set_error("cuTensorMapEncodeTiled entry point not available");
     return SIR_E_CUDA;
   }
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : bk == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
@@ -302,6 +524,61 @@ int conv_tile_n(int N) {
   return best;
 }
 
+}  // namespace sir
+
+namespace sir {
+namespace {
+// Column tile for the halo kernel: np patches share a tile, so np * BN accumulator columns per TMEM buffer (<= 256).
+int halo_tile_n(int N, int np) {
+  int best = 16;
+  long best_cols = -1;
+  for (int bn = 16; bn * np <= 256; bn += 16) {
+    const long cols = (long)ceil_div(N, bn) * bn;
+    if (best_cols < 0 || cols < best_cols || (cols == best_cols && bn > best)) {
+      best = bn;
+      best_cols = cols;
+    }
+  }
+  return best;
+}
+struct HaloPlan {
+  HaloParams hp;
+  size_t smem;
+  double l2_bytes;  // modelled L2 -> shared-memory traffic of the whole launch
+  bool ok;
+};
+HaloPlan plan_halo(int B, int H, int W, int C, int kh, int kw, int pad, int N, int cp16) {
+  HaloPlan pl{};
+  HaloParams& hp = pl.hp;
+  ConvParams& p = hp.c;
+  p.Ho = H + 2 * pad - kh + 1;
+  p.Wo = W + 2 * pad - kw + 1;
+  hp.np = p.Ho > kHaloTH ? 2 : 1;
+  p.N = N;
+  p.BN = halo_tile_n(N, hp.np);
+  p.n_tiles_n = ceil_div(N, p.BN);
+  p.taps = kh * kw;
+  p.kw = kw;
+  p.pad = pad;
+  hp.hw = kHaloTW + kw - 1;
+  hp.hh = kHaloTH + kh - 1;
+  hp.cp16 = cp16;
+  hp.chunks32 = ceil_div(cp16, 32);
+  p.tiles_x = ceil_div(p.Wo, kHaloTW);
+  p.tiles_y = ceil_div(p.Ho, kHaloTH * hp.np);
+  const long long total = (long long)B * p.tiles_x * p.tiles_y * p.n_tiles_n;
+  const uint32_t a_stage = ((uint32_t)hp.np * 2 * 4 * hp.hw * hp.hh * 16 + 1023u) & ~1023u;
+  const uint32_t b_stage = (uint32_t)p.BN * 64;
+  const uint32_t tail = 8u * (2 * kHaloAStages + 2 * kHaloMaxBStages + 4) + 16 + 8 * 32 * 16 * 4;
+  const long long room = 220ll * 1024 - 1024 - tail - (long long)kHaloAStages * a_stage;
+  hp.b_stages = (int)std::min<long long>(kHaloMaxBStages, room / b_stage);
+  pl.ok = total < (1ll << 31) && hp.b_stages >= 4 && hp.hw * 16 < (1 << 18) && 4 * hp.hw * hp.hh * 16 < (1 << 18);
+  p.total_tiles = (int)total;
+  pl.smem = 1024 + (size_t)kHaloAStages * a_stage + (size_t)hp.b_stages * b_stage + tail;
+  pl.l2_bytes = (double)total * ((double)hp.chunks32 * hp.np * 2 * 4 * hp.hw * hp.hh * 16 + (double)p.taps * (cp16 / 16) * b_stage);
+  return pl;
+}
+}  // namespace
 }  // namespace sir
 
 using namespace sir;
@@ -372,6 +649,57 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
   p.stages = std::min<int>(kConvMaxStages, (int)((220u * 1024 - 1024 - tail) / stage_bytes));
   SIR_CHECK_ARG(p.stages >= 2, "sir_feat_conv: tile does not fit shared memory");
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail;
+
+  if (p.taps > 1 && (p.chunks * bk) % 16 == 0) {
+    HaloPlan pl = plan_halo(B, H, W, C, kh, kw, pad, N, p.chunks * bk);
+    const double std_bytes = (double)total * p.taps * p.chunks * stage_bytes;
+    static const char* force = getenv("SIR_CONV_HALO");  // "0" / "1" force the choice (testing)
+    const bool want = force ? force[0] == '1' : pl.l2_bytes < 0.8 * std_bytes;
+    if (pl.ok && want && n_rows_alloc >= pl.hp.c.n_tiles_n * pl.hp.c.BN) {
+      HaloParams& hp = pl.hp;
+      hp.c.w_exp = w_exp;
+      hp.c.amax_in = d_amax_in;
+      hp.c.bias = d_bias;
+      hp.c.residual = d_residual;
+      hp.c.out = d_out;
+      hp.c.amax_out = d_amax_out;
+      hp.c.ldc = ldc;
+      CUtensorMap hxh, hxl, hwh, hwl;
+      {
+        cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)B};
+        cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[5] = {8, (cuuint32_t)hp.hw, (cuuint32_t)hp.hh, 4, 1};
+        int rc = encode(&hxh, d_xhi, 5, dims, strides, box, 0, "activation hi (halo)");
+        if (rc) return rc;
+        rc = encode(&hxl, d_xlo, 5, dims, strides, box, 0, "activation lo (halo)");
+        if (rc) return rc;
+      }
+      {
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)n_rows_alloc};
+        cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+        cuuint32_t box[2] = {16, (cuuint32_t)hp.c.BN};
+        int rc = encode(&hwh, d_whi, 2, dims, strides, box, 16, "weights hi (halo)");
+        if (rc) return rc;
+        rc = encode(&hwl, d_wlo, 2, dims, strides, box, 16, "weights lo (halo)");
+        if (rc) return rc;
+      }
+      static thread_local bool halo_configured[3] = {false, false, false};
+      const void* hfn = act == 0 ? (const void*)conv_halo_kernel<0> : act == 1 ? (const void*)conv_halo_kernel<1> : (const void*)conv_halo_kernel<2>;
+      if (!halo_configured[act]) {
+        SIR_CUDA(cudaFuncSetAttribute(hfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024)));
+        halo_configured[act] = true;
+      }
+      const unsigned hgrid = (unsigned)std::min<long long>(hp.c.total_tiles, sm_count());
+      if (act == 0)
+        conv_halo_kernel<0><<<hgrid, kConvThreads, pl.smem, (cudaStream_t)stream>>>(hxh, hxl, hwh, hwl, hp);
+      else if (act == 1)
+        conv_halo_kernel<1><<<hgrid, kConvThreads, pl.smem, (cudaStream_t)stream>>>(hxh, hxl, hwh, hwl, hp);
+      else
+        conv_halo_kernel<2><<<hgrid, kConvThreads, pl.smem, (cudaStream_t)stream>>>(hxh, hxl, hwh, hwl, hp);
+      SIR_LAUNCH_CHECK("conv_halo_kernel");
+      return SIR_OK;
+    }
+  }
 
   CUtensorMap txh, txl, twh, twl;
   {
