@@ -207,12 +207,18 @@ int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int 
  * (sir_feat_im2col_split with a 1x1 kernel and Kp = C), C % 8 == 0.  Weights [n_rows_alloc][taps*Cp] fp16 hi/lo with
  * k = (ky*kw + kx)*Cp + c, Cp = C rounded up to bk (16 or 32), rows zero padded to a multiple of
  * sir_feat_conv_tile_n(N).  A GEMM over an explicit [M][K] matrix is the call with B=H=1, W=M, C=K, kh=kw=1.
+ * Chaining without a split pass: with d_out_hi/d_out_lo the epilogue also (or only, d_out = NULL) writes the
+ * result as the next convolution's operand planes [pixels][N] (N % 8 == 0), scaled by 2^e with
+ * e = 15 - ceil(log2(amax_in*bound_mult + bound_add + amax_res)), an a-priori bound of |out| the caller derives
+ * from the weights (max row L1 norm, max |bias|); e goes to *d_exp_out and is handed to the consumer as d_exp_in
+ * (NULL = planes from sir_feat_im2col_split, scaled from the measured amax).
  * Replaces the torch Conv2d/BatchNorm/SiLU modules the reference runs at network.py:234-235. */
 int sir_feat_conv_tile_n(int N);
 int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
                   int kw, int pad, int bk, const uint16_t* d_whi, const uint16_t* d_wlo, int N, int n_rows_alloc, int w_exp,
                   const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
-                  void* stream);
+                  const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
+                  float bound_add, const float* d_amax_res, void* stream);
 int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
                   const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
                   const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream);

@@ -45,12 +45,32 @@ struct ConvParams {
   int stages;
   int w_exp;
   const float* amax_in;
+  const int* exp_in;      // exponent the input planes were written with; NULL: derived from amax_in (split pass)
   const float* bias;
   const float* residual;
-  float* out;
+  float* out;             // float32 output (may be NULL when only the operand planes are wanted)
   float* amax_out;
   int ldc;
+  __half* out_hi;         // optional: the output again as fp16 hi/lo operand planes [pixels][N] for the next convolution
+  __half* out_lo;
+  int* exp_out;           // exponent used for those planes (written by CTA 0)
+  float bound_mult, bound_add;  // |out| <= amax_in * bound_mult + bound_add (+ amax_res): a-priori bound -> plane exponent
+  const float* amax_res;
 };
+
+// Input-plane exponent and the un-scale factor of the accumulator.
+__device__ __forceinline__ float conv_unscale(const ConvParams& p) {
+  const int e_in = p.exp_in ? *p.exp_in : scale_exp_from_amax(*p.amax_in);
+  return ldexpf(1.0f, -(e_in + p.w_exp));
+}
+// Exponent e with bound * 2^e < 2^15 (fp16 planes cannot overflow); the bound only uses values final before the launch.
+__device__ __forceinline__ int conv_plane_exp(const ConvParams& p) {
+  const float bound = fmaf(*p.amax_in, p.bound_mult, p.bound_add) + (p.amax_res ? *p.amax_res : 0.0f);
+  if (!(bound > 0.0f) || !isfinite(bound)) return 0;
+  int ex;
+  (void)frexpf(bound, &ex);
+  return max(-100, min(100, 15 - ex));
+}
 
 template <int ACT>
 __device__ __forceinline__ float conv_act(float v) {
@@ -60,10 +80,10 @@ __device__ __forceinline__ float conv_act(float v) {
 }
 
 // Epilogue of one 128 x BN accumulator tile: this warp owns 32 TMEM lanes (rows) and every second 16-column chunk.
-// row_off[ps]: element offset of output row (ps*8 + lane/4) of the warp's 32 rows, or -1 if outside the image.
+// pix[ps]: output pixel index of row (ps*8 + lane/4) of the warp's 32 rows, or -1 if outside the image.
 template <int ACT>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t tacc, float* xp, int lane, int half, int nt,
-                                                   const long long (&row_off)[4], float unscale, float& local_max) {
+                                                   const long long (&pix)[4], float unscale, float oscale, float& local_max) {
   const int rs = lane >> 2, c4 = lane & 3;
   const int n_chunks = p.BN >> 4;
   for (int ci = half; ci < n_chunks; ci += 2) {
@@ -87,24 +107,38 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
       }
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
-        if (row_off[ps] < 0) continue;
+        if (pix[ps] < 0) continue;
+        const long long row_off = pix[ps] * p.ldc;
         const int row = ps * 8 + rs;
         const float4 a = *reinterpret_cast<const float4*>(xp + row * 16 + 4 * (c4 ^ ((row >> 1) & 3)));
         float o[4] = {conv_act<ACT>(fmaf(a.x, unscale, bb[0])), conv_act<ACT>(fmaf(a.y, unscale, bb[1])),
                       conv_act<ACT>(fmaf(a.z, unscale, bb[2])), conv_act<ACT>(fmaf(a.w, unscale, bb[3]))};
-        float* dst = p.out + row_off[ps] + n;
+        float* dst = p.out + row_off + n;
         if (full4) {
           if (p.residual) {
-            const float4 rr = *reinterpret_cast<const float4*>(p.residual + row_off[ps] + n);
+            const float4 rr = *reinterpret_cast<const float4*>(p.residual + row_off + n);
             o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
           }
-          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.out) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.out_hi) {  // the same values as the next convolution's operand planes (N % 8 == 0 guaranteed by the host)
+            __align__(8) __half hi[4];
+            __align__(8) __half lo[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float sv = o[t] * oscale;
+              hi[t] = __float2half_rn(sv);
+              lo[t] = __float2half_rn(sv - __half2float(hi[t]));
+            }
+            const long long so = pix[ps] * p.N + n;
+            *reinterpret_cast<uint2*>(p.out_hi + so) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(p.out_lo + so) = *reinterpret_cast<const uint2*>(lo);
+          }
           local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
         } else {
           for (int t = 0; n + t < p.N; ++t) {
             float ov = o[t];
-            if (p.residual) ov += p.residual[row_off[ps] + n + t];
-            dst[t] = ov;
+            if (p.residual) ov += p.residual[row_off + n + t];
+            if (p.out) dst[t] = ov;
             local_max = fmaxf(local_max, fabsf(ov));
           }
         }
@@ -225,8 +259,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     const int q = warp & 3, half = (warp - 2) >> 2;
     float* xp = xpose + (warp - 2) * (32 * 16);
     const int rs = lane >> 2;
-    const int e_total = scale_exp_from_amax(*p.amax_in) + p.w_exp;
-    const float unscale = ldexpf(1.0f, -e_total);
+    const float unscale = conv_unscale(p);
+    float oscale = 1.0f;
+    if (p.out_hi) {
+      const int e_out = conv_plane_exp(p);
+      oscale = ldexpf(1.0f, e_out);
+      if (blockIdx.x == 0 && threadIdx.x == 64) *p.exp_out = e_out;
+    }
     float local_max = 0.0f;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -234,17 +273,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
       const int px = mt % p.tiles_x, r1 = mt / p.tiles_x;
       const int py = r1 % p.tiles_y, b = r1 / p.tiles_y;
-      long long row_off[4];  // element offset of the 4 rows this lane stores per chunk; -1 = outside the image
+      long long pix[4];  // output pixel of the 4 rows this lane stores per chunk; -1 = outside the image
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
         const int r = q * 32 + ps * 8 + rs;
         const int oy = py * p.TH + (r >> p.tw_log2), ox = px * TW + (r & (TW - 1));
-        row_off[ps] = (oy < p.Ho && ox < p.Wo) ? (((long long)b * p.Ho + oy) * p.Wo + ox) * p.ldc : -1;
+        pix[ps] = (oy < p.Ho && ox < p.Wo) ? ((long long)b * p.Ho + oy) * p.Wo + ox : -1;
       }
       ptx::mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + buf * kConvAccStride + ((uint32_t)(q * 32) << 16);
-      conv_epilogue_tile<ACT>(p, tacc, xp, lane, half, nt, row_off, unscale, local_max);
+      conv_epilogue_tile<ACT>(p, tacc, xp, lane, half, nt, pix, unscale, oscale, local_max);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_acc_empty(buf));
@@ -434,8 +473,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
     const int q4 = warp & 3, half = (warp - 2) >> 2;
     float* xp = xpose + (warp - 2) * (32 * 16);
     const int rs = lane >> 2;
-    const int e_total = scale_exp_from_amax(*p.amax_in) + p.w_exp;
-    const float unscale = ldexpf(1.0f, -e_total);
+    const float unscale = conv_unscale(p);
+    float oscale = 1.0f;
+    if (p.out_hi) {
+      const int e_out = conv_plane_exp(p);
+      oscale = ldexpf(1.0f, e_out);
+      if (blockIdx.x == 0 && threadIdx.x == 64) *p.exp_out = e_out;
+    }
     float local_max = 0.0f;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -445,15 +489,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
       ptx::mbar_wait(bar_acc_full(buf), (lt >> 1) & 1);
       ptx::tc_fence_after();
       for (int q = 0; q < hp.np; ++q) {
-        long long row_off[4];
+        long long pix[4];
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) {
           const int r = q4 * 32 + ps * 8 + rs;
           const int oy = (py * hp.np + q) * kHaloTH + (r >> 3), ox = px * kHaloTW + (r & 7);
-          row_off[ps] = (oy < p.Ho && ox < p.Wo) ? (((long long)b * p.Ho + oy) * p.Wo + ox) * p.ldc : -1;
+          pix[ps] = (oy < p.Ho && ox < p.Wo) ? ((long long)b * p.Ho + oy) * p.Wo + ox : -1;
         }
         const uint32_t tacc = tmem_base + buf * kConvAccStride + q * p.BN + ((uint32_t)(q4 * 32) << 16);
-        conv_epilogue_tile<ACT>(p, tacc, xp, lane, half, nt, row_off, unscale, local_max);
+        conv_epilogue_tile<ACT>(p, tacc, xp, lane, half, nt, pix, unscale, oscale, local_max);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -588,8 +632,12 @@ extern "C" int sir_feat_conv_tile_n(int N) { return N > 0 ? conv_tile_n(N) : 0; 
 extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
                              int kw, int pad, int bk, const uint16_t* d_whi, const uint16_t* d_wlo, int N, int n_rows_alloc, int w_exp,
                              const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
-                             void* stream) {
-  SIR_CHECK_ARG(d_xhi && d_xlo && d_whi && d_wlo && d_amax_in && d_bias && d_out, "sir_feat_conv: null pointer");
+                             const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
+                             float bound_add, const float* d_amax_res, void* stream) {
+  SIR_CHECK_ARG(d_xhi && d_xlo && d_whi && d_wlo && d_amax_in && d_bias && (d_out || d_out_hi), "sir_feat_conv: null pointer");
+  SIR_CHECK_ARG(!d_out_hi || (d_out_lo && d_exp_out && N % 8 == 0 && ((uintptr_t)d_out_hi & 15) == 0 && ((uintptr_t)d_out_lo & 15) == 0 &&
+                              bound_mult >= 0.0f && bound_add >= 0.0f),
+                "sir_feat_conv: operand-plane output needs d_out_lo, d_exp_out, N %% 8 == 0 and a non-negative bound");
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && kh > 0 && kw > 0 && pad >= 0 && N > 0 && ldc >= N,
                 "sir_feat_conv: bad shape B=%d H=%d W=%d C=%d (C must be a multiple of 8) k=%dx%d N=%d ldc=%d", B, H, W, C, kh, kw, N, ldc);
   SIR_CHECK_ARG(bk == 16 || bk == 32, "sir_feat_conv: bk must be 16 or 32, got %d", bk);
@@ -603,6 +651,8 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
   p.n_tiles_n = ceil_div(N, p.BN);
   SIR_CHECK_ARG(n_rows_alloc >= p.n_tiles_n * p.BN, "sir_feat_conv: weight matrix needs %d zero-padded rows, has %d", p.n_tiles_n * p.BN,
                 n_rows_alloc);
+  SIR_CHECK_ARG(d_out || N % 4 == 0, "sir_feat_conv: plane-only output needs N %% 4 == 0");
+  SIR_CHECK_ARG(!d_residual || !d_out_hi || d_amax_res, "sir_feat_conv: residual + operand planes need d_amax_res");
   SIR_CHECK_ARG(((uintptr_t)d_bias & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ldc % 4 == 0 && (!d_residual || ((uintptr_t)d_residual & 15) == 0) &&
                     ((uintptr_t)d_xhi & 15) == 0 && ((uintptr_t)d_xlo & 15) == 0 && ((uintptr_t)d_whi & 15) == 0 && ((uintptr_t)d_wlo & 15) == 0,
                 "sir_feat_conv: operands must be 16-byte aligned and ldc a multiple of 4");
@@ -639,11 +689,18 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
   p.total_tiles = (int)total;
   p.w_exp = w_exp;
   p.amax_in = d_amax_in;
+  p.exp_in = d_exp_in;
   p.bias = d_bias;
   p.residual = d_residual;
   p.out = d_out;
   p.amax_out = d_amax_out;
   p.ldc = ldc;
+  p.out_hi = (__half*)d_out_hi;
+  p.out_lo = (__half*)d_out_lo;
+  p.exp_out = d_exp_out;
+  p.bound_mult = bound_mult;
+  p.bound_add = bound_add;
+  p.amax_res = d_residual ? d_amax_res : nullptr;
   const uint32_t stage_bytes = (uint32_t)(2 * kConvBM + 2 * p.BN) * bk * 2;
   const uint32_t tail = 8u * (2 * kConvMaxStages + 4) + 16 + 8 * 32 * 16 * 4;
   p.stages = std::min<int>(kConvMaxStages, (int)((220u * 1024 - 1024 - tail) / stage_bytes));
@@ -659,11 +716,18 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
       HaloParams& hp = pl.hp;
       hp.c.w_exp = w_exp;
       hp.c.amax_in = d_amax_in;
+      hp.c.exp_in = d_exp_in;
       hp.c.bias = d_bias;
       hp.c.residual = d_residual;
       hp.c.out = d_out;
       hp.c.amax_out = d_amax_out;
       hp.c.ldc = ldc;
+      hp.c.out_hi = p.out_hi;
+      hp.c.out_lo = p.out_lo;
+      hp.c.exp_out = d_exp_out;
+      hp.c.bound_mult = bound_mult;
+      hp.c.bound_add = bound_add;
+      hp.c.amax_res = p.amax_res;
       CUtensorMap hxh, hxl, hwh, hwl;
       {
         cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)B};

@@ -285,6 +285,9 @@ class _Program:
                 bn = int(nat.lib.sir_feat_conv_tile_n(cout))
                 rows = (cout + bn - 1) // bn * bn
                 w = p["w"].permute(0, 2, 3, 1)  # [cout][ky][kx][cin]
+                # |out| <= amax_in * max_n sum|w[n]| + max|bias| (SiLU/ReLU do not grow it): a-priori scale of emitted planes
+                p["bound_mult"] = float(p["w"].double().abs().flatten(1).sum(1).max()) * (1.0 + 1e-5)
+                p["bound_add"] = float(p["bias"].abs().max()) * (1.0 + 1e-5)
                 implicit = p["stride"] == 1 and cin % 8 == 0
                 if implicit:  # K = (tap, channel) with the channels of a tap padded to the K step
                     bk = 32 if cin % 32 == 0 else 16 if cin % 16 == 0 else 32
@@ -313,6 +316,22 @@ class _Program:
             elif op.kind == "affine" and p["scale"] is not None:
                 p["scale"], p["shift"] = p["scale"].to(device), p["shift"].to(device)
 
+        # Which convolution outputs are handed on as fp16 operand planes (written by the producer's epilogue, no
+        # split pass) and which are (also) needed in float32.
+        def takes_planes(u: _Op) -> bool:
+            return u.kind == "conv" and u.p["implicit"] and u.p["chan_scale"] is None
+
+        for op in self.ops:
+            if op.kind != "conv":
+                continue
+            t = op.dst
+            plane_users = [u for u in self.ops if u.src == t and takes_planes(u)]
+            other = t == self.out_id or any(
+                (u.src == t and not takes_planes(u)) or u.p.get("residual") == t or u.p.get("chan_scale") == t for u in self.ops)
+            ok = op.p["c_off"] is None and op.p["cout"] % 8 == 0 and os.environ.get("SIR_NO_PLANE_CHAIN", "") != "1"
+            op.p["emit_planes"] = bool(plane_users) and ok
+            op.p["emit_f32"] = other or not op.p["emit_planes"]
+
     @staticmethod
     def _out_hw(h: int, w: int, k: int, kw: int, s: int, pd: int) -> tuple[int, int]:
         return (h + 2 * pd - k) // s + 1, (w + 2 * pd - kw) // s + 1
@@ -335,6 +354,8 @@ class _Program:
 
         squeezed = {op.src for op in self.ops if op.kind == "se"}
         pooled: dict[int, tuple[torch.Tensor, int]] = {}
+        planes: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}  # tensor id -> fp16 hi/lo operand planes from its producer
+        exps = torch.zeros(self.n_tensors, dtype=torch.int32, device=dev)
 
         def aptr(tid: int) -> C.c_void_p:
             return C.c_void_p(amax.data_ptr() + 4 * tid)
@@ -349,12 +370,18 @@ class _Program:
                 cs = tensors[p["chan_scale"]] if p["chan_scale"] is not None else None
                 res = tensors[p["residual"]] if p["residual"] is not None else None
                 if p["c_off"] is None:
-                    out = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float32, device=dev)
-                    out_ptr, ldc = _ptr(out), p["cout"]
+                    out = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float32, device=dev if p["emit_f32"] else "meta")
+                    out_ptr, ldc = (_ptr(out) if p["emit_f32"] else None), p["cout"]
                 else:  # growth channels of a dense layer go straight into the block's buffer
                     out = tensors[op.dst]
                     out_ptr, ldc = C.c_void_p(out.data_ptr() + 4 * p["c_off"]), int(out.shape[3])
-                if p["implicit"]:  # split once into fp16 hi/lo NHWC planes; the kernel gathers the taps itself
+                exp_in = None
+                if p["implicit"] and cs is None and op.src in planes:  # operand planes came from the producer's epilogue
+                    ahi, alo = planes[op.src]
+                    exp_in = C.c_void_p(exps.data_ptr() + 4 * op.src)
+                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"])
+                    launch_counter.add(-1)
+                elif p["implicit"]:  # split once into fp16 hi/lo NHWC planes; the kernel gathers the taps itself
                     ahi = torch.empty((b, h, w, c), dtype=torch.float16, device=dev)
                     alo = torch.empty_like(ahi)
                     nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, 1, 1, 1, 0, _ptr(cs), c, _ptr(ahi), _ptr(alo), st),
@@ -366,9 +393,17 @@ class _Program:
                     nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
                                                             _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
                     geom = (1, 1, m, p["kp"], 1, 1, 0)
+                ohi = olo = exp_out = None
+                if p["emit_planes"]:
+                    ohi = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float16, device=dev)
+                    olo = torch.empty_like(ohi)
+                    planes[op.dst] = (ohi, olo)
+                    exp_out = C.c_void_p(exps.data_ptr() + 4 * op.dst)
                 nat.check(nat.lib.sir_feat_conv(_ptr(ahi), _ptr(alo), aptr(op.src), *geom, p["bk"], _ptr(p["whi"]), _ptr(p["wlo"]),
                                                 p["cout"], p["rows"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
-                                                out_ptr, ldc, aptr(op.dst), st), "sir_feat_conv")
+                                                out_ptr, ldc, aptr(op.dst), exp_in, _ptr(ohi), _ptr(olo), exp_out, p["bound_mult"],
+                                                p["bound_add"], aptr(p["residual"]) if p["residual"] is not None else None, st),
+                          "sir_feat_conv")
                 launch_counter.add(2)
             elif op.kind == "dwconv":
                 ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
@@ -421,6 +456,7 @@ class _Program:
             tensors[op.dst] = out
             for tid in [t for t, lu in last_use.items() if lu == i and t != self.out_id]:
                 tensors.pop(tid, None)
+                planes.pop(tid, None)
         return tensors[self.out_id]
 
 
