@@ -222,6 +222,12 @@ int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_a
 int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
                   const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
                   const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream);
+/* sir_feat_conv_c3k3: 3x3 Conv2d of a 3-channel NHWC image (the stem, K = 27) + bias + activation in float32 on the
+ * CUDA cores; weights [27][Cout] with row = (ky*3 + kx)*3 + c, Cout % 8 == 0.  Optional operand-plane output as in
+ * sir_feat_conv. */
+int sir_feat_conv_c3k3(const float* d_in, const float* d_amax_in, int B, int H, int W, int stride, int pad, const float* d_w,
+                       const float* d_bias, int Cout, int act, float* d_out, float* d_amax_out, uint16_t* d_out_hi,
+                       uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult, float bound_add, void* stream);
 int sir_feat_dwconv_pool_parts(int k, int stride, int C, int Ho, int Wo);
 int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, const float* d_w,
                     const float* d_bias, int act, float* d_out, float* d_amax_out, float* d_pool_part, void* stream);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "sir_feat_conv": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p,
                             _p, _p, _p, _p, C.c_float, C.c_float, _p, _p]),
     "sir_feat_gemm": (_i, [_p, _p, _p, C.c_longlong, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p]),
+    "sir_feat_conv_c3k3": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, C.c_float, C.c_float, _p]),
     "sir_feat_dwconv_pool_parts": (_i, [_i, _i, _i, _i, _i]),
     "sir_feat_dwconv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p]),
     "sir_feat_pool_sum": (_i, [_p, _i, _i, _i, _p, _p]),

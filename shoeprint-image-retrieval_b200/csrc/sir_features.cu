@@ -147,6 +147,92 @@ __global__ void __launch_bounds__(256) clahe_apply_to_nhwc_kernel(const uint8_t*
   if ((threadIdx.x & 31) == 0) atomic_max_nonneg(amax, local);
 }
 
+// ------------------------------------------------------------------------------------------ K1 (first layer)
+// 3x3 convolution of the 3-channel input image (the backbone's stem, K = 27): too thin for the tensor cores, so it
+// runs in float32 on the CUDA cores, one thread per output pixel, the 27 inputs in registers and the [27][Cout] weights
+// in shared memory.  Optionally also writes the result as the next convolution's fp16 operand planes (see sir_feat_conv).
+template <int ACT>
+__global__ void __launch_bounds__(256) conv_c3k3_kernel(const float* __restrict__ in, const float* __restrict__ amax_in, int B, int H,
+                                                        int W, int stride, int pad, int Ho, int Wo, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int Cout, float* __restrict__ out,
+                                                        float* __restrict__ amax_out, __half* __restrict__ out_hi,
+                                                        __half* __restrict__ out_lo, int* __restrict__ exp_out, float bound_mult,
+                                                        float bound_add) {
+  extern __shared__ float sw[];  // [27][Cout] weights, [Cout] bias
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias[i];
+  __syncthreads();
+  float oscale = 1.0f;
+  if (out_hi) {
+    const float bound = fmaf(*amax_in, bound_mult, bound_add);
+    int e_out = 0;
+    if (bound > 0.0f && isfinite(bound)) {
+      int ex;
+      (void)frexpf(bound, &ex);
+      e_out = max(-100, min(100, 15 - ex));
+    }
+    oscale = ldexpf(1.0f, e_out);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e_out;
+  }
+  const size_t total = (size_t)B * Ho * Wo;
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo);
+    size_t r = i / Wo;
+    const int oy = (int)(r % Ho), b = (int)(r / Ho);
+    float x[27];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * stride - pad + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const float* src = in + (((size_t)b * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[(ky * 3 + kx) * 3 + c] = ok ? __ldg(src + c) : 0.0f;
+      }
+    }
+    for (int co = 0; co < Cout; co += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Cout + co + j];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + co);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + co + 4);
+        acc[0] = fmaf(x[k], w0.x, acc[0]); acc[1] = fmaf(x[k], w0.y, acc[1]); acc[2] = fmaf(x[k], w0.z, acc[2]); acc[3] = fmaf(x[k], w0.w, acc[3]);
+        acc[4] = fmaf(x[k], w1.x, acc[4]); acc[5] = fmaf(x[k], w1.y, acc[5]); acc[6] = fmaf(x[k], w1.z, acc[6]); acc[7] = fmaf(x[k], w1.w, acc[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (ACT == 1) acc[j] = __fdividef(acc[j], 1.0f + __expf(-acc[j]));
+        if (ACT == 2) acc[j] = fmaxf(acc[j], 0.0f);
+        local = fmaxf(local, fabsf(acc[j]));
+      }
+      if (out) {
+        float4* dst = reinterpret_cast<float4*>(out + i * Cout + co);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      if (out_hi) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sv = acc[j] * oscale;
+          hi[j] = __float2half_rn(sv);
+          lo[j] = __float2half_rn(sv - __half2float(hi[j]));
+        }
+        *reinterpret_cast<uint4*>(out_hi + i * Cout + co) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(out_lo + i * Cout + co) = *reinterpret_cast<const uint4*>(lo);
+      }
+    }
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0 && amax_out) atomic_max_nonneg(amax_out, local);
+}
+
 // ------------------------------------------------------------------------------------------ K1a
 // im2col + split: A[m][k] = in[b][oy*s - pad + ky][ox*s - pad + kx][c] * chan_scale[b][c], k = (ky*kw + kx)*C + c,
 // scaled by 2^e(amax_in) and split into fp16 hi/lo.  One thread produces 8 consecutive k (16 bytes).
@@ -818,6 +904,27 @@ extern "C" int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const
   dim3 grid((unsigned)ceil_div((int)M, kGemmBM), (unsigned)ceil_div(N, p.BN));
   gemm_tc_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ta, tb, tc, td, p);
   SIR_LAUNCH_CHECK("gemm_tc_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_conv_c3k3(const float* d_in, const float* d_amax_in, int B, int H, int W, int stride, int pad, const float* d_w,
+                                  const float* d_bias, int Cout, int act, float* d_out, float* d_amax_out, uint16_t* d_out_hi,
+                                  uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult, float bound_add, void* stream) {
+  SIR_CHECK_ARG(d_in && d_amax_in && d_w && d_bias && (d_out || d_out_hi), "sir_feat_conv_c3k3: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && stride > 0 && pad >= 0 && Cout > 0 && Cout % 8 == 0 && Cout <= 256, "sir_feat_conv_c3k3: bad shape");
+  SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_conv_c3k3: unknown activation %d", act);
+  SIR_CHECK_ARG(!d_out_hi || (d_out_lo && d_exp_out), "sir_feat_conv_c3k3: operand planes need d_out_lo and d_exp_out");
+  SIR_CHECK_ARG((((uintptr_t)d_out | (uintptr_t)d_out_hi | (uintptr_t)d_out_lo) & 15) == 0, "sir_feat_conv_c3k3: outputs must be 16-byte aligned");
+  const int Ho = (H + 2 * pad - 3) / stride + 1, Wo = (W + 2 * pad - 3) / stride + 1;
+  SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_conv_c3k3: empty output");
+  const size_t smem = (size_t)28 * Cout * 4;
+  const unsigned grid = grid_for((size_t)B * Ho * Wo);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SIR_C3(A_) conv_c3k3_kernel<A_><<<grid, 256, smem, st>>>(d_in, d_amax_in, B, H, W, stride, pad, Ho, Wo, d_w, d_bias, Cout, d_out, d_amax_out, \
+                                                                   (__half*)d_out_hi, (__half*)d_out_lo, d_exp_out, bound_mult, bound_add)
+  if (act == 0) SIR_C3(0); else if (act == 1) SIR_C3(1); else SIR_C3(2);
+#undef SIR_C3
+  SIR_LAUNCH_CHECK("conv_c3k3_kernel");
   return SIR_OK;
 }
 

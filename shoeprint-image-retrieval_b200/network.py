@@ -289,6 +289,9 @@ class _Program:
                 p["bound_mult"] = float(p["w"].double().abs().flatten(1).sum(1).max()) * (1.0 + 1e-5)
                 p["bound_add"] = float(p["bias"].abs().max()) * (1.0 + 1e-5)
                 implicit = p["stride"] == 1 and cin % 8 == 0
+                p["direct"] = cin == 3 and k == 3 and kw == 3 and cout % 8 == 0 and cout <= 256 and p["c_off"] is None
+                if p["direct"]:  # the stem: float32 on the CUDA cores, weights [27][cout]
+                    p["w_direct"] = w.reshape(cout, 27).t().contiguous().to(device)
                 if implicit:  # K = (tap, channel) with the channels of a tap padded to the K step
                     bk = 32 if cin % 32 == 0 else 16 if cin % 16 == 0 else 32
                     cp = (cin + bk - 1) // bk * bk
@@ -375,6 +378,22 @@ class _Program:
                 else:  # growth channels of a dense layer go straight into the block's buffer
                     out = tensors[op.dst]
                     out_ptr, ldc = C.c_void_p(out.data_ptr() + 4 * p["c_off"]), int(out.shape[3])
+                ohi = olo = exp_out = None
+                if p["emit_planes"]:
+                    ohi = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float16, device=dev)
+                    olo = torch.empty_like(ohi)
+                    planes[op.dst] = (ohi, olo)
+                    exp_out = C.c_void_p(exps.data_ptr() + 4 * op.dst)
+                if p["direct"] and cs is None and res is None:
+                    nat.check(nat.lib.sir_feat_conv_c3k3(_ptr(src), aptr(op.src), b, h, w, p["stride"], p["pad"], _ptr(p["w_direct"]),
+                                                         _ptr(p["bias_d"]), p["cout"], p["act"], out_ptr, aptr(op.dst), _ptr(ohi), _ptr(olo),
+                                                         exp_out, p["bound_mult"], p["bound_add"], st), "sir_feat_conv_c3k3")
+                    launch_counter.add()
+                    tensors[op.dst] = out
+                    for tid in [t for t, lu in last_use.items() if lu == i and t != self.out_id]:
+                        tensors.pop(tid, None)
+                        planes.pop(tid, None)
+                    continue
                 exp_in = None
                 if p["implicit"] and cs is None and op.src in planes:  # operand planes came from the producer's epilogue
                     ahi, alo = planes[op.src]
@@ -393,12 +412,6 @@ class _Program:
                     nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
                                                             _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
                     geom = (1, 1, m, p["kp"], 1, 1, 0)
-                ohi = olo = exp_out = None
-                if p["emit_planes"]:
-                    ohi = torch.empty((b, ho, wo, p["cout"]), dtype=torch.float16, device=dev)
-                    olo = torch.empty_like(ohi)
-                    planes[op.dst] = (ohi, olo)
-                    exp_out = C.c_void_p(exps.data_ptr() + 4 * op.dst)
                 nat.check(nat.lib.sir_feat_conv(_ptr(ahi), _ptr(alo), aptr(op.src), *geom, p["bk"], _ptr(p["whi"]), _ptr(p["wlo"]),
                                                 p["cout"], p["rows"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
                                                 out_ptr, ldc, aptr(op.dst), exp_in, _ptr(ohi), _ptr(olo), exp_out, p["bound_mult"],
@@ -532,6 +545,8 @@ class Model:
         self.max_batch_bytes = 4 << 30  # cap on the live tensors of one layer
         self.max_batch = 64
         self._host_clahe = os.environ.get("SIR_HOST_CLAHE", "") == "1"
+        self._copy_stream: torch.cuda.Stream | None = None
+        self._pinned_bufs: dict[tuple, torch.Tensor] = {}
 
     def _host_transform(self, *, gray: bool):
         mean, std = np.array(self.mean, np.float32), np.array(self.std, np.float32)
@@ -557,9 +572,13 @@ class Model:
     def _forward_uint8(self, batch: np.ndarray, *, apply_clahe: bool = False) -> torch.Tensor:
         """uint8 images ``[B,H,W]`` or ``[B,H,W,3]`` -> feature maps ``[B,C,h,w]`` on the device.
         ``apply_clahe``: the (grayscale) batch is raw and CLAHE runs on the GPU; otherwise it is already equalised."""
-        b, h, w = batch.shape[:3]
-        in_ch = 1 if batch.ndim == 3 else 3
         d_img = torch.from_numpy(np.ascontiguousarray(batch)).to(self.device, non_blocking=True)
+        return self._forward_device(d_img, apply_clahe=apply_clahe)
+
+    def _forward_device(self, d_img: torch.Tensor, *, apply_clahe: bool) -> torch.Tensor:
+        """The same for a uint8 batch already on the device."""
+        b, h, w = (int(v) for v in d_img.shape[:3])
+        in_ch = 1 if d_img.ndim == 3 else 3
         x0 = torch.empty((b, h, w, 3), dtype=torch.float32, device=self.device)
         amax0 = torch.zeros(1, dtype=torch.float32, device=self.device)
         mean = (C.c_float * 3)(*self.mean)
@@ -581,6 +600,16 @@ class Model:
         nat.check(nat.lib.sir_feat_nhwc_to_nchw(_ptr(y), bo, ho * wo, co, _ptr(out), _stream()), "sir_feat_nhwc_to_nchw")
         launch_counter.add()
         return out
+
+    def _pinned(self, kind: str, slot: int, shape: tuple, dtype: torch.dtype) -> torch.Tensor:
+        """Reusable page-locked staging buffer (two slots per kind and shape)."""
+        key = (kind, slot, tuple(int(v) for v in shape), dtype)
+        buf = self._pinned_bufs.get(key)
+        if buf is None:
+            for k in [k for k in self._pinned_bufs if k[0] == kind and k[1] == slot]:
+                del self._pinned_bufs[k]
+            buf = self._pinned_bufs[key] = torch.empty(key[2], dtype=dtype).pin_memory()
+        return buf
 
     def _batch_limit(self, h: int, w: int) -> int:
         """Images per forward pass: the largest (input + fp16 operand planes + output) of any layer within
@@ -623,18 +652,51 @@ class Model:
         for i, im in enumerate(images):
             by_shape.setdefault(tuple(im.shape), []).append(i)
         bar = tqdm(total=len(images)) if progress else None
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        pending: tuple | None = None  # (image indices, pinned host maps, copy-done event, device maps)
+
+        def collect(pend: tuple) -> None:
+            chunk, host, done, _dev = pend
+            done.synchronize()
+            arr = host.numpy()
+            for j, i in enumerate(chunk):
+                results[i] = arr[j].squeeze().copy()
+            if bar is not None:
+                bar.update(len(chunk))
+
+        # Two-deep pipeline: while the GPU works on chunk i the host stages chunk i+1 into pinned memory and copies the
+        # maps of chunk i-1 out of the pinned result buffer; results leave the device on a side stream.
+        step = 0
         for shp, idx in by_shape.items():
             limit = self._batch_limit(shp[0], shp[1])
+            gpu_clahe = len(shp) == 2 and not self._host_clahe
             for s in range(0, len(idx), limit):
                 chunk = idx[s : s + limit]
-                if len(shp) == 2 and not self._host_clahe:
-                    maps = self._forward_uint8(np.stack([images[i] for i in chunk]), apply_clahe=True).cpu().numpy()
+                stage = self._pinned("in", step % 2, (limit, *shp), torch.uint8)[: len(chunk)]
+                if gpu_clahe:
+                    np.stack([images[i] for i in chunk], out=stage.numpy())
                 else:
-                    maps = self._forward_uint8(np.stack([self._clahe(images[i]) for i in chunk])).cpu().numpy()
-                for j, i in enumerate(chunk):
-                    results[i] = maps[j].squeeze()
-                if bar is not None:
-                    bar.update(len(chunk))
+                    np.stack([self._clahe(images[i]) for i in chunk], out=stage.numpy())
+                d_img = torch.empty(stage.shape, dtype=torch.uint8, device=self.device)
+                d_img.copy_(stage, non_blocking=True)
+                maps = self._forward_device(d_img, apply_clahe=gpu_clahe)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                host = self._pinned("out", step % 2, (limit, *maps.shape[1:]), torch.float32)[: len(chunk)]
+                done = torch.cuda.Event()
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ready)
+                    host.copy_(maps, non_blocking=True)
+                    done.record(self._copy_stream)
+                maps.record_stream(self._copy_stream)
+                if pending is not None:
+                    collect(pending)
+                pending = (chunk, host, done, maps)
+                step += 1
+        if pending is not None:
+            collect(pending)
         if bar is not None:
             bar.close()
         return results
