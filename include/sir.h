@@ -179,12 +179,11 @@ int sir_merge_topk(const float* d_vals, const int32_t* d_idx, int P, int Q, int 
  *
  * sir_feat_image_to_nhwc: ToTensor + (grayscale repeat) + Normalize, network.py:51-87.
  *   d_img uint8 [B][H][W] (in_ch 1) or [B][H][W][3]; h_mean/h_std: 3 host floats.
- * sir_feat_im2col_split + sir_feat_gemm: Conv2d (groups 1, any kernel/stride/pad) with folded
- *   BatchNorm, bias, activation and optional residual add (FusedMBConv/MBConv skip connection).
- *   A [M = B*Ho*Wo][Kp] f16 hi/lo, k = (ky*kw + kx)*C + c, Kp a multiple of 32;  d_chan_scale
- *   [B][C] or NULL multiplies the input per (image, channel) (squeeze-excitation scale).
- *   Weights d_bhi/d_blo [n_rows_alloc][Kp] f16 = W * 2^w_exp split hi/lo, rows >= N zero.
- *   out[m][n] = act(A.B^T * 2^-(e(amax_in)+w_exp) + bias[n]) + residual[m][n], row stride ldc.
+ * sir_feat_im2col_split: the operand pass of a convolution.  With a 1x1 kernel and Kp = C it is the split of a
+ *   float32 NHWC tensor into the fp16 hi/lo planes sir_feat_conv reads; with kh*kw > 1 it gathers the explicit
+ *   im2col matrix A [M = B*Ho*Wo][Kp], k = (ky*kw + kx)*C + c (used for strided convolutions, then multiplied by
+ *   sir_feat_conv as a 1 x M "image" with C = Kp).  Values are scaled by 2^e(amax_in); d_chan_scale [B][C] or NULL
+ *   multiplies the input per (image, channel) (squeeze-excitation scale).
  * sir_feat_dwconv: depthwise k x k Conv2d + folded BN bias + activation; weights [k][k][C].  If d_pool_part is
  *   not NULL it also receives the squeeze of a following SqueezeExcitation as partial sums over pixels,
  *   [B][parts][C] with parts = sir_feat_dwconv_pool_parts(k, stride, C, Ho, Wo) (fused into the 3x3 fast path).
@@ -204,9 +203,8 @@ int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int 
                           int pad, const float* d_chan_scale, int Kp, uint16_t* d_ahi, uint16_t* d_alo, void* stream);
 /* sir_feat_conv: Conv2d (groups 1, stride 1, square zero padding) + folded BN bias + activation (+ residual) as an
  * implicit GEMM: no im2col matrix.  d_xhi/d_xlo: the input split into fp16 hi/lo NHWC planes [B][H][W][C]
- * (sir_feat_im2col_split with a 1x1 kernel and Kp = C), C % 8 == 0.  Weights [n_rows_alloc][taps*Cp] fp16 hi/lo with
- * k = (ky*kw + kx)*Cp + c, Cp = C rounded up to bk (16 or 32), rows zero padded to a multiple of
- * sir_feat_conv_tile_n(N).  A GEMM over an explicit [M][K] matrix is the call with B=H=1, W=M, C=K, kh=kw=1.
+ * (sir_feat_im2col_split with a 1x1 kernel and Kp = C), C % 8 == 0.  Weights: d_wpack from sir_feat_conv_pack_weights,
+ * packed for the tile sir_feat_conv_plan reports for this shape; K order k = (ky*kw + kx)*Cp + c, Cp = C rounded up to bk.  A GEMM over an explicit [M][K] matrix is the call with B=H=1, W=M, C=K, kh=kw=1.
  * Chaining without a split pass: with d_out_hi/d_out_lo the epilogue also (or only, d_out = NULL) writes the
  * result as the next convolution's operand planes [pixels][N] (N % 8 == 0), scaled by 2^e with
  * e = 15 - ceil(log2(amax_in*bound_mult + bound_add + amax_res)), an a-priori bound of |out| the caller derives
@@ -214,14 +212,19 @@ int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int 
  * (NULL = planes from sir_feat_im2col_split, scaled from the measured amax).
  * Replaces the torch Conv2d/BatchNorm/SiLU modules the reference runs at network.py:234-235. */
 int sir_feat_conv_tile_n(int N);
+/* The weights reach the kernel as ready-made shared-memory images, one contiguous block per pipeline stage (a plain bulk
+ * copy; tensor-map loads of 32/64-byte weight rows are bound by the TMA unit's row rate).  sir_feat_conv_plan: tile width,
+ * K granule (16 or 32 channels) and byte size of the packed weights for a shape; sir_feat_conv_pack_weights: [n_rows][Kp]
+ * fp16 hi/lo matrices (k = (ky*kw + kx)*Cp + c) -> that layout, [n_tile][k_step][hi | lo][tile_n][granule] swizzled. */
+int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int* tile_n, int* granule,
+                       long long* pack_bytes);
+int sir_feat_conv_pack_weights(const uint16_t* d_whi, const uint16_t* d_wlo, int n_rows, int Kp, int tile_n, int granule,
+                               uint8_t* d_pack, void* stream);
 int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
-                  int kw, int pad, int bk, const uint16_t* d_whi, const uint16_t* d_wlo, int N, int n_rows_alloc, int w_exp,
+                  int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int N, int w_exp,
                   const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
                   const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
                   float bound_add, const float* d_amax_res, void* stream);
-int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
-                  const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
-                  const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream);
 /* sir_feat_conv_c3k3: 3x3 Conv2d of a 3-channel NHWC image (the stem, K = 27) + bias + activation in float32 on the
  * CUDA cores; weights [27][Cout] with row = (ky*3 + kx)*3 + c, Cout % 8 == 0.  Optional operand-plane output as in
  * sir_feat_conv. */

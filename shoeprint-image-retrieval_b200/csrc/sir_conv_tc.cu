@@ -44,6 +44,7 @@ struct ConvParams {
   int total_tiles;
   int stages;
   int w_exp;
+  const uint8_t* wpack;   // weights as per-stage shared-memory images: [n_tile][k_step][hi | lo][BN][granule], swizzled
   const float* amax_in;
   const int* exp_in;      // exponent the input planes were written with; NULL: derived from amax_in (split pass)
   const float* bias;
@@ -149,8 +150,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
 
 template <int ACT>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
-               const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -180,8 +180,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_xhi);
     ptx::prefetch_tmap(&tm_xlo);
-    ptx::prefetch_tmap(&tm_whi);
-    ptx::prefetch_tmap(&tm_wlo);
   }
   if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
   ptx::tc_fence_before();
@@ -194,29 +192,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      uint32_t it = 0;
+      // ring position as running counters: a runtime modulo / division per K step costs more than the step's MMAs
+      uint32_t slot = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
         const int px = mt % p.tiles_x, r1 = mt / p.tiles_x;
         const int py = r1 % p.tiles_y, b = r1 / p.tiles_y;
-        const int x0 = px * TW - p.pad, y0 = py * p.TH - p.pad, n0 = nt * p.BN;
+        const int x0 = px * TW - p.pad, y0 = py * p.TH - p.pad;
+        // The weight stage is ONE contiguous bulk copy of a pre-swizzled image: a tensor-map load of narrow rows
+        // (32 / 64 B) is bound by the TMA unit's row rate, which starved the MMAs.
+        const uint8_t* wsrc = p.wpack + (size_t)nt * k_iters * (2 * b_bytes);
         int tap_y = 0, tap_x = 0, chunk = 0;
-        for (int ks = 0; ks < k_iters; ++ks, ++it) {
-          const uint32_t slot = it % p.stages;
-          ptx::mbar_wait(bar_empty(slot), ((it / p.stages) & 1) ^ 1);
+        for (int ks = 0; ks < k_iters; ++ks) {
+          ptx::mbar_wait(bar_empty(slot), phase ^ 1);
           ptx::mbar_arrive_expect_tx(bar_full(slot), stage_bytes);
           const uint32_t dst = base + slot * stage_bytes;
           const int c0 = chunk * p.bk;
           ptx::tma_load_4d(dst, &tm_xhi, bar_full(slot), c0, x0 + tap_x, y0 + tap_y, b);
           ptx::tma_load_4d(dst + a_bytes, &tm_xlo, bar_full(slot), c0, x0 + tap_x, y0 + tap_y, b);
-          ptx::tma_load_2d(dst + 2 * a_bytes, &tm_whi, bar_full(slot), ks * p.bk, n0);
-          ptx::tma_load_2d(dst + 2 * a_bytes + b_bytes, &tm_wlo, bar_full(slot), ks * p.bk, n0);
+          ptx::bulk_load(dst + 2 * a_bytes, wsrc + (size_t)ks * (2 * b_bytes), 2 * b_bytes, bar_full(slot));
           if (++chunk == p.chunks) {
             chunk = 0;
             if (++tap_x == p.kw) {
               tap_x = 0;
               ++tap_y;
             }
+          }
+          if (++slot == (uint32_t)p.stages) {
+            slot = 0;
+            phase ^= 1;
           }
         }
       }
@@ -226,7 +230,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       const uint32_t idesc = ptx::make_idesc_f16(kConvBM, p.BN);
       const uint32_t sbo = (uint32_t)p.bk * 16, layout = p.bk == 32 ? 4u : 6u;  // 8 rows of 64 B / 32 B
       const int k16s = p.bk / 16;
-      uint32_t it = 0;
+      // descriptors of stage 0; a stage / operand / K16 step further is an addition to the 16-byte address field
+      const uint64_t desc0 = ptx::make_smem_desc(base, 16, sbo, layout);
+      const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4, b16 = b_bytes >> 4;
+      uint32_t slot = 0, phase = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
@@ -234,22 +241,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         ptx::tc_fence_after();
         const uint32_t acc = tmem_base + buf * kConvAccStride;
         uint32_t accumulate = 0;
-        for (int ks = 0; ks < k_iters; ++ks, ++it) {
-          const uint32_t slot = it % p.stages;
-          ptx::mbar_wait(bar_full(slot), (it / p.stages) & 1);
+        for (int ks = 0; ks < k_iters; ++ks) {
+          ptx::mbar_wait(bar_full(slot), phase);
           ptx::tc_fence_after();
-          const uint32_t a_hi = base + slot * stage_bytes, a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
-          for (int kk = 0; kk < k16s; ++kk) {
-            const uint64_t da_hi = ptx::make_smem_desc(a_hi + 32u * kk, 16, sbo, layout);
-            const uint64_t da_lo = ptx::make_smem_desc(a_lo + 32u * kk, 16, sbo, layout);
-            const uint64_t db_hi = ptx::make_smem_desc(b_hi + 32u * kk, 16, sbo, layout);
-            const uint64_t db_lo = ptx::make_smem_desc(b_lo + 32u * kk, 16, sbo, layout);
+          uint64_t da_hi = desc0 + slot * stage16;
+          for (int kk = 0; kk < k16s; ++kk, da_hi += 2) {  // +32 B inside the swizzled row
+            const uint64_t da_lo = da_hi + a16, db_hi = da_hi + 2 * a16, db_lo = db_hi + b16;
             ptx::mma_f16_ss(acc, da_hi, db_hi, idesc, accumulate);
             ptx::mma_f16_ss(acc, da_lo, db_hi, idesc, 1);
             ptx::mma_f16_ss(acc, da_hi, db_lo, idesc, 1);
             accumulate = 1;
           }
           ptx::tc_commit(bar_empty(slot));
+          if (++slot == (uint32_t)p.stages) {
+            slot = 0;
+            phase ^= 1;
+          }
         }
         ptx::tc_commit(bar_acc_full(buf));
       }
@@ -319,8 +326,7 @@ struct HaloParams {
 
 template <int ACT>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
-                 const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const HaloParams hp) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, const HaloParams hp) {
   const ConvParams& p = hp.c;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -360,8 +366,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_xhi);
     ptx::prefetch_tmap(&tm_xlo);
-    ptx::prefetch_tmap(&tm_whi);
-    ptx::prefetch_tmap(&tm_wlo);
   }
   if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
   ptx::tc_fence_before();
@@ -381,12 +385,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
   if (warp == 0) {
     if (ptx::elect_one()) {
       // items = (tile, chunk) in order; the halo of item i+1 is requested before the weight stages of item i
-      uint32_t a_it = 0, b_it = 0;
+      uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;  // running ring positions (no runtime division per step)
       auto load_halo = [&](int tile, int chunk) {
         int nt, px, py, b;
         decode(tile, nt, px, py, b);
-        const uint32_t slot = a_it % kHaloAStages;
-        ptx::mbar_wait(bar_a_empty(slot), ((a_it / kHaloAStages) & 1) ^ 1);
+        const uint32_t slot = a_slot;
+        ptx::mbar_wait(bar_a_empty(slot), a_phase ^ 1);
         ptx::mbar_arrive_expect_tx(bar_a_full(slot), a_stage);
         const uint32_t dst = base + slot * a_stage_al;
         for (int q = 0; q < hp.np; ++q) {
@@ -394,12 +398,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
           ptx::tma_load_5d(dst + q * 2 * plane_bytes, &tm_xhi, bar_a_full(slot), 0, x0, y0, chunk * 4, b);
           ptx::tma_load_5d(dst + q * 2 * plane_bytes + plane_bytes, &tm_xlo, bar_a_full(slot), 0, x0, y0, chunk * 4, b);
         }
-        ++a_it;
+        if (++a_slot == kHaloAStages) {
+          a_slot = 0;
+          a_phase ^= 1;
+        }
       };
       int tile = blockIdx.x;
       if (tile < p.total_tiles) load_halo(tile, 0);
       for (; tile < p.total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles_n) * p.BN;
+        const uint8_t* wsrc = p.wpack + (size_t)(tile % p.n_tiles_n) * (p.taps * (hp.cp16 >> 4)) * b_stage;
         for (int chunk = 0; chunk < hp.chunks32; ++chunk) {
           if (chunk + 1 < hp.chunks32)
             load_halo(tile, chunk + 1);
@@ -407,13 +414,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
             load_halo(tile + gridDim.x, 0);
           const int k16s = min(2, (hp.cp16 - chunk * 32) >> 4);
           for (int tap = 0; tap < p.taps; ++tap) {
-            for (int kk = 0; kk < k16s; ++kk, ++b_it) {
-              const uint32_t slot = b_it % hp.b_stages;
-              ptx::mbar_wait(bar_b_empty(slot), ((b_it / hp.b_stages) & 1) ^ 1);
+            for (int kk = 0; kk < k16s; ++kk) {
+              const uint32_t slot = b_slot;
+              ptx::mbar_wait(bar_b_empty(slot), b_phase ^ 1);
               ptx::mbar_arrive_expect_tx(bar_b_full(slot), b_stage);
-              const int k0 = tap * hp.cp16 + chunk * 32 + kk * 16;
-              ptx::tma_load_2d(b_base + slot * b_stage, &tm_whi, bar_b_full(slot), k0, n0);
-              ptx::tma_load_2d(b_base + slot * b_stage + b_half, &tm_wlo, bar_b_full(slot), k0, n0);
+              const int k16 = tap * (hp.cp16 >> 4) + chunk * 2 + kk;
+              ptx::bulk_load(b_base + slot * b_stage, wsrc + (size_t)k16 * b_stage, b_stage, bar_b_full(slot));
+              if (++b_slot == (uint32_t)hp.b_stages) {
+                b_slot = 0;
+                b_phase ^= 1;
+              }
             }
           }
         }
@@ -423,7 +433,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_f16(kConvBM, p.BN);
       const uint32_t a_sbo = (uint32_t)hp.hw * 16, a_lbo = slab_bytes;
-      uint32_t a_it = 0, b_it = 0;
+      // stage-0 descriptors; other stages / planes / taps / K16 steps are additions to the 16-byte address field
+      const uint64_t da0 = ptx::make_smem_desc(base, a_lbo, a_sbo, 0);
+      const uint64_t db0 = ptx::make_smem_desc(b_base, 16, 256, 6);
+      const uint32_t plane16 = plane_bytes >> 4, slab2_16 = (2 * slab_bytes) >> 4, a_stage16 = a_stage_al >> 4;
+      const uint32_t b_stage16 = b_stage >> 4, b_half16 = b_half >> 4;
+      uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
@@ -431,40 +446,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
         ptx::tc_fence_after();
         const uint32_t acc = tmem_base + buf * kConvAccStride;
         uint32_t accumulate = 0;
-        for (int chunk = 0; chunk < hp.chunks32; ++chunk, ++a_it) {
-          const uint32_t aslot = a_it % kHaloAStages;
-          ptx::mbar_wait(bar_a_full(aslot), (a_it / kHaloAStages) & 1);
+        for (int chunk = 0; chunk < hp.chunks32; ++chunk) {
+          ptx::mbar_wait(bar_a_full(a_slot), a_phase);
           ptx::tc_fence_after();
-          const uint32_t a0 = base + aslot * a_stage_al;
+          const uint64_t da_stage = da0 + a_slot * a_stage16;
           const int k16s = min(2, (hp.cp16 - chunk * 32) >> 4);
-          int ky = 0, kx = 0;
+          int kx = 0;
+          uint32_t tap16 = 0;  // (ky * hw + kx) in 16-byte units
           for (int tap = 0; tap < p.taps; ++tap) {
-            const uint32_t tap_off = (uint32_t)(ky * hp.hw + kx) * 16;
-            for (int kk = 0; kk < k16s; ++kk, ++b_it) {
-              const uint32_t slot = b_it % hp.b_stages;
-              ptx::mbar_wait(bar_b_full(slot), (b_it / hp.b_stages) & 1);
+            for (int kk = 0; kk < k16s; ++kk) {
+              ptx::mbar_wait(bar_b_full(b_slot), b_phase);
               ptx::tc_fence_after();
-              const uint32_t b_hi = b_base + slot * b_stage;
-              const uint64_t db_hi = ptx::make_smem_desc(b_hi, 16, 256, 6);
-              const uint64_t db_lo = ptx::make_smem_desc(b_hi + b_half, 16, 256, 6);
-              for (int q = 0; q < hp.np; ++q) {
-                const uint32_t a_hi = a0 + q * 2 * plane_bytes + tap_off + (uint32_t)kk * 2 * slab_bytes;
-                const uint64_t da_hi = ptx::make_smem_desc(a_hi, a_lbo, a_sbo, 0);
-                const uint64_t da_lo = ptx::make_smem_desc(a_hi + plane_bytes, a_lbo, a_sbo, 0);
+              const uint64_t db_hi = db0 + b_slot * b_stage16, db_lo = db_hi + b_half16;
+              uint64_t da_hi = da_stage + tap16 + kk * slab2_16;
+              for (int q = 0; q < hp.np; ++q, da_hi += 2 * plane16) {
+                const uint64_t da_lo = da_hi + plane16;
                 const uint32_t d = acc + q * p.BN;
                 ptx::mma_f16_ss(d, da_hi, db_hi, idesc, accumulate);
                 ptx::mma_f16_ss(d, da_lo, db_hi, idesc, 1);
                 ptx::mma_f16_ss(d, da_hi, db_lo, idesc, 1);
               }
               accumulate = 1;
-              ptx::tc_commit(bar_b_empty(slot));
+              ptx::tc_commit(bar_b_empty(b_slot));
+              if (++b_slot == (uint32_t)hp.b_stages) {
+                b_slot = 0;
+                b_phase ^= 1;
+              }
             }
+            ++tap16;
             if (++kx == p.kw) {
               kx = 0;
-              ++ky;
+              tap16 += hp.hw - p.kw;
             }
           }
-          ptx::tc_commit(bar_a_empty(aslot));
+          ptx::tc_commit(bar_a_empty(a_slot));
+          if (++a_slot == kHaloAStages) {
+            a_slot = 0;
+            a_phase ^= 1;
+          }
         }
         ptx::tc_commit(bar_acc_full(buf));
       }
@@ -597,7 +616,11 @@ HaloPlan plan_halo(int B, int H, int W, int C, int kh, int kw, int pad, int N, i
   ConvParams& p = hp.c;
   p.Ho = H + 2 * pad - kh + 1;
   p.Wo = W + 2 * pad - kw + 1;
-  hp.np = p.Ho > kHaloTH ? 2 : 1;
+  // The MMA is bound by its shared-memory operand reads (A: 4 KB per 128 x N x 16 instruction whatever N is), so a wide
+  // N tile beats sharing a weight stage between two patches; only narrow layers (N <= 64) pair patches.
+  static const char* np_env = getenv("SIR_CONV_HALO_NP");
+  hp.np = np_env ? atoi(np_env) : (N <= 64 ? 2 : 1);
+  if (p.Ho <= kHaloTH) hp.np = 1;
   p.N = N;
   p.BN = halo_tile_n(N, hp.np);
   p.n_tiles_n = ceil_div(N, p.BN);
@@ -625,53 +648,48 @@ HaloPlan plan_halo(int B, int H, int W, int C, int kh, int kw, int pad, int N, i
 }  // namespace
 }  // namespace sir
 
-using namespace sir;
+namespace sir {
+namespace {
+// Everything the launch needs that depends only on the shapes: which kernel, its tiles, its shared memory.
+struct ConvPlan {
+  bool halo;
+  ConvParams p;    // the 4-D patch kernel
+  HaloPlan hpl;    // the halo kernel (valid when halo)
+  size_t smem;
+  int gB, gH, gW;  // image geometry seen by the patch kernel (a 1x1 convolution is one 1 x M row)
+  int Kp;
+  int BN, granule, n_tiles_n, k_steps;  // layout of the packed weights
+};
 
-extern "C" int sir_feat_conv_tile_n(int N) { return N > 0 ? conv_tile_n(N) : 0; }
-
-extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
-                             int kw, int pad, int bk, const uint16_t* d_whi, const uint16_t* d_wlo, int N, int n_rows_alloc, int w_exp,
-                             const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
-                             const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
-                             float bound_add, const float* d_amax_res, void* stream) {
-  SIR_CHECK_ARG(d_xhi && d_xlo && d_whi && d_wlo && d_amax_in && d_bias && (d_out || d_out_hi), "sir_feat_conv: null pointer");
-  SIR_CHECK_ARG(!d_out_hi || (d_out_lo && d_exp_out && N % 8 == 0 && ((uintptr_t)d_out_hi & 15) == 0 && ((uintptr_t)d_out_lo & 15) == 0 &&
-                              bound_mult >= 0.0f && bound_add >= 0.0f),
-                "sir_feat_conv: operand-plane output needs d_out_lo, d_exp_out, N %% 8 == 0 and a non-negative bound");
-  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && kh > 0 && kw > 0 && pad >= 0 && N > 0 && ldc >= N,
-                "sir_feat_conv: bad shape B=%d H=%d W=%d C=%d (C must be a multiple of 8) k=%dx%d N=%d ldc=%d", B, H, W, C, kh, kw, N, ldc);
+int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, ConvPlan* out) {
+  SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && kh > 0 && kw > 0 && pad >= 0 && N > 0,
+                "sir_feat_conv: bad shape B=%d H=%d W=%d C=%d (C must be a multiple of 8) k=%dx%d N=%d", B, H, W, C, kh, kw, N);
   SIR_CHECK_ARG(bk == 16 || bk == 32, "sir_feat_conv: bk must be 16 or 32, got %d", bk);
-  SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_conv: unknown activation %d", act);
   const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
   SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_conv: empty output");
-  SIR_CHECK_ARG((long long)B * Ho * Wo * (long long)ldc < (1ll << 40), "sir_feat_conv: output too large");
-  ConvParams p{};
+  ConvPlan& pl = *out;
+  pl = ConvPlan{};
+  ConvParams& p = pl.p;
   p.N = N;
   p.BN = conv_tile_n(N);
   p.n_tiles_n = ceil_div(N, p.BN);
-  SIR_CHECK_ARG(n_rows_alloc >= p.n_tiles_n * p.BN, "sir_feat_conv: weight matrix needs %d zero-padded rows, has %d", p.n_tiles_n * p.BN,
-                n_rows_alloc);
-  SIR_CHECK_ARG(d_out || N % 4 == 0, "sir_feat_conv: plane-only output needs N %% 4 == 0");
-  SIR_CHECK_ARG(!d_residual || !d_out_hi || d_amax_res, "sir_feat_conv: residual + operand planes need d_amax_res");
-  SIR_CHECK_ARG(((uintptr_t)d_bias & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ldc % 4 == 0 && (!d_residual || ((uintptr_t)d_residual & 15) == 0) &&
-                    ((uintptr_t)d_xhi & 15) == 0 && ((uintptr_t)d_xlo & 15) == 0 && ((uintptr_t)d_whi & 15) == 0 && ((uintptr_t)d_wlo & 15) == 0,
-                "sir_feat_conv: operands must be 16-byte aligned and ldc a multiple of 4");
   p.taps = kh * kw;
   p.kw = kw;
   p.pad = pad;
   p.bk = bk;
   p.chunks = ceil_div(C, bk);
-  const int Kp = p.taps * p.chunks * bk;
-  // image geometry seen by the kernel; a 1x1 convolution is flattened to one 1 x M row so that no patch is ragged
-  int gB = B, gH = H, gW = W;
+  pl.Kp = p.taps * p.chunks * bk;
+  pl.gB = B;
+  pl.gH = H;
+  pl.gW = W;
   if (p.taps == 1 && pad == 0) {
     SIR_CHECK_ARG((long long)B * H * W < (1ll << 31), "sir_feat_conv: too many rows");
-    gW = B * H * W;
-    gH = 1;
-    gB = 1;
+    pl.gW = B * H * W;
+    pl.gH = 1;
+    pl.gB = 1;
   }
-  p.Ho = gH + 2 * pad - kh + 1;
-  p.Wo = gW + 2 * pad - kw + 1;
+  p.Ho = pl.gH + 2 * pad - kh + 1;
+  p.Wo = pl.gW + 2 * pad - kw + 1;
   long long best_tiles = -1;
   for (int l2 = 7; l2 >= 0; --l2) {  // patch = (128 >> l2) rows x (1 << l2) columns; prefer wide patches on ties
     const int tw = 1 << l2, th = kConvBM >> l2;
@@ -684,9 +702,114 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
   }
   p.tiles_x = ceil_div(p.Wo, 1 << p.tw_log2);
   p.tiles_y = ceil_div(p.Ho, p.TH);
-  const long long total = (long long)gB * p.tiles_x * p.tiles_y * p.n_tiles_n;
+  const long long total = (long long)pl.gB * p.tiles_x * p.tiles_y * p.n_tiles_n;
   SIR_CHECK_ARG(total < (1ll << 31), "sir_feat_conv: too many tiles");
   p.total_tiles = (int)total;
+  const uint32_t stage_bytes = (uint32_t)(2 * kConvBM + 2 * p.BN) * bk * 2;
+  const uint32_t tail = 8u * (2 * kConvMaxStages + 4) + 16 + 8 * 32 * 16 * 4;
+  p.stages = std::min<int>(kConvMaxStages, (int)((220u * 1024 - 1024 - tail) / stage_bytes));
+  SIR_CHECK_ARG(p.stages >= 2, "sir_feat_conv: tile does not fit shared memory");
+  pl.smem = 1024 + (size_t)p.stages * stage_bytes + tail;
+  pl.BN = p.BN;
+  pl.granule = bk;
+  pl.n_tiles_n = p.n_tiles_n;
+  pl.k_steps = p.taps * p.chunks;
+  if (p.taps > 1) {
+    pl.hpl = plan_halo(B, H, W, C, kh, kw, pad, N, p.chunks * bk);
+    // activation-side TMA rows per output row and K16 step: the patch kernel refetches the patch for every tap,
+    // the halo kernel fetches patch + halo once per 32-channel chunk (16-byte rows)
+    static const char* force = getenv("SIR_CONV_HALO");  // "0" / "1" force the choice (testing)
+    pl.halo = pl.hpl.ok && (force ? force[0] == '1' : true);
+    if (pl.halo) {
+      pl.BN = pl.hpl.hp.c.BN;
+      pl.granule = 16;
+      pl.n_tiles_n = pl.hpl.hp.c.n_tiles_n;
+      pl.k_steps = p.taps * (pl.hpl.hp.cp16 >> 4);
+      pl.smem = pl.hpl.smem;
+    }
+  }
+  return SIR_OK;
+}
+
+// weights [rows][Kp] hi/lo -> per-stage shared-memory images [n_tile][k_step][hi | lo][BN][granule] with the 32- / 64-byte
+// swizzle the UMMA descriptors expect (16-byte chunk index XOR row bits), rows beyond n_rows read as zero
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __half* __restrict__ whi, const __half* __restrict__ wlo, int n_rows, int Kp,
+                                                           int BN, int g, int n_tiles_n, int k_steps, __half* __restrict__ out) {
+  const int chunks = g / 8;  // 16-byte chunks per row
+  const size_t total = (size_t)n_tiles_n * k_steps * 2 * BN * chunks;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % chunks);
+    size_t r = i / chunks;
+    const int row = (int)(r % BN);
+    r /= BN;
+    const int plane = (int)(r & 1);
+    r >>= 1;
+    const int ks = (int)(r % k_steps), nt = (int)(r / k_steps);
+    const int n = nt * BN + row, k = ks * g + c * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < n_rows && k < Kp) v = *reinterpret_cast<const uint4*>((plane ? wlo : whi) + (size_t)n * Kp + k);
+    const int cs = g == 16 ? (c ^ ((row >> 2) & 1)) : (c ^ ((row >> 1) & 3));
+    *reinterpret_cast<uint4*>(out + ((((size_t)nt * k_steps + ks) * 2 + plane) * BN + row) * g + cs * 8) = v;
+  }
+}
+}  // namespace
+}  // namespace sir
+
+using namespace sir;
+
+extern "C" int sir_feat_conv_tile_n(int N) { return N > 0 ? conv_tile_n(N) : 0; }
+
+extern "C" int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int* tile_n, int* granule,
+                                  long long* pack_bytes) {
+  ConvPlan pl;
+  const int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, &pl);
+  if (rc) return rc;
+  if (tile_n) *tile_n = pl.BN;
+  if (granule) *granule = pl.granule;
+  if (pack_bytes) *pack_bytes = (long long)pl.n_tiles_n * pl.k_steps * 2 * pl.BN * pl.granule * 2;
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_conv_pack_weights(const uint16_t* d_whi, const uint16_t* d_wlo, int n_rows, int Kp, int tile_n, int granule,
+                                          uint8_t* d_pack, void* stream) {
+  SIR_CHECK_ARG(d_whi && d_wlo && d_pack && n_rows > 0 && Kp > 0 && Kp % 8 == 0, "sir_feat_conv_pack_weights: bad argument");
+  SIR_CHECK_ARG(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0 && (granule == 16 || granule == 32) && Kp % granule == 0,
+                "sir_feat_conv_pack_weights: bad tile (tile_n %d, granule %d, Kp %d)", tile_n, granule, Kp);
+  SIR_CHECK_ARG((((uintptr_t)d_whi | (uintptr_t)d_wlo | (uintptr_t)d_pack) & 15) == 0, "sir_feat_conv_pack_weights: pointers must be 16-byte aligned");
+  const int n_tiles_n = ceil_div(n_rows, tile_n), k_steps = Kp / granule;
+  const size_t total = (size_t)n_tiles_n * k_steps * 2 * tile_n * (granule / 8);
+  pack_weights_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)d_whi, (const __half*)d_wlo, n_rows, Kp, tile_n, granule, n_tiles_n, k_steps, (__half*)d_pack);
+  SIR_LAUNCH_CHECK("pack_weights_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
+                             int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int N, int w_exp,
+                             const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
+                             const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
+                             float bound_add, const float* d_amax_res, void* stream) {
+  SIR_CHECK_ARG(d_xhi && d_xlo && d_wpack && d_amax_in && d_bias && (d_out || d_out_hi), "sir_feat_conv: null pointer");
+  SIR_CHECK_ARG(!d_out_hi || (d_out_lo && d_exp_out && N % 8 == 0 && ((uintptr_t)d_out_hi & 15) == 0 && ((uintptr_t)d_out_lo & 15) == 0 &&
+                              bound_mult >= 0.0f && bound_add >= 0.0f),
+                "sir_feat_conv: operand-plane output needs d_out_lo, d_exp_out, N %% 8 == 0 and a non-negative bound");
+  SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_conv: unknown activation %d", act);
+  ConvPlan pl;
+  int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, &pl);
+  if (rc) return rc;
+  SIR_CHECK_ARG(ldc >= N, "sir_feat_conv: ldc %d < N %d", ldc, N);
+  SIR_CHECK_ARG(pack_tile_n == pl.BN && pack_granule == pl.granule,
+                "sir_feat_conv: weights packed for tile_n %d / granule %d, this shape needs %d / %d (sir_feat_conv_plan)", pack_tile_n,
+                pack_granule, pl.BN, pl.granule);
+  const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
+  SIR_CHECK_ARG((long long)B * Ho * Wo * (long long)ldc < (1ll << 40), "sir_feat_conv: output too large");
+  SIR_CHECK_ARG(d_out || N % 4 == 0, "sir_feat_conv: plane-only output needs N %% 4 == 0");
+  SIR_CHECK_ARG(!d_residual || !d_out_hi || d_amax_res, "sir_feat_conv: residual + operand planes need d_amax_res");
+  SIR_CHECK_ARG(((uintptr_t)d_bias & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ldc % 4 == 0 && (!d_residual || ((uintptr_t)d_residual & 15) == 0) &&
+                    ((uintptr_t)d_xhi & 15) == 0 && ((uintptr_t)d_xlo & 15) == 0 && ((uintptr_t)d_wpack & 15) == 0,
+                "sir_feat_conv: operands must be 16-byte aligned and ldc a multiple of 4");
+  ConvParams& p = pl.halo ? pl.hpl.hp.c : pl.p;
+  p.wpack = d_wpack;
   p.w_exp = w_exp;
   p.amax_in = d_amax_in;
   p.exp_in = d_exp_in;
@@ -701,102 +824,56 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
   p.bound_mult = bound_mult;
   p.bound_add = bound_add;
   p.amax_res = d_residual ? d_amax_res : nullptr;
-  const uint32_t stage_bytes = (uint32_t)(2 * kConvBM + 2 * p.BN) * bk * 2;
-  const uint32_t tail = 8u * (2 * kConvMaxStages + 4) + 16 + 8 * 32 * 16 * 4;
-  p.stages = std::min<int>(kConvMaxStages, (int)((220u * 1024 - 1024 - tail) / stage_bytes));
-  SIR_CHECK_ARG(p.stages >= 2, "sir_feat_conv: tile does not fit shared memory");
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail;
+  cudaStream_t st = (cudaStream_t)stream;
 
-  if (p.taps > 1 && (p.chunks * bk) % 16 == 0) {
-    HaloPlan pl = plan_halo(B, H, W, C, kh, kw, pad, N, p.chunks * bk);
-    const double std_bytes = (double)total * p.taps * p.chunks * stage_bytes;
-    static const char* force = getenv("SIR_CONV_HALO");  // "0" / "1" force the choice (testing)
-    const bool want = force ? force[0] == '1' : pl.l2_bytes < 0.8 * std_bytes;
-    if (pl.ok && want && n_rows_alloc >= pl.hp.c.n_tiles_n * pl.hp.c.BN) {
-      HaloParams& hp = pl.hp;
-      hp.c.w_exp = w_exp;
-      hp.c.amax_in = d_amax_in;
-      hp.c.exp_in = d_exp_in;
-      hp.c.bias = d_bias;
-      hp.c.residual = d_residual;
-      hp.c.out = d_out;
-      hp.c.amax_out = d_amax_out;
-      hp.c.ldc = ldc;
-      hp.c.out_hi = p.out_hi;
-      hp.c.out_lo = p.out_lo;
-      hp.c.exp_out = d_exp_out;
-      hp.c.bound_mult = bound_mult;
-      hp.c.bound_add = bound_add;
-      hp.c.amax_res = p.amax_res;
-      CUtensorMap hxh, hxl, hwh, hwl;
-      {
-        cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)B};
-        cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
-        cuuint32_t box[5] = {8, (cuuint32_t)hp.hw, (cuuint32_t)hp.hh, 4, 1};
-        int rc = encode(&hxh, d_xhi, 5, dims, strides, box, 0, "activation hi (halo)");
-        if (rc) return rc;
-        rc = encode(&hxl, d_xlo, 5, dims, strides, box, 0, "activation lo (halo)");
-        if (rc) return rc;
-      }
-      {
-        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)n_rows_alloc};
-        cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-        cuuint32_t box[2] = {16, (cuuint32_t)hp.c.BN};
-        int rc = encode(&hwh, d_whi, 2, dims, strides, box, 16, "weights hi (halo)");
-        if (rc) return rc;
-        rc = encode(&hwl, d_wlo, 2, dims, strides, box, 16, "weights lo (halo)");
-        if (rc) return rc;
-      }
-      static thread_local bool halo_configured[3] = {false, false, false};
-      const void* hfn = act == 0 ? (const void*)conv_halo_kernel<0> : act == 1 ? (const void*)conv_halo_kernel<1> : (const void*)conv_halo_kernel<2>;
-      if (!halo_configured[act]) {
-        SIR_CUDA(cudaFuncSetAttribute(hfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024)));
-        halo_configured[act] = true;
-      }
-      const unsigned hgrid = (unsigned)std::min<long long>(hp.c.total_tiles, sm_count());
-      if (act == 0)
-        conv_halo_kernel<0><<<hgrid, kConvThreads, pl.smem, (cudaStream_t)stream>>>(hxh, hxl, hwh, hwl, hp);
-      else if (act == 1)
-        conv_halo_kernel<1><<<hgrid, kConvThreads, pl.smem, (cudaStream_t)stream>>>(hxh, hxl, hwh, hwl, hp);
-      else
-        conv_halo_kernel<2><<<hgrid, kConvThreads, pl.smem, (cudaStream_t)stream>>>(hxh, hxl, hwh, hwl, hp);
-      SIR_LAUNCH_CHECK("conv_halo_kernel");
-      return SIR_OK;
+  if (pl.halo) {
+    HaloParams& hp = pl.hpl.hp;
+    CUtensorMap hxh, hxl;
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)hp.hw, (cuuint32_t)hp.hh, 4, 1};
+    rc = encode(&hxh, d_xhi, 5, dims, strides, box, 0, "activation hi (halo)");
+    if (rc) return rc;
+    rc = encode(&hxl, d_xlo, 5, dims, strides, box, 0, "activation lo (halo)");
+    if (rc) return rc;
+    static thread_local bool halo_configured[3] = {false, false, false};
+    const void* hfn = act == 0 ? (const void*)conv_halo_kernel<0> : act == 1 ? (const void*)conv_halo_kernel<1> : (const void*)conv_halo_kernel<2>;
+    if (!halo_configured[act]) {
+      SIR_CUDA(cudaFuncSetAttribute(hfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024)));
+      halo_configured[act] = true;
     }
+    const unsigned hgrid = (unsigned)std::min<long long>(hp.c.total_tiles, sm_count());
+    if (act == 0)
+      conv_halo_kernel<0><<<hgrid, kConvThreads, pl.smem, st>>>(hxh, hxl, hp);
+    else if (act == 1)
+      conv_halo_kernel<1><<<hgrid, kConvThreads, pl.smem, st>>>(hxh, hxl, hp);
+    else
+      conv_halo_kernel<2><<<hgrid, kConvThreads, pl.smem, st>>>(hxh, hxl, hp);
+    SIR_LAUNCH_CHECK("conv_halo_kernel");
+    return SIR_OK;
   }
 
-  CUtensorMap txh, txl, twh, twl;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gB};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)gW * C * 2, (cuuint64_t)gH * gW * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(1 << p.tw_log2), (cuuint32_t)p.TH, 1};
-    int rc = encode(&txh, d_xhi, 4, dims, strides, box, bk, "activation hi");
-    if (rc) return rc;
-    rc = encode(&txl, d_xlo, 4, dims, strides, box, bk, "activation lo");
-    if (rc) return rc;
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)n_rows_alloc};
-    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.BN};
-    int rc = encode(&twh, d_whi, 2, dims, strides, box, bk, "weights hi");
-    if (rc) return rc;
-    rc = encode(&twl, d_wlo, 2, dims, strides, box, bk, "weights lo");
-    if (rc) return rc;
-  }
-  static thread_local size_t configured[3] = {0, 0, 0};
+  CUtensorMap txh, txl;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)pl.gW, (cuuint64_t)pl.gH, (cuuint64_t)pl.gB};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)pl.gW * C * 2, (cuuint64_t)pl.gH * pl.gW * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(1 << p.tw_log2), (cuuint32_t)p.TH, 1};
+  rc = encode(&txh, d_xhi, 4, dims, strides, box, bk, "activation hi");
+  if (rc) return rc;
+  rc = encode(&txl, d_xlo, 4, dims, strides, box, bk, "activation lo");
+  if (rc) return rc;
+  static thread_local bool configured[3] = {false, false, false};
   const void* fn = act == 0 ? (const void*)conv_tc_kernel<0> : act == 1 ? (const void*)conv_tc_kernel<1> : (const void*)conv_tc_kernel<2>;
-  if (smem > configured[act]) {
+  if (!configured[act]) {
     SIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024)));
-    configured[act] = 221 * 1024;
+    configured[act] = true;
   }
-  const unsigned grid = (unsigned)std::min<long long>(total, sm_count());
+  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, sm_count());
   if (act == 0)
-    conv_tc_kernel<0><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(txh, txl, twh, twl, p);
+    conv_tc_kernel<0><<<grid, kConvThreads, pl.smem, st>>>(txh, txl, p);
   else if (act == 1)
-    conv_tc_kernel<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(txh, txl, twh, twl, p);
+    conv_tc_kernel<1><<<grid, kConvThreads, pl.smem, st>>>(txh, txl, p);
   else
-    conv_tc_kernel<2><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(txh, txl, twh, twl, p);
+    conv_tc_kernel<2><<<grid, kConvThreads, pl.smem, st>>>(txh, txl, p);
   SIR_LAUNCH_CHECK("conv_tc_kernel");
   return SIR_OK;
 }

@@ -1,15 +1,15 @@
 // Feature stage (K1-K3): the truncated CNN backbone of network.py:185-186,234-235 as hand-written
 // sm_100a kernels, operator by operator.  Activations are float32 NHWC in HBM.
 //
-//   K1  convolution (any kernel/stride/pad, groups=1) = im2col_split_kernel (gather + fp16 hi/lo
-//       split, per-tensor power-of-two scaling from a device-side running |max|) followed by
-//       gemm_tc_kernel: tcgen05.mma (kind::f16, fp32 accumulate in TMEM) fed by TMA through a
-//       4-stage mbarrier ring, three MMAs per K step (hi*hi + lo*hi + hi*lo) for fp32-grade
-//       results, epilogue fused: un-scale, + bias (folded BatchNorm), SiLU / ReLU, + residual.
-//   K2  depthwise k x k convolution + bias + activation (CUDA cores, HBM bound), global average
-//       pool for the squeeze.
-//   K3  squeeze-excitation MLP (two tiny FCs, SiLU, sigmoid); the channel scale is applied by the
-//       im2col/split pass of the following 1x1 projection, i.e. fused into its operand load.
+//   K1  convolution (groups=1): the tensor-core kernels live in sir_conv_tc.cu (implicit GEMM over fp16 hi/lo
+//       NHWC planes).  Here: im2col_split_kernel = the split pass (float32 -> hi/lo planes with a per-tensor
+//       power-of-two scale from a device-side running |max|, optional squeeze-excitation channel scale), which
+//       for strided convolutions also gathers an explicit im2col matrix; conv_c3k3_kernel = the 3-channel stem
+//       in float32 on the CUDA cores.
+//   K2  depthwise k x k convolution + bias + activation (CUDA cores, HBM bound), the squeeze of a following
+//       SqueezeExcitation fused as partial sums.
+//   K3  squeeze-excitation MLP (two tiny FCs, SiLU, sigmoid); the channel scale is applied by the split pass
+//       of the following 1x1 projection, i.e. fused into its operand load.
 //
 // Reference semantics: torchvision Conv2d / BatchNorm2d(eval) / SiLU / SqueezeExcitation /
 // MaxPool2d as composed by torchvision.models.efficientnet / vgg (third party; the reference only
@@ -320,164 +320,6 @@ __global__ void __launch_bounds__(256) im2col_split_c8_kernel(const float* __res
   }
 }
 
-// ------------------------------------------------------------------------------------------ K1b
-// C[m][n] = act((A_hi+A_lo)[m][:] . (B_hi+B_lo)[n][:] * 2^-(ea+ew) + bias[n]) (+ residual[m][n])
-constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
-constexpr int kGemmStages = 3;  // 96 KB of operand stages: two CTAs fit one SM and overlap epilogue with mainloop
-constexpr int kGemmBM = 128;
-constexpr int kGemmBK = 32;
-constexpr uint32_t kGemmSub = 8192;  // one operand half of one stage (128 rows x 64 B)
-
-struct GemmParams {
-  int M, N, Kp, BN;
-  int w_exp;
-  const float* amax_in;
-  const float* bias;
-  const float* residual;
-  float* out;
-  float* amax_out;
-  int ldc, act;
-  uint32_t tmem_cols;
-};
-
-__global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
-               const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - ptx::smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar0 = base + kGemmStages * 4 * kGemmSub;
-  auto bar_full = [&](int i) { return bar0 + 8u * i; };
-  auto bar_empty = [&](int i) { return bar0 + 8u * (kGemmStages + i); };
-  const uint32_t bar_acc = bar0 + 8u * (2 * kGemmStages);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kGemmStages * 4 * kGemmSub + 8u * (2 * kGemmStages + 1));
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kGemmStages; ++i) {
-      ptx::mbar_init(bar_full(i), 1);
-      ptx::mbar_init(bar_empty(i), 1);
-    }
-    ptx::mbar_init(bar_acc, 1);
-    ptx::fence_barrier_init();
-    ptx::prefetch_tmap(&tm_ahi);
-    ptx::prefetch_tmap(&tm_alo);
-    ptx::prefetch_tmap(&tm_bhi);
-    ptx::prefetch_tmap(&tm_blo);
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot))),
-                 "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * p.BN;
-  const int nk = p.Kp / kGemmBK;
-  const uint32_t stage_tx = 2 * kGemmSub + 2 * (uint32_t)p.BN * 64;
-
-  if (warp == 0) {
-    if (ptx::elect_one()) {
-      for (int ks = 0; ks < nk; ++ks) {
-        const int slot = ks % kGemmStages;
-        ptx::mbar_wait(bar_empty(slot), ((ks / kGemmStages) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(bar_full(slot), stage_tx);
-        const uint32_t dst = base + slot * 4 * kGemmSub;
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                     "l"(reinterpret_cast<uint64_t>(&tm_ahi)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(m0)
-                     : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst + kGemmSub),
-                     "l"(reinterpret_cast<uint64_t>(&tm_alo)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(m0)
-                     : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst + 2 * kGemmSub),
-                     "l"(reinterpret_cast<uint64_t>(&tm_bhi)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(n0)
-                     : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst + 3 * kGemmSub),
-                     "l"(reinterpret_cast<uint64_t>(&tm_blo)), "r"(bar_full(slot)), "r"(ks * kGemmBK), "r"(n0)
-                     : "memory");
-      }
-    }
-  } else if (warp == 1) {
-    if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc_f16(kGemmBM, p.BN);
-      uint32_t accumulate = 0;
-      for (int ks = 0; ks < nk; ++ks) {
-        const int slot = ks % kGemmStages;
-        ptx::mbar_wait(bar_full(slot), (ks / kGemmStages) & 1);
-        ptx::tc_fence_after();
-        const uint32_t a_hi = base + slot * 4 * kGemmSub, a_lo = a_hi + kGemmSub, b_hi = a_hi + 2 * kGemmSub, b_lo = a_hi + 3 * kGemmSub;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {  // two K16 steps per 32-wide stage: +32 B inside the 64B-swizzle row
-          const uint64_t da_hi = ptx::make_smem_desc(a_hi + 32u * kk, 16, 512, 4);
-          const uint64_t da_lo = ptx::make_smem_desc(a_lo + 32u * kk, 16, 512, 4);
-          const uint64_t db_hi = ptx::make_smem_desc(b_hi + 32u * kk, 16, 512, 4);
-          const uint64_t db_lo = ptx::make_smem_desc(b_lo + 32u * kk, 16, 512, 4);
-          ptx::mma_f16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
-          ptx::mma_f16_ss(tmem_base, da_lo, db_hi, idesc, 1);
-          ptx::mma_f16_ss(tmem_base, da_hi, db_lo, idesc, 1);
-          accumulate = 1;
-        }
-        ptx::tc_commit(bar_empty(slot));
-      }
-      ptx::tc_commit(bar_acc);
-    }
-  } else {
-    // epilogue: warps 2..5 own TMEM lane quarters 2,3,0,1
-    const int q4 = warp & 3;
-    const int m = m0 + q4 * 32 + lane;
-    const int e_total = scale_exp_from_amax(*p.amax_in) + p.w_exp;
-    const float unscale = ldexpf(1.0f, -e_total);
-    ptx::mbar_wait(bar_acc, 0);
-    ptx::tc_fence_after();
-    float local_max = 0.0f;
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + c0, v);
-      ptx::tmem_ld_wait();
-      if (m < p.M) {
-        float* orow = p.out + (size_t)m * p.ldc;
-        const float* rrow = p.residual ? p.residual + (size_t)m * p.ldc : nullptr;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n + 3 < p.N) {
-            float4 o;
-            const float4 bb = *reinterpret_cast<const float4*>(p.bias + n);
-            o.x = act_apply(fmaf(__uint_as_float(v[j]), unscale, bb.x), p.act);
-            o.y = act_apply(fmaf(__uint_as_float(v[j + 1]), unscale, bb.y), p.act);
-            o.z = act_apply(fmaf(__uint_as_float(v[j + 2]), unscale, bb.z), p.act);
-            o.w = act_apply(fmaf(__uint_as_float(v[j + 3]), unscale, bb.w), p.act);
-            if (rrow) {
-              const float4 rr = *reinterpret_cast<const float4*>(rrow + n);
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-            }
-            *reinterpret_cast<float4*>(orow + n) = o;
-            local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-          } else {
-            for (int t = 0; t < 4; ++t) {
-              if (n + t < p.N) {
-                float o = act_apply(fmaf(__uint_as_float(v[j + t]), unscale, p.bias[n + t]), p.act);
-                if (rrow) o += rrow[n + t];
-                orow[n + t] = o;
-                local_max = fmaxf(local_max, fabsf(o));
-              }
-            }
-          }
-        }
-      }
-    }
-    local_max = warp_max(local_max);
-    if (lane == 0 && p.amax_out) atomic_max_nonneg(p.amax_out, local_max);
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------ K2
 // depthwise k x k convolution, NHWC float32, weights [k][k][C], + bias, + activation
 __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, int B, int H, int W, int C, int k, int stride,
@@ -771,38 +613,6 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------ host
 namespace {
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-// row-major fp16 matrix [rows][Kp], box = [box_rows][32], 64-byte swizzle, OOB rows read as zero
-int make_matrix_map(CUtensorMap* tm, const void* ptr, long long rows, int Kp, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return SIR_E_CUDA;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(matrix %lld x %d) failed with CUresult %d", rows, Kp, (int)r);
-    return SIR_E_CUDA;
-  }
-  return SIR_OK;
-}
 unsigned grid_for(size_t work, int per_block = 256) { return (unsigned)std::min<size_t>((work + per_block - 1) / per_block, 148 * 32); }
 }  // namespace
 }  // namespace sir
@@ -859,51 +669,6 @@ extern "C" int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, 
     im2col_split_kernel<<<grid_for(work), 256, 0, (cudaStream_t)stream>>>(d_in, d_amax_in, B, H, W, C, kh, kw, stride, pad, Ho, Wo,
                                                                            d_chan_scale, Kp, (__half*)d_ahi, (__half*)d_alo);
   SIR_LAUNCH_CHECK("im2col_split_kernel");
-  return SIR_OK;
-}
-
-extern "C" int sir_feat_gemm(const uint16_t* d_ahi, const uint16_t* d_alo, const float* d_amax_in, long long M, int Kp,
-                             const uint16_t* d_bhi, const uint16_t* d_blo, int N, int n_rows_alloc, int w_exp, const float* d_bias,
-                             const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out, void* stream) {
-  SIR_CHECK_ARG(d_ahi && d_alo && d_bhi && d_blo && d_amax_in && d_bias && d_out, "sir_feat_gemm: null pointer");
-  SIR_CHECK_ARG(M > 0 && M < (1ll << 31) && N > 0 && Kp > 0 && Kp % 32 == 0 && ldc >= N, "sir_feat_gemm: bad shape M=%lld N=%d Kp=%d", M, N, Kp);
-  SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_gemm: unknown activation %d", act);
-  GemmParams p{};
-  p.M = (int)M;
-  p.N = N;
-  p.Kp = Kp;
-  p.BN = std::min(128, round_up(N, 32));
-  SIR_CHECK_ARG(n_rows_alloc >= round_up(N, p.BN), "sir_feat_gemm: weight matrix needs %d zero-padded rows, has %d", round_up(N, p.BN), n_rows_alloc);
-  p.w_exp = w_exp;
-  p.amax_in = d_amax_in;
-  p.bias = d_bias;
-  p.residual = d_residual;
-  p.out = d_out;
-  p.amax_out = d_amax_out;
-  p.ldc = ldc;
-  p.act = act;
-  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;
-  SIR_CHECK_ARG(((uintptr_t)d_bias & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ldc % 4 == 0 &&
-                    (!d_residual || ((uintptr_t)d_residual & 15) == 0),
-                "sir_feat_gemm: bias/out/residual must be 16-byte aligned and ldc a multiple of 4");
-  CUtensorMap ta, tb, tc, td;
-  int rc = make_matrix_map(&ta, d_ahi, M, Kp, kGemmBM);
-  if (rc) return rc;
-  rc = make_matrix_map(&tb, d_alo, M, Kp, kGemmBM);
-  if (rc) return rc;
-  rc = make_matrix_map(&tc, d_bhi, n_rows_alloc, Kp, p.BN);
-  if (rc) return rc;
-  rc = make_matrix_map(&td, d_blo, n_rows_alloc, Kp, p.BN);
-  if (rc) return rc;
-  const size_t smem = 1024 + kGemmStages * 4 * kGemmSub + 256;
-  static thread_local bool configured = false;
-  if (!configured) {
-    SIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  dim3 grid((unsigned)ceil_div((int)M, kGemmBM), (unsigned)ceil_div(N, p.BN));
-  gemm_tc_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ta, tb, tc, td, p);
-  SIR_LAUNCH_CHECK("gemm_tc_kernel");
   return SIR_OK;
 }
 

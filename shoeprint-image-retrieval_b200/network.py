@@ -339,6 +339,20 @@ class _Program:
     def _out_hw(h: int, w: int, k: int, kw: int, s: int, pd: int) -> tuple[int, int]:
         return (h + 2 * pd - k) // s + 1, (w + 2 * pd - kw) // s + 1
 
+    def _packed_weights(self, p: dict, geom: tuple, st: C.c_void_p) -> tuple[torch.Tensor, int, int]:
+        """The layer's weights as per-stage shared-memory images for the tile the library plans for this shape
+        (packed on the device the first time a tile shape is needed, then cached)."""
+        tile_n, granule, nbytes = C.c_int(), C.c_int(), C.c_longlong()
+        nat.check(nat.lib.sir_feat_conv_plan(*geom, p["bk"], p["cout"], C.byref(tile_n), C.byref(granule), C.byref(nbytes)), "sir_feat_conv_plan")
+        key = (tile_n.value, granule.value)
+        packs = p.setdefault("packs", {})
+        if key not in packs:
+            buf = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            nat.check(nat.lib.sir_feat_conv_pack_weights(_ptr(p["whi"]), _ptr(p["wlo"]), p["rows"], p["kp"], key[0], key[1], _ptr(buf), st),
+                      "sir_feat_conv_pack_weights")
+            packs[key] = buf
+        return packs[key], key[0], key[1]
+
     def run(self, x0: torch.Tensor, amax0: torch.Tensor) -> torch.Tensor:  # noqa: C901, PLR0915
         """x0: normalised input [B,H,W,3] float32 NHWC; amax0: 1-element tensor with its max |x|."""
         dev = self.device
@@ -412,8 +426,9 @@ class _Program:
                     nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
                                                             _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
                     geom = (1, 1, m, p["kp"], 1, 1, 0)
-                nat.check(nat.lib.sir_feat_conv(_ptr(ahi), _ptr(alo), aptr(op.src), *geom, p["bk"], _ptr(p["whi"]), _ptr(p["wlo"]),
-                                                p["cout"], p["rows"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
+                wpack, tile_n, granule = self._packed_weights(p, geom, st)
+                nat.check(nat.lib.sir_feat_conv(_ptr(ahi), _ptr(alo), aptr(op.src), *geom, p["bk"], _ptr(wpack), tile_n, granule,
+                                                p["cout"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
                                                 out_ptr, ldc, aptr(op.dst), exp_in, _ptr(ohi), _ptr(olo), exp_out, p["bound_mult"],
                                                 p["bound_add"], aptr(p["residual"]) if p["residual"] is not None else None, st),
                           "sir_feat_conv")
