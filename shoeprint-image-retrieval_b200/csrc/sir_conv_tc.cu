@@ -20,6 +20,7 @@
 //               running max |out| for the next layer's scaling
 // Bound: tensor pipe for wide layers (three MMAs per algorithmic MAC), L2->smem operand feed otherwise.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -82,68 +83,63 @@ __device__ __forceinline__ float conv_act(float v) {
 
 // Epilogue of one 128 x BN accumulator tile: this warp owns 32 TMEM lanes (rows) and every second 16-column chunk.
 // pix[ps]: output pixel index of row (ps*8 + lane/4) of the warp's 32 rows, or -1 if outside the image.
+// One chunk: 32 rows x 16 columns arrive row-per-lane from TMEM, are transposed through shared memory (XOR swizzle,
+// conflict free both ways) so that each lane then owns 4 consecutive columns of 4 rows: stores and residual loads are
+// row contiguous (64 B per row, full sectors).
+template <int ACT>
+__device__ __forceinline__ void conv_epilogue_chunk(const ConvParams& p, const uint32_t (&v)[16], float* xp, int lane, int n,
+                                                    const long long (&pix)[4], float unscale, float oscale, float& local_max) {
+  const int rs = lane >> 2, c4 = lane & 3;
+  const bool live = n < p.N;  // N % 4 == 0: a lane's 4 columns are all inside or all outside
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(xp + lane * 16 + 4 * (j ^ ((lane >> 1) & 3))) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  if (!live) return;
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    if (pix[ps] < 0) continue;
+    const long long row_off = pix[ps] * p.ldc + n;
+    const int row = ps * 8 + rs;
+    const float4 a = *reinterpret_cast<const float4*>(xp + row * 16 + 4 * (c4 ^ ((row >> 1) & 3)));
+    float4 o = make_float4(conv_act<ACT>(fmaf(a.x, unscale, bb.x)), conv_act<ACT>(fmaf(a.y, unscale, bb.y)),
+                           conv_act<ACT>(fmaf(a.z, unscale, bb.z)), conv_act<ACT>(fmaf(a.w, unscale, bb.w)));
+    if (p.residual) {
+      const float4 rr = *reinterpret_cast<const float4*>(p.residual + row_off);
+      o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+    }
+    if (p.out) *reinterpret_cast<float4*>(p.out + row_off) = o;
+    if (p.out_hi) {  // the same values as the next convolution's operand planes
+      const float s0 = o.x * oscale, s1 = o.y * oscale, s2 = o.z * oscale, s3 = o.w * oscale;
+      const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+      const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(s0 - b01.x, s1 - b01.y), l23 = __floats2half2_rn(s2 - b23.x, s3 - b23.y);
+      const long long so = pix[ps] * p.N + n;
+      *reinterpret_cast<uint2*>(p.out_hi + so) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      *reinterpret_cast<uint2*>(p.out_lo + so) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+    local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t tacc, float* xp, int lane, int half, int nt,
                                                    const long long (&pix)[4], float unscale, float oscale, float& local_max) {
-  const int rs = lane >> 2, c4 = lane & 3;
-  const int n_chunks = p.BN >> 4;
-  for (int ci = half; ci < n_chunks; ci += 2) {
-    uint32_t v[16];
-    ptx::tmem_ld_32x16(tacc + ci * 16, v);
+  const int n_chunks = p.BN >> 4, n_base = nt * p.BN + (lane & 3) * 4;
+  // two register sets: the TMEM load of the next chunk is in flight while the current one is processed
+  uint32_t va[16], vb[16];
+  if (half < n_chunks) ptx::tmem_ld_32x16(tacc + half * 16, va);
+  for (int ci = half; ci < n_chunks; ci += 4) {
     ptx::tmem_ld_wait();
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<uint4*>(xp + lane * 16 + 4 * (j ^ ((lane >> 1) & 3))) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
-    const int n = nt * p.BN + ci * 16 + c4 * 4;
-    if (n < p.N) {
-      const bool full4 = n + 3 < p.N;
-      float bb[4] = {0.f, 0.f, 0.f, 0.f};
-      if (full4) {
-        const float4 t = *reinterpret_cast<const float4*>(p.bias + n);
-        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
-      } else {
-        for (int t = 0; n + t < p.N; ++t) bb[t] = p.bias[n + t];
-      }
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        if (pix[ps] < 0) continue;
-        const long long row_off = pix[ps] * p.ldc;
-        const int row = ps * 8 + rs;
-        const float4 a = *reinterpret_cast<const float4*>(xp + row * 16 + 4 * (c4 ^ ((row >> 1) & 3)));
-        float o[4] = {conv_act<ACT>(fmaf(a.x, unscale, bb[0])), conv_act<ACT>(fmaf(a.y, unscale, bb[1])),
-                      conv_act<ACT>(fmaf(a.z, unscale, bb[2])), conv_act<ACT>(fmaf(a.w, unscale, bb[3]))};
-        float* dst = p.out + row_off + n;
-        if (full4) {
-          if (p.residual) {
-            const float4 rr = *reinterpret_cast<const float4*>(p.residual + row_off + n);
-            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-          }
-          if (p.out) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-          if (p.out_hi) {  // the same values as the next convolution's operand planes (N % 8 == 0 guaranteed by the host)
-            __align__(8) __half hi[4];
-            __align__(8) __half lo[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float sv = o[t] * oscale;
-              hi[t] = __float2half_rn(sv);
-              lo[t] = __float2half_rn(sv - __half2float(hi[t]));
-            }
-            const long long so = pix[ps] * p.N + n;
-            *reinterpret_cast<uint2*>(p.out_hi + so) = *reinterpret_cast<const uint2*>(hi);
-            *reinterpret_cast<uint2*>(p.out_lo + so) = *reinterpret_cast<const uint2*>(lo);
-          }
-          local_max = fmaxf(local_max, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
-        } else {
-          for (int t = 0; n + t < p.N; ++t) {
-            float ov = o[t];
-            if (p.residual) ov += p.residual[row_off + n + t];
-            if (p.out) dst[t] = ov;
-            local_max = fmaxf(local_max, fabsf(ov));
-          }
-        }
-      }
+    if (ci + 2 < n_chunks) ptx::tmem_ld_32x16(tacc + (ci + 2) * 16, vb);
+    conv_epilogue_chunk<ACT>(p, va, xp, lane, n_base + ci * 16, pix, unscale, oscale, local_max);
+    if (ci + 2 < n_chunks) {
+      ptx::tmem_ld_wait();
+      if (ci + 4 < n_chunks) ptx::tmem_ld_32x16(tacc + (ci + 4) * 16, va);
+      conv_epilogue_chunk<ACT>(p, vb, xp, lane, n_base + (ci + 2) * 16, pix, unscale, oscale, local_max);
     }
   }
 }
@@ -665,6 +661,7 @@ int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && kh > 0 && kw > 0 && pad >= 0 && N > 0,
                 "sir_feat_conv: bad shape B=%d H=%d W=%d C=%d (C must be a multiple of 8) k=%dx%d N=%d", B, H, W, C, kh, kw, N);
   SIR_CHECK_ARG(bk == 16 || bk == 32, "sir_feat_conv: bk must be 16 or 32, got %d", bk);
+  SIR_CHECK_ARG(N % 4 == 0, "sir_feat_conv: N = %d must be a multiple of 4", N);
   const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
   SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_conv: empty output");
   ConvPlan& pl = *out;

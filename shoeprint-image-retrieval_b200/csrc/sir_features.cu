@@ -428,18 +428,14 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
       }
     };
     const int oy0 = strip * kDwRows, oy1 = min(Ho, oy0 + kDwRows);
-    float4 r0[3], r1[3], r2[3];
-    load_row(oy0 * S - 1, r0);
-    load_row(oy0 * S, r1);
     float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int oy = oy0; oy < oy1; ++oy) {
-      load_row(oy * S + 1, r2);
+    auto emit = [&](int oy, const float4 (&a)[3], const float4 (&m)[3], const float4 (&z)[3]) {
       float4 acc = bb;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        acc = f4_fma(r0[kx], wv[kx], acc);
-        acc = f4_fma(r1[kx], wv[3 + kx], acc);
-        acc = f4_fma(r2[kx], wv[6 + kx], acc);
+        acc = f4_fma(a[kx], wv[kx], acc);
+        acc = f4_fma(m[kx], wv[3 + kx], acc);
+        acc = f4_fma(z[kx], wv[6 + kx], acc);
       }
       float4 o;
       if (ACT == 1) {
@@ -453,13 +449,34 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
       *reinterpret_cast<float4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
       pool.x += o.x; pool.y += o.y; pool.z += o.z; pool.w += o.w;
       local = fmaxf(local, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-      if (S == 1) {
+    };
+    if (S == 1) {
+      // two output rows per iteration: the six loads of the two new input rows are in flight together
+      float4 r0[3], r1[3], r2[3], r3[3];
+      load_row(oy0 - 1, r0);
+      load_row(oy0, r1);
+      int oy = oy0;
+      for (; oy + 1 < oy1; oy += 2) {
+        load_row(oy + 1, r2);
+        load_row(oy + 2, r3);
+        emit(oy, r0, r1, r2);
+        emit(oy + 1, r1, r2, r3);
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) { r0[kx] = r1[kx]; r1[kx] = r2[kx]; }
-      } else {
+        for (int kx = 0; kx < 3; ++kx) { r0[kx] = r2[kx]; r1[kx] = r3[kx]; }
+      }
+      if (oy < oy1) {
+        load_row(oy + 1, r2);
+        emit(oy, r0, r1, r2);
+      }
+    } else {
+      float4 r0[3], r1[3], r2[3];
+      load_row(oy0 * S - 1, r0);
+      for (int oy = oy0; oy < oy1; ++oy) {
+        load_row(oy * S, r1);
+        load_row(oy * S + 1, r2);
+        emit(oy, r0, r1, r2);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) r0[kx] = r2[kx];
-        if (oy + 1 < oy1) load_row((oy + 1) * S, r1);
       }
     }
     if (pool_part) *reinterpret_cast<float4*>(pool_part + ((size_t)b * strips * Wo + (size_t)strip * Wo + ox) * C + c) = pool;

@@ -276,6 +276,7 @@ class _Program:
         comp.peephole()
         self.ops = comp.ops
         self.n_tensors = comp.n_tensors
+        self.launch_log: list[str] | None = None  # profiling aid: one label per kernel launched by run()
         self.out_id = comp.cur if not self.ops else self.ops[-1].dst
         self.device = device
         for op in self.ops:
@@ -369,6 +370,7 @@ class _Program:
                 if op.p.get(key) is not None:
                     last_use[op.p[key]] = i
 
+        log = self.launch_log
         squeezed = {op.src for op in self.ops if op.kind == "se"}
         pooled: dict[int, tuple[torch.Tensor, int]] = {}
         planes: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}  # tensor id -> fp16 hi/lo operand planes from its producer
@@ -377,10 +379,20 @@ class _Program:
         def aptr(tid: int) -> C.c_void_p:
             return C.c_void_p(amax.data_ptr() + 4 * tid)
 
+        def describe(op: _Op, n0: int) -> None:
+            q = op.p
+            text = op.kind
+            if op.kind == "conv":
+                text = f"conv k{q['k']} s{q['stride']} {q['cin']}->{q['cout']}" + (" +planes" if q["emit_planes"] else "") + ("" if q["emit_f32"] else " -f32")
+            elif op.kind == "dwconv":
+                text = f"dw k{q['k']} s{q['stride']}"
+            log.extend([text] * (launch_counter.n - n0))
+
         for i, op in enumerate(self.ops):
             p = op.p
             src = tensors[op.src]
             b, h, w, c = (int(v) for v in src.shape)
+            n_before = launch_counter.n
             if op.kind == "conv":
                 ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
                 m = b * ho * wo
@@ -407,6 +419,8 @@ class _Program:
                     for tid in [t for t, lu in last_use.items() if lu == i and t != self.out_id]:
                         tensors.pop(tid, None)
                         planes.pop(tid, None)
+                    if log is not None:
+                        describe(op, n_before)
                     continue
                 exp_in = None
                 if p["implicit"] and cs is None and op.src in planes:  # operand planes came from the producer's epilogue
@@ -482,6 +496,8 @@ class _Program:
             else:  # pragma: no cover
                 raise AssertionError(op.kind)
             tensors[op.dst] = out
+            if log is not None:
+                describe(op, n_before)
             for tid in [t for t, lu in last_use.items() if lu == i and t != self.out_id]:
                 tensors.pop(tid, None)
                 planes.pop(tid, None)

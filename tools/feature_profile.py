@@ -15,24 +15,21 @@ cfg = {"model": {"type": mtype, "clahe_clip_limit": 2.0, "clahe_tile_grid_size":
 model = network.Model(cfg, block, random_init_seed=0)
 batch = np.random.default_rng(0).integers(0, 256, size=(b, 800, 300), dtype=np.uint8)
 model._forward_uint8(batch, apply_clahe=True); torch.cuda.synchronize()
+model.program.launch_log = []
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     model._forward_uint8(batch, apply_clahe=True); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
-# per-launch list in launch order, with the program's op shapes beside it
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=60))
 evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "sir::" in e.name], key=lambda e: e.time_range.start)
-desc = []
-for op in model.program.ops:
-    p = op.p
-    if op.kind == "conv":
-        d = f"conv k{p['k']} s{p['stride']} {p['cin']}->{p['cout']} kp{p['kp']}"
-        desc += [d, d]
-    elif op.kind == "dwconv":
-        desc += [f"dw k{p['k']} s{p['stride']}"]
-    elif op.kind == "se":
-        desc += ["se", "se"]
-    else:
-        desc += [op.kind]
-body = [e for e in evs if "clahe" not in e.name and "nhwc_to_nchw" not in e.name]
-for e, d in zip(body, desc):
-    short = e.name.split("(")[0].replace("sir::", "")
-    print(f"{short:24s} {e.device_time:8.1f} us  {d}")
+body = [e for e in evs if "clahe" not in e.name and "nhwc_to_nchw" not in e.name and "pack_weights" not in e.name]
+labels = model.program.launch_log
+assert len(body) == len(labels), (len(body), len(labels))
+import collections
+agg = collections.OrderedDict()
+for e, d in zip(body, labels):
+    short = e.name.split("(")[0].replace("sir::", "").replace("void ", "")
+    key = (short, d)
+    n, t = agg.get(key, (0, 0.0))
+    agg[key] = (n + 1, t + e.device_time)
+print(f"{'kernel':28s} {'layer':38s} {'n':>3s} {'avg us':>9s} {'total ms':>9s}")
+for (short, d), (n, t) in agg.items():
+    print(f"{short:28s} {d:38s} {n:3d} {t / n:9.1f} {t / 1e3:9.3f}")
