@@ -187,6 +187,8 @@ int sir_merge_topk(const float* d_vals, const int32_t* d_idx, int P, int Q, int 
  * sir_feat_dwconv: depthwise k x k Conv2d + folded BN bias + activation; weights [k][k][C].  If d_pool_part is
  *   not NULL it also receives the squeeze of a following SqueezeExcitation as partial sums over pixels,
  *   [B][parts][C] with parts = sir_feat_dwconv_pool_parts(k, stride, C, Ho, Wo) (fused into the 3x3 fast path).
+ *   The 3x3 fast path can also (or only, d_out = NULL) write its result as operand planes for sir_feat_conv
+ *   (d_out_hi/d_out_lo/d_exp_out, bound = amax_in * bound_mult + bound_add as there).
  * sir_feat_pool_sum: the same squeeze for any other producer, one part: [B][HW][C] -> [B][1][C].
  * sir_feat_se_scale: SqueezeExcitation._scale: avg = sum of parts / HW (d_avg [B][C] scratch), fc1 [S][C] + SiLU, fc2 given
  *   transposed as [S][C] + sigmoid -> d_scale [B][C].
@@ -216,12 +218,19 @@ int sir_feat_conv_tile_n(int N);
  * copy; tensor-map loads of 32/64-byte weight rows are bound by the TMA unit's row rate).  sir_feat_conv_plan: tile width,
  * K granule (16 or 32 channels) and byte size of the packed weights for a shape; sir_feat_conv_pack_weights: [n_rows][Kp]
  * fp16 hi/lo matrices (k = (ky*kw + kx)*Cp + c) -> that layout, [n_tile][k_step][hi | lo][tile_n][granule] swizzled. */
-int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int* tile_n, int* granule,
-                       long long* pack_bytes);
+int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int per_image, int* tile_n,
+                       int* granule, long long* pack_bytes);
+/* sir_feat_conv_scale_weights: one weight set per image with the SqueezeExcitation scale folded in,
+ * W_b[n][k] = W[n][k] * d_scale[b][k mod Cp] (torchvision SqueezeExcitation.forward, scale * input, followed by the
+ * 1x1 projection), packed like sir_feat_conv_pack_weights, B sets of pack_bytes; used with per_image = 1, which keeps
+ * every row tile inside one image.  The projection then reads the depthwise output's own operand planes: no pass over
+ * the activation between the depthwise convolution and the projection. */
+int sir_feat_conv_scale_weights(const uint16_t* d_whi, const uint16_t* d_wlo, int n_rows, int Kp, int Cp, int C,
+                                const float* d_scale, int B, int tile_n, int granule, uint8_t* d_pack, void* stream);
 int sir_feat_conv_pack_weights(const uint16_t* d_whi, const uint16_t* d_wlo, int n_rows, int Kp, int tile_n, int granule,
                                uint8_t* d_pack, void* stream);
 int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
-                  int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int N, int w_exp,
+                  int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int per_image, int N, int w_exp,
                   const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
                   const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
                   float bound_add, const float* d_amax_res, void* stream);
@@ -233,7 +242,8 @@ int sir_feat_conv_c3k3(const float* d_in, const float* d_amax_in, int B, int H, 
                        uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult, float bound_add, void* stream);
 int sir_feat_dwconv_pool_parts(int k, int stride, int C, int Ho, int Wo);
 int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, const float* d_w,
-                    const float* d_bias, int act, float* d_out, float* d_amax_out, float* d_pool_part, void* stream);
+                    const float* d_bias, int act, float* d_out, float* d_amax_out, float* d_pool_part, const float* d_amax_in,
+                    uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult, float bound_add, void* stream);
 int sir_feat_pool_sum(const float* d_in, int B, int HW, int C, float* d_pool_part, void* stream);
 int sir_feat_se_scale(const float* d_pool_part, int B, int parts, int HW, int C, int S, const float* d_w1, const float* d_b1,
                       const float* d_w2t, const float* d_b2, float* d_avg, float* d_scale, void* stream);

@@ -46,6 +46,7 @@ struct ConvParams {
   int stages;
   int w_exp;
   const uint8_t* wpack;   // weights as per-stage shared-memory images: [n_tile][k_step][hi | lo][BN][granule], swizzled
+  long long wpack_image_bytes;  // 0: one weight set; else one set per image (squeeze-excitation scale folded into the weights)
   const float* amax_in;
   const int* exp_in;      // exponent the input planes were written with; NULL: derived from amax_in (split pass)
   const float* bias;
@@ -197,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int x0 = px * TW - p.pad, y0 = py * p.TH - p.pad;
         // The weight stage is ONE contiguous bulk copy of a pre-swizzled image: a tensor-map load of narrow rows
         // (32 / 64 B) is bound by the TMA unit's row rate, which starved the MMAs.
-        const uint8_t* wsrc = p.wpack + (size_t)nt * k_iters * (2 * b_bytes);
+        const uint8_t* wsrc = p.wpack + (size_t)b * p.wpack_image_bytes + (size_t)nt * k_iters * (2 * b_bytes);
         int tap_y = 0, tap_x = 0, chunk = 0;
         for (int ks = 0; ks < k_iters; ++ks) {
           ptx::mbar_wait(bar_empty(slot), phase ^ 1);
@@ -657,7 +658,7 @@ struct ConvPlan {
   int BN, granule, n_tiles_n, k_steps;  // layout of the packed weights
 };
 
-int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, ConvPlan* out) {
+int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int per_image, ConvPlan* out) {
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && kh > 0 && kw > 0 && pad >= 0 && N > 0,
                 "sir_feat_conv: bad shape B=%d H=%d W=%d C=%d (C must be a multiple of 8) k=%dx%d N=%d", B, H, W, C, kh, kw, N);
   SIR_CHECK_ARG(bk == 16 || bk == 32, "sir_feat_conv: bk must be 16 or 32, got %d", bk);
@@ -679,11 +680,12 @@ int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N
   pl.gB = B;
   pl.gH = H;
   pl.gW = W;
-  if (p.taps == 1 && pad == 0) {
+  SIR_CHECK_ARG(!per_image || (p.taps == 1 && pad == 0), "sir_feat_conv: per-image weights need a 1x1 convolution");
+  if (p.taps == 1 && pad == 0) {  // flat rows; with per-image weights one row per image so that no tile straddles two images
     SIR_CHECK_ARG((long long)B * H * W < (1ll << 31), "sir_feat_conv: too many rows");
-    pl.gW = B * H * W;
+    pl.gW = per_image ? H * W : B * H * W;
     pl.gH = 1;
-    pl.gB = 1;
+    pl.gB = per_image ? B : 1;
   }
   p.Ho = pl.gH + 2 * pad - kh + 1;
   p.Wo = pl.gW + 2 * pad - kw + 1;
@@ -749,17 +751,71 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __half* __restr
     *reinterpret_cast<uint4*>(out + ((((size_t)nt * k_steps + ks) * 2 + plane) * BN + row) * g + cs * 8) = v;
   }
 }
+// per-image weights W_b[n][k] = W[n][k] * scale[b][channel(k)] (SqueezeExcitation folded into the projection), re-split into
+// hi/lo and written in the packed layout, one set per image
+__global__ void __launch_bounds__(256) scale_pack_weights_kernel(const __half* __restrict__ whi, const __half* __restrict__ wlo, int n_rows,
+                                                                 int Kp, int Cp, int C, const float* __restrict__ scale, int B, int BN, int g,
+                                                                 int n_tiles_n, int k_steps, __half* __restrict__ out) {
+  const int chunks = g / 8;
+  const size_t per_image = (size_t)n_tiles_n * k_steps * 2 * BN * chunks, total = per_image / 2 * B;  // one thread writes hi and lo
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % chunks);
+    size_t r = i / chunks;
+    const int row = (int)(r % BN);
+    r /= BN;
+    const int ks = (int)(r % k_steps);
+    r /= k_steps;
+    const int nt = (int)(r % n_tiles_n), b = (int)(r / n_tiles_n);
+    const int n = nt * BN + row, k = ks * g + c * 8;
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hi[j] = lo[j] = __float2half_rn(0.0f);
+    if (n < n_rows && k < Kp) {
+      const uint4 vh = *reinterpret_cast<const uint4*>(whi + (size_t)n * Kp + k), vl = *reinterpret_cast<const uint4*>(wlo + (size_t)n * Kp + k);
+      const __half* ph = reinterpret_cast<const __half*>(&vh);
+      const __half* pl = reinterpret_cast<const __half*>(&vl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = (k + j) % Cp;
+        const float sc = ch < C ? scale[(size_t)b * C + ch] : 0.0f;
+        const float v = (__half2float(ph[j]) + __half2float(pl[j])) * sc;
+        hi[j] = __float2half_rn(v);
+        lo[j] = __float2half_rn(v - __half2float(hi[j]));
+      }
+    }
+    const int cs = g == 16 ? (c ^ ((row >> 2) & 1)) : (c ^ ((row >> 1) & 3));
+    __half* dst = out + (size_t)b * per_image * 8 + ((((size_t)nt * k_steps + ks) * 2) * BN + row) * g + cs * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + (size_t)BN * g) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
 }  // namespace
 }  // namespace sir
 
 using namespace sir;
 
+extern "C" int sir_feat_conv_scale_weights(const uint16_t* d_whi, const uint16_t* d_wlo, int n_rows, int Kp, int Cp, int C,
+                                           const float* d_scale, int B, int tile_n, int granule, uint8_t* d_pack, void* stream) {
+  SIR_CHECK_ARG(d_whi && d_wlo && d_scale && d_pack && n_rows > 0 && Kp > 0 && Kp % 8 == 0 && B > 0 && C > 0 && Cp >= C && Kp % Cp == 0,
+                "sir_feat_conv_scale_weights: bad argument");
+  SIR_CHECK_ARG(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0 && (granule == 16 || granule == 32) && Kp % granule == 0,
+                "sir_feat_conv_scale_weights: bad tile (tile_n %d, granule %d, Kp %d)", tile_n, granule, Kp);
+  SIR_CHECK_ARG((((uintptr_t)d_whi | (uintptr_t)d_wlo | (uintptr_t)d_pack) & 15) == 0, "sir_feat_conv_scale_weights: pointers must be 16-byte aligned");
+  const int n_tiles_n = ceil_div(n_rows, tile_n), k_steps = Kp / granule;
+  const size_t total = (size_t)B * n_tiles_n * k_steps * tile_n * (granule / 8);
+  scale_pack_weights_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)d_whi, (const __half*)d_wlo, n_rows, Kp, Cp, C, d_scale, B, tile_n, granule, n_tiles_n, k_steps, (__half*)d_pack);
+  SIR_LAUNCH_CHECK("scale_pack_weights_kernel");
+  return SIR_OK;
+}
+
 extern "C" int sir_feat_conv_tile_n(int N) { return N > 0 ? conv_tile_n(N) : 0; }
 
-extern "C" int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int* tile_n, int* granule,
-                                  long long* pack_bytes) {
+extern "C" int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int per_image, int* tile_n,
+                                  int* granule, long long* pack_bytes) {
   ConvPlan pl;
-  const int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, &pl);
+  const int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, per_image, &pl);
   if (rc) return rc;
   if (tile_n) *tile_n = pl.BN;
   if (granule) *granule = pl.granule;
@@ -782,7 +838,8 @@ extern "C" int sir_feat_conv_pack_weights(const uint16_t* d_whi, const uint16_t*
 }
 
 extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
-                             int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int N, int w_exp,
+                             int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int per_image, int N,
+                             int w_exp,
                              const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
                              const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
                              float bound_add, const float* d_amax_res, void* stream) {
@@ -792,7 +849,7 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
                 "sir_feat_conv: operand-plane output needs d_out_lo, d_exp_out, N %% 8 == 0 and a non-negative bound");
   SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_conv: unknown activation %d", act);
   ConvPlan pl;
-  int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, &pl);
+  int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, per_image, &pl);
   if (rc) return rc;
   SIR_CHECK_ARG(ldc >= N, "sir_feat_conv: ldc %d < N %d", ldc, N);
   SIR_CHECK_ARG(pack_tile_n == pl.BN && pack_granule == pl.granule,
@@ -807,6 +864,7 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
                 "sir_feat_conv: operands must be 16-byte aligned and ldc a multiple of 4");
   ConvParams& p = pl.halo ? pl.hpl.hp.c : pl.p;
   p.wpack = d_wpack;
+  p.wpack_image_bytes = per_image ? (long long)pl.n_tiles_n * pl.k_steps * 2 * pl.BN * pl.granule * 2 : 0;
   p.w_exp = w_exp;
   p.amax_in = d_amax_in;
   p.exp_in = d_exp_in;

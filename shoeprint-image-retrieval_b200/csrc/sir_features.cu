@@ -16,6 +16,7 @@
 // selects and truncates them, network.py:121-186).  ToTensor + Normalize (network.py:51-87) are
 // image_to_nhwc_kernel.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "sir_common.cuh"
 #include "sir_ptx.cuh"
@@ -403,8 +404,22 @@ template <int S, int ACT>
 __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restrict__ in, int B, int H, int W, int C, int Ho, int Wo,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            float* __restrict__ out, float* __restrict__ amax,
-                                                           float* __restrict__ pool_part) {
+                                                           float* __restrict__ pool_part, const float* __restrict__ amax_in,
+                                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                           int* __restrict__ exp_out, float bound_mult, float bound_add) {
   const int C4 = C >> 2, strips = (Ho + kDwRows - 1) / kDwRows;
+  float oscale = 1.0f;
+  if (out_hi) {  // operand planes for the following projection, a-priori exponent as in sir_feat_conv
+    const float bound = fmaf(*amax_in, bound_mult, bound_add);
+    int e_out = 0;
+    if (bound > 0.0f && isfinite(bound)) {
+      int ex;
+      (void)frexpf(bound, &ex);
+      e_out = max(-100, min(100, 15 - ex));
+    }
+    oscale = ldexpf(1.0f, e_out);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e_out;
+  }
   const size_t total = (size_t)B * strips * Wo * C4;
   float local = 0.0f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -446,7 +461,16 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
       } else {
         o = acc;
       }
-      *reinterpret_cast<float4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
+      const size_t off = (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+      if (out) *reinterpret_cast<float4*>(out + off) = o;
+      if (out_hi) {
+        const float s0 = o.x * oscale, s1 = o.y * oscale, s2 = o.z * oscale, s3 = o.w * oscale;
+        const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(s0 - b01.x, s1 - b01.y), l23 = __floats2half2_rn(s2 - b23.x, s3 - b23.y);
+        *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
       pool.x += o.x; pool.y += o.y; pool.z += o.z; pool.w += o.w;
       local = fmaxf(local, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
     };
@@ -715,8 +739,13 @@ extern "C" int sir_feat_dwconv_pool_parts(int k, int stride, int C, int Ho, int 
 }
 
 extern "C" int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, int k, int stride, int pad, const float* d_w,
-                               const float* d_bias, int act, float* d_out, float* d_amax_out, float* d_pool_part, void* stream) {
-  SIR_CHECK_ARG(d_in && d_w && d_bias && d_out, "sir_feat_dwconv: null pointer");
+                               const float* d_bias, int act, float* d_out, float* d_amax_out, float* d_pool_part, const float* d_amax_in,
+                               uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult, float bound_add,
+                               void* stream) {
+  SIR_CHECK_ARG(d_in && d_w && d_bias && (d_out || d_out_hi), "sir_feat_dwconv: null pointer");
+  SIR_CHECK_ARG(!d_out_hi || (d_out_lo && d_exp_out && d_amax_in && k == 3 && pad == 1 && (stride == 1 || stride == 2) && C % 8 == 0 &&
+                              (((uintptr_t)d_out_hi | (uintptr_t)d_out_lo) & 15) == 0 && bound_mult >= 0.0f && bound_add >= 0.0f),
+                "sir_feat_dwconv: operand planes need the 3x3 fast path (pad 1, stride 1|2, C %% 8 == 0), d_out_lo, d_exp_out, d_amax_in");
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "sir_feat_dwconv: bad shape");
   SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_dwconv: unknown activation %d", act);
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
@@ -725,7 +754,9 @@ extern "C" int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, in
   const bool aligned = C % 4 == 0 && (((uintptr_t)d_in | (uintptr_t)d_w | (uintptr_t)d_bias | (uintptr_t)d_out | (uintptr_t)d_pool_part) & 15) == 0;
   if (aligned && k == 3 && pad == 1 && (stride == 1 || stride == 2)) {
     const unsigned grid = grid_for((size_t)B * ceil_div(Ho, kDwRows) * Wo * (C / 4));
-#define SIR_DW3(S_, A_) dwconv3_rows_kernel<S_, A_><<<grid, 256, 0, st>>>(d_in, B, H, W, C, Ho, Wo, d_w, d_bias, d_out, d_amax_out, d_pool_part)
+#define SIR_DW3(S_, A_)                                                                                                          \
+  dwconv3_rows_kernel<S_, A_><<<grid, 256, 0, st>>>(d_in, B, H, W, C, Ho, Wo, d_w, d_bias, d_out, d_amax_out, d_pool_part, d_amax_in, \
+                                                    (__half*)d_out_hi, (__half*)d_out_lo, d_exp_out, bound_mult, bound_add)
     if (stride == 1) {
       if (act == 0) SIR_DW3(1, 0); else if (act == 1) SIR_DW3(1, 1); else SIR_DW3(1, 2);
     } else {
@@ -735,6 +766,7 @@ extern "C" int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, in
     SIR_LAUNCH_CHECK("dwconv3_rows_kernel");
     return SIR_OK;
   }
+  SIR_CHECK_ARG(d_out && !d_out_hi, "sir_feat_dwconv: this shape takes the generic path, which writes float32 only");
   if (aligned)
     dwconv_c4_kernel<<<grid_for((size_t)B * Ho * Wo * (C / 4)), 256, 0, st>>>(d_in, B, H, W, C, k, stride, pad, Ho, Wo, d_w, d_bias, act, d_out,
                                                                              d_amax_out);

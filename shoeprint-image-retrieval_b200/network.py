@@ -311,6 +311,8 @@ class _Program:
                          implicit=implicit, bk=bk)
                 del p["w"]
             elif op.kind == "dwconv":
+                p["bound_mult"] = float(p["w"].double().abs().flatten(1).sum(1).max()) * (1.0 + 1e-5)
+                p["bound_add"] = float(p["bias"].abs().max()) * (1.0 + 1e-5)
                 p.update(w_d=p["w"][:, 0].permute(1, 2, 0).contiguous().to(device), bias_d=p["bias"].to(device))
                 del p["w"]
             elif op.kind == "se":
@@ -336,6 +338,22 @@ class _Program:
             op.p["emit_planes"] = bool(plane_users) and ok
             op.p["emit_f32"] = other or not op.p["emit_planes"]
 
+        # MBConv: depthwise 3x3 -> SqueezeExcitation -> 1x1 projection.  The depthwise kernel writes the projection's operand
+        # planes itself and the SE scale is folded into per-image projection weights, so nothing re-reads the activation.
+        for op in self.ops:
+            if op.kind != "dwconv":
+                continue
+            t = op.dst
+            users = [u for u in self.ops if u.src == t or u.p.get("residual") == t or u.p.get("chan_scale") == t]
+            convs = [u for u in users if u.kind == "conv"]
+            fast = op.p["k"] == 3 and op.p["kw"] == 3 and op.p["pad"] == 1 and op.p["stride"] in (1, 2) and op.p["c"] % 8 == 0
+            ok = (len(convs) == 1 and all(u.kind in ("conv", "se") and u.src == t for u in users) and t != self.out_id
+                  and convs[0].p["implicit"] and convs[0].p["k"] == 1 and convs[0].p["kw"] == 1 and convs[0].p["pad"] == 0
+                  and convs[0].p["chan_scale"] is not None and os.environ.get("SIR_NO_PLANE_CHAIN", "") != "1")
+            op.p["emit_planes"] = bool(ok and fast)
+            if op.p["emit_planes"]:
+                convs[0].p["scaled_planes"] = True
+
     @staticmethod
     def _out_hw(h: int, w: int, k: int, kw: int, s: int, pd: int) -> tuple[int, int]:
         return (h + 2 * pd - k) // s + 1, (w + 2 * pd - kw) // s + 1
@@ -344,7 +362,7 @@ class _Program:
         """The layer's weights as per-stage shared-memory images for the tile the library plans for this shape
         (packed on the device the first time a tile shape is needed, then cached)."""
         tile_n, granule, nbytes = C.c_int(), C.c_int(), C.c_longlong()
-        nat.check(nat.lib.sir_feat_conv_plan(*geom, p["bk"], p["cout"], C.byref(tile_n), C.byref(granule), C.byref(nbytes)), "sir_feat_conv_plan")
+        nat.check(nat.lib.sir_feat_conv_plan(*geom, p["bk"], p["cout"], 0, C.byref(tile_n), C.byref(granule), C.byref(nbytes)), "sir_feat_conv_plan")
         key = (tile_n.value, granule.value)
         packs = p.setdefault("packs", {})
         if key not in packs:
@@ -353,6 +371,16 @@ class _Program:
                       "sir_feat_conv_pack_weights")
             packs[key] = buf
         return packs[key], key[0], key[1]
+
+    def _scaled_weights(self, p: dict, geom: tuple, scale: torch.Tensor, st: C.c_void_p) -> tuple[torch.Tensor, int, int]:
+        """One packed weight set per image with the squeeze-excitation scale ``[B,C]`` folded in."""
+        tile_n, granule, nbytes = C.c_int(), C.c_int(), C.c_longlong()
+        nat.check(nat.lib.sir_feat_conv_plan(*geom, p["bk"], p["cout"], 1, C.byref(tile_n), C.byref(granule), C.byref(nbytes)), "sir_feat_conv_plan")
+        b, cin = geom[0], geom[3]
+        buf = torch.empty((b, nbytes.value), dtype=torch.uint8, device=self.device)
+        nat.check(nat.lib.sir_feat_conv_scale_weights(_ptr(p["whi"]), _ptr(p["wlo"]), p["rows"], p["kp"], p["kp"] // (p["k"] * p["kw"]), cin,
+                                                      _ptr(scale), b, tile_n.value, granule.value, _ptr(buf), st), "sir_feat_conv_scale_weights")
+        return buf, tile_n.value, granule.value
 
     def run(self, x0: torch.Tensor, amax0: torch.Tensor) -> torch.Tensor:  # noqa: C901, PLR0915
         """x0: normalised input [B,H,W,3] float32 NHWC; amax0: 1-element tensor with its max |x|."""
@@ -423,7 +451,14 @@ class _Program:
                         describe(op, n_before)
                     continue
                 exp_in = None
-                if p["implicit"] and cs is None and op.src in planes:  # operand planes came from the producer's epilogue
+                per_image = 0
+                if p.get("scaled_planes") and op.src in planes:
+                    # depthwise planes + SE scale folded into one weight set per image (no pass over the activation)
+                    ahi, alo = planes[op.src]
+                    exp_in = C.c_void_p(exps.data_ptr() + 4 * op.src)
+                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"])
+                    per_image = 1
+                elif p["implicit"] and cs is None and op.src in planes:  # operand planes came from the producer's epilogue
                     ahi, alo = planes[op.src]
                     exp_in = C.c_void_p(exps.data_ptr() + 4 * op.src)
                     geom = (b, h, w, c, p["k"], p["kw"], p["pad"])
@@ -440,8 +475,11 @@ class _Program:
                     nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
                                                             _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
                     geom = (1, 1, m, p["kp"], 1, 1, 0)
-                wpack, tile_n, granule = self._packed_weights(p, geom, st)
-                nat.check(nat.lib.sir_feat_conv(_ptr(ahi), _ptr(alo), aptr(op.src), *geom, p["bk"], _ptr(wpack), tile_n, granule,
+                if per_image:
+                    wpack, tile_n, granule = self._scaled_weights(p, geom, cs, st)
+                else:
+                    wpack, tile_n, granule = self._packed_weights(p, geom, st)
+                nat.check(nat.lib.sir_feat_conv(_ptr(ahi), _ptr(alo), aptr(op.src), *geom, p["bk"], _ptr(wpack), tile_n, granule, per_image,
                                                 p["cout"], p["w_exp"], _ptr(p["bias_d"]), _ptr(res), p["act"],
                                                 out_ptr, ldc, aptr(op.dst), exp_in, _ptr(ohi), _ptr(olo), exp_out, p["bound_mult"],
                                                 p["bound_add"], aptr(p["residual"]) if p["residual"] is not None else None, st),
@@ -449,14 +487,23 @@ class _Program:
                 launch_counter.add(2)
             elif op.kind == "dwconv":
                 ho, wo = self._out_hw(h, w, p["k"], p["kw"], p["stride"], p["pad"])
-                out = torch.empty((b, ho, wo, c), dtype=torch.float32, device=dev)
+                emit = p.get("emit_planes", False)
+                out = torch.empty((b, ho, wo, c), dtype=torch.float32, device="meta" if emit else dev)
                 part = None
                 if op.dst in squeezed:  # a SqueezeExcitation follows: its global sum is produced here
                     parts = int(nat.lib.sir_feat_dwconv_pool_parts(p["k"], p["stride"], c, ho, wo))
                     part = torch.empty((b, parts, c), dtype=torch.float32, device=dev)
                     pooled[op.dst] = (part, parts)
+                ohi = olo = exp_out = None
+                if emit:  # the projection reads these planes; the SE scale goes into its weights
+                    ohi = torch.empty((b, ho, wo, c), dtype=torch.float16, device=dev)
+                    olo = torch.empty_like(ohi)
+                    planes[op.dst] = (ohi, olo)
+                    exp_out = C.c_void_p(exps.data_ptr() + 4 * op.dst)
                 nat.check(nat.lib.sir_feat_dwconv(_ptr(src), b, h, w, c, p["k"], p["stride"], p["pad"], _ptr(p["w_d"]),
-                                                  _ptr(p["bias_d"]), p["act"], _ptr(out), aptr(op.dst), _ptr(part), st), "sir_feat_dwconv")
+                                                  _ptr(p["bias_d"]), p["act"], None if emit else _ptr(out), aptr(op.dst), _ptr(part),
+                                                  aptr(op.src), _ptr(ohi), _ptr(olo), exp_out, p["bound_mult"], p["bound_add"], st),
+                          "sir_feat_dwconv")
                 launch_counter.add()
             elif op.kind == "se":
                 if op.src in pooled:
