@@ -20,7 +20,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     model._forward_uint8(batch, apply_clahe=True); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=60))
 evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "sir::" in e.name], key=lambda e: e.time_range.start)
-body = [e for e in evs if "clahe" not in e.name and "nhwc_to_nchw" not in e.name and "pack_weights" not in e.name]
+body = [e for e in evs if "clahe" not in e.name and "nhwc_to_nchw" not in e.name and "::pack_weights_kernel" not in e.name]
 labels = model.program.launch_log
 assert len(body) == len(labels), (len(body), len(labels))
 import collections
