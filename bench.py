@@ -172,7 +172,7 @@ def feature_stage_numbers(args) -> dict:
     cfg = {"model": {"type": "EfficientNetV2_M", "clahe_clip_limit": 2.0, "clahe_tile_grid_size": [8, 8]}}
     model = network.Model(cfg, 6, random_init_seed=0)
     rng = np.random.default_rng(0)
-    n = 192  # three 64-image chunks: the API overlaps staging / result copies with the next chunk's kernels
+    n = 512  # eight 64-image chunks: the API overlaps staging / result copies with the next chunk's kernels
     imgs = [np.clip(np.kron(rng.integers(0, 256, size=(100, 38)), np.ones((8, 8))) + rng.normal(0, 10, (800, 304)), 0, 255).astype(np.uint8)[:, :300] for _ in range(n)]
     imgs = [np.ascontiguousarray(im) for im in imgs]
     model.get_multiple_feature_maps(imgs[:64], progress=False)

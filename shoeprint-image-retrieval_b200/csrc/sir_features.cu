@@ -420,14 +420,21 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
     oscale = ldexpf(1.0f, e_out);
     if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e_out;
   }
-  const size_t total = (size_t)B * strips * Wo * C4;
+  // One block = tile_x adjacent output columns (one warp each) x 128 channels (4 per lane) x one strip of rows: the three
+  // threads that need an input value sit in the same block, so two of the three fetches hit L1 instead of going to L2
+  // (with a flat thread -> output mapping the column neighbours landed on other SMs and L2 carried 3.7x the tensor).
+  const int tile_x = blockDim.x >> 5, x_tiles = (Wo + tile_x - 1) / tile_x, c_groups = (C4 + 31) >> 5;
+  const size_t total = (size_t)B * strips * x_tiles * c_groups;
   float local = 0.0f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    size_t r = i / C4;
-    const int ox = (int)(r % Wo);
-    r /= Wo;
+  for (size_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const int cg = (int)(item % c_groups);
+    size_t r = item / c_groups;
+    const int xt = (int)(r % x_tiles);
+    r /= x_tiles;
     const int strip = (int)(r % strips), b = (int)(r / strips);
+    const int c4 = cg * 32 + (threadIdx.x & 31), ox = xt * tile_x + (threadIdx.x >> 5);
+    if (c4 >= C4 || ox >= Wo) continue;
+    const int c = c4 * 4;
     float4 wv[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c));
@@ -753,9 +760,19 @@ extern "C" int sir_feat_dwconv(const float* d_in, int B, int H, int W, int C, in
   cudaStream_t st = (cudaStream_t)stream;
   const bool aligned = C % 4 == 0 && (((uintptr_t)d_in | (uintptr_t)d_w | (uintptr_t)d_bias | (uintptr_t)d_out | (uintptr_t)d_pool_part) & 15) == 0;
   if (aligned && k == 3 && pad == 1 && (stride == 1 || stride == 2)) {
-    const unsigned grid = grid_for((size_t)B * ceil_div(Ho, kDwRows) * Wo * (C / 4));
+    // columns per block: 4..8 warps, whichever leaves the fewest idle column slots (ties -> the wider tile)
+    int tile_x = 8;
+    for (int t = 8, best = 1 << 30; t >= 4; --t) {
+      const int slots = ceil_div(Wo, t) * t;
+      if (slots < best) {
+        best = slots;
+        tile_x = t;
+      }
+    }
+    const size_t items = (size_t)B * ceil_div(Ho, kDwRows) * ceil_div(Wo, tile_x) * ceil_div(C / 4, 32);
+    const unsigned grid = (unsigned)std::min<size_t>(items, 148 * 8);  // persistent blocks: few atomics on the running |max|
 #define SIR_DW3(S_, A_)                                                                                                          \
-  dwconv3_rows_kernel<S_, A_><<<grid, 256, 0, st>>>(d_in, B, H, W, C, Ho, Wo, d_w, d_bias, d_out, d_amax_out, d_pool_part, d_amax_in, \
+  dwconv3_rows_kernel<S_, A_><<<grid, tile_x * 32, 0, st>>>(d_in, B, H, W, C, Ho, Wo, d_w, d_bias, d_out, d_amax_out, d_pool_part, d_amax_in, \
                                                     (__half*)d_out_hi, (__half*)d_out_lo, d_exp_out, bound_mult, bound_add)
     if (stride == 1) {
       if (act == 0) SIR_DW3(1, 0); else if (act == 1) SIR_DW3(1, 1); else SIR_DW3(1, 2);

@@ -26,7 +26,7 @@ assert len(body) == len(labels), (len(body), len(labels))
 import collections
 agg = collections.OrderedDict()
 for e, d in zip(body, labels):
-    short = e.name.split("(")[0].replace("sir::", "").replace("void ", "")
+    short = __import__("re").search(r"(\w+_kernel(?:<[^>]*>)?)", e.name).group(1)
     key = (short, d)
     n, t = agg.get(key, (0, 0.0))
     agg[key] = (n + 1, t + e.device_time)
