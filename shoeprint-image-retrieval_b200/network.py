@@ -35,6 +35,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Any
 
@@ -264,6 +265,9 @@ def _split_fp16(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, int]:
     hi = xs.half()
     lo = (xs - hi.float()).half()
     return hi.contiguous(), lo.contiguous(), e
+
+
+_COPY_THREADS = 4  # host threads that copy finished feature maps out of the pinned result buffer
 
 
 class _Program:
@@ -624,6 +628,7 @@ class Model:
         self.max_batch = 64
         self._host_clahe = os.environ.get("SIR_HOST_CLAHE", "") == "1"
         self._copy_stream: torch.cuda.Stream | None = None
+        self._copy_pool = ThreadPoolExecutor(max_workers=_COPY_THREADS)
         self._pinned_bufs: dict[tuple, torch.Tensor] = {}
 
     def _host_transform(self, *, gray: bool):
@@ -736,13 +741,25 @@ class Model:
         pending: tuple | None = None  # (image indices, pinned host maps, copy-done event, device maps)
 
         def collect(pend: tuple) -> None:
+            """Copy a finished chunk out of its pinned buffer: one pageable block per chunk, filled by a few threads
+            (the cost is first-touch page faults, which numpy's copy takes with the GIL released)."""
             chunk, host, done, _dev = pend
             done.synchronize()
             arr = host.numpy()
+            block = np.empty(arr.shape, arr.dtype)
+            n = len(chunk)
+            parts = min(_COPY_THREADS, n)
+
+            def fill(a: int, b: int) -> None:
+                block[a:b] = arr[a:b]
+
+            jobs = [self._copy_pool.submit(fill, n * t // parts, n * (t + 1) // parts) for t in range(parts)]
+            for j in jobs:
+                j.result()
             for j, i in enumerate(chunk):
-                results[i] = arr[j].squeeze().copy()
+                results[i] = block[j].squeeze()
             if bar is not None:
-                bar.update(len(chunk))
+                bar.update(n)
 
         # Two-deep pipeline: while the GPU works on chunk i the host stages chunk i+1 into pinned memory and copies the
         # maps of chunk i-1 out of the pinned result buffer; results leave the device on a side stream.
