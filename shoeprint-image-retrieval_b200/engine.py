@@ -120,6 +120,18 @@ class MapSet:
         dev = _require_cuda()
         if len(maps) == 0:
             raise ValueError("empty list of feature maps")
+        resident = maps.device_copies() if hasattr(maps, "device_copies") else None
+        if resident is not None:  # the feature stage left these maps on the device (network.FeatureMapList): no upload
+            groups = []
+            for tensor, idx in resident:
+                shp = tuple(int(v) for v in tensor.shape[1:])
+                if len(shp) != 3 or shp[1] <= 2 * EDGE or shp[2] <= 2 * EDGE:
+                    raise ValueError(f"feature map of shape {shp} vanishes after the 2-cell crop (similarity.py:92-93)")
+                groups.append(MapGroup(tensor.contiguous(), torch.tensor(idx, dtype=torch.int64)))
+            chans = {int(g.maps.shape[1]) for g in groups}
+            if len(chans) != 1:
+                raise ValueError(f"feature maps disagree on the channel count: {sorted(chans)}")
+            return MapSet(groups, len(maps), chans.pop(), 0)
         by_shape: dict[tuple[int, int, int], list[int]] = {}
         for i, m in enumerate(maps):
             if m.ndim != 3:
@@ -593,8 +605,12 @@ def rank_true_matches(scores: torch.Tensor, true_idx, k: int = 0, g0: int = 0, t
 
 def compare(probe_maps, gallery_maps, matching_pairs, rotations=None, scales=None, precision: str = DEFAULT_PRECISION, k: int = 0):
     """Host lists in, (ranks int32 [Q] on host, scores [Q,G] on device, top-k lists) out."""
-    probes = probe_maps if isinstance(probe_maps, MapSet) else MapSet.from_host(list(probe_maps))
-    gallery = gallery_maps if isinstance(gallery_maps, MapSet) else MapSet.from_host(list(gallery_maps))
+    def ingest(maps):  # a FeatureMapList keeps its device copies only if it is passed through as is
+        if isinstance(maps, MapSet):
+            return maps
+        return MapSet.from_host(maps if hasattr(maps, "device_copies") else list(maps))
+
+    probes, gallery = ingest(probe_maps), ingest(gallery_maps)
     scores = score_matrix(probes, gallery, rotations, scales, precision)
     count_gt, _, tv, ti, _ = rank_true_matches(scores, matching_pairs, k)
     ranks = (count_gt + 1).to("cpu").numpy().astype(np.int32)

@@ -270,6 +270,32 @@ def _split_fp16(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, int]:
 _COPY_THREADS = 4  # host threads that copy finished feature maps out of the pinned result buffer
 
 
+class FeatureMapList(list):
+    """What ``get_multiple_feature_maps`` returns: the reference's list of ``[C,h,w]`` float32 arrays
+    (``network.py:246-269``) that also remembers the device-resident copies the maps were read back from.
+    ``compare_maps`` uses those copies when the list still holds the very same arrays, so the maps do not
+    travel host -> device again.  Replacing an element falls back to the host arrays; writing
+    into an array in place is not detected."""
+
+    device_groups: list | None = None
+    _ids: tuple = ()
+
+    def attach_device_copies(self, chunks: list) -> None:
+        by_shape: dict[tuple, tuple[list[int], list[torch.Tensor]]] = {}
+        for shp, idx, maps in chunks:
+            ids, parts = by_shape.setdefault(shp, ([], []))
+            ids.extend(idx)
+            parts.append(maps)
+        self.device_groups = [(torch.cat(parts) if len(parts) > 1 else parts[0], ids) for ids, parts in by_shape.values()]
+        self._ids = tuple(id(a) for a in self)
+
+    def device_copies(self) -> list | None:
+        """``[(tensor [n,C,h,w], list indices)]`` if every element is still the array that was returned, else None."""
+        if self.device_groups is None or len(self) != len(self._ids) or any(id(a) != i for a, i in zip(self, self._ids)):
+            return None
+        return self.device_groups
+
+
 class _Program:
     """Compiled backbone: device-resident weights + the executor."""
 
@@ -739,6 +765,7 @@ class Model:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         pending: tuple | None = None  # (image indices, pinned host maps, copy-done event, device maps)
+        device_chunks: list[tuple[tuple, list[int], torch.Tensor]] = []
 
         def collect(pend: tuple) -> None:
             """Copy a finished chunk out of its pinned buffer: one pageable block per chunk, filled by a few threads
@@ -789,9 +816,14 @@ class Model:
                 if pending is not None:
                     collect(pending)
                 pending = (chunk, host, done, maps)
+                device_chunks.append((tuple(maps.shape[1:]), chunk, maps))
                 step += 1
         if pending is not None:
             collect(pending)
         if bar is not None:
             bar.close()
-        return results
+        out = FeatureMapList(results)
+        budget = float(os.environ.get("SIR_DEVICE_MAP_CACHE_GB", "16")) * 2**30
+        if sum(m.numel() * 4 for _, _, m in device_chunks) <= budget:
+            out.attach_device_copies(device_chunks)
+        return out

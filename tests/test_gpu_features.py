@@ -137,3 +137,28 @@ def test_model_gpu_clahe_path_matches_host_clahe_path(monkeypatch):
     model._host_clahe = True
     b = model.get_feature_maps(img)
     np.testing.assert_array_equal(a, b)
+
+
+def test_device_resident_handoff_to_compare():
+    """maps returned by get_multiple_feature_maps keep device copies; compare uses them (no H2D) and gives
+    the same ranks and scores as the host lists.  Replacing an element falls back to the host path."""
+    from src.shoeprint_image_retrieval import engine, network
+
+    model = network.Model(_config("EfficientNetV2_M"), 5, random_init_seed=3)
+    prints = [_image(100 + i, 192 + 32 * (i % 2), 128) for i in range(6)]
+    marks = [p[16:-16, 8:-8].copy() for p in prints[:4]]
+    g_maps = model.get_multiple_feature_maps(prints, progress=False)
+    p_maps = model.get_multiple_feature_maps(marks, progress=False)
+    assert isinstance(g_maps, list) and g_maps.device_copies() is not None
+    for a, (t, idx) in [(g_maps, grp) for grp in g_maps.device_copies()]:
+        for j, i in enumerate(idx):
+            np.testing.assert_array_equal(a[i], t[j].cpu().numpy())
+    pairs = np.arange(4)
+    assert engine.MapSet.from_host(g_maps).h2d_bytes == 0
+    assert engine.MapSet.from_host(list(g_maps)).h2d_bytes > 0
+    r_dev, s_dev, _ = engine.compare(p_maps, g_maps, pairs, [-10, 10], None)
+    r_host, s_host, _ = engine.compare(list(p_maps), list(g_maps), pairs, [-10, 10], None)
+    np.testing.assert_array_equal(r_dev, r_host)
+    assert torch.equal(s_dev, s_host)
+    g_maps[0] = g_maps[0] * 1.0  # a different array object: the device copy is no longer trusted
+    assert g_maps.device_copies() is None and engine.MapSet.from_host(g_maps).h2d_bytes > 0
