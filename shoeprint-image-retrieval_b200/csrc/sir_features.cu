@@ -439,17 +439,22 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
 #pragma unroll
     for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
-    const float* img = in + (size_t)b * H * W * C + c;
-    const int ix0 = ox * S - 1;
+    // the kernel is instruction bound (ncu: issue slots 56 % busy at 21 % occupancy): all index arithmetic is 32-bit, hoisted
+    // out of the row loop; column validity is decided once per thread
+    const int ix0 = ox * S - 1, row_pitch = W * C;
+    const float* img = in + (size_t)b * H * W * C + c + ix0 * C;  // column ix0 of row 0 (may point before the row: only read if valid)
+    const bool v0 = ix0 >= 0, v1 = ix0 + 1 < W, v2 = ix0 + 2 < W;  // ix0 + 1 >= 0 and ix0 < W always hold
     auto load_row = [&](int iy, float4 (&row)[3]) {
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ix0 + kx;
-        row[kx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const float4*>(img + ((size_t)iy * W + ix) * C))
-                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      const bool vy = iy >= 0 && iy < H;
+      const float* rp = img + iy * row_pitch;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      row[0] = (vy && v0) ? __ldg(reinterpret_cast<const float4*>(rp)) : z;
+      row[1] = (vy && v1) ? __ldg(reinterpret_cast<const float4*>(rp + C)) : z;
+      row[2] = (vy && v2) ? __ldg(reinterpret_cast<const float4*>(rp + 2 * C)) : z;
     };
     const int oy0 = strip * kDwRows, oy1 = min(Ho, oy0 + kDwRows);
+    const int out_pitch = Wo * C;
+    const size_t out_base = (((size_t)b * Ho + oy0) * Wo + ox) * C + c;
     float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
     auto emit = [&](int oy, const float4 (&a)[3], const float4 (&m)[3], const float4 (&z)[3]) {
       float4 acc = bb;
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
       } else {
         o = acc;
       }
-      const size_t off = (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+      const size_t off = out_base + (size_t)((oy - oy0) * out_pitch);
       if (out) *reinterpret_cast<float4*>(out + off) = o;
       if (out_hi) {
         const float s0 = o.x * oscale, s1 = o.y * oscale, s2 = o.z * oscale, s3 = o.w * oscale;
