@@ -711,14 +711,16 @@ class Model:
         return out
 
     def _pinned(self, kind: str, slot: int, shape: tuple, dtype: torch.dtype) -> torch.Tensor:
-        """Reusable page-locked staging buffer (two slots per kind and shape)."""
-        key = (kind, slot, tuple(int(v) for v in shape), dtype)
-        buf = self._pinned_bufs.get(key)
-        if buf is None:
-            for k in [k for k in self._pinned_bufs if k[0] == kind and k[1] == slot]:
+        """Reusable page-locked staging buffer (two slots per kind and shape).  Both slots are created together: page-locking
+        tens of megabytes takes milliseconds and would otherwise land inside the second chunk of every first call."""
+        shape = tuple(int(v) for v in shape)
+        key = (kind, slot, shape, dtype)
+        if key not in self._pinned_bufs:
+            for k in [k for k in self._pinned_bufs if k[0] == kind]:
                 del self._pinned_bufs[k]
-            buf = self._pinned_bufs[key] = torch.empty(key[2], dtype=dtype).pin_memory()
-        return buf
+            for sl in (0, 1):
+                self._pinned_bufs[(kind, sl, shape, dtype)] = torch.empty(shape, dtype=dtype).pin_memory()
+        return self._pinned_bufs[key]
 
     def _batch_limit(self, h: int, w: int) -> int:
         """Images per forward pass: the largest (input + fp16 operand planes + output) of any layer within
