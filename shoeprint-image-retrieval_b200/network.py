@@ -289,6 +289,9 @@ class FeatureMapList(list):
         self.device_groups = [(torch.cat(parts) if len(parts) > 1 else parts[0], ids) for ids, parts in by_shape.values()]
         self._ids = tuple(id(a) for a in self)
 
+    def __reduce__(self):  # pickles (and deep-copies) as the plain list of arrays; the device copies stay behind
+        return (list, (list(self),))
+
     def device_copies(self) -> list | None:
         """``[(tensor [n,C,h,w], list indices)]`` if every element is still the array that was returned, else None."""
         if self.device_groups is None or len(self) != len(self._ids) or any(id(a) != i for a, i in zip(self, self._ids)):
