@@ -203,7 +203,7 @@ int sir_feat_image_to_nhwc(const uint8_t* d_img, int B, int H, int W, int in_ch,
                            float* d_out, float* d_amax_out, void* stream);
 int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int H, int W, int C, int kh, int kw, int stride,
                           int pad, const float* d_chan_scale, int Kp, uint16_t* d_ahi, uint16_t* d_alo, void* stream);
-/* sir_feat_conv: Conv2d (groups 1, stride 1, square zero padding) + folded BN bias + activation (+ residual) as an
+/* sir_feat_conv: Conv2d (groups 1, square zero padding, any stride: strided patches are fetched with TMA element strides) + folded BN bias + activation (+ residual) as an
  * implicit GEMM: no im2col matrix.  d_xhi/d_xlo: the input split into fp16 hi/lo NHWC planes [B][H][W][C]
  * (sir_feat_im2col_split with a 1x1 kernel and Kp = C), C % 8 == 0.  Weights: d_wpack from sir_feat_conv_pack_weights,
  * packed for the tile sir_feat_conv_plan reports for this shape; K order k = (ky*kw + kx)*Cp + c, Cp = C rounded up to bk.  A GEMM over an explicit [M][K] matrix is the call with B=H=1, W=M, C=K, kh=kw=1.
@@ -218,8 +218,8 @@ int sir_feat_conv_tile_n(int N);
  * copy; tensor-map loads of 32/64-byte weight rows are bound by the TMA unit's row rate).  sir_feat_conv_plan: tile width,
  * K granule (16 or 32 channels) and byte size of the packed weights for a shape; sir_feat_conv_pack_weights: [n_rows][Kp]
  * fp16 hi/lo matrices (k = (ky*kw + kx)*Cp + c) -> that layout, [n_tile][k_step][hi | lo][tile_n][granule] swizzled. */
-int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int per_image, int* tile_n,
-                       int* granule, long long* pack_bytes);
+int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int stride, int bk, int N, int per_image,
+                       int* tile_n, int* granule, long long* pack_bytes);
 /* sir_feat_conv_scale_weights: one weight set per image with the SqueezeExcitation scale folded in,
  * W_b[n][k] = W[n][k] * d_scale[b][k mod Cp] (torchvision SqueezeExcitation.forward, scale * input, followed by the
  * 1x1 projection), packed like sir_feat_conv_pack_weights, B sets of pack_bytes; used with per_image = 1, which keeps
@@ -230,7 +230,7 @@ int sir_feat_conv_scale_weights(const uint16_t* d_whi, const uint16_t* d_wlo, in
 int sir_feat_conv_pack_weights(const uint16_t* d_whi, const uint16_t* d_wlo, int n_rows, int Kp, int tile_n, int granule,
                                uint8_t* d_pack, void* stream);
 int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
-                  int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int per_image, int N, int w_exp,
+                  int kw, int pad, int stride, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int per_image, int N, int w_exp,
                   const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
                   const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
                   float bound_add, const float* d_amax_res, void* stream);

@@ -52,10 +52,10 @@ SIGNATURES = {
     "sir_feat_image_to_nhwc": (_i, [_p, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p]),
     "sir_feat_im2col_split": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     "sir_feat_conv_tile_n": (_i, [_i]),
-    "sir_feat_conv_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_longlong)]),
+    "sir_feat_conv_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_longlong)]),
     "sir_feat_conv_scale_weights": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
     "sir_feat_conv_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
-    "sir_feat_conv": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p,
+    "sir_feat_conv": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p,
                             _p, _p, _p, _p, C.c_float, C.c_float, _p, _p]),
     "sir_feat_conv_c3k3": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, C.c_float, C.c_float, _p]),
     "sir_feat_dwconv_pool_parts": (_i, [_i, _i, _i, _i, _i]),

@@ -1,6 +1,6 @@
-// Feature stage K1: Conv2d (groups 1, stride 1) as an implicit GEMM on the tcgen05 tensor cores.
+// Feature stage K1: Conv2d (groups 1) as an implicit GEMM on the tcgen05 tensor cores.
 //
-//   out[b][oy][ox][n] = act( sum_{ky,kx,c} x[b][oy+ky-pad][ox+kx-pad][c] * w[n][ky][kx][c] + bias[n] ) (+ residual)
+//   out[b][oy][ox][n] = act( sum_{ky,kx,c} x[b][s*oy+ky-pad][s*ox+kx-pad][c] * w[n][ky][kx][c] + bias[n] ) (+ residual)
 //
 // (torchvision Conv2d + folded BatchNorm + SiLU/ReLU as composed by network.py:121-186.)  The
 // activation arrives as two fp16 NHWC planes (hi + lo = the float32 value times a power of two,
@@ -39,6 +39,7 @@ struct ConvParams {
   int Ho, Wo;             // output grid of one image (1 x M for flat GEMMs)
   int N, BN, n_tiles_n;
   int taps, kw, pad;
+  int stride;             // spatial stride (1 or 2 ...): the patch load walks the input with TMA element strides
   int chunks, bk;         // K step = bk channels of one tap; chunks = Cp / bk
   int tw_log2, TH;        // patch = TH x (1 << tw_log2) pixels = 128 rows
   int tiles_x, tiles_y;
@@ -200,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
         const int px = mt % p.tiles_x, r1 = mt / p.tiles_x;
         const int py = r1 % p.tiles_y, b = r1 / p.tiles_y;
-        const int x0 = px * TW - p.pad, y0 = py * p.TH - p.pad;
+        const int x0 = px * TW * p.stride - p.pad, y0 = py * p.TH * p.stride - p.pad;
         // The weight stage is ONE contiguous bulk copy of a pre-swizzled image: a tensor-map load of narrow rows
         // (32 / 64 B) is bound by the TMA unit's row rate, which starved the MMAs.
         const uint8_t* wsrc = p.wpack + (size_t)b * p.wpack_image_bytes + (size_t)nt * k_iters * (2 * b_bytes);
@@ -548,13 +549,13 @@ EncodeTiledFn conv_encode_fn() {
 }
 // bk: 32 -> 64-byte swizzle, 16 -> 32-byte swizzle, 0 -> no swizzle
 int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, int bk,
-           const char* what) {
+           const char* what, int spatial_stride = 1) {
   EncodeTiledFn fn = conv_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return SIR_E_CUDA;
   }
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};  // dims 1, 2 = x, y of the 4-D patch map
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : bk == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -663,13 +664,14 @@ struct ConvPlan {
   int BN, granule, n_tiles_n, k_steps;  // layout of the packed weights
 };
 
-int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int per_image, ConvPlan* out) {
+int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int stride, int bk, int N, int per_image, ConvPlan* out) {
   SIR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && kh > 0 && kw > 0 && pad >= 0 && N > 0,
                 "sir_feat_conv: bad shape B=%d H=%d W=%d C=%d (C must be a multiple of 8) k=%dx%d N=%d", B, H, W, C, kh, kw, N);
   SIR_CHECK_ARG(bk == 16 || bk == 32, "sir_feat_conv: bk must be 16 or 32, got %d", bk);
   SIR_CHECK_ARG(N % 4 == 0, "sir_feat_conv: N = %d must be a multiple of 4", N);
-  const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
-  SIR_CHECK_ARG(Ho > 0 && Wo > 0, "sir_feat_conv: empty output");
+  SIR_CHECK_ARG(stride >= 1 && stride <= 8, "sir_feat_conv: stride %d not supported", stride);
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  SIR_CHECK_ARG(H + 2 * pad >= kh && W + 2 * pad >= kw && Ho > 0 && Wo > 0, "sir_feat_conv: empty output");
   ConvPlan& pl = *out;
   pl = ConvPlan{};
   ConvParams& p = pl.p;
@@ -678,6 +680,7 @@ int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N
   p.n_tiles_n = ceil_div(N, p.BN);
   p.taps = kh * kw;
   p.kw = kw;
+  p.stride = stride;
   p.pad = pad;
   p.bk = bk;
   p.chunks = ceil_div(C, bk);
@@ -685,15 +688,15 @@ int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N
   pl.gB = B;
   pl.gH = H;
   pl.gW = W;
-  SIR_CHECK_ARG(!per_image || (p.taps == 1 && pad == 0), "sir_feat_conv: per-image weights need a 1x1 convolution");
-  if (p.taps == 1 && pad == 0) {  // flat rows; with per-image weights one row per image so that no tile straddles two images
+  SIR_CHECK_ARG(!per_image || (p.taps == 1 && pad == 0 && stride == 1), "sir_feat_conv: per-image weights need a 1x1 convolution");
+  if (p.taps == 1 && pad == 0 && stride == 1) {  // flat rows; with per-image weights one row per image so that no tile straddles two images
     SIR_CHECK_ARG((long long)B * H * W < (1ll << 31), "sir_feat_conv: too many rows");
     pl.gW = per_image ? H * W : B * H * W;
     pl.gH = 1;
     pl.gB = per_image ? B : 1;
   }
-  p.Ho = pl.gH + 2 * pad - kh + 1;
-  p.Wo = pl.gW + 2 * pad - kw + 1;
+  p.Ho = (pl.gH + 2 * pad - kh) / stride + 1;
+  p.Wo = (pl.gW + 2 * pad - kw) / stride + 1;
   long long best_tiles = -1;
   for (int l2 = 7; l2 >= 0; --l2) {  // patch = (128 >> l2) rows x (1 << l2) columns; prefer wide patches on ties
     const int tw = 1 << l2, th = kConvBM >> l2;
@@ -718,7 +721,7 @@ int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N
   pl.granule = bk;
   pl.n_tiles_n = p.n_tiles_n;
   pl.k_steps = p.taps * p.chunks;
-  if (p.taps > 1) {
+  if (p.taps > 1 && stride == 1) {
     pl.hpl = plan_halo(B, H, W, C, kh, kw, pad, N, p.chunks * bk);
     // activation-side TMA rows per output row and K16 step: the patch kernel refetches the patch for every tap,
     // the halo kernel fetches patch + halo once per 32-channel chunk (16-byte rows)
@@ -817,10 +820,10 @@ extern "C" int sir_feat_conv_scale_weights(const uint16_t* d_whi, const uint16_t
 
 extern "C" int sir_feat_conv_tile_n(int N) { return N > 0 ? conv_tile_n(N) : 0; }
 
-extern "C" int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int bk, int N, int per_image, int* tile_n,
-                                  int* granule, long long* pack_bytes) {
+extern "C" int sir_feat_conv_plan(int B, int H, int W, int C, int kh, int kw, int pad, int stride, int bk, int N, int per_image,
+                                  int* tile_n, int* granule, long long* pack_bytes) {
   ConvPlan pl;
-  const int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, per_image, &pl);
+  const int rc = make_plan(B, H, W, C, kh, kw, pad, stride, bk, N, per_image, &pl);
   if (rc) return rc;
   if (tile_n) *tile_n = pl.BN;
   if (granule) *granule = pl.granule;
@@ -843,7 +846,7 @@ extern "C" int sir_feat_conv_pack_weights(const uint16_t* d_whi, const uint16_t*
 }
 
 extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const float* d_amax_in, int B, int H, int W, int C, int kh,
-                             int kw, int pad, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int per_image, int N,
+                             int kw, int pad, int stride, int bk, const uint8_t* d_wpack, int pack_tile_n, int pack_granule, int per_image, int N,
                              int w_exp,
                              const float* d_bias, const float* d_residual, int act, float* d_out, int ldc, float* d_amax_out,
                              const int32_t* d_exp_in, uint16_t* d_out_hi, uint16_t* d_out_lo, int32_t* d_exp_out, float bound_mult,
@@ -854,13 +857,13 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
                 "sir_feat_conv: operand-plane output needs d_out_lo, d_exp_out, N %% 8 == 0 and a non-negative bound");
   SIR_CHECK_ARG(act >= 0 && act <= 2, "sir_feat_conv: unknown activation %d", act);
   ConvPlan pl;
-  int rc = make_plan(B, H, W, C, kh, kw, pad, bk, N, per_image, &pl);
+  int rc = make_plan(B, H, W, C, kh, kw, pad, stride, bk, N, per_image, &pl);
   if (rc) return rc;
   SIR_CHECK_ARG(ldc >= N, "sir_feat_conv: ldc %d < N %d", ldc, N);
   SIR_CHECK_ARG(pack_tile_n == pl.BN && pack_granule == pl.granule,
                 "sir_feat_conv: weights packed for tile_n %d / granule %d, this shape needs %d / %d (sir_feat_conv_plan)", pack_tile_n,
                 pack_granule, pl.BN, pl.granule);
-  const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   SIR_CHECK_ARG((long long)B * Ho * Wo * (long long)ldc < (1ll << 40), "sir_feat_conv: output too large");
   SIR_CHECK_ARG(d_out || N % 4 == 0, "sir_feat_conv: plane-only output needs N %% 4 == 0");
   SIR_CHECK_ARG(!d_residual || !d_out_hi || d_amax_res, "sir_feat_conv: residual + operand planes need d_amax_res");
@@ -916,10 +919,13 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
   CUtensorMap txh, txl;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)pl.gW, (cuuint64_t)pl.gH, (cuuint64_t)pl.gB};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)pl.gW * C * 2, (cuuint64_t)pl.gH * pl.gW * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(1 << p.tw_log2), (cuuint32_t)p.TH, 1};
-  rc = encode(&txh, d_xhi, 4, dims, strides, box, bk, "activation hi");
+  // strided convolution: the box spans stride * (patch extent) input pixels and the TMA unit picks every stride-th one
+  // (element strides; verified with tools/tma_stride_probe.cu: origin in input coordinates, dense patch in shared memory)
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)((1 << p.tw_log2) * stride), (cuuint32_t)(p.TH * stride), 1};
+  SIR_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "sir_feat_conv: stride %d too large for the patch", stride);
+  rc = encode(&txh, d_xhi, 4, dims, strides, box, bk, "activation hi", stride);
   if (rc) return rc;
-  rc = encode(&txl, d_xlo, 4, dims, strides, box, bk, "activation lo");
+  rc = encode(&txl, d_xlo, 4, dims, strides, box, bk, "activation lo", stride);
   if (rc) return rc;
   static thread_local bool configured[3] = {false, false, false};
   const void* fn = act == 0 ? (const void*)conv_tc_kernel<0> : act == 1 ? (const void*)conv_tc_kernel<1> : (const void*)conv_tc_kernel<2>;

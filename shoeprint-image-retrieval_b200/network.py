@@ -322,7 +322,7 @@ class _Program:
                 # |out| <= amax_in * max_n sum|w[n]| + max|bias| (SiLU/ReLU do not grow it): a-priori scale of emitted planes
                 p["bound_mult"] = float(p["w"].double().abs().flatten(1).sum(1).max()) * (1.0 + 1e-5)
                 p["bound_add"] = float(p["bias"].abs().max()) * (1.0 + 1e-5)
-                implicit = p["stride"] == 1 and cin % 8 == 0
+                implicit = cin % 8 == 0  # any stride: strided patches come through TMA element strides
                 p["direct"] = cin == 3 and k == 3 and kw == 3 and cout % 8 == 0 and cout <= 256 and p["c_off"] is None
                 if p["direct"]:  # the stem: float32 on the CUDA cores, weights [27][cout]
                     p["w_direct"] = w.reshape(cout, 27).t().contiguous().to(device)
@@ -489,25 +489,25 @@ class _Program:
                     # depthwise planes + SE scale folded into one weight set per image (no pass over the activation)
                     ahi, alo = planes[op.src]
                     exp_in = C.c_void_p(exps.data_ptr() + 4 * op.src)
-                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"])
+                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"], p["stride"])
                     per_image = 1
                 elif p["implicit"] and cs is None and op.src in planes:  # operand planes came from the producer's epilogue
                     ahi, alo = planes[op.src]
                     exp_in = C.c_void_p(exps.data_ptr() + 4 * op.src)
-                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"])
+                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"], p["stride"])
                     launch_counter.add(-1)
                 elif p["implicit"]:  # split once into fp16 hi/lo NHWC planes; the kernel gathers the taps itself
                     ahi = torch.empty((b, h, w, c), dtype=torch.float16, device=dev)
                     alo = torch.empty_like(ahi)
                     nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, 1, 1, 1, 0, _ptr(cs), c, _ptr(ahi), _ptr(alo), st),
                               "sir_feat_im2col_split")
-                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"])
+                    geom = (b, h, w, c, p["k"], p["kw"], p["pad"], p["stride"])
                 else:
                     ahi = torch.empty((m, p["kp"]), dtype=torch.float16, device=dev)
                     alo = torch.empty_like(ahi)
                     nat.check(nat.lib.sir_feat_im2col_split(_ptr(src), aptr(op.src), b, h, w, c, p["k"], p["kw"], p["stride"], p["pad"],
                                                             _ptr(cs), p["kp"], _ptr(ahi), _ptr(alo), st), "sir_feat_im2col_split")
-                    geom = (1, 1, m, p["kp"], 1, 1, 0)
+                    geom = (1, 1, m, p["kp"], 1, 1, 0, 1)
                 if per_image:
                     wpack, tile_n, granule = self._scaled_weights(p, geom, cs, st)
                 else:

@@ -50,7 +50,7 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def _run_conv(nat, x, w, bias, pad, act, *, residual=None, chan_scale=None, planes_out=False, force_halo=None):
+def _run_conv(nat, x, w, bias, pad, act, *, residual=None, chan_scale=None, planes_out=False, stride=1):
     """x [B,H,W,C] float32 cuda NHWC; returns (out [B,Ho,Wo,N] float32, (hi, lo, e) or None)."""
     b, h, wd, c = x.shape
     cout, cin, kh, kw = w.shape
@@ -63,7 +63,7 @@ def _run_conv(nat, x, w, bias, pad, act, *, residual=None, chan_scale=None, plan
     whi, wlo, w_exp, rows, kp = _weights(nat, w, bk)
     per_image = 1 if chan_scale is not None else 0
     tile_n, granule, nbytes = C.c_int(), C.c_int(), C.c_longlong()
-    nat.check(nat.lib.sir_feat_conv_plan(b, h, wd, c, kh, kw, pad, bk, cout, per_image, C.byref(tile_n), C.byref(granule), C.byref(nbytes)))
+    nat.check(nat.lib.sir_feat_conv_plan(b, h, wd, c, kh, kw, pad, stride, bk, cout, per_image, C.byref(tile_n), C.byref(granule), C.byref(nbytes)))
     if per_image:
         pack = torch.empty((b, nbytes.value), dtype=torch.uint8, device="cuda")
         nat.check(nat.lib.sir_feat_conv_scale_weights(_p(whi), _p(wlo), rows, kp, kp // (kh * kw), cin, _p(chan_scale), b, tile_n.value,
@@ -71,7 +71,7 @@ def _run_conv(nat, x, w, bias, pad, act, *, residual=None, chan_scale=None, plan
     else:
         pack = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
         nat.check(nat.lib.sir_feat_conv_pack_weights(_p(whi), _p(wlo), rows, kp, tile_n.value, granule.value, _p(pack), st))
-    ho, wo = h + 2 * pad - kh + 1, wd + 2 * pad - kw + 1
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (wd + 2 * pad - kw) // stride + 1
     out = torch.empty((b, ho, wo, cout), dtype=torch.float32, device="cuda")
     amax_out = torch.zeros(1, device="cuda")
     bias_d = bias.float().cuda().contiguous()
@@ -84,7 +84,7 @@ def _run_conv(nat, x, w, bias, pad, act, *, residual=None, chan_scale=None, plan
         amax_res = residual.abs().max().reshape(1).float()
     bound_mult = float(w.double().abs().flatten(1).sum(1).max()) * (1 + 1e-5)
     bound_add = float(bias.abs().max()) * (1 + 1e-5)
-    nat.check(nat.lib.sir_feat_conv(_p(xhi), _p(xlo), _p(amax), b, h, wd, c, kh, kw, pad, bk, _p(pack), tile_n.value, granule.value, per_image,
+    nat.check(nat.lib.sir_feat_conv(_p(xhi), _p(xlo), _p(amax), b, h, wd, c, kh, kw, pad, stride, bk, _p(pack), tile_n.value, granule.value, per_image,
                                     cout, w_exp, _p(bias_d), _p(residual), act, _p(out), cout, _p(amax_out), None, _p(ohi), _p(olo),
                                     _p(exp_out), bound_mult, bound_add, _p(amax_res), st))
     torch.cuda.synchronize()
@@ -92,11 +92,11 @@ def _run_conv(nat, x, w, bias, pad, act, *, residual=None, chan_scale=None, plan
     return out, ((ohi, olo, int(exp_out)) if planes_out else None)
 
 
-def _reference(x, w, bias, pad, act, residual=None, chan_scale=None):
+def _reference(x, w, bias, pad, act, residual=None, chan_scale=None, stride=1):
     xd = x.double().permute(0, 3, 1, 2)
     if chan_scale is not None:
         xd = xd * chan_scale.double()[:, :, None, None]
-    y = F.conv2d(xd, w.double().cuda(), bias.double().cuda(), padding=pad)
+    y = F.conv2d(xd, w.double().cuda(), bias.double().cuda(), padding=pad, stride=stride)
     y = F.silu(y) if act == 1 else F.relu(y) if act == 2 else y
     y = y.permute(0, 2, 3, 1)
     return y + residual.double() if residual is not None else y
@@ -173,17 +173,31 @@ def test_conv_operand_planes_chain():
     whi, wlo, w_exp, rows, kp = _weights(nat, w2, bk)
     bsz, h, wd, c = out1.shape
     tile_n, granule, nbytes = C.c_int(), C.c_int(), C.c_longlong()
-    nat.check(nat.lib.sir_feat_conv_plan(bsz, h, wd, c, 1, 1, 0, bk, 48, 0, C.byref(tile_n), C.byref(granule), C.byref(nbytes)))
+    nat.check(nat.lib.sir_feat_conv_plan(bsz, h, wd, c, 1, 1, 0, 1, bk, 48, 0, C.byref(tile_n), C.byref(granule), C.byref(nbytes)))
     pack = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
     nat.check(nat.lib.sir_feat_conv_pack_weights(_p(whi), _p(wlo), rows, kp, tile_n.value, granule.value, _p(pack), st))
     out2 = torch.empty((bsz, h, wd, 48), dtype=torch.float32, device="cuda")
     amax1 = out1.abs().max().reshape(1)
     e_dev = torch.tensor([e], dtype=torch.int32, device="cuda")
-    nat.check(nat.lib.sir_feat_conv(_p(hi), _p(lo), _p(amax1), bsz, h, wd, c, 1, 1, 0, bk, _p(pack), tile_n.value, granule.value, 0, 48, w_exp,
+    nat.check(nat.lib.sir_feat_conv(_p(hi), _p(lo), _p(amax1), bsz, h, wd, c, 1, 1, 0, 1, bk, _p(pack), tile_n.value, granule.value, 0, 48, w_exp,
                                     _p(b2.cuda()), None, 0, _p(out2), 48, None, _p(e_dev), None, None, None, 0.0, 0.0, None, st))
     torch.cuda.synchronize()
     ref = _reference(_reference(x, w1, b1, 1, 1).float(), w2, b2, 0, 0)
     assert _rel(out2, ref) < 2 * OP_REL_L2
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,k,pad,stride", [(2, 41, 30, 24, 96, 3, 1, 2), (1, 64, 37, 48, 192, 3, 1, 2), (2, 33, 20, 64, 128, 1, 0, 2), (1, 50, 31, 32, 64, 5, 2, 3)])
+def test_strided_conv_matches_torch(b, h, w, cin, cout, k, pad, stride):
+    """Strided convolutions: the patch of every tap is fetched with TMA element strides (no im2col matrix)."""
+    from src.shoeprint_image_retrieval import _native as nat
+
+    g = torch.Generator().manual_seed(77 + cin + stride)
+    x = (torch.randn((b, h, w, cin), generator=g) * 2).cuda()
+    wt = torch.randn((cout, cin, k, k), generator=g) / (cin * k * k) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    out, _ = _run_conv(nat, x, wt, bias, pad, 1, stride=stride)
+    rel = _rel(out, _reference(x, wt, bias, pad, 1, stride=stride))
+    assert rel < OP_REL_L2, rel
 
 
 def test_conv_per_image_scaled_weights():
@@ -257,6 +271,6 @@ def test_conv_rejects_mismatched_pack():
     pack = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
     out = torch.zeros((1, 8, 8, 64), device="cuda")
     bias = torch.zeros(64, device="cuda")
-    rc = nat.lib.sir_feat_conv(_p(x), _p(x), _p(amax), 1, 8, 8, 32, 1, 1, 0, 32, _p(pack), 16, 32, 0, 64, 0, _p(bias), None, 0, _p(out), 64, None,
+    rc = nat.lib.sir_feat_conv(_p(x), _p(x), _p(amax), 1, 8, 8, 32, 1, 1, 0, 1, 32, _p(pack), 16, 32, 0, 64, 0, _p(bias), None, 0, _p(out), 64, None,
                                None, None, None, None, 0.0, 0.0, None, _stream())
     assert rc != 0 and b"packed for" in nat.lib.sir_last_error()
