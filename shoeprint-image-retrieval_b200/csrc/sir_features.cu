@@ -435,28 +435,44 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
     const int c4 = cg * 32 + (threadIdx.x & 31), ox = xt * tile_x + (threadIdx.x >> 5);
     if (c4 >= C4 || ox >= Wo) continue;
     const int c = c4 * 4;
+    // The kernel is instruction bound (ncu: issue slots 56 % busy at 21 % occupancy, two thirds of it integer work), so the row loop
+    // carries no index arithmetic and no per-load predicates: a column outside the image is handled by ZEROING ITS WEIGHTS once per
+    // thread (its loads then go to a clamped, valid address and contribute nothing), the three column pointers advance by one row
+    // pitch per input row, and a row outside the image is one predicate for its three loads.
+    const int ix0 = ox * S - 1;
+    const bool v0 = ix0 >= 0, v2 = ix0 + 2 < W;  // the centre column ix0 + 1 always exists
     float4 wv[9];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c));
+    for (int t = 0; t < 9; ++t) {
+      const bool live = (t % 3 == 0) ? v0 : (t % 3 == 2) ? v2 : true;
+      wv[t] = live ? __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c)) : zero4;
+    }
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
-    // the kernel is instruction bound (ncu: issue slots 56 % busy at 21 % occupancy): all index arithmetic is 32-bit, hoisted
-    // out of the row loop; column validity is decided once per thread
-    const int ix0 = ox * S - 1, row_pitch = W * C;
-    const float* img = in + (size_t)b * H * W * C + c + ix0 * C;  // column ix0 of row 0 (may point before the row: only read if valid)
-    const bool v0 = ix0 >= 0, v1 = ix0 + 1 < W, v2 = ix0 + 2 < W;  // ix0 + 1 >= 0 and ix0 < W always hold
-    auto load_row = [&](int iy, float4 (&row)[3]) {
-      const bool vy = iy >= 0 && iy < H;
-      const float* rp = img + iy * row_pitch;
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      row[0] = (vy && v0) ? __ldg(reinterpret_cast<const float4*>(rp)) : z;
-      row[1] = (vy && v1) ? __ldg(reinterpret_cast<const float4*>(rp + C)) : z;
-      row[2] = (vy && v2) ? __ldg(reinterpret_cast<const float4*>(rp + 2 * C)) : z;
-    };
+    const int row_pitch = W * C;
     const int oy0 = strip * kDwRows, oy1 = min(Ho, oy0 + kDwRows);
+    const float* img = in + (size_t)b * H * W * C + c;
+    int iy = oy0 * S - 1;  // next input row to load
+    const float* p0 = img + (ptrdiff_t)iy * row_pitch + (v0 ? ix0 : ix0 + 1) * C;
+    const float* p1 = img + (ptrdiff_t)iy * row_pitch + (ix0 + 1) * C;
+    const float* p2 = img + (ptrdiff_t)iy * row_pitch + (v2 ? ix0 + 2 : ix0 + 1) * C;
+    auto load_next = [&](float4 (&row)[3]) {
+      if (iy >= 0 && iy < H) {
+        row[0] = __ldg(reinterpret_cast<const float4*>(p0));
+        row[1] = __ldg(reinterpret_cast<const float4*>(p1));
+        row[2] = __ldg(reinterpret_cast<const float4*>(p2));
+      } else {
+        row[0] = row[1] = row[2] = zero4;
+      }
+      ++iy;
+      p0 += row_pitch;
+      p1 += row_pitch;
+      p2 += row_pitch;
+    };
     const int out_pitch = Wo * C;
-    const size_t out_base = (((size_t)b * Ho + oy0) * Wo + ox) * C + c;
-    float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto emit = [&](int oy, const float4 (&a)[3], const float4 (&m)[3], const float4 (&z)[3]) {
+    size_t off = (((size_t)b * Ho + oy0) * Wo + ox) * C + c;  // running output offset
+    float4 pool = zero4;
+    auto emit = [&](const float4 (&a)[3], const float4 (&m)[3], const float4 (&z)[3]) {
       float4 acc = bb;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
@@ -473,7 +489,6 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
       } else {
         o = acc;
       }
-      const size_t off = out_base + (size_t)((oy - oy0) * out_pitch);
       if (out) *reinterpret_cast<float4*>(out + off) = o;
       if (out_hi) {
         const float s0 = o.x * oscale, s1 = o.y * oscale, s2 = o.z * oscale, s3 = o.w * oscale;
@@ -483,34 +498,35 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
         *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
         *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
       }
+      off += out_pitch;
       pool.x += o.x; pool.y += o.y; pool.z += o.z; pool.w += o.w;
       local = fmaxf(local, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
     };
     if (S == 1) {
       // two output rows per iteration: the six loads of the two new input rows are in flight together
       float4 r0[3], r1[3], r2[3], r3[3];
-      load_row(oy0 - 1, r0);
-      load_row(oy0, r1);
+      load_next(r0);
+      load_next(r1);
       int oy = oy0;
       for (; oy + 1 < oy1; oy += 2) {
-        load_row(oy + 1, r2);
-        load_row(oy + 2, r3);
-        emit(oy, r0, r1, r2);
-        emit(oy + 1, r1, r2, r3);
+        load_next(r2);
+        load_next(r3);
+        emit(r0, r1, r2);
+        emit(r1, r2, r3);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) { r0[kx] = r2[kx]; r1[kx] = r3[kx]; }
       }
       if (oy < oy1) {
-        load_row(oy + 1, r2);
-        emit(oy, r0, r1, r2);
+        load_next(r2);
+        emit(r0, r1, r2);
       }
     } else {
       float4 r0[3], r1[3], r2[3];
-      load_row(oy0 * S - 1, r0);
+      load_next(r0);
       for (int oy = oy0; oy < oy1; ++oy) {
-        load_row(oy * S, r1);
-        load_row(oy * S + 1, r2);
-        emit(oy, r0, r1, r2);
+        load_next(r1);
+        load_next(r2);
+        emit(r0, r1, r2);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) r0[kx] = r2[kx];
       }
