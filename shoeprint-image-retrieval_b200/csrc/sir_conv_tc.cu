@@ -202,8 +202,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         const int px = mt % p.tiles_x, r1 = mt / p.tiles_x;
         const int py = r1 % p.tiles_y, b = r1 / p.tiles_y;
         const int x0 = px * TW * p.stride - p.pad, y0 = py * p.TH * p.stride - p.pad;
-        // The weight stage is ONE contiguous bulk copy of a pre-swizzled image: a tensor-map load of narrow rows
-        // (32 / 64 B) is bound by the TMA unit's row rate, which starved the MMAs.
+        // The weight stage is ONE contiguous bulk copy of a pre-swizzled image instead of a tensor-map load of hundreds of
+        // 32 / 64-byte rows (measured: 1 - 5 % faster per layer, and one instruction per stage in the producer).
         const uint8_t* wsrc = p.wpack + (size_t)b * p.wpack_image_bytes + (size_t)nt * k_iters * (2 * b_bytes);
         int tap_y = 0, tap_x = 0, chunk = 0;
         for (int ks = 0; ks < k_iters; ++ks) {
@@ -308,12 +308,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------------------
 // Halo variant for k x k kernels (stride 1): the A operand of ALL taps comes from one shared-memory copy of the
-// patch plus its halo.  conv_tc_kernel fetches the shifted patch once per tap, i.e. kh*kw times, and is bound by
-// the L2 -> shared-memory feed; here one 5-D TMA box per 32-channel chunk lands the (16+kh-1) x (8+kw-1) pixel
+// patch plus its halo.  conv_tc_kernel fetches the shifted patch once per tap, i.e. kh*kw times from L2; here one 5-D TMA box per 32-channel chunk lands the (16+kh-1) x (8+kw-1) pixel
 // halo as [slab of 8 channels][y][x][8 ch], which is the un-swizzled K-major core-matrix layout: 8 consecutive
 // pixels of a patch row are the 8 rows of a core matrix (16 B apart), the next patch row is SBO = one halo row
 // further, the next 8 channels LBO = one slab further, and tap (ky,kx) is nothing but a different start address.
-// Two patches (32 x 8 pixels) share every weight stage, which halves the weight traffic per output.
+// Narrow layers (N <= 64) process two patches (32 x 8 pixels) per weight stage.
 constexpr int kHaloTW = 8, kHaloTH = 16;  // patch = 16 rows x 8 columns of output pixels
 constexpr int kHaloAStages = 3;
 constexpr int kHaloMaxBStages = 12;
@@ -610,7 +609,6 @@ int halo_tile_n(int N, int np) {
 struct HaloPlan {
   HaloParams hp;
   size_t smem;
-  double l2_bytes;  // modelled L2 -> shared-memory traffic of the whole launch
   bool ok;
 };
 HaloPlan plan_halo(int B, int H, int W, int C, int kh, int kw, int pad, int N, int cp16) {
@@ -619,8 +617,8 @@ HaloPlan plan_halo(int B, int H, int W, int C, int kh, int kw, int pad, int N, i
   ConvParams& p = hp.c;
   p.Ho = H + 2 * pad - kh + 1;
   p.Wo = W + 2 * pad - kw + 1;
-  // The MMA is bound by its shared-memory operand reads (A: 4 KB per 128 x N x 16 instruction whatever N is), so a wide
-  // N tile beats sharing a weight stage between two patches; only narrow layers (N <= 64) pair patches.
+  // Measured: one patch per tile with the widest N wins for N > 64 (a 128 x N x 16 MMA costs max(61, 0.51 N) cycles, so two patches
+  // with half the N double the MMA time although they halve the weight bytes); narrow layers (N <= 64) pair patches.
   static const char* np_env = getenv("SIR_CONV_HALO_NP");
   hp.np = np_env ? atoi(np_env) : (N <= 64 ? 2 : 1);
   if (p.Ho <= kHaloTH) hp.np = 1;
@@ -645,7 +643,6 @@ HaloPlan plan_halo(int B, int H, int W, int C, int kh, int kw, int pad, int N, i
   pl.ok = total < (1ll << 31) && hp.b_stages >= 4 && hp.hw * 16 < (1 << 18) && 4 * hp.hw * hp.hh * 16 < (1 << 18);
   p.total_tiles = (int)total;
   pl.smem = 1024 + (size_t)kHaloAStages * a_stage + (size_t)hp.b_stages * b_stage + tail;
-  pl.l2_bytes = (double)total * ((double)hp.chunks32 * hp.np * 2 * 4 * hp.hw * hp.hh * 16 + (double)p.taps * (cp16 / 16) * b_stage);
   return pl;
 }
 }  // namespace
