@@ -192,7 +192,10 @@ def feature_stage_numbers(args) -> dict:
     dev = 2 * 64 / (e0.elapsed_time(e1) * 1e-3)
     out = {"unit": "images/s", "model": "EfficientNetV2_M[:6]", "input": "800x300 uint8", "map": list(maps[0].shape),
            "e2e_images_per_s": e2e, "device_images_per_s": dev, "gflop_per_image": 34.72,
-           "device_tflops_algorithmic": dev * 34.72e-3}
+           "device_tflops_algorithmic": dev * 34.72e-3,
+           # whole stage (CLAHE, depthwise, SE, layout change included) against the measured sustained bf16 peak; the convolutions
+           # spend three fp16 MMAs per algorithmic MAC (float32-grade hi/lo products), so the tensor-pipe share is 3x this
+           "roofline_frac_algorithmic": dev * 34.72e-3 / _peaks()["bf16"], "mma_per_algorithmic_mac": 3}
     if not args.no_cpu:
         from oracle import features as ofeat
 
