@@ -30,7 +30,9 @@
 
 namespace sir {
 
-constexpr int kConvThreads = 320;
+constexpr int kConvEpiParts = 3;                              // epilogue warps per TMEM lane quarter
+constexpr int kConvEpiWarps = 4 * kConvEpiParts;
+constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;         // warp 0 TMA, warp 1 MMA, then the epilogue warps
 constexpr int kConvBM = 128;
 constexpr int kConvMaxStages = 8;
 constexpr uint32_t kConvAccStride = 256;  // TMEM columns between the two accumulator buffers
@@ -83,7 +85,8 @@ __device__ __forceinline__ float conv_act(float v) {
   return v;
 }
 
-// Epilogue of one 128 x BN accumulator tile: this warp owns 32 TMEM lanes (rows) and every second 16-column chunk.
+// Epilogue of one 128 x BN accumulator tile: this warp owns 32 TMEM lanes (rows) and every kConvEpiParts-th 16-column chunk
+// (`half` = which of them).
 // pix[ps]: output pixel index of row (ps*8 + lane/4) of the warp's 32 rows, or -1 if outside the image.
 // One chunk: 32 rows x 16 columns arrive row-per-lane from TMEM, are transposed through shared memory (XOR swizzle,
 // conflict free both ways) so that each lane then owns 4 consecutive columns of 4 rows: stores and residual loads are
@@ -139,14 +142,14 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
   // two register sets: the TMEM load of the next chunk is in flight while the current one is processed
   uint32_t va[16], vb[16];
   if (half < n_chunks) ptx::tmem_ld_32x16(tacc + half * 16, va);
-  for (int ci = half; ci < n_chunks; ci += 4) {
+  for (int ci = half; ci < n_chunks; ci += 2 * kConvEpiParts) {
     ptx::tmem_ld_wait();
-    if (ci + 2 < n_chunks) ptx::tmem_ld_32x16(tacc + (ci + 2) * 16, vb);
+    if (ci + kConvEpiParts < n_chunks) ptx::tmem_ld_32x16(tacc + (ci + kConvEpiParts) * 16, vb);
     conv_epilogue_chunk<ACT>(p, va, xp, lane, n_base + ci * 16, pix, unscale, oscale, local_max);
-    if (ci + 2 < n_chunks) {
+    if (ci + kConvEpiParts < n_chunks) {
       ptx::tmem_ld_wait();
-      if (ci + 4 < n_chunks) ptx::tmem_ld_32x16(tacc + (ci + 4) * 16, va);
-      conv_epilogue_chunk<ACT>(p, vb, xp, lane, n_base + (ci + 2) * 16, pix, unscale, oscale, local_max);
+      if (ci + 2 * kConvEpiParts < n_chunks) ptx::tmem_ld_32x16(tacc + (ci + 2 * kConvEpiParts) * 16, va);
+      conv_epilogue_chunk<ACT>(p, vb, xp, lane, n_base + (ci + kConvEpiParts) * 16, pix, unscale, oscale, local_max);
     }
   }
 }
@@ -178,7 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_acc_full(i), 1);
-      ptx::mbar_init(bar_acc_empty(i), 8);
+      ptx::mbar_init(bar_acc_empty(i), kConvEpiWarps);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_xhi);
@@ -363,7 +366,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_acc_full(i), 1);
-      ptx::mbar_init(bar_acc_empty(i), 8);
+      ptx::mbar_init(bar_acc_empty(i), kConvEpiWarps);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_xhi);
@@ -637,7 +640,7 @@ HaloPlan plan_halo(int B, int H, int W, int C, int kh, int kw, int pad, int N, i
   const long long total = (long long)B * p.tiles_x * p.tiles_y * p.n_tiles_n;
   const uint32_t a_stage = ((uint32_t)hp.np * 2 * 4 * hp.hw * hp.hh * 16 + 1023u) & ~1023u;
   const uint32_t b_stage = (uint32_t)p.BN * 64;
-  const uint32_t tail = 8u * (2 * kHaloAStages + 2 * kHaloMaxBStages + 4) + 16 + 8 * 32 * 16 * 4;
+  const uint32_t tail = 8u * (2 * kHaloAStages + 2 * kHaloMaxBStages + 4) + 16 + kConvEpiWarps * 32 * 16 * 4;
   const long long room = 220ll * 1024 - 1024 - tail - (long long)kHaloAStages * a_stage;
   hp.b_stages = (int)std::min<long long>(kHaloMaxBStages, room / b_stage);
   pl.ok = total < (1ll << 31) && hp.b_stages >= 4 && hp.hw * 16 < (1 << 18) && 4 * hp.hw * hp.hh * 16 < (1 << 18);
@@ -710,7 +713,7 @@ int make_plan(int B, int H, int W, int C, int kh, int kw, int pad, int stride, i
   SIR_CHECK_ARG(total < (1ll << 31), "sir_feat_conv: too many tiles");
   p.total_tiles = (int)total;
   const uint32_t stage_bytes = (uint32_t)(2 * kConvBM + 2 * p.BN) * bk * 2;
-  const uint32_t tail = 8u * (2 * kConvMaxStages + 4) + 16 + 8 * 32 * 16 * 4;
+  const uint32_t tail = 8u * (2 * kConvMaxStages + 4) + 16 + kConvEpiWarps * 32 * 16 * 4;
   p.stages = std::min<int>(kConvMaxStages, (int)((220u * 1024 - 1024 - tail) / stage_bytes));
   SIR_CHECK_ARG(p.stages >= 2, "sir_feat_conv: tile does not fit shared memory");
   pl.smem = 1024 + (size_t)p.stages * stage_bytes + tail;
