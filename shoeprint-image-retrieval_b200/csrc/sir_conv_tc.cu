@@ -15,7 +15,7 @@
 //   warp 0      TMA producer: per K step (tap, 16/32-channel chunk) A_hi, A_lo, B_hi, B_lo into a ring
 //   warp 1      TMEM owner + MMA issuer: hi*hi + lo*hi + hi*lo (fp32-grade), accumulators double
 //               buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of i+1
-//   warps 2-9   epilogue: tcgen05.ld 16 columns, transpose through shared memory so that global
+//   warps 2-13  epilogue: tcgen05.ld 16 columns, transpose through shared memory so that global
 //               stores / residual loads are row contiguous, un-scale + bias + activation + residual,
 //               running max |out| for the next layer's scaling
 // Bound: tensor pipe for wide layers (three MMAs per algorithmic MAC), L2->smem operand feed otherwise.
