@@ -268,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       }
     }
   } else {
-    // epilogue warps 2..9: TMEM lane quarter = warp % 4, the two warps of a quarter take alternate 16-column chunks
+    // epilogue warps: TMEM lane quarter = warp % 4, the kConvEpiParts warps of a quarter take every kConvEpiParts-th 16-column chunk
     const int q = warp & 3, half = (warp - 2) >> 2;
     float* xp = xpose + (warp - 2) * (32 * 16);
     const int rs = lane >> 2;
