@@ -64,6 +64,14 @@ __host__ __device__ inline int tpl_row_taps(int Wm, int row_align) { return roun
 __host__ __device__ inline int tpl_kpad_aligned(int Hm, int Wm, int row_align) { return round_up(Hm * tpl_row_taps(Wm, row_align), 32); }
 __host__ __device__ inline int gal_pitch8(int Wp) { return round_up(Wp, 16); }  // 1-byte operands: 16 cells = 16 bytes
 
+// SiLU for the fused epilogues: v / (1 + e^-v) with ex2.approx and rcp.approx (2 MUFU + 3 FP32 ops, relative error ~2^-22;
+// 1 + e^-v >= 1, so the reciprocal needs none of the range handling __fdividef carries; v -> -inf gives -0).
+__device__ __forceinline__ float silu_fast(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + __expf(-v)));
+  return v * r;
+}
+
 // Feature stage: exponent e with amax * 2^e in [2^9, 2^10); 0 for an all-zero tensor.
 __device__ __forceinline__ int scale_exp_from_amax(float amax) {
   if (!(amax > 0.0f) || !isfinite(amax)) return 0;

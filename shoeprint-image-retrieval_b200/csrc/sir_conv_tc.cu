@@ -80,7 +80,7 @@ __device__ __forceinline__ int conv_plane_exp(const ConvParams& p) {
 
 template <int ACT>
 __device__ __forceinline__ float conv_act(float v) {
-  if (ACT == 1) return __fdividef(v, 1.0f + __expf(-v));  // SiLU
+  if (ACT == 1) return silu_fast(v);
   if (ACT == 2) return fmaxf(v, 0.0f);                    // ReLU
   return v;
 }
@@ -101,10 +101,12 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvParams& p, const u
   // residual rows: all four loads are issued before the transposition so that their (DRAM) latencies overlap each other and
   // the shared-memory round trip; loading each right before its use left the epilogue stalled on them half of its time
   float4 rr[4];
+  if (p.residual) {
 #pragma unroll
-  for (int ps = 0; ps < 4; ++ps) {
-    rr[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.residual && live && pix[ps] >= 0) rr[ps] = *reinterpret_cast<const float4*>(p.residual + pix[ps] * p.ldc + n);
+    for (int ps = 0; ps < 4; ++ps) {
+      rr[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && pix[ps] >= 0) rr[ps] = *reinterpret_cast<const float4*>(p.residual + pix[ps] * p.ldc + n);
+    }
   }
   __syncwarp();
 #pragma unroll
@@ -120,7 +122,9 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvParams& p, const u
     const float4 a = *reinterpret_cast<const float4*>(xp + row * 16 + 4 * (c4 ^ ((row >> 1) & 3)));
     float4 o = make_float4(conv_act<ACT>(fmaf(a.x, unscale, bb.x)), conv_act<ACT>(fmaf(a.y, unscale, bb.y)),
                            conv_act<ACT>(fmaf(a.z, unscale, bb.z)), conv_act<ACT>(fmaf(a.w, unscale, bb.w)));
-    o.x += rr[ps].x; o.y += rr[ps].y; o.z += rr[ps].z; o.w += rr[ps].w;
+    if (p.residual) {
+      o.x += rr[ps].x; o.y += rr[ps].y; o.z += rr[ps].z; o.w += rr[ps].w;
+    }
     if (p.out) *reinterpret_cast<float4*>(p.out + row_off) = o;
     if (p.out_hi) {  // the same values as the next convolution's operand planes
       const float s0 = o.x * oscale, s1 = o.y * oscale, s2 = o.z * oscale, s3 = o.w * oscale;

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) conv_c3k3_kernel(const float* __restrict_
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (ACT == 1) acc[j] = __fdividef(acc[j], 1.0f + __expf(-acc[j]));
+        if (ACT == 1) acc[j] = silu_fast(acc[j]);
         if (ACT == 2) acc[j] = fmaxf(acc[j], 0.0f);
         local = fmaxf(local, fabsf(acc[j]));
       }
@@ -482,8 +482,7 @@ __global__ void __launch_bounds__(256) dwconv3_rows_kernel(const float* __restri
       }
       float4 o;
       if (ACT == 1) {
-        o = make_float4(__fdividef(acc.x, 1.0f + __expf(-acc.x)), __fdividef(acc.y, 1.0f + __expf(-acc.y)),
-                        __fdividef(acc.z, 1.0f + __expf(-acc.z)), __fdividef(acc.w, 1.0f + __expf(-acc.w)));
+        o = make_float4(silu_fast(acc.x), silu_fast(acc.y), silu_fast(acc.z), silu_fast(acc.w));
       } else if (ACT == 2) {
         o = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
       } else {
