@@ -95,3 +95,19 @@ def test_matching_path_fails_loudly_without_cuda():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         engine.MapSet.from_host([np.zeros((2, 8, 8), np.float32)])
+
+
+def test_feature_map_list_is_a_plain_list_without_device_copies():
+    """network.FeatureMapList (what get_multiple_feature_maps returns) behaves as the reference's list of arrays: no device
+    copies unless the feature stage attached them, pickles / copies as a plain list."""
+    import copy
+    import pickle
+
+    import numpy as np
+
+    from src.shoeprint_image_retrieval.network import FeatureMapList
+
+    maps = FeatureMapList([np.zeros((2, 5, 6), np.float32), np.ones((2, 7, 6), np.float32)])
+    assert isinstance(maps, list) and len(maps) == 2 and maps.device_copies() is None
+    for clone in (pickle.loads(pickle.dumps(maps)), copy.deepcopy(maps)):
+        assert type(clone) is list and len(clone) == 2 and np.array_equal(clone[1], maps[1])
