@@ -40,6 +40,9 @@ extern "C" {
 #define SIR_PREC_FP32_SIMT 2 /* CUDA cores, fp32 FMA (exact-order independent check path) */
 #define SIR_PREC_FP16_FP8C 3 /* tcgen05, hi*hi in fp16 + the two correction products in fp8 e4m3 (2/3 of the
                                 FP16X3 tensor cycles, ~2^-14 relative per product); own entry points *_fp8c */
+#define SIR_PREC_FP16_REFINE 4 /* tcgen05 screening with plain fp16 operands (1 MMA per K step) + exact float32
+                                  re-evaluation of the positions that can hold the maximum (parity grade, default);
+                                  entry points sir_ncc_screen + sir_ncc_refine */
 
 const char* sir_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
@@ -150,6 +153,34 @@ int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uin
                          int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe, float* d_scores,
                          int score_ld, int g0, int precision, void* stream);
 
+/* Screen + refine (SIR_PREC_FP16_REFINE).  The reference needs ONE number per (probe, gallery): the maximum of the
+ * correlation surface over positions and variants (similarity.py:106-108, 365-367).  sir_ncc_screen computes the
+ * whole surface on the tensor cores with plain fp16 operands (d_ghi, d_thi; good to ~2e-4 relative), max-reduces it
+ * into d_approx exactly like sir_ncc_scores does into d_scores (caller zeroes it first), and leaves one 8-byte
+ * record per (column n, gallery g, 16x8 position patch p) in d_rec[(n*G + g)*NP + p], NP = ceil(Hp/16)*ceil(Wp/8):
+ *   .x = the patch maximum (float32 bits, score units), .y = up to three candidate rows (8 bits each: row>>3 = y
+ *   offset, row&7 = x offset inside the patch) and, in the top byte, the number of rows within the margin
+ *   tau(m) = tau_rel*|m| + tau_abs of the patch maximum (saturated; > 3 = "every position of the patch").
+ * sir_ncc_refine then evaluates, in float32 from the hi + lo operand pairs, exactly the candidate positions of the
+ * records whose maximum is within tau of the pair's screened maximum d_approx, and max-reduces the exact values into
+ * d_scores (caller zeroes it first).  tau must cover twice the screening error.  d_rnorm (one template shape) or
+ * d_rnorm_tab (multi-shape bucket, one table pointer per 16-column chunk as in sir_ncc_scores_multi): exactly one is
+ * non-NULL; Hb x Wb is the K layout of the packed templates (= Hm x Wm for a single shape), rows padded to 8 taps
+ * (sir_template_pack / sir_template_pack_embed with SIR_PREC_FP16X3).  d_stats: NULL or 4 device counters
+ * ([0] positions evaluated, [1] records with more than 3 rows, [2] tiles with work), accumulated.
+ * sir_ncc_screen_rec_count: number of 8-byte records d_rec must hold. */
+long long sir_ncc_screen_rec_count(int G, int Hp, int Wp, int ncols);
+int sir_ncc_screen(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
+                   int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hb, int Wb,
+                   const int32_t* d_col2probe, float* d_approx, int score_ld, int g0, float tau_rel, float tau_abs, void* d_rec,
+                   void* stream);
+int sir_ncc_refine(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
+                   int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hb, int Wb,
+                   const int32_t* d_col2probe, const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel,
+                   float tau_abs, const void* d_rec, unsigned long long* d_stats, void* stream);
+/* cudaMemsetAsync(d_ptr, 0, bytes) on `stream`: the path zeroes its score / operand buffers through the library. */
+int sir_memset_zero(void* d_ptr, size_t bytes, void* stream);
+
 /* Planning aid (host only, nothing is launched): estimated SM cycles per (gallery, 256-column tile, channel)
  * of the tensor-core kernel for this shape and precision mode -- the larger of the MMA time of the
  * non-skipped K stages and the shifted-entry generation time under the shared-memory plan the launch
@@ -169,6 +200,10 @@ int sir_rank_topk(const float* d_scores, int Q, int G, int score_ld, const float
 /* Merge P shards' [Q][k] lists (as gathered by ncclAllGather: [P][Q][k]) into the global k best. */
 int sir_merge_topk(const float* d_vals, const int32_t* d_idx, int P, int Q, int k,
                    float* d_out_val, int32_t* d_out_idx, void* stream);
+
+/* d_out[q][d_order[j]] = d_in[q][j] for q < Q, j < G: score columns computed shape group by shape group go back to
+ * the caller's gallery order (d_order: int32 [G], a permutation). */
+int sir_scatter_columns(const float* d_in, int Q, int G, int ld_in, const int32_t* d_order, float* d_out, int ld_out, void* stream);
 
 /* ------------------------------------------------------------------ feature stage (K1-K3)
  * The truncated backbone of network.py:185-186,234-235, operator by operator.  Activations are

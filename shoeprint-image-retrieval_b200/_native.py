@@ -16,7 +16,9 @@ PREC_FP16X3 = 0
 PREC_FP16X1 = 1
 PREC_FP32_SIMT = 2
 PREC_FP16_FP8C = 3
-PRECISIONS = {"fp16x3": PREC_FP16X3, "fp16x1": PREC_FP16X1, "fp32_simt": PREC_FP32_SIMT, "fp16_fp8c": PREC_FP16_FP8C}
+PREC_FP16_REFINE = 4
+PRECISIONS = {"fp16x3": PREC_FP16X3, "fp16x1": PREC_FP16X1, "fp32_simt": PREC_FP32_SIMT, "fp16_fp8c": PREC_FP16_FP8C,
+              "fp16_refine": PREC_FP16_REFINE}
 
 _p = C.c_void_p
 _i = C.c_int
@@ -44,10 +46,15 @@ SIGNATURES = {
     "sir_ncc_scores_fp8c": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "sir_template_pack_embed": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "sir_ncc_scores_multi": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+    "sir_ncc_screen_rec_count": (C.c_longlong, [_i, _i, _i, _i]),
+    "sir_ncc_screen": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, C.c_float, C.c_float, _p, _p]),
+    "sir_ncc_refine": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, C.c_float, C.c_float, _p, _p, _p]),
+    "sir_memset_zero": (_i, [_p, C.c_size_t, _p]),
     "sir_ncc_cost": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
     "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
     "sir_rank_topk": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "sir_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "sir_scatter_columns": (_i, [_p, _i, _i, _i, _p, _p, _i, _p]),
     "sir_feat_clahe_to_nhwc": (_i, [_p, _i, _i, _i, C.c_double, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p, _p, _p]),
     "sir_feat_image_to_nhwc": (_i, [_p, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p]),
     "sir_feat_im2col_split": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),

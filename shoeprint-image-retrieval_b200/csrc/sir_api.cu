@@ -8,7 +8,8 @@ int launch_ncc_simt(const float* d_gz, const float* d_rnorm, int G, int C, int H
 int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l, const float* d_rnorm, int G,
                   int C, int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
                   int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
-                  int passes, cudaStream_t st, double* cost_out, const float* const* d_rnorm_tab);
+                  int passes, cudaStream_t st, double* cost_out, const float* const* d_rnorm_tab, uint2* d_rec, float tau_rel,
+                  float tau_abs);
 }  // namespace sir
 
 using namespace sir;
@@ -27,10 +28,10 @@ extern "C" int sir_ncc_scores(const uint16_t* d_ghi, const uint16_t* d_glo, cons
   switch (precision) {
     case SIR_PREC_FP16X3:
       return launch_ncc_tc(d_ghi, d_glo, nullptr, nullptr, d_rnorm, G, C, Hp, Wp, d_thi, d_tlo, nullptr, nullptr, ncols, ncols_alloc,
-                           Hm, Wm, d_col2probe, d_scores, score_ld, g0, 3, st, nullptr, nullptr);
+                           Hm, Wm, d_col2probe, d_scores, score_ld, g0, 3, st, nullptr, nullptr, nullptr, 0.0f, 0.0f);
     case SIR_PREC_FP16X1:
       return launch_ncc_tc(d_ghi, d_glo, nullptr, nullptr, d_rnorm, G, C, Hp, Wp, d_thi, d_tlo, nullptr, nullptr, ncols, ncols_alloc,
-                           Hm, Wm, d_col2probe, d_scores, score_ld, g0, 1, st, nullptr, nullptr);
+                           Hm, Wm, d_col2probe, d_scores, score_ld, g0, 1, st, nullptr, nullptr, nullptr, 0.0f, 0.0f);
     case SIR_PREC_FP32_SIMT:
       return launch_ncc_simt(d_gz, d_rnorm, G, C, Hp, Wp, d_t32, ncols, ncols_alloc, Hm, Wm, d_col2probe, d_scores,
                              score_ld, g0, st);
@@ -49,7 +50,7 @@ extern "C" int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, 
   SIR_CHECK_ARG(Hm > 0 && Wm > 0 && ncols > 0 && ncols <= ncols_alloc, "sir_ncc_scores_fp8c: bad template block");
   SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_scores_fp8c: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
   return launch_ncc_tc(d_ghi, nullptr, d_g8a, d_g8l, d_rnorm, G, C, Hp, Wp, d_thi, nullptr, d_t8b, d_t8l, ncols, ncols_alloc, Hm, Wm,
-                       d_col2probe, d_scores, score_ld, g0, 2, (cudaStream_t)stream, nullptr, nullptr);
+                       d_col2probe, d_scores, score_ld, g0, 2, (cudaStream_t)stream, nullptr, nullptr, nullptr, 0.0f, 0.0f);
 }
 
 // Multi-shape column tiles: the columns of the block were packed with sir_template_pack_embed into the K
@@ -67,5 +68,36 @@ extern "C" int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo
   SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_scores_multi: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
   SIR_CHECK_ARG(precision == SIR_PREC_FP16X3 || precision == SIR_PREC_FP16_FP8C, "sir_ncc_scores_multi: precision %d not supported", precision);
   return launch_ncc_tc(d_ghi, d_glo, d_g8a, d_g8l, nullptr, G, C, Hp, Wp, d_thi, d_tlo, d_t8b, d_t8l, ncols, ncols_alloc, Hb, Wb, d_col2probe,
-                       d_scores, score_ld, g0, precision == SIR_PREC_FP16X3 ? 3 : 2, (cudaStream_t)stream, nullptr, d_rnorm_tab);
+                       d_scores, score_ld, g0, precision == SIR_PREC_FP16X3 ? 3 : 2, (cudaStream_t)stream, nullptr, d_rnorm_tab, nullptr, 0.0f, 0.0f);
+}
+
+// Screening pass of SIR_PREC_FP16_REFINE: the correlation with plain fp16 operands (one MMA per K step, the tensor
+// pipe's full rate) -- good to ~2e-4 relative, not parity grade by itself.  d_approx receives the approximate pair
+// maxima (same layout and floor as d_scores of sir_ncc_scores) and d_rec one record per (column, gallery, 16x8
+// position patch): the patch maximum and the rows within tau(m) = tau_rel*|m| + tau_abs of it.  sir_ncc_refine then
+// re-evaluates exactly those positions in float32.  d_rnorm / d_rnorm_tab: exactly one is non-NULL (single shape /
+// multi-shape bucket as in sir_ncc_scores_multi).
+extern "C" long long sir_ncc_screen_rec_count(int G, int Hp, int Wp, int ncols) {
+  if (G <= 0 || Hp <= 0 || Wp <= 0 || ncols <= 0) return 0;
+  return (long long)ncols * G * ceil_div(Hp, 16) * ceil_div(Wp, 8);
+}
+
+extern "C" int sir_ncc_screen(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
+                              int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hb, int Wb,
+                              const int32_t* d_col2probe, float* d_approx, int score_ld, int g0, float tau_rel, float tau_abs,
+                              void* d_rec, void* stream) {
+  SIR_CHECK_ARG((d_rnorm != nullptr) != (d_rnorm_tab != nullptr), "sir_ncc_screen: give d_rnorm or d_rnorm_tab, not both");
+  SIR_CHECK_ARG(d_col2probe && d_approx && d_rec, "sir_ncc_screen: null pointer");
+  SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0, "sir_ncc_screen: empty gallery");
+  SIR_CHECK_ARG(Hb > 0 && Wb > 0 && ncols > 0 && ncols <= ncols_alloc, "sir_ncc_screen: bad template block");
+  SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_screen: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
+  SIR_CHECK_ARG(tau_rel >= 0.0f && tau_abs >= 0.0f, "sir_ncc_screen: negative candidate margin");
+  return launch_ncc_tc(d_ghi, d_glo, nullptr, nullptr, d_rnorm, G, C, Hp, Wp, d_thi, d_tlo, nullptr, nullptr, ncols, ncols_alloc, Hb, Wb,
+                       d_col2probe, d_approx, score_ld, g0, 1, (cudaStream_t)stream, nullptr, d_rnorm_tab, (uint2*)d_rec, tau_rel, tau_abs);
+}
+
+extern "C" int sir_memset_zero(void* d_ptr, size_t bytes, void* stream) {
+  SIR_CHECK_ARG(d_ptr || bytes == 0, "sir_memset_zero: null pointer");
+  if (bytes) SIR_CUDA(cudaMemsetAsync(d_ptr, 0, bytes, (cudaStream_t)stream));
+  return SIR_OK;
 }

@@ -86,6 +86,11 @@ struct TcParams {
   uint32_t gs_half_elems;  // staging cells per half per buffer >= gs_rows * (Pe + 16)
   int gs_rows;             // rows of the staging TMA box (max rows any segment needs)
   int gs_bufs;             // 2: stage one segment ahead; 1: no lookahead (very wide templates)
+  // screening mode (SIR_PREC_FP16_REFINE): `scores` is the APPROXIMATE pair maximum and every work unit also leaves
+  // a record (tile maximum, rows within the candidate margin of it) for sir_ncc_refine; NULL otherwise
+  uint2* rec;
+  float tau_rel, tau_abs;  // candidate margin tau(m) = tau_rel * |m| + tau_abs, in accumulator units
+  uint32_t off_mask;       // [4][256] candidate-row masks next to the column maxima
 };
 
 struct Seg {
@@ -524,17 +529,64 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
         for (int j8 = 0; j8 < 8; ++j8) r_cur[j8] = r_next[j8];
       }
       // max over the tile's valid positions, then over the 4 lane quarters, then into scores
+      if (p.rec == nullptr) {
 #pragma unroll
-      for (int j = 0; j < 128; ++j) {
-        const float v = warp_max(valid ? total[j] : -INFINITY);
-        if (lane == 0) colmax[q4 * kTileN + half * 128 + j] = v;
-      }
-      ptx::named_bar_sync(2, kEpiWarps * 32);
-      {
-        const int col = ew * 32 + lane;
-        const float v = fmaxf(fmaxf(colmax[col], colmax[kTileN + col]), fmaxf(colmax[2 * kTileN + col], colmax[3 * kTileN + col]));
-        const int n = nt * kTileN + col;
-        if (n < p.ncols) atomic_max_nonneg(&p.scores[(size_t)p.col2probe[n] * p.score_ld + p.g0 + g], v * p.out_scale);
+        for (int j = 0; j < 128; ++j) {
+          const float v = warp_max(valid ? total[j] : -INFINITY);
+          if (lane == 0) colmax[q4 * kTileN + half * 128 + j] = v;
+        }
+        ptx::named_bar_sync(2, kEpiWarps * 32);
+        {
+          const int col = ew * 32 + lane;
+          const float v = fmaxf(fmaxf(colmax[col], colmax[kTileN + col]), fmaxf(colmax[2 * kTileN + col], colmax[3 * kTileN + col]));
+          const int n = nt * kTileN + col;
+          if (n < p.ncols) atomic_max_nonneg(&p.scores[(size_t)p.col2probe[n] * p.score_ld + p.g0 + g], v * p.out_scale);
+        }
+      } else {
+        // Screening: the fp16 surface is only good to ~2e-4 relative, so next to the maximum the unit reports WHICH
+        // rows could hold the true maximum: all rows within tau of the tile maximum.  f(m) = m - tau(m) is increasing,
+        // so the rows within tau of a lane quarter's own maximum are a superset of that quarter's share.
+        uint32_t* colmask = reinterpret_cast<uint32_t*>(base_ptr + p.off_mask);  // [4][256]
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const float t = valid ? total[j] : -INFINITY;
+          const float m = warp_max(t);
+          const uint32_t bits = __ballot_sync(0xffffffffu, t >= m - (p.tau_rel * fabsf(m) + p.tau_abs));
+          if (lane == 0) {
+            colmax[q4 * kTileN + half * 128 + j] = m;
+            colmask[q4 * kTileN + half * 128 + j] = bits;
+          }
+        }
+        ptx::named_bar_sync(2, kEpiWarps * 32);
+        {
+          const int col = ew * 32 + lane;
+          const int n = nt * kTileN + col;
+          if (n < p.ncols) {
+            float mq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mq[q] = colmax[q * kTileN + col];
+            const float v = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+            const float thr = v - (p.tau_rel * fabsf(v) + p.tau_abs);
+            // info: up to three candidate rows (8 bits each) + their total count, saturated at 255; more than
+            // three makes the refinement evaluate every position of the patch (rare)
+            uint32_t info = 0, cnt = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (mq[q] >= thr) {
+                uint32_t bits = colmask[q * kTileN + col];
+                while (bits) {
+                  const uint32_t r = __ffs(bits) - 1;
+                  bits &= bits - 1;
+                  if (cnt < 3) info |= (uint32_t)(q * 32 + r) << (8 * cnt);
+                  ++cnt;
+                }
+              }
+            }
+            info |= min(cnt, 255u) << 24;
+            p.rec[((size_t)n * p.G + g) * NP + pidx] = make_uint2(__float_as_uint(v * p.out_scale), info);
+            atomic_max_nonneg(&p.scores[(size_t)p.col2probe[n] * p.score_ld + p.g0 + g], v * p.out_scale);
+          }
+        }
       }
       ptx::named_bar_sync(2, kEpiWarps * 32);
     }
@@ -657,7 +709,8 @@ int make_gallery_map8(CUtensorMap* tm, const uint8_t* ptr, int planes, int Hp, i
 int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l, const float* d_rnorm, int G,
                   int C, int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
                   int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
-                  int passes, cudaStream_t st, double* cost_out, const float* const* d_rnorm_tab) {
+                  int passes, cudaStream_t st, double* cost_out, const float* const* d_rnorm_tab, uint2* d_rec, float tau_rel,
+                  float tau_abs) {
   // cost_out != NULL: dry run -- plan only, report the estimated SM cycles per (gallery, 256-column tile,
   // channel) and return without touching any pointer (sir_ncc_cost)
   SIR_CHECK_ARG(d_ghi && d_thi, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
@@ -690,6 +743,9 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   p.nunits = (long long)p.ntiles_n * p.Gp * p.npy * p.npx;
   p.passes = passes;
   p.out_scale = 1.0f / ((float)C * (float)(1 << kTemplateScaleLog2));
+  p.rec = d_rec;
+  p.tau_rel = tau_rel;
+  p.tau_abs = tau_abs / p.out_scale;  // the epilogue compares unscaled accumulator sums
 
   // shared memory plan: B ring, 2 E buffers (x halves), row staging, column maxima, barriers
   const int halves = passes == 3 ? 2 : passes == 2 ? 3 : 1;          // operand arrays per E buffer
@@ -711,7 +767,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
         const size_t gs_half = (size_t)(max_rows + 1) * (Pe + 16);  // cells
         const size_t gs8 = passes == 2 ? (size_t)round_up((max_rows + 1) * (Pe + 32), 128) : 0;  // bytes of one 1-byte window
         const size_t gs_buf = gs16 * (size_t)round_up((int)gs_half, 64) * 2 + 2 * gs8;
-        const size_t fixed = 2 * halves * (e_half + 128) + (size_t)gsb * gs_buf + 4 * kTileN * 4 + 512;
+        const size_t fixed = 2 * halves * (e_half + 128) + (size_t)gsb * gs_buf + (d_rec ? 2 : 1) * 4 * kTileN * 4 + 512;
         if (fixed + (size_t)nb_min * stage_bytes <= limit) {
           p.nbstages = (int)std::min<size_t>(nb_max, (limit - fixed) / stage_bytes);
           p.seg_stages = seg;
@@ -755,7 +811,8 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   p.off_e = p.off_b + p.nbstages * stage_bytes;
   p.off_gs = p.off_e + 2 * p.nhalf * p.e_half_bytes;
   p.off_cm = (uint32_t)round_up((int)(p.off_gs + p.gs_bufs * (gs16 * p.gs_half_elems * 2 + 2 * p.gs8_bytes)), 16);
-  p.off_bar = p.off_cm + 4 * kTileN * 4;
+  p.off_mask = p.off_cm + 4 * kTileN * 4;
+  p.off_bar = p.off_mask + (d_rec ? 4 * kTileN * 4 : 0);
   const size_t smem = 1024 + p.off_bar + 512;
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_scores: shared-memory plan overflow (%zu bytes)", smem);
 
@@ -821,10 +878,11 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
 
 extern "C" int sir_ncc_cost(int precision, int G, int Hp, int Wp, int Hm, int Wm, double* h_cost) {
   SIR_CHECK_ARG(h_cost && G > 0 && Hp > 0 && Wp > 0 && Hm > 0 && Wm > 0, "sir_ncc_cost: bad argument");
-  const int passes = precision == SIR_PREC_FP16X3 ? 3 : precision == SIR_PREC_FP16_FP8C ? 2 : precision == SIR_PREC_FP16X1 ? 1 : 0;
+  const int passes = precision == SIR_PREC_FP16X3 ? 3 : precision == SIR_PREC_FP16_FP8C ? 2
+                     : (precision == SIR_PREC_FP16X1 || precision == SIR_PREC_FP16_REFINE) ? 1 : 0;
   SIR_CHECK_ARG(passes != 0, "sir_ncc_cost: precision %d has no tensor-core plan", precision);
   alignas(16) static const uint16_t dummy16[8] = {0};
   alignas(16) static const uint8_t dummy8[16] = {0};
   return sir::launch_ncc_tc(dummy16, dummy16, dummy8, dummy8, nullptr, G, 1, Hp, Wp, dummy16, dummy16, dummy8, dummy8, 256, 256, Hm, Wm,
-                            nullptr, nullptr, 0, 0, passes, nullptr, h_cost, nullptr);
+                            nullptr, nullptr, 0, 0, passes, nullptr, h_cost, nullptr, nullptr, 0.0f, 0.0f);
 }

@@ -5,6 +5,7 @@
 // row is enough.  HBM bound: 4*Q*G bytes read once (16-byte vector loads), Q*(8k+8) written.
 #include "sir_common.cuh"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace sir {
@@ -162,9 +163,32 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict
   }
 }
 
+// out[q][order[j]] = in[q][j]: puts score columns that were computed shape group by shape group back into the
+// caller's gallery order (reads coalesced, one 4-byte scatter per score).
+__global__ void __launch_bounds__(256) scatter_columns_kernel(const float* __restrict__ in, int Q, int G, int ld_in,
+                                                              const int32_t* __restrict__ order, float* __restrict__ out, int ld_out) {
+  const size_t total = (size_t)Q * G;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t q = i / G;
+    const int j = (int)(i - q * G);
+    out[q * ld_out + __ldg(order + j)] = in[q * ld_in + j];
+  }
+}
+
 }  // namespace sir
 
 using namespace sir;
+
+extern "C" int sir_scatter_columns(const float* d_in, int Q, int G, int ld_in, const int32_t* d_order, float* d_out, int ld_out,
+                                   void* stream) {
+  SIR_CHECK_ARG(d_in && d_order && d_out, "sir_scatter_columns: null pointer");
+  SIR_CHECK_ARG(Q > 0 && G > 0 && ld_in >= G && ld_out >= G, "sir_scatter_columns: bad shape Q=%d G=%d ld=%d/%d", Q, G, ld_in, ld_out);
+  const size_t total = (size_t)Q * G;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  scatter_columns_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, Q, G, ld_in, d_order, d_out, ld_out);
+  SIR_LAUNCH_CHECK("scatter_columns_kernel");
+  return SIR_OK;
+}
 
 extern "C" int sir_true_scores(const float* d_scores, int Q, int G, int score_ld, const int32_t* d_true_idx, int g0,
                                float* d_true_score, void* stream) {

@@ -269,6 +269,33 @@ def _split_fp16(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, int]:
 
 _COPY_THREADS = 4  # host threads that copy finished feature maps out of the pinned result buffer
 
+# Caches across ``Model`` objects.  ``run.py:17-24`` builds a new ``Model`` and recomputes the features of ALL
+# shoeprints for every size cluster: the compiled backbone is kept per (model string, block,
+# weights), and the feature maps of an image list per (that key, CLAHE settings, content hash of the images), so a
+# cluster that shares its block and scale with an earlier one gets the same ``FeatureMapList`` back -- device copies
+# and packed gallery operands included -- without a single kernel launch.  ``SIR_FEATURE_CACHE`` = number of image
+# lists kept (default 4, 0 disables).
+_PROGRAM_CACHE: dict[tuple, tuple] = {}
+_FEATURE_CACHE: "dict[tuple, FeatureMapList]" = {}
+feature_cache_stats = {"hits": 0, "misses": 0}
+
+
+def clear_caches() -> None:
+    _PROGRAM_CACHE.clear()
+    _FEATURE_CACHE.clear()
+    feature_cache_stats.update(hits=0, misses=0)
+
+
+def _images_digest(images: list[np.ndarray]) -> bytes:
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    for im in images:
+        a = np.ascontiguousarray(im)
+        h.update(repr((a.shape, a.dtype.str)).encode())
+        h.update(a.data)
+    return h.digest()
+
 
 class FeatureMapList(list):
     """What ``get_multiple_feature_maps`` returns: the reference's list of ``[C,h,w]`` float32 arrays
@@ -279,6 +306,11 @@ class FeatureMapList(list):
 
     device_groups: list | None = None
     _ids: tuple = ()
+
+    def __init__(self, *args) -> None:
+        super().__init__(*args)
+        #: packed gallery operands of these maps (filled by ``engine.compare`` when the list is used as a gallery)
+        self.operand_cache: dict = {}
 
     def attach_device_copies(self, chunks: list) -> None:
         by_shape: dict[tuple, tuple[list[int], list[torch.Tensor]]] = {}
@@ -639,20 +671,26 @@ class Model:
         ctor, tag, (mean, std) = _MODELS[model_str]
         if random_init_seed is None and os.environ.get("SIR_RANDOM_INIT_SEED"):
             random_init_seed = int(os.environ["SIR_RANDOM_INIT_SEED"])
-        if random_init_seed is None:
-            net = getattr(models, ctor)(weights=tag)  # downloads / reads torchvision's cache like the reference
-        else:
-            gen_state = torch.random.get_rng_state()
-            torch.manual_seed(random_init_seed)
-            net = getattr(models, ctor)(weights=None)
-            torch.random.set_rng_state(gen_state)
-        net.eval()
-        layers = list(net.features.children())[:block]  # network.py:185
-        self.model = nn.Sequential(*layers).eval()       # kept for introspection (weights live here, on the host)
+        weights_key = tag if random_init_seed is None else f"seed{random_init_seed}"
+        self._key = (model_str, int(block), weights_key, self.device.index)
+        if self._key not in _PROGRAM_CACHE:
+            if random_init_seed is None:
+                net = getattr(models, ctor)(weights=tag)  # downloads / reads torchvision's cache like the reference
+            else:
+                gen_state = torch.random.get_rng_state()
+                torch.manual_seed(random_init_seed)
+                net = getattr(models, ctor)(weights=None)
+                torch.random.set_rng_state(gen_state)
+            net.eval()
+            layers = list(net.features.children())[:block]  # network.py:185
+            if len(_PROGRAM_CACHE) >= 4:
+                _PROGRAM_CACHE.pop(next(iter(_PROGRAM_CACHE)))
+            _PROGRAM_CACHE[self._key] = (nn.Sequential(*layers).eval(), _Program(layers, self.device))
+        # the module list is kept for introspection (weights live there, on the host)
+        self.model, self.program = _PROGRAM_CACHE[self._key]
         self.mean, self.std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
         self.transform = self._host_transform(gray=True)
         self.transform_rgb = self._host_transform(gray=False)
-        self.program = _Program(layers, self.device)
         self.max_batch_bytes = 4 << 30  # cap on the live tensors of one layer
         self.max_batch = 64
         self._host_clahe = os.environ.get("SIR_HOST_CLAHE", "") == "1"
@@ -761,6 +799,21 @@ class Model:
     def get_multiple_feature_maps(self, images: list[np.ndarray], *, progress: bool = True) -> list[np.ndarray]:
         """List of images -> list of feature maps, same order (``network.py:246-269``).  Images of
         equal shape are pushed through the backbone as one batch."""
+        slots = int(os.environ.get("SIR_FEATURE_CACHE", "4"))
+        cache_key = None
+        if slots > 0 and len(images) > 0:
+            model_cfg = self.config["model"]
+            cache_key = (self._key, float(model_cfg["clahe_clip_limit"]), tuple(model_cfg["clahe_tile_grid_size"]), self._host_clahe,
+                         len(images), _images_digest(images))
+            hit = _FEATURE_CACHE.get(cache_key)
+            if hit is not None and hit.device_copies() is not None:
+                feature_cache_stats["hits"] += 1
+                _FEATURE_CACHE[cache_key] = _FEATURE_CACHE.pop(cache_key)  # most recently used last
+                if progress:
+                    with tqdm(total=len(images)) as bar:
+                        bar.update(len(images))
+                return hit
+            feature_cache_stats["misses"] += 1
         results: list[Any] = [None] * len(images)
         by_shape: dict[tuple, list[int]] = {}
         for i, im in enumerate(images):
@@ -831,4 +884,8 @@ class Model:
         budget = float(os.environ.get("SIR_DEVICE_MAP_CACHE_GB", "16")) * 2**30
         if sum(m.numel() * 4 for _, _, m in device_chunks) <= budget:
             out.attach_device_copies(device_chunks)
+            if cache_key is not None:
+                while len(_FEATURE_CACHE) >= slots:
+                    _FEATURE_CACHE.pop(next(iter(_FEATURE_CACHE)))
+                _FEATURE_CACHE[cache_key] = out
         return out

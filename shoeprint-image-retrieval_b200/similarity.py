@@ -34,7 +34,9 @@ if TYPE_CHECKING:
 
 _PAD = engine.EDGE
 
-#: scores ``[Q, G]`` (torch, on the device) and top-k lists of the most recent ``compare_maps`` call
+#: scores ``[Q, G]`` (torch, on the device), top-k lists and host->device bytes (``h2d_bytes``: (shoemarks,
+#: shoeprints); 0 when the maps came from ``Model.get_multiple_feature_maps`` and were still resident on the
+#: device) of the most recent ``compare_maps`` call
 last_result: dict = {}
 
 
@@ -50,6 +52,17 @@ class MultiProcessingTrackers:
 
 def _as_f32(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+def _ingest(maps):
+    """The caller's list, untouched when it can be used as is: a ``network.FeatureMapList`` whose device
+    copies are still valid is handed through as the very same object (``engine`` then reads the maps where
+    the feature stage left them, no upload); in any other list only the elements that are not already
+    C-contiguous float32 arrays are converted."""
+    copies = getattr(maps, "device_copies", None)
+    if copies is not None and copies() is not None:
+        return maps
+    return [m if isinstance(m, np.ndarray) and m.dtype == np.float32 and m.flags.c_contiguous else _as_f32(m) for m in maps]
 
 
 def compare_maps(
@@ -73,13 +86,16 @@ def compare_maps(
     top_k = int(comparison.get("top_k", 0))
     if len(matching_pairs) < len(shoemark_maps):
         raise IndexError("matching_pairs is shorter than shoemark_maps")
+    pairs = [int(v) for v in matching_pairs[: len(shoemark_maps)]]
+    if any(v < 0 or v >= len(shoeprint_maps) for v in pairs):  # the reference fails in _get_rank (similarity.py:386)
+        raise IndexError("matching_pairs holds an index outside shoeprint_maps")
 
     n_variants = len(engine.variant_plan(rotations, scales))
     with tqdm(total=n_variants * len(shoemark_maps)) as pbar:
         ranks, scores, topk = engine.compare(
-            [_as_f32(m) for m in shoemark_maps],
-            [_as_f32(m) for m in shoeprint_maps],
-            list(matching_pairs[: len(shoemark_maps)]),
+            _ingest(shoemark_maps),
+            _ingest(shoeprint_maps),
+            pairs,
             rotations,
             scales,
             precision=precision,
@@ -89,7 +105,7 @@ def compare_maps(
             pbar.write(f"Print {shoemark_id} true match ranked {rank}")  # similarity.py:375
         pbar.update(pbar.total)
     last_result.clear()
-    last_result.update(scores=scores, topk=topk)
+    last_result.update(scores=scores, topk=topk, h2d_bytes=engine.last_h2d_bytes)
     return ranks
 
 

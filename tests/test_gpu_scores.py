@@ -43,7 +43,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-5), ("fp16x3", REL_TOL), ("fp16_fp8c", REL_TOL)])
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-5), ("fp16x3", REL_TOL), ("fp16_fp8c", REL_TOL), ("fp16_refine", 2e-5)])
 @pytest.mark.parametrize("case", CASES)
 def test_scores_match_oracle(eng, case, precision, tol):
     from oracle import compare as ocmp
@@ -104,6 +104,8 @@ def test_simt_and_tensor_core_agree_at_reference_shapes(eng):
         _check(b, a)
         c8 = eng.score_matrix(ps, gs, [-5, 5], None, "fp16_fp8c").cpu().numpy()
         _check(c8, a)
+        rf = eng.score_matrix(ps, gs, [-5, 5], None, "fp16_refine").cpu().numpy()
+        _check(rf, a, 1e-5)
         print(f"C={c}: max rel err fp16x3 {np.max(np.abs(b - a) / np.maximum(a, 1e-3)):.2e}, fp16_fp8c {np.max(np.abs(c8 - a) / np.maximum(a, 1e-3)):.2e}")
         assert np.all(a.argmax(1) == pairs.cpu().numpy())
 
@@ -151,12 +153,13 @@ def test_idempotent_and_gallery_permutation_invariant(eng):
     gal = synth.device_gallery(51, 40, 16, 30, 20)
     prb, _ = synth.device_probes(52, gal, 20)
     ps = eng.MapSet.from_device(prb)
-    a = eng.score_matrix(ps, eng.MapSet.from_device(gal), [7], None, "fp16x3")
-    b = eng.score_matrix(ps, eng.MapSet.from_device(gal), [7], None, "fp16x3")
-    assert torch.equal(a, b)
-    perm = torch.randperm(40, device="cuda")
-    c = eng.score_matrix(ps, eng.MapSet.from_device(gal[perm].contiguous()), [7], None, "fp16x3")
-    assert torch.equal(c, a[:, perm])
+    for precision in ("fp16x3", "fp16_refine"):
+        a = eng.score_matrix(ps, eng.MapSet.from_device(gal), [7], None, precision)
+        b = eng.score_matrix(ps, eng.MapSet.from_device(gal), [7], None, precision)
+        assert torch.equal(a, b)
+        perm = torch.randperm(40, device="cuda")
+        c = eng.score_matrix(ps, eng.MapSet.from_device(gal[perm].contiguous()), [7], None, precision)
+        assert torch.equal(c, a[:, perm])
 
 
 def test_full_bench_size_properties(eng):
@@ -197,7 +200,7 @@ def test_gallery_chunking_does_not_change_scores(eng):
     assert torch.equal(whole, pieces)
 
 
-@pytest.mark.parametrize("precision", ["fp16_fp8c", "fp16x3"])
+@pytest.mark.parametrize("precision", ["fp16_fp8c", "fp16x3", "fp16_refine"])
 def test_heavy_tailed_feature_maps_stay_within_tolerance(eng, precision):
     """Post-activation CNN features are heavy tailed; cube the synthetic maps so single cells reach
     ~100x the typical magnitude of their channel and check the split-precision modes still meet 1e-4
@@ -211,3 +214,30 @@ def test_heavy_tailed_feature_maps_stay_within_tolerance(eng, precision):
     _, want = ocmp.compare_maps_oracle(probes, gallery, pairs, [-5, 5], None)
     _check(scores.cpu().numpy(), want)
     assert list(ranks) == [1, 1, 1, 1]
+
+
+def test_refinement_finds_the_exact_maximum(eng):
+    """The default mode screens in fp16 and re-evaluates only the positions within the candidate margin of a pair's
+    screened maximum (engine.TAU_REL / TAU_ABS).  A missed maximum would show up as a score BELOW the float32 CUDA-core
+    evaluation of the whole surface: check 64,000 pairs (x 4 variants) for that, and that the work list stays short
+    (about one position per pair and launch, not one per variant or per patch)."""
+    from src.shoeprint_image_retrieval import synth
+
+    gal = synth.device_gallery(91, 160, 24, 34, 21)
+    prb, _ = synth.device_probes(92, gal, 400)
+    ps, gs = eng.MapSet.from_device(prb), eng.MapSet.from_device(gal)
+    rot = [-10, 5, 20]
+    exact = eng.score_matrix(ps, gs, rot, None, "fp32_simt")
+    eng.collect_refine_stats = True
+    eng.refine_stats(reset=True)
+    try:
+        got = eng.score_matrix(ps, gs, rot, None, "fp16_refine")
+        stats = eng.refine_stats(reset=True)
+    finally:
+        eng.collect_refine_stats = False
+    err = ((got - exact).abs() / exact.abs().clamp_min(1e-3)).max().item()
+    assert err < 5e-6, err
+    pairs = 400 * 160
+    assert pairs <= stats["positions"] < 3 * pairs, stats
+    screened = eng.score_matrix(ps, gs, rot, None, "fp16x1")
+    assert ((screened - exact).abs() / exact.abs().clamp_min(1e-3)).max().item() > err  # the screen alone is looser
