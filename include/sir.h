@@ -161,23 +161,31 @@ int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uin
  *   .x = the patch maximum (float32 bits, score units), .y = up to three candidate rows (8 bits each: row>>3 = y
  *   offset, row&7 = x offset inside the patch) and, in the top byte, the number of rows within the margin
  *   tau(m) = tau_rel*|m| + tau_abs of the patch maximum (saturated; > 3 = "every position of the patch").
- * sir_ncc_refine then evaluates, in float32 from the hi + lo operand pairs, exactly the candidate positions of the
- * records whose maximum is within tau of the pair's screened maximum d_approx, and max-reduces the exact values into
- * d_scores (caller zeroes it first).  tau must cover twice the screening error.  d_rnorm (one template shape) or
- * d_rnorm_tab (multi-shape bucket, one table pointer per 16-column chunk as in sir_ncc_scores_multi): exactly one is
- * non-NULL; Hb x Wb is the K layout of the packed templates (= Hm x Wm for a single shape), rows padded to 8 taps
- * (sir_template_pack / sir_template_pack_embed with SIR_PREC_FP16X3).  d_stats: NULL or 4 device counters
- * ([0] positions evaluated, [1] records with more than 3 rows, [2] tiles with work), accumulated.
- * sir_ncc_screen_rec_count: number of 8-byte records d_rec must hold. */
+ * sir_ncc_refine then evaluates in float32 -- from d_g32 (sir_gallery_pack_f32) and d_t32p (sir_template_pack_screen),
+ * the float32 values the fp16 operands were rounded from -- exactly the candidate positions of the records whose
+ * maximum is within tau of the pair's screened maximum d_approx, and max-reduces the exact values into d_scores
+ * (caller zeroes it first).  tau must cover twice the screening error.  d_rnorm (one template shape) or d_rnorm_tab
+ * (multi-shape bucket, one table pointer per 16-column chunk as in sir_ncc_scores_multi): exactly one is non-NULL;
+ * Hb x Wb is the K layout of the packed templates (= Hm x Wm for a single shape), rows padded to 8 taps.
+ * d_stats: NULL or 4 device counters ([0] positions evaluated, [1] records with more than 3 rows, [2] tiles with
+ * work), accumulated.  sir_ncc_screen_rec_count: number of 8-byte records d_rec must hold.
+ *
+ * sir_gallery_pack_f32: sir_gallery_pack that also writes d_g32 [G][C][Hp][WP] float32 = (g - mean) * 2^e, rows
+ * padded with zeros like d_ghi (NULL: not written).  sir_template_pack_screen: d_thi as sir_template_pack and
+ * d_t32p [C][ncols_alloc][Kpad] float32 = (t - mean)/sqrt(E) * 2^10 in the same padded K layout; Hb x Wb >= the true
+ * shape selects a bucket layout (anchor on anchor) as in sir_template_pack_embed. */
+int sir_gallery_pack_f32(const float* d_gallery, int G, int C, int hg, int wg, uint16_t* d_ghi, uint16_t* d_glo, int32_t* d_gexp,
+                         float* d_gz, float* d_g32, void* stream);
+int sir_template_pack_screen(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
+                             uint16_t* d_thi, float* d_t32p, void* stream);
 long long sir_ncc_screen_rec_count(int G, int Hp, int Wp, int ncols);
-int sir_ncc_screen(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
-                   int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hb, int Wb,
-                   const int32_t* d_col2probe, float* d_approx, int score_ld, int g0, float tau_rel, float tau_abs, void* d_rec,
-                   void* stream);
-int sir_ncc_refine(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
-                   int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hb, int Wb,
-                   const int32_t* d_col2probe, const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel,
-                   float tau_abs, const void* d_rec, unsigned long long* d_stats, void* stream);
+int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
+                   const uint16_t* d_thi, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe, float* d_approx,
+                   int score_ld, int g0, float tau_rel, float tau_abs, void* d_rec, void* stream);
+int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
+                   const float* d_t32p, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe,
+                   const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel, float tau_abs, const void* d_rec,
+                   unsigned long long* d_stats, void* stream);
 /* cudaMemsetAsync(d_ptr, 0, bytes) on `stream`: the path zeroes its score / operand buffers through the library. */
 int sir_memset_zero(void* d_ptr, size_t bytes, void* stream);
 

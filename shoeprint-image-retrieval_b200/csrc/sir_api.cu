@@ -82,8 +82,8 @@ extern "C" long long sir_ncc_screen_rec_count(int G, int Hp, int Wp, int ncols) 
   return (long long)ncols * G * ceil_div(Hp, 16) * ceil_div(Wp, 8);
 }
 
-extern "C" int sir_ncc_screen(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
-                              int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hb, int Wb,
+extern "C" int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
+                              int Hp, int Wp, const uint16_t* d_thi, int ncols, int ncols_alloc, int Hb, int Wb,
                               const int32_t* d_col2probe, float* d_approx, int score_ld, int g0, float tau_rel, float tau_abs,
                               void* d_rec, void* stream) {
   SIR_CHECK_ARG((d_rnorm != nullptr) != (d_rnorm_tab != nullptr), "sir_ncc_screen: give d_rnorm or d_rnorm_tab, not both");
@@ -92,7 +92,7 @@ extern "C" int sir_ncc_screen(const uint16_t* d_ghi, const uint16_t* d_glo, cons
   SIR_CHECK_ARG(Hb > 0 && Wb > 0 && ncols > 0 && ncols <= ncols_alloc, "sir_ncc_screen: bad template block");
   SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_screen: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
   SIR_CHECK_ARG(tau_rel >= 0.0f && tau_abs >= 0.0f, "sir_ncc_screen: negative candidate margin");
-  return launch_ncc_tc(d_ghi, d_glo, nullptr, nullptr, d_rnorm, G, C, Hp, Wp, d_thi, d_tlo, nullptr, nullptr, ncols, ncols_alloc, Hb, Wb,
+  return launch_ncc_tc(d_ghi, nullptr, nullptr, nullptr, d_rnorm, G, C, Hp, Wp, d_thi, nullptr, nullptr, nullptr, ncols, ncols_alloc, Hb, Wb,
                        d_col2probe, d_approx, score_ld, g0, 1, (cudaStream_t)stream, nullptr, d_rnorm_tab, (uint2*)d_rec, tau_rel, tau_abs);
 }
 

@@ -6,34 +6,36 @@
 // maximum can be: every (column, gallery, patch) record whose screened maximum lies within the candidate margin of
 // the pair's screened maximum names the rows that are within the margin of it, and this kernel evaluates
 //
-//     s(n, g, y, x) = (1/C) sum_c rnorm_c[g][y,x] * sum_{u,v} (t_hi + t_lo)[n][c][u,v] * (g_hi + g_lo)[g][c][y+u-a][x+v-b]
+//     s(n, g, y, x) = (1/C) sum_c rnorm_c[g][y,x] * sum_{u,v} t32[n][c][u,v] * g32[g][c][y+u-a][x+v-b]
 //
-// for exactly those positions in float32 (the hi + lo pairs carry 22 significant bits) and max-reduces the result
-// into d_scores.  The margin covers twice the screening error, so the position of the true maximum is always among
-// the candidates; if it ever were not, the result would still be an exactly evaluated correlation value within
-// 2 * (screening error) of the true maximum.
+// for exactly those positions in float32 (t32, g32: the float32 values the fp16 operands were rounded from) and
+// max-reduces the result into d_scores.  The margin covers twice the screening error, so the position of the true
+// maximum is always among the candidates; if it ever were not, the result would still be an exactly evaluated
+// correlation value within 2 * (screening error) of the true maximum.
 //
-// One CTA owns a tile of TN columns x TG gallery prints.  Per channel it stages the tile's template columns and
-// gallery planes in shared memory as float32 (each operand byte is read once per tile, not once per candidate);
-// a warp takes one candidate at a time, lanes spread over (template row, tap), zero rows of the "same" padding are
-// skipped.  The work list is built without atomics (block scan over per-thread counts), so every run evaluates the
-// same candidates in the same order.
+// One CTA owns a tile of TN columns x TG gallery prints.  Per channel the tile's template columns and gallery
+// planes that have work are staged in shared memory by plain bulk copies (cp.async.bulk, one per plane, issued by
+// a producer warp, lanes in parallel, into a two-stage ring guarded by full/empty mbarriers: channel c+1 lands while
+// channel c is being multiplied), so every operand byte is read once per tile instead of once per candidate.  Each
+// of the eight consumer warps takes one candidate at a time, lanes spread over (template row, tap); template rows
+// that only meet the "same"-mode zero padding are skipped.  The work list is built without
+// atomics (block scan over per-thread counts): every run evaluates the same candidates in the same order.
 #include <algorithm>
 
 #include "sir_common.cuh"
+#include "sir_ptx.cuh"
 
 namespace sir {
 
-constexpr int kRefThreads = 256;
-constexpr int kRefWarps = kRefThreads / 32;
+constexpr int kRefWarps = 8;                       // consumer warps (one candidate position at a time each)
+constexpr int kRefThreads = 32 * (kRefWarps + 1);  // + one producer warp issuing the bulk copies
+constexpr int kRefStages = 2;
 
 struct RefineParams {
-  const __half* ghi;
-  const __half* glo;
+  const float* g32;
+  const float* t32;
   const float* rnorm;
   const float* const* rnorm_tab;
-  const __half* thi;
-  const __half* tlo;
   const int32_t* col2probe;
   const float* approx;
   float* scores;
@@ -55,7 +57,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* to
   if (lane == 31) scratch[wid] = inc;
   __syncthreads();
   int base = 0, sum = 0;
-  for (int i = 0; i < kRefWarps; ++i) {
+  for (int i = 0; i < kRefThreads / 32; ++i) {
     if (i < wid) base += scratch[i];
     sum += scratch[i];
   }
@@ -65,14 +67,15 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* to
 }
 
 __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefineParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int PG = p.Hp * p.WP;  // cells of one packed gallery plane
-  float* tpl = reinterpret_cast<float*>(smem_raw);                 // [TN][Kpad]
-  float* gal = tpl + (size_t)p.TN * p.Kpad;                        // [TG][PG]
-  uint2* list = reinterpret_cast<uint2*>(gal + (size_t)p.TG * PG);  // [cap] (j | i << 8, y | x << 16)
-  float* acc = reinterpret_cast<float*>(list + p.cap);             // [cap]
-  int* flags = reinterpret_cast<int*>(acc + p.cap);                // [TN + TG]
-  int* scratch = flags + p.TN + p.TG;                              // [kRefWarps]
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int PG = p.Hp * p.WP;                           // cells of one packed gallery plane
+  const size_t buf_floats = (size_t)p.TN * p.Kpad + (size_t)p.TG * PG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // full[kRefStages], empty[kRefStages]
+  float* bufs = reinterpret_cast<float*>(smem_raw + 128);           // [kRefStages][ [TN][Kpad] + [TG][PG] ]
+  uint2* list = reinterpret_cast<uint2*>(bufs + kRefStages * buf_floats);  // [cap] (j | i << 8, y | x << 16)
+  float* acc = reinterpret_cast<float*>(list + p.cap);              // [cap]
+  int* flags = reinterpret_cast<int*>(acc + p.cap);                 // [TN + TG]
+  int* scratch = flags + p.TN + p.TG;                               // [warps]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = (blockIdx.x / p.tiles_g) * p.TN, gt0 = (blockIdx.x % p.tiles_g) * p.TG;
@@ -109,15 +112,25 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
   int total = 0;
   const int base = block_exclusive_scan(mine, scratch, &total);
   if (total == 0) return;
-  if (p.stats && tid == 0) {
-    atomicAdd(p.stats + 0, (unsigned long long)total);
-    atomicAdd(p.stats + 2, 1ull);
+  if (tid == 0) {
+    for (int st = 0; st < kRefStages; ++st) {
+      ptx::mbar_init(ptx::smem_u32(bars + st), 1);                      // full: the producer's expect_tx arrival + the bytes
+      ptx::mbar_init(ptx::smem_u32(bars + kRefStages + st), kRefWarps);  // empty: one arrival per consumer warp
+    }
+    ptx::fence_barrier_init();
+    if (p.stats) {
+      atomicAdd(p.stats + 0, (unsigned long long)total);
+      atomicAdd(p.stats + 2, 1ull);
+    }
   }
 
   const int a = p.Hb / 2, b = p.Wb / 2;
-  // lanes over (template row, tap): rows of up to 32 taps share a pass when they divide the warp
-  const int vl = (p.rowk <= 32 && 32 % p.rowk == 0) ? p.rowk : 32;
+  // lanes over (template row, tap): vl lanes along a row (the largest power of two that divides the padded row, which
+  // is a multiple of 8), 32 / vl rows per pass -- every lane has work whatever the row length
+  const int vl = (p.rowk % 32 == 0) ? 32 : (p.rowk % 16 == 0) ? 16 : 8;
   const int rpp = 32 / vl, lv = lane % vl, lr = lane / vl;
+  const uint32_t tbytes = (uint32_t)p.Kpad * 4u, gbytes = (uint32_t)PG * 4u;
+  uint32_t it = 0;  // channel iterations so far (stage = it % kRefStages, barrier parity = (it / kRefStages) & 1)
 
   for (int r0 = 0; r0 < total; r0 += p.cap) {
     const int nl = min(p.cap, total - r0);
@@ -155,74 +168,72 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
     }
     __syncthreads();
 
-    for (int c = 0; c < p.C; ++c) {
-      // ---- stage the flagged template columns and gallery planes of this channel as float32
-      const int tch = p.Kpad / 8, gch = PG / 8;
-      for (int idx = tid; idx < p.TN * tch; idx += kRefThreads) {
-        const int j = idx / tch, ch = idx - j * tch;
-        if (!flags[j]) continue;
-        const size_t off = ((size_t)c * p.ncols_alloc + n0 + j) * p.Kpad + (size_t)ch * 8;
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.thi + off));
-        const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.tlo + off));
-        const __half2* hh = reinterpret_cast<const __half2*>(&h);
-        const __half2* ll = reinterpret_cast<const __half2*>(&l);
-        float4 o0, o1;
-        float2 x0 = __half22float2(hh[0]), y0 = __half22float2(ll[0]);
-        float2 x1 = __half22float2(hh[1]), y1 = __half22float2(ll[1]);
-        o0 = make_float4(x0.x + y0.x, x0.y + y0.y, x1.x + y1.x, x1.y + y1.y);
-        x0 = __half22float2(hh[2]); y0 = __half22float2(ll[2]);
-        x1 = __half22float2(hh[3]); y1 = __half22float2(ll[3]);
-        o1 = make_float4(x0.x + y0.x, x0.y + y0.y, x1.x + y1.x, x1.y + y1.y);
-        float4* dst = reinterpret_cast<float4*>(tpl + (size_t)j * p.Kpad + (size_t)ch * 8);
-        dst[0] = o0;
-        dst[1] = o1;
-      }
-      for (int idx = tid; idx < p.TG * gch; idx += kRefThreads) {
-        const int i = idx / gch, ch = idx - i * gch;
-        if (!flags[p.TN + i]) continue;
-        const size_t off = ((size_t)(gt0 + i) * p.C + c) * PG + (size_t)ch * 8;
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.ghi + off));
-        const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.glo + off));
-        const __half2* hh = reinterpret_cast<const __half2*>(&h);
-        const __half2* ll = reinterpret_cast<const __half2*>(&l);
-        float4 o0, o1;
-        float2 x0 = __half22float2(hh[0]), y0 = __half22float2(ll[0]);
-        float2 x1 = __half22float2(hh[1]), y1 = __half22float2(ll[1]);
-        o0 = make_float4(x0.x + y0.x, x0.y + y0.y, x1.x + y1.x, x1.y + y1.y);
-        x0 = __half22float2(hh[2]); y0 = __half22float2(ll[2]);
-        x1 = __half22float2(hh[3]); y1 = __half22float2(ll[3]);
-        o1 = make_float4(x0.x + y0.x, x0.y + y0.y, x1.x + y1.x, x1.y + y1.y);
-        float4* dst = reinterpret_cast<float4*>(gal + (size_t)i * PG + (size_t)ch * 8);
-        dst[0] = o0;
-        dst[1] = o1;
-      }
-      __syncthreads();
-      // ---- one warp per candidate position
-      for (int e = warp; e < nl; e += kRefWarps) {
-        const uint2 en = list[e];
-        const int j = en.x & 0xff, i = en.x >> 8, y = en.y & 0xffff, x = en.y >> 16;
-        const int u_lo = max(0, a - y), u_hi = min(p.Hb, p.Hp + a - y);  // template rows that meet the map
-        const float* T = tpl + (size_t)j * p.Kpad;
-        const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
-        float part = 0.0f;
-        for (int v0 = 0; v0 < p.rowk; v0 += vl) {
-          const int v = v0 + lv, gx = x + v - b;
-          if (v < p.rowk && gx >= 0 && gx < p.Wp) {
-            const float* tp = T + (u_lo + lr) * p.rowk + v;
-            const float* gp = Gs + (u_lo + lr) * p.WP + v;
-#pragma unroll 4
-            for (int u = u_lo + lr; u < u_hi; u += rpp, tp += rpp * p.rowk, gp += rpp * p.WP) part = fmaf(*tp, *gp, part);
-          }
-        }
-        part = warp_sum(part);
+    if (warp == kRefWarps) {
+      // ---- producer warp: per channel, one bulk copy per flagged plane (lanes issue in parallel) into the next free stage
+      uint32_t bytes = 0;
+      for (int k = 0; k < p.TN + p.TG; ++k) bytes += flags[k] ? (k < p.TN ? tbytes : gbytes) : 0u;
+      for (int c = 0; c < p.C; ++c, ++it) {
+        const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
+        const uint32_t full = ptx::smem_u32(bars + st);
+        ptx::mbar_wait(ptx::smem_u32(bars + kRefStages + st), par ^ 1u);  // consumers are done with this stage
+        float* dst = bufs + st * buf_floats;
         if (lane == 0) {
-          const int n = n0 + j, g = gt0 + i;
-          const float* table = p.rnorm_tab ? p.rnorm_tab[n >> 4] : p.rnorm;
-          acc[e] = fmaf(part, __ldg(table + ((size_t)g * p.C + c) * M + y * p.Wp + x), acc[e]);
+          ptx::fence_proxy_async_smem();  // the consumers' generic reads of this stage precede the async writes
+          ptx::mbar_arrive_expect_tx(full, bytes);
+        }
+        __syncwarp();
+        for (int k = lane; k < p.TN + p.TG; k += 32) {
+          if (!flags[k]) continue;
+          if (k < p.TN)
+            ptx::bulk_load(ptx::smem_u32(dst + (size_t)k * p.Kpad), p.t32 + ((size_t)c * p.ncols_alloc + n0 + k) * p.Kpad, tbytes, full);
+          else
+            ptx::bulk_load(ptx::smem_u32(dst + (size_t)p.TN * p.Kpad + (size_t)(k - p.TN) * PG),
+                           p.g32 + ((size_t)(gt0 + k - p.TN) * p.C + c) * PG, gbytes, full);
         }
       }
-      __syncthreads();
+    } else {
+      // ---- consumer warps: one candidate position at a time
+      for (int c = 0; c < p.C; ++c, ++it) {
+        const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(bars + st), par);
+        const float* tpl = bufs + st * buf_floats;
+        const float* gal = tpl + (size_t)p.TN * p.Kpad;
+        for (int e = warp; e < nl; e += kRefWarps) {
+          const uint2 en = list[e];
+          const int j = en.x & 0xff, i = en.x >> 8, y = en.y & 0xffff, x = en.y >> 16;
+          float rn = 0.0f;
+          if (lane == 0) {  // issued now, needed after the dot product
+            const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + j) >> 4] : p.rnorm;
+            rn = __ldg(table + ((size_t)(gt0 + i) * p.C + c) * M + y * p.Wp + x);
+          }
+          const int u_lo = max(0, a - y), u_hi = min(p.Hb, p.Hp + a - y);  // template rows that meet the map
+          const float* T = tpl + (size_t)j * p.Kpad;
+          const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
+          float part0 = 0.0f, part1 = 0.0f;
+          for (int v0 = 0; v0 < p.rowk; v0 += vl) {
+            const int v = v0 + lv, gx = x + v - b;
+            if (v < p.rowk && gx >= 0 && gx < p.Wp) {
+              const int ts = rpp * p.rowk, gs = rpp * p.WP;
+              const float* tp = T + (u_lo + lr) * p.rowk + v;
+              const float* gp = Gs + (u_lo + lr) * p.WP + v;
+              int u = u_lo + lr;
+              for (; u + 3 * rpp < u_hi; u += 4 * rpp, tp += 4 * ts, gp += 4 * gs) {
+                part0 = fmaf(tp[0], gp[0], part0);
+                part1 = fmaf(tp[ts], gp[gs], part1);
+                part0 = fmaf(tp[2 * ts], gp[2 * gs], part0);
+                part1 = fmaf(tp[3 * ts], gp[3 * gs], part1);
+              }
+              for (; u < u_hi; u += rpp, tp += ts, gp += gs) part0 = fmaf(*tp, *gp, part0);
+            }
+          }
+          const float part = warp_sum(part0 + part1);
+          if (lane == 0) acc[e] = fmaf(part, rn, acc[e]);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + kRefStages + st));
+      }
     }
+    __syncthreads();
     for (int e = tid; e < nl; e += kRefThreads) {
       const int n = n0 + (list[e].x & 0xff), g = gt0 + (list[e].x >> 8);
       atomic_max_nonneg(&p.scores[(size_t)p.col2probe[n] * p.score_ld + p.g0 + g], acc[e] * p.inv_scale);
@@ -235,22 +246,22 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
 
 using namespace sir;
 
-extern "C" int sir_ncc_refine(const uint16_t* d_ghi, const uint16_t* d_glo, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
-                              int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, int ncols, int ncols_alloc, int Hb, int Wb,
-                              const int32_t* d_col2probe, const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel,
-                              float tau_abs, const void* d_rec, unsigned long long* d_stats, void* stream) {
+extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
+                              const float* d_t32p, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe,
+                              const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel, float tau_abs, const void* d_rec,
+                              unsigned long long* d_stats, void* stream) {
   SIR_CHECK_ARG((d_rnorm != nullptr) != (d_rnorm_tab != nullptr), "sir_ncc_refine: give d_rnorm or d_rnorm_tab, not both");
-  SIR_CHECK_ARG(d_ghi && d_glo && d_thi && d_tlo && d_col2probe && d_approx && d_scores && d_rec, "sir_ncc_refine: null pointer");
+  SIR_CHECK_ARG(d_g32 && d_t32p && d_col2probe && d_approx && d_scores && d_rec, "sir_ncc_refine: null pointer");
   SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0 && Hb > 0 && Wb > 0 && ncols > 0 && ncols <= ncols_alloc, "sir_ncc_refine: bad shape");
   SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_refine: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
   SIR_CHECK_ARG(Hp < 65536 && Wp < 65536, "sir_ncc_refine: map too large");
+  SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_g32) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_t32p) & 15) == 0,
+                "sir_ncc_refine: operands must be 16-byte aligned");
   RefineParams p{};
-  p.ghi = (const __half*)d_ghi;
-  p.glo = (const __half*)d_glo;
+  p.g32 = d_g32;
+  p.t32 = d_t32p;
   p.rnorm = d_rnorm;
   p.rnorm_tab = d_rnorm_tab;
-  p.thi = (const __half*)d_thi;
-  p.tlo = (const __half*)d_tlo;
   p.col2probe = d_col2probe;
   p.approx = d_approx;
   p.scores = d_scores;
@@ -265,30 +276,24 @@ extern "C" int sir_ncc_refine(const uint16_t* d_ghi, const uint16_t* d_glo, cons
   p.score_ld = score_ld; p.g0 = g0;
   p.tau_rel = tau_rel; p.tau_abs = tau_abs;
   p.inv_scale = 1.0f / ((float)C * (float)(1 << kTemplateScaleLog2));
-  p.cap = 1024;
-  // tile: as many (column, gallery) pairs per CTA as the staged planes allow (every operand byte is then read once
-  // per tile); columns get the larger share because consecutive CTAs walk the gallery tiles of one column tile
-  const size_t budget = 200 * 1024, fixed = (size_t)p.cap * 12 + 4 * (32 + 32 + kRefWarps) + 64;
+  p.cap = 512;
+  // tile: as many (column, gallery) pairs per CTA as two staged channel buffers allow (every operand byte is then
+  // read once per tile); ties go to more columns because consecutive CTAs walk the gallery tiles of one column tile
+  const size_t budget = 220 * 1024, fixed = 128 + (size_t)p.cap * 12 + 4 * (32 + 32 + kRefThreads / 32) + 64;
   const size_t tbytes = (size_t)p.Kpad * 4, gbytes = (size_t)Hp * p.WP * 4;
   int best_tn = 0, best_tg = 0;
   for (int tn = 32; tn >= 1; tn >>= 1)
     for (int tg = 32; tg >= 1; tg >>= 1)
-      if (fixed + tn * tbytes + tg * gbytes <= budget && (tn * tg > best_tn * best_tg || (tn * tg == best_tn * best_tg && tn > best_tn))) {
+      if (fixed + kRefStages * (tn * tbytes + tg * gbytes) <= budget && (tn * tg > best_tn * best_tg || (tn * tg == best_tn * best_tg && tn > best_tn))) {
         best_tn = tn;
         best_tg = tg;
       }
   SIR_CHECK_ARG(best_tn > 0, "sir_ncc_refine: template %dx%d / map %dx%d do not fit shared memory", Hb, Wb, Hp, Wp);
-  p.TN = std::min(best_tn, round_up(ncols, 1));
+  p.TN = best_tn;
   p.TG = best_tg;
   p.tiles_g = ceil_div(G, p.TG);
-  const size_t smem = fixed + p.TN * tbytes + p.TG * gbytes;
-  int dev = 0;
-  SIR_CUDA(cudaGetDevice(&dev));
-  static thread_local size_t configured[16] = {0};
-  if (smem > 48 * 1024 && (dev >= 16 || smem > configured[dev])) {
-    SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (dev < 16) configured[dev] = smem;
-  }
+  const size_t smem = fixed + kRefStages * (p.TN * tbytes + p.TG * gbytes);
+  SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   const long long blocks = (long long)ceil_div(ncols, p.TN) * p.tiles_g;
   SIR_CHECK_ARG(blocks < (1ll << 31), "sir_ncc_refine: too many tiles");
   ncc_refine_kernel<<<(unsigned)blocks, kRefThreads, smem, (cudaStream_t)stream>>>(p);

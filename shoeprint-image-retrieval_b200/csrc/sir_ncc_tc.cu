@@ -715,7 +715,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   // channel) and return without touching any pointer (sir_ncc_cost)
   SIR_CHECK_ARG(d_ghi && d_thi, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
   if (passes == 2) SIR_CHECK_ARG(d_g8a && d_g8l && d_t8b && d_t8l, "sir_ncc_scores_fp8c: needs the e4m3 companion operands");
-  else SIR_CHECK_ARG(d_glo && d_tlo, "sir_ncc_scores(tcgen05): needs the fp16 lo operands");
+  else if (passes == 3) SIR_CHECK_ARG(d_glo && d_tlo, "sir_ncc_scores(tcgen05): needs the fp16 lo operands");
   SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_thi) & 15) == 0, "sir_ncc_scores: template operands must be 16-byte aligned");
   TcParams p{};
   p.ghi = (const __half*)d_ghi;
@@ -834,9 +834,10 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
     rc = make_gallery_map8(&tm_gx, d_g8a, G * C, Hp, Wp, Pe + 32, p.gs_rows);
     if (rc) return rc;
   } else {
-    rc = make_template_map(&tm_lo, d_tlo, Kpad, ncols_alloc, C, kTileN / cg);
+    // one-pass modes never touch the lo maps: alias them to the hi operands when the caller has none
+    rc = make_template_map(&tm_lo, d_tlo ? d_tlo : d_thi, Kpad, ncols_alloc, C, kTileN / cg);
     if (rc) return rc;
-    rc = make_gallery_map(&tm_glo, d_glo, G * C, Hp, Wp, Pe + 16, p.gs_rows);
+    rc = make_gallery_map(&tm_glo, d_glo ? d_glo : d_ghi, G * C, Hp, Wp, Pe + 16, p.gs_rows);
     if (rc) return rc;
     tm_x = tm_lo;
     tm_gx = tm_glo;

@@ -19,7 +19,7 @@ __device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_f
 // K5 gallery: one CTA per (gallery, channel).  Reads 4 B/cell, writes 4 B/cell (hi+lo) [+4 gz].
 __global__ void __launch_bounds__(256) gallery_pack_kernel(const float* __restrict__ gal, int C, int hg, int wg,
                                                            __half* __restrict__ ghi, __half* __restrict__ glo,
-                                                           int32_t* __restrict__ gexp, float* __restrict__ gz) {
+                                                           int32_t* __restrict__ gexp, float* __restrict__ gz, float* __restrict__ g32) {
   __shared__ double sred[32];
   __shared__ float fred[32];
   const int Hp = hg - 2 * kEdge, Wp = wg - 2 * kEdge, M = Hp * Wp;
@@ -51,15 +51,17 @@ __global__ void __launch_bounds__(256) gallery_pack_kernel(const float* __restri
   for (int i = threadIdx.x; i < Hp * WP; i += blockDim.x) {
     const int y = i / WP, x = i - y * WP;
     __half h = __ushort_as_half(0), l = __ushort_as_half(0);
+    float s = 0.0f;
     if (x < Wp) {
       const float z = src[(y + kEdge) * wg + x + kEdge] - mean;
-      const float s = ldexpf(z, e);
+      s = ldexpf(z, e);
       h = __float2half_rn(s);
       l = __float2half_rn(s - __half2float(h));
       if (gz) gz[gc * M + y * Wp + x] = z;
     }
     ghi[gc * Hp * WP + i] = h;
     glo[gc * Hp * WP + i] = l;
+    if (g32) g32[gc * Hp * WP + i] = s;
   }
 }
 
@@ -69,7 +71,8 @@ __global__ void __launch_bounds__(256) gallery_pack_kernel(const float* __restri
 // 8 cells) and the operands leave as 16-byte stores.
 __global__ void __launch_bounds__(256) gallery_pack_warp_kernel(const float* __restrict__ gal, long long planes, int hg, int wg,
                                                                 __half* __restrict__ ghi, __half* __restrict__ glo,
-                                                                int32_t* __restrict__ gexp, float* __restrict__ gz) {
+                                                                int32_t* __restrict__ gexp, float* __restrict__ gz,
+                                                                float* __restrict__ g32) {
   extern __shared__ float slab[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int Hp = hg - 2 * kEdge, Wp = wg - 2 * kEdge, M = Hp * Wp, HW = hg * wg, WP = gal_pitch(Wp);
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(256) gallery_pack_warp_kernel(const float* __r
       const float* row = ch + (y + kEdge) * wg + kEdge + x0;
       __align__(16) __half h8[8];
       __align__(16) __half l8[8];
+      __align__(16) float s8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float sc = 0.0f;
@@ -118,11 +122,17 @@ __global__ void __launch_bounds__(256) gallery_pack_warp_kernel(const float* __r
           sc = ldexpf(z, e);
           if (gz) gz[gc * M + y * Wp + x0 + j] = z;
         }
+        s8[j] = sc;
         h8[j] = __float2half_rn(sc);
         l8[j] = __float2half_rn(sc - __half2float(h8[j]));
       }
       *reinterpret_cast<uint4*>(ghi + gc * Hp * WP + (size_t)o * 8) = *reinterpret_cast<const uint4*>(h8);
       *reinterpret_cast<uint4*>(glo + gc * Hp * WP + (size_t)o * 8) = *reinterpret_cast<const uint4*>(l8);
+      if (g32) {
+        float4* d = reinterpret_cast<float4*>(g32 + gc * Hp * WP + (size_t)o * 8);
+        d[0] = *reinterpret_cast<const float4*>(s8);
+        d[1] = *reinterpret_cast<const float4*>(s8 + 4);
+      }
     }
     __syncwarp();
   }
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
 __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restrict__ maps, int C, int h, int w, int Hb, int Wb, int col0,
                                                             int ncols_alloc, int row_align, __half* __restrict__ thi,
                                                             __half* __restrict__ tlo, float* __restrict__ t32,
-                                                            uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l) {
+                                                            uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l, float* __restrict__ t32p) {
   __shared__ double sred[32];
   const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm;
   const int rowk = tpl_row_taps(Wb, row_align), Kpad = tpl_kpad_aligned(Hb, Wb, row_align);
@@ -377,6 +387,7 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
     const __half hi = __float2half_rn(s);
     const float lo = s - __half2float(hi);
     thi[col * Kpad + k] = hi;
+    if (t32p) t32p[col * Kpad + k] = s;
     if (tlo) tlo[col * Kpad + k] = __float2half_rn(lo);
     if (t8b) {  // fp8 copies for the correction MMAs: (B_hi / 64) and (B_lo * 64), see sir_ncc_tc.cu
       t8b[col * Kpad + k] = to_e4m3(__half2float(hi) * kFp8HiScale);
@@ -390,7 +401,8 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
                                                                  int Hb, int Wb, int col0, int ncols_alloc, int row_align,
                                                                  __half* __restrict__ thi,
                                                                  __half* __restrict__ tlo, float* __restrict__ t32,
-                                                                 uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l) {
+                                                                 uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l,
+                                                                 float* __restrict__ t32p) {
   extern __shared__ float slab[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm, HW = h * w;
@@ -435,6 +447,7 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
       __align__(16) __half l8[8];
       __align__(8) uint8_t b8[8];
       __align__(8) uint8_t q8[8];
+      __align__(16) float s8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int v = vb0 + j - ox;
@@ -444,6 +457,7 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
           if (t32) t32[col * K + u * Wm + v] = tn;
         }
         const float sc = ldexpf(tn, kTemplateScaleLog2);
+        s8[j] = sc;
         h8[j] = __float2half_rn(sc);
         const float lo = sc - __half2float(h8[j]);
         l8[j] = __float2half_rn(lo);
@@ -451,6 +465,11 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
         q8[j] = to_e4m3(lo * kFp8LoScale);
       }
       *reinterpret_cast<uint4*>(thi + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(h8);
+      if (t32p) {
+        float4* d = reinterpret_cast<float4*>(t32p + col * Kpad + (size_t)o * 8);
+        d[0] = *reinterpret_cast<const float4*>(s8);
+        d[1] = *reinterpret_cast<const float4*>(s8 + 4);
+      }
       if (tlo) *reinterpret_cast<uint4*>(tlo + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(l8);
       if (t8b) {
         *reinterpret_cast<uint2*>(t8b + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint2*>(b8);
@@ -490,6 +509,11 @@ using namespace sir;
 
 extern "C" int sir_gallery_pack(const float* d_gallery, int G, int C, int hg, int wg, uint16_t* d_ghi, uint16_t* d_glo,
                                 int32_t* d_gexp, float* d_gz, void* stream) {
+  return sir_gallery_pack_f32(d_gallery, G, C, hg, wg, d_ghi, d_glo, d_gexp, d_gz, nullptr, stream);
+}
+
+extern "C" int sir_gallery_pack_f32(const float* d_gallery, int G, int C, int hg, int wg, uint16_t* d_ghi, uint16_t* d_glo,
+                                    int32_t* d_gexp, float* d_gz, float* d_g32, void* stream) {
   SIR_CHECK_ARG(d_gallery && d_ghi && d_glo && d_gexp, "sir_gallery_pack: null pointer");
   SIR_CHECK_ARG(G > 0 && C > 0, "sir_gallery_pack: empty gallery (G=%d C=%d)", G, C);
   SIR_CHECK_ARG(hg > 2 * kEdge && wg > 2 * kEdge, "sir_gallery_pack: map %dx%d vanishes after the 2-cell crop", hg, wg);
@@ -498,10 +522,10 @@ extern "C" int sir_gallery_pack(const float* d_gallery, int G, int C, int hg, in
     const long long planes = (long long)G * C;
     const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 148 * 8);
     gallery_pack_warp_kernel<<<blocks, 256, 8 * slab, (cudaStream_t)stream>>>(d_gallery, planes, hg, wg, (__half*)d_ghi, (__half*)d_glo,
-                                                                               d_gexp, d_gz);
+                                                                               d_gexp, d_gz, d_g32);
   } else {
     gallery_pack_kernel<<<(unsigned)((size_t)G * C), 256, 0, (cudaStream_t)stream>>>(
-        d_gallery, C, hg, wg, (__half*)d_ghi, (__half*)d_glo, d_gexp, d_gz);
+        d_gallery, C, hg, wg, (__half*)d_ghi, (__half*)d_glo, d_gexp, d_gz, d_g32);
   }
   SIR_LAUNCH_CHECK("gallery_pack_kernel");
   return SIR_OK;
@@ -695,16 +719,16 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
 extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }
 
 static void launch_template_pack(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc, int row_align,
-                                 __half* thi, __half* tlo, float* t32, uint8_t* t8b, uint8_t* t8l, cudaStream_t st) {
+                                 __half* thi, __half* tlo, float* t32, uint8_t* t8b, uint8_t* t8l, cudaStream_t st, float* t32p = nullptr) {
   const size_t slab = (size_t)h * w * sizeof(float);
   if (8 * slab <= 48 * 1024) {
     const long long planes = (long long)N * C;
     const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 148 * 8);
     template_pack_warp_kernel<<<blocks, 256, 8 * slab, st>>>(d_maps, planes, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32,
-                                                             t8b, t8l);
+                                                             t8b, t8l, t32p);
   } else {
     template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, st>>>(d_maps, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32, t8b,
-                                                                    t8l);
+                                                                    t8l, t32p);
   }
 }
 
@@ -762,6 +786,23 @@ extern "C" int sir_template_pack_embed(const float* d_maps, int N, int C, int h,
   SIR_CHECK_ARG(fp8c ? (d_t8b && d_t8l) : (d_tlo != nullptr), "sir_template_pack_embed: missing companion operands for precision %d", precision);
   launch_template_pack(d_maps, N, C, h, w, Hb, Wb, col0, ncols_alloc, fp8c ? 16 : 8, (__half*)d_thi, fp8c ? nullptr : (__half*)d_tlo, nullptr,
                        fp8c ? d_t8b : nullptr, fp8c ? d_t8l : nullptr, (cudaStream_t)stream);
+  SIR_LAUNCH_CHECK("template_pack_kernel");
+  return SIR_OK;
+}
+
+// Screen + refine operands (SIR_PREC_FP16_REFINE): d_thi as sir_template_pack (rows padded to 8 taps) for the tensor-core
+// screening pass and d_t32p [C][ncols_alloc][Kpad] float32 = (t - mean)/sqrt(E) * 2^10 in the same padded K layout for the
+// exact re-evaluation.  Hb x Wb >= the true template shape selects a bucket layout (anchor on anchor, zeros elsewhere) as in
+// sir_template_pack_embed; pass the true shape for a single-shape block.
+extern "C" int sir_template_pack_screen(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
+                                        uint16_t* d_thi, float* d_t32p, void* stream) {
+  SIR_CHECK_ARG(d_maps && d_thi && d_t32p, "sir_template_pack_screen: null pointer");
+  SIR_CHECK_ARG(N > 0 && C > 0 && h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack_screen: bad input shape");
+  SIR_CHECK_ARG(Hb >= h - 2 * kEdge && Wb >= w - 2 * kEdge, "sir_template_pack_screen: bucket %dx%d smaller than template %dx%d", Hb, Wb,
+                h - 2 * kEdge, w - 2 * kEdge);
+  SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack_screen: columns [%d,%d) outside %d", col0, col0 + N, ncols_alloc);
+  launch_template_pack(d_maps, N, C, h, w, Hb, Wb, col0, ncols_alloc, 8, (__half*)d_thi, nullptr, nullptr, nullptr, nullptr,
+                       (cudaStream_t)stream, d_t32p);
   SIR_LAUNCH_CHECK("template_pack_kernel");
   return SIR_OK;
 }

@@ -47,12 +47,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (the launch fails with an error) instead of hanging the GPU.  The bound
+// is ~2 s with -DSIR_DEBUG_BARRIERS and about two minutes otherwise: under profiler replay, MPS time slicing or
+// a preempted context a legitimate wait can take seconds, and a trap would kill a healthy context.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+#ifdef SIR_DEBUG_BARRIERS
+  constexpr long long kLimit = 4000000000LL;
+#else
+  constexpr long long kLimit = 240000000000LL;
+#endif
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > kLimit) {
 #ifdef SIR_DEBUG_BARRIERS
       printf("sir: mbarrier timeout block %d thread %d bar_off %u parity %u\n", blockIdx.x, threadIdx.x, bar & 0xfff, parity);
 #endif

@@ -219,6 +219,7 @@ class GalleryOperands:
     gexp: torch.Tensor
     gz: torch.Tensor | None
     ids: torch.Tensor
+    g32: torch.Tensor | None = None       # float32 copy of the scaled operand (exact re-evaluation of fp16_refine)
     _rnorm: dict = field(default_factory=dict)
     _fp8: tuple | None = None
     _source: MapGroup | None = None       # kept so the other orientation can be packed on demand
@@ -231,7 +232,7 @@ class GalleryOperands:
             if self._source is None:
                 raise RuntimeError("this gallery pack does not hold its source maps")
             grp = MapGroup(transpose_maps(self._source.maps), self._source.ids)
-            self._transposed = GalleryOperands.pack(grp, self._keep_fp32)
+            self._transposed = GalleryOperands.pack(grp, self._keep_fp32, self.g32 is not None)
             self._transposed._source = None
         return self._transposed
 
@@ -250,7 +251,7 @@ class GalleryOperands:
         return self._fp8
 
     @staticmethod
-    def pack(group: MapGroup, keep_fp32: bool) -> "GalleryOperands":
+    def pack(group: MapGroup, keep_fp32: bool, with_f32: bool = False) -> "GalleryOperands":
         n, c, h, w = (int(v) for v in group.maps.shape)
         hp, wp = h - 2 * EDGE, w - 2 * EDGE
         dev = group.maps.device
@@ -258,12 +259,13 @@ class GalleryOperands:
         glo = torch.empty_like(ghi)
         gexp = torch.empty((n, c), dtype=torch.int32, device=dev)
         gz = torch.empty((n, c, hp, wp), dtype=torch.float32, device=dev) if keep_fp32 else None
+        g32 = torch.empty(ghi.shape, dtype=torch.float32, device=dev) if with_f32 else None
         nat.check(
-            nat.lib.sir_gallery_pack(_ptr(group.maps), n, c, h, w, _ptr(ghi), _ptr(glo), _ptr(gexp), _ptr(gz), _stream()),
-            "sir_gallery_pack",
+            nat.lib.sir_gallery_pack_f32(_ptr(group.maps), n, c, h, w, _ptr(ghi), _ptr(glo), _ptr(gexp), _ptr(gz), _ptr(g32), _stream()),
+            "sir_gallery_pack_f32",
         )
         launch_counter.add()
-        ops = GalleryOperands(n, c, hp, wp, ghi, glo, gexp, gz, group.ids)
+        ops = GalleryOperands(n, c, hp, wp, ghi, glo, gexp, gz, group.ids, g32)
         ops._source, ops._keep_fp32 = group, keep_fp32
         return ops
 
@@ -394,14 +396,18 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[Gall
         raise ValueError("fp16_refine needs the approximate score buffer")
     kpad = int(nat.lib.sir_template_kpad_fp8c(hm, wm) if fp8c else nat.lib.sir_template_kpad(hm, wm))
     thi = torch.empty((c, ncols, kpad), dtype=torch.float16, device=dev)
-    tlo = None if fp8c else torch.empty_like(thi)
+    tlo = None if (fp8c or refine) else torch.empty_like(thi)
+    t32p = torch.empty((c, ncols, kpad), dtype=torch.float32, device=dev) if refine else None
     t8b = torch.empty((c, ncols, kpad), dtype=torch.uint8, device=dev) if fp8c else None
     t8l = torch.empty_like(t8b) if fp8c else None
     t32 = torch.empty((c, ncols, hm * wm), dtype=torch.float32, device=dev) if simt else None
     col0 = 0
     for m in block.maps:
         n = int(m.shape[0])
-        if fp8c:
+        if refine:
+            nat.check(nat.lib.sir_template_pack_screen(_ptr(m), n, c, h, w, hm, wm, col0, ncols, _ptr(thi), _ptr(t32p), _stream()),
+                      "sir_template_pack_screen")
+        elif fp8c:
             nat.check(
                 nat.lib.sir_template_pack_fp8c(_ptr(m), n, c, h, w, col0, ncols, _ptr(thi), _ptr(t8b), _ptr(t8l), _stream()),
                 "sir_template_pack_fp8c",
@@ -423,7 +429,7 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[Gall
             rec = torch.empty((int(nat.lib.sir_ncc_screen_rec_count(ops.G, ops.Hp, ops.Wp, ncols)), 2), dtype=torch.int32, device=dev)
             nat.check(
                 nat.lib.sir_ncc_screen(
-                    _ptr(ops.ghi), _ptr(ops.glo), _ptr(rn), None, ops.G, ops.C, ops.Hp, ops.Wp, _ptr(thi), _ptr(tlo), ncols, ncols, hm, wm,
+                    _ptr(ops.ghi), _ptr(rn), None, ops.G, ops.C, ops.Hp, ops.Wp, _ptr(thi), ncols, ncols, hm, wm,
                     _ptr(col2probe), _ptr(approx), int(approx.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec), _stream(),
                 ),
                 "sir_ncc_screen",
@@ -460,7 +466,7 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[Gall
                 rv0.record()
             nat.check(
                 nat.lib.sir_ncc_refine(
-                    _ptr(ops.ghi), _ptr(ops.glo), _ptr(rn), None, ops.G, ops.C, ops.Hp, ops.Wp, _ptr(thi), _ptr(tlo), ncols, ncols, hm, wm,
+                    _ptr(ops.g32), _ptr(rn), None, ops.G, ops.C, ops.Hp, ops.Wp, _ptr(t32p), ncols, ncols, hm, wm,
                     _ptr(col2probe), _ptr(approx), _ptr(scores), int(scores.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec), _stats_ptr(),
                     _stream(),
                 ),
@@ -534,7 +540,8 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
     ncols = sum(-(-blk.ncols // 16) * 16 for _, _, blk in oriented)
     kpad = int(nat.lib.sir_template_kpad_fp8c(hb, wb) if fp8c else nat.lib.sir_template_kpad(hb, wb))
     thi = _zeros((c, ncols, kpad), torch.float16, dev)
-    tlo = None if fp8c else _zeros((c, ncols, kpad), torch.float16, dev)
+    tlo = None if (fp8c or refine) else _zeros((c, ncols, kpad), torch.float16, dev)
+    t32p = _zeros((c, ncols, kpad), torch.float32, dev) if refine else None
     t8b = _zeros((c, ncols, kpad), torch.uint8, dev) if fp8c else None
     t8l = _zeros((c, ncols, kpad), torch.uint8, dev) if fp8c else None
     col2probe = torch.zeros(ncols, dtype=torch.int32)
@@ -555,8 +562,12 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
         start = col0
         for m in maps:
             n = int(m.shape[0])
-            nat.check(nat.lib.sir_template_pack_embed(_ptr(m), n, c, h, w, hb, wb, col0, ncols, nat.PREC_FP16X3 if refine else mode, _ptr(thi), _ptr(tlo), _ptr(t8b),
-                                                      _ptr(t8l), _stream()), "sir_template_pack_embed")
+            if refine:
+                nat.check(nat.lib.sir_template_pack_screen(_ptr(m), n, c, h, w, hb, wb, col0, ncols, _ptr(thi), _ptr(t32p), _stream()),
+                          "sir_template_pack_screen")
+            else:
+                nat.check(nat.lib.sir_template_pack_embed(_ptr(m), n, c, h, w, hb, wb, col0, ncols, mode, _ptr(thi), _ptr(tlo), _ptr(t8b),
+                                                          _ptr(t8l), _stream()), "sir_template_pack_embed")
             launch_counter.add()
             col0 += n
         col2probe[start:col0] = torch.cat(blk.ids).to(torch.int32)
@@ -570,14 +581,14 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
         rec = torch.empty((int(nat.lib.sir_ncc_screen_rec_count(gops.G, gops.Hp, gops.Wp, ncols)), 2), dtype=torch.int32, device=dev)
         nat.check(
             nat.lib.sir_ncc_screen(
-                _ptr(gops.ghi), _ptr(gops.glo), None, _ptr(d_tab), gops.G, gops.C, gops.Hp, gops.Wp, _ptr(thi), _ptr(tlo), ncols, ncols, hb, wb,
+                _ptr(gops.ghi), None, _ptr(d_tab), gops.G, gops.C, gops.Hp, gops.Wp, _ptr(thi), ncols, ncols, hb, wb,
                 _ptr(d_c2p), _ptr(approx), int(approx.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec), _stream(),
             ),
             "sir_ncc_screen",
         )
         nat.check(
             nat.lib.sir_ncc_refine(
-                _ptr(gops.ghi), _ptr(gops.glo), None, _ptr(d_tab), gops.G, gops.C, gops.Hp, gops.Wp, _ptr(thi), _ptr(tlo), ncols, ncols, hb, wb,
+                _ptr(gops.g32), None, _ptr(d_tab), gops.G, gops.C, gops.Hp, gops.Wp, _ptr(t32p), ncols, ncols, hb, wb,
                 _ptr(d_c2p), _ptr(approx), _ptr(scores), int(scores.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec), _stats_ptr(), _stream(),
             ),
             "sir_ncc_refine",
@@ -608,6 +619,7 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
         raise ValueError(f"probe maps have {probes.channels} channels, gallery maps {gallery.channels}")
     prec = nat.PRECISIONS[precision]
     keep32 = prec == nat.PREC_FP32_SIMT
+    with32 = prec == nat.PREC_FP16_REFINE
     # gallery groups are cut into chunks so that the per-chunk operands (packs, transposed copy, window
     # norms: ~3x the chunk's float32 bytes) stay bounded; small galleries are packed once up front,
     # large ones chunk by chunk inside every column block (packing is ~2 % of the correlation time)
@@ -629,12 +641,14 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
         if len(prepacked) != len(chunks) or any(o.G != int(ch.maps.shape[0]) or not torch.equal(o.ids, ch.ids) for o, ch in zip(prepacked, chunks)):
             raise ValueError("packed_gallery does not match the gallery's groups (it must hold one pack per shape group, "
                              f"each at most {gallery_chunk_bytes} bytes of maps)")
+        if with32 and any(o.g32 is None for o in prepacked):
+            raise ValueError("precision 'fp16_refine' needs gallery packs made with with_f32=True")
     elif total_bytes <= gallery_chunk_bytes:
-        key = ("packed", keep32)
+        key = ("packed", keep32, with32)
         if operand_cache is not None and key in operand_cache:
             prepacked = operand_cache[key]
         else:
-            prepacked = [GalleryOperands.pack(ch, keep_fp32=keep32) for ch in chunks]
+            prepacked = [GalleryOperands.pack(ch, keep32, with32) for ch in chunks]
             if operand_cache is not None:
                 operand_cache[key] = prepacked
     ld = (gallery.count + 3) // 4 * 4  # 16-byte aligned rows for the vectorised rank kernel
@@ -652,7 +666,7 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
             _score_block(blk, key, prepacked, offsets, grouped, prec, approx)
             return
         for ch, off in zip(chunks, offsets):
-            _score_block(blk, key, [GalleryOperands.pack(ch, keep_fp32=keep32)], [off], grouped, prec, approx)
+            _score_block(blk, key, [GalleryOperands.pack(ch, keep32, with32)], [off], grouped, prec, approx)
 
     pending: dict[tuple[int, int], _Block] = {}
     for rot, scale in variant_plan(rotations, scales):
@@ -683,7 +697,7 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
             _score_buckets(small, prepacked, offsets, grouped, prec, approx=approx)
         else:
             for ch, off in zip(chunks, offsets):
-                _score_buckets(small, [GalleryOperands.pack(ch, keep_fp32=False)], [off], grouped, prec, approx=approx)
+                _score_buckets(small, [GalleryOperands.pack(ch, False, with32)], [off], grouped, prec, approx=approx)
 
     # un-group the gallery axis back to the caller's order
     order = torch.cat([ch.ids for ch in chunks])
