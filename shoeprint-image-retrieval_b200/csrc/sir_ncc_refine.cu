@@ -27,7 +27,7 @@
 
 namespace sir {
 
-constexpr int kRefWarps = 8;                       // consumer warps (one candidate position at a time each)
+constexpr int kRefWarps = 16;                      // consumer warps (one candidate position at a time each)
 constexpr int kRefThreads = 32 * (kRefWarps + 1);  // + one producer warp issuing the bulk copies
 constexpr int kRefStages = 2;
 
@@ -43,6 +43,7 @@ struct RefineParams {
   unsigned long long* stats;  // optional: [0] positions evaluated, [1] records that listed more than 3 rows, [2] tiles with work
   int G, C, Hp, Wp, WP, Hb, Wb, rowk, Kpad, ncols, ncols_alloc, npx, NP, score_ld, g0;
   int TN, TG, cap, tiles_g;
+  int vl, ru, rv;  // lane mapping: vl lanes along a template row, the 32 / vl lane groups split ru ways over rows, rv ways over row chunks
   float tau_rel, tau_abs, inv_scale;
 };
 
@@ -125,10 +126,9 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
   }
 
   const int a = p.Hb / 2, b = p.Wb / 2;
-  // lanes over (template row, tap): vl lanes along a row (the largest power of two that divides the padded row, which
-  // is a multiple of 8), 32 / vl rows per pass -- every lane has work whatever the row length
-  const int vl = (p.rowk % 32 == 0) ? 32 : (p.rowk % 16 == 0) ? 16 : 8;
-  const int rpp = 32 / vl, lv = lane % vl, lr = lane / vl;
+  // lanes over (template row, tap): vl lanes along a row; the 32 / vl lane groups are dealt over rows (ru) and over the
+  // vl-tap chunks of a row (rv), whichever split gives the longest inner loop for this shape (chosen by the host)
+  const int vl = p.vl, lv = lane % vl, grp = lane / vl, gu = grp % p.ru, gv = grp / p.ru, nchunk = p.rowk / vl;
   const uint32_t tbytes = (uint32_t)p.Kpad * 4u, gbytes = (uint32_t)PG * 4u;
   uint32_t it = 0;  // channel iterations so far (stage = it % kRefStages, barrier parity = (it / kRefStages) & 1)
 
@@ -193,40 +193,53 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
       }
     } else {
       // ---- consumer warps: one candidate position at a time
+      constexpr int kSlots = 4;  // entries of a warp held per lane: covers cap <= kRefWarps * 32 * kSlots
       for (int c = 0; c < p.C; ++c, ++it) {
         const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
+        // this channel's window norms of the warp's entries, one gather before the wait (entry warp + kRefWarps * t in lane t % 32)
+        float rnv[kSlots];
+#pragma unroll
+        for (int s4 = 0; s4 < kSlots; ++s4) {
+          const int e = warp + kRefWarps * (lane + 32 * s4);
+          rnv[s4] = 0.0f;
+          if (e < nl) {
+            const uint2 en = list[e];
+            const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en.x & 0xff)) >> 4] : p.rnorm;
+            rnv[s4] = __ldg(table + ((size_t)(gt0 + (int)(en.x >> 8)) * p.C + c) * M + (en.y & 0xffff) * p.Wp + (en.y >> 16));
+          }
+        }
         ptx::mbar_wait(ptx::smem_u32(bars + st), par);
         const float* tpl = bufs + st * buf_floats;
         const float* gal = tpl + (size_t)p.TN * p.Kpad;
-        for (int e = warp; e < nl; e += kRefWarps) {
+        int t = 0;
+        for (int e = warp; e < nl; e += kRefWarps, ++t) {
           const uint2 en = list[e];
           const int j = en.x & 0xff, i = en.x >> 8, y = en.y & 0xffff, x = en.y >> 16;
-          float rn = 0.0f;
-          if (lane == 0) {  // issued now, needed after the dot product
-            const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + j) >> 4] : p.rnorm;
-            rn = __ldg(table + ((size_t)(gt0 + i) * p.C + c) * M + y * p.Wp + x);
-          }
           const int u_lo = max(0, a - y), u_hi = min(p.Hb, p.Hp + a - y);  // template rows that meet the map
           const float* T = tpl + (size_t)j * p.Kpad;
           const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
           float part0 = 0.0f, part1 = 0.0f;
-          for (int v0 = 0; v0 < p.rowk; v0 += vl) {
-            const int v = v0 + lv, gx = x + v - b;
-            if (v < p.rowk && gx >= 0 && gx < p.Wp) {
-              const int ts = rpp * p.rowk, gs = rpp * p.WP;
-              const float* tp = T + (u_lo + lr) * p.rowk + v;
-              const float* gp = Gs + (u_lo + lr) * p.WP + v;
-              int u = u_lo + lr;
-              for (; u + 3 * rpp < u_hi; u += 4 * rpp, tp += 4 * ts, gp += 4 * gs) {
+          const int ts = p.ru * p.rowk, gs = p.ru * p.WP;
+          for (int ch = gv; ch < nchunk; ch += p.rv) {
+            const int v = ch * vl + lv, gx = x + v - b;
+            if (gx >= 0 && gx < p.Wp) {
+              const float* tp = T + (u_lo + gu) * p.rowk + v;
+              const float* gp = Gs + (u_lo + gu) * p.WP + v;
+              int u = u_lo + gu;
+              for (; u + 3 * p.ru < u_hi; u += 4 * p.ru, tp += 4 * ts, gp += 4 * gs) {
                 part0 = fmaf(tp[0], gp[0], part0);
                 part1 = fmaf(tp[ts], gp[gs], part1);
                 part0 = fmaf(tp[2 * ts], gp[2 * gs], part0);
                 part1 = fmaf(tp[3 * ts], gp[3 * gs], part1);
               }
-              for (; u < u_hi; u += rpp, tp += ts, gp += gs) part0 = fmaf(*tp, *gp, part0);
+              for (; u < u_hi; u += p.ru, tp += ts, gp += gs) part0 = fmaf(*tp, *gp, part0);
             }
           }
           const float part = warp_sum(part0 + part1);
+          float rn = rnv[0];
+#pragma unroll
+          for (int s4 = 1; s4 < kSlots; ++s4) rn = (t >> 5) == s4 ? rnv[s4] : rn;
+          rn = __shfl_sync(0xffffffffu, rn, t & 31);
           if (lane == 0) acc[e] = fmaf(part, rn, acc[e]);
         }
         __syncwarp();
@@ -276,7 +289,7 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
   p.score_ld = score_ld; p.g0 = g0;
   p.tau_rel = tau_rel; p.tau_abs = tau_abs;
   p.inv_scale = 1.0f / ((float)C * (float)(1 << kTemplateScaleLog2));
-  p.cap = 512;
+  p.cap = 1024;
   // tile: as many (column, gallery) pairs per CTA as two staged channel buffers allow (every operand byte is then
   // read once per tile); ties go to more columns because consecutive CTAs walk the gallery tiles of one column tile
   const size_t budget = 220 * 1024, fixed = 128 + (size_t)p.cap * 12 + 4 * (32 + 32 + kRefThreads / 32) + 64;
@@ -289,6 +302,23 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
         best_tg = tg;
       }
   SIR_CHECK_ARG(best_tn > 0, "sir_ncc_refine: template %dx%d / map %dx%d do not fit shared memory", Hb, Wb, Hp, Wp);
+  static_assert(kRefWarps * 32 * 4 >= 1024, "every list entry of a warp needs a lane slot for its window norm");
+  // lane mapping: the inner loop walks template rows; estimated instructions per (position, channel) for a split of the lane
+  // groups over rows (ru) and row chunks (rv): chunk rounds x (set-up + rows per lane x ~3.3)
+  p.vl = (p.rowk % 32 == 0) ? 32 : (p.rowk % 16 == 0) ? 16 : 8;
+  {
+    const int groups = 32 / p.vl, nchunk = p.rowk / p.vl;
+    double best = 1e30;
+    for (int ru = 1; ru <= groups; ru <<= 1) {
+      const int rv = groups / ru;
+      const double cost = ceil_div(nchunk, rv) * (15.0 + ceil_div(Hb, ru) * 3.3);
+      if (cost < best) {
+        best = cost;
+        p.ru = ru;
+        p.rv = rv;
+      }
+    }
+  }
   p.TN = best_tn;
   p.TG = best_tg;
   p.tiles_g = ceil_div(G, p.TG);

@@ -21,7 +21,31 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "merge_ranks", "compare_sharded"]
+__all__ = ["shard_range", "merge_ranks", "compare_sharded", "phase_events"]
+
+#: when set to a dict, every phase of the sharded rank appends a (start, end) CUDA-event pair under its name
+#: ("scores", "true_score", "allreduce_max", "rank_topk", "allreduce_sum", "allgather", "merge_topk"); bench.py reads it
+phase_events: dict | None = None
+
+
+class _Phase:
+    """``with _Phase("name"):`` brackets a phase with CUDA events on the current stream when ``phase_events`` is set."""
+
+    def __init__(self, name: str) -> None:
+        self.name = name
+
+    def __enter__(self):
+        if phase_events is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if phase_events is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            phase_events.setdefault(self.name, []).append((self.e0, e1))
+        return False
 
 
 def shard_range(total: int, world: int, rank: int) -> tuple[int, int]:
@@ -58,21 +82,24 @@ def merge_ranks(true_score, count_gt, count_ge, topk_val, topk_idx, group=None, 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     k = int(topk_val.shape[1])
     if world > 1:
-        counts = torch.stack([count_gt, count_ge]).to(torch.int32)
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-        count_gt, count_ge = counts[0], counts[1]
+        with _Phase("allreduce_sum"):
+            counts = torch.stack([count_gt, count_ge]).to(torch.int32)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+            count_gt, count_ge = counts[0], counts[1]
         if k > 0:
             q = topk_val.shape[0]
-            all_v = torch.empty((world, q, k), dtype=topk_val.dtype, device=topk_val.device)
-            all_i = torch.empty((world, q, k), dtype=topk_idx.dtype, device=topk_idx.device)
-            dist.all_gather(list(all_v.unbind(0)), topk_val.contiguous(), group=group)
-            dist.all_gather(list(all_i.unbind(0)), topk_idx.contiguous(), group=group)
-            topk_val, topk_idx = (merge_fn or _merge_topk_cuda)(all_v, all_i, k)
+            with _Phase("allgather"):
+                all_v = torch.empty((world, q, k), dtype=topk_val.dtype, device=topk_val.device)
+                all_i = torch.empty((world, q, k), dtype=topk_idx.dtype, device=topk_idx.device)
+                dist.all_gather(list(all_v.unbind(0)), topk_val.contiguous(), group=group)
+                dist.all_gather(list(all_i.unbind(0)), topk_idx.contiguous(), group=group)
+            with _Phase("merge_topk"):
+                topk_val, topk_idx = (merge_fn or _merge_topk_cuda)(all_v, all_i, k)
     return count_gt + 1, torch.clamp(count_ge, min=1), topk_val, topk_idx
 
 
 def compare_sharded(probes, gallery_shard, true_idx, g0: int, rotations=None, scales=None,
-                    precision: str = "fp16_fp8c", k: int = 0, group=None, packed_gallery=None):
+                    precision: str = "fp16_refine", k: int = 0, group=None, packed_gallery=None):
     """Sharded compare pass on this rank: ``probes`` are replicated, ``gallery_shard`` holds global
     gallery indices ``[g0, g0 + G_local)``, ``true_idx`` are GLOBAL gallery indices.
 
@@ -80,19 +107,23 @@ def compare_sharded(probes, gallery_shard, true_idx, g0: int, rotations=None, sc
     from . import _native as nat
     from . import engine
 
-    scores = engine.score_matrix(probes, gallery_shard, rotations, scales, precision, packed_gallery=packed_gallery)
+    with _Phase("scores"):
+        scores = engine.score_matrix(probes, gallery_shard, rotations, scales, precision, packed_gallery=packed_gallery)
     q, g = scores.shape
     dev = scores.device
     tidx = torch.as_tensor(true_idx, dtype=torch.int32).to(dev)
-    true_score = torch.empty(q, dtype=torch.float32, device=dev)
-    nat.check(
-        nat.lib.sir_true_scores(C.c_void_p(scores.data_ptr()), q, g, int(scores.stride(0)), C.c_void_p(tidx.data_ptr()), g0,
-                                C.c_void_p(true_score.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-        "sir_true_scores",
-    )
-    engine.launch_counter.add()
+    with _Phase("true_score"):
+        true_score = torch.empty(q, dtype=torch.float32, device=dev)
+        nat.check(
+            nat.lib.sir_true_scores(C.c_void_p(scores.data_ptr()), q, g, int(scores.stride(0)), C.c_void_p(tidx.data_ptr()), g0,
+                                    C.c_void_p(true_score.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            "sir_true_scores",
+        )
+        engine.launch_counter.add()
     if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(true_score, op=dist.ReduceOp.MAX, group=group)
-    gt, ge, tv, ti, _ = engine.rank_true_matches(scores, tidx, k, g0=g0, true_score=true_score)
+        with _Phase("allreduce_max"):
+            dist.all_reduce(true_score, op=dist.ReduceOp.MAX, group=group)
+    with _Phase("rank_topk"):
+        gt, ge, tv, ti, _ = engine.rank_true_matches(scores, tidx, k, g0=g0, true_score=true_score)
     ranks, _, tv, ti = merge_ranks(true_score, gt, ge, tv, ti, group=group)
     return ranks.to(torch.int32), tv, ti, scores

@@ -9,7 +9,10 @@ Public names, arguments and results follow the reference (``similarity.py:26-386
 * ``MultiProcessingTrackers`` kept importable (``similarity.py:111-126``).
 
 The work happens on the GPU through ``engine`` / ``libsir.so``; ``comparison.n_processes`` is
-accepted and ignored (one process drives one GPU).  Differences a caller can observe:
+accepted and ignored (one process drives one GPU).  Under ``torchrun`` (``torch.distributed`` initialised with
+more than one rank) the call is SPMD: every rank passes the same lists, scores ALL shoemarks against its contiguous
+share of the shoeprints (``sharding.shard_range``), and the ranks are merged over NCCL (``sharding.compare_sharded``);
+every rank returns the same result.  Differences a caller can observe:
 
 * with both ``rotations`` and ``scales`` set the reference's progress loop never terminates
   (it waits for ``(R+1)(S+1)*Q`` ticks while the workers produce ``(1+(R+1)S)*Q``; SURVEY.md
@@ -91,18 +94,40 @@ def compare_maps(
         raise IndexError("matching_pairs holds an index outside shoeprint_maps")
 
     n_variants = len(engine.variant_plan(rotations, scales))
-    with tqdm(total=n_variants * len(shoemark_maps)) as pbar:
-        ranks, scores, topk = engine.compare(
-            _ingest(shoemark_maps),
-            _ingest(shoeprint_maps),
-            pairs,
-            rotations,
-            scales,
-            precision=precision,
-            k=top_k,
-        )
-        for shoemark_id, rank in enumerate(ranks):
-            pbar.write(f"Print {shoemark_id} true match ranked {rank}")  # similarity.py:375
+    world = rank = 0
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+    except ImportError:  # pragma: no cover
+        pass
+    with tqdm(total=n_variants * len(shoemark_maps), disable=rank != 0) as pbar:
+        if world > 1:
+            from . import sharding
+
+            g0, g1 = sharding.shard_range(len(shoeprint_maps), world, rank)
+            if g1 <= g0:
+                raise ValueError(f"{len(shoeprint_maps)} shoeprints cannot be shared among {world} ranks")
+            probes = engine.MapSet.from_host(_ingest(shoemark_maps))
+            shard = engine.MapSet.from_host(_ingest(shoeprint_maps[g0:g1]))
+            engine.last_h2d_bytes = (probes.h2d_bytes, shard.h2d_bytes)
+            d_ranks, tv, ti, scores = sharding.compare_sharded(probes, shard, pairs, g0, rotations, scales, precision, top_k)
+            ranks = d_ranks.to("cpu").numpy().astype(np.int32)
+            topk = (tv, ti)
+        else:
+            ranks, scores, topk = engine.compare(
+                _ingest(shoemark_maps),
+                _ingest(shoeprint_maps),
+                pairs,
+                rotations,
+                scales,
+                precision=precision,
+                k=top_k,
+            )
+        if rank == 0:
+            for shoemark_id, rk in enumerate(ranks):
+                pbar.write(f"Print {shoemark_id} true match ranked {rk}")  # similarity.py:375
         pbar.update(pbar.total)
     last_result.clear()
     last_result.update(scores=scores, topk=topk, h2d_bytes=engine.last_h2d_bytes)
