@@ -16,6 +16,9 @@ Ragged inputs are grouped by shape on the host (the reference never pads: datalo
 from __future__ import annotations
 
 import ctypes as C
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -49,6 +52,11 @@ DEFAULT_PRECISION = "fp16_refine"
 #: (measured, tests/precision_study.py) and <= ~1e-5 absolute on near-zero scores; tau covers twice that with margin.
 TAU_REL = 1.0e-3
 TAU_ABS = 2.0e-5
+
+#: probes uploaded from host lists travel in chunks of this many maps; a chunk's columns are launched once at least
+#: FLUSH_MIN_COLS of one template shape have accumulated, while the next chunk is still being copied
+PROBE_CHUNK = 512
+FLUSH_MIN_COLS = 4096
 
 
 class _LaunchCounter:
@@ -118,17 +126,116 @@ def _require_cuda() -> torch.device:
 
 # --------------------------------------------------------------------------- inputs
 
+class _Pending:
+    """An upload in flight: ``wait()`` blocks the host until the copy has been queued and makes the current stream
+    wait for it."""
+
+    def __init__(self) -> None:
+        self.flag = threading.Event()
+        self.cuda_event: torch.cuda.Event | None = None
+        self.error: BaseException | None = None
+
+    def wait(self) -> None:
+        self.flag.wait()
+        if self.error is not None:
+            raise self.error
+        torch.cuda.current_stream().wait_event(self.cuda_event)
+
+
+class _Uploader:
+    """Host -> device copies of feature-map lists from ordinary (pageable) numpy arrays.
+
+    ``cudaMemcpy`` from pageable memory is staged by the driver on one thread (~10 GB/s) and blocks the caller.  Here a
+    background thread fills a ring of page-locked buffers with several copy threads (numpy releases the GIL) and queues
+    one large asynchronous DMA per buffer on a side stream, so the caller goes on launching kernels for the maps that
+    have already arrived (``engine.compare`` scores probe chunk i while chunk i+1 is on its way)."""
+
+    BUF_BYTES = 64 << 20
+    NBUF = 3
+    THREADS = max(2, min(8, (os.cpu_count() or 2) // 2))
+    _instances: dict = {}
+
+    @classmethod
+    def get(cls, dev: torch.device) -> "_Uploader":
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        if key not in cls._instances:
+            cls._instances[key] = cls(torch.device("cuda", key))
+        return cls._instances[key]
+
+    def __init__(self, dev: torch.device) -> None:
+        self.dev = dev
+        self.stream = torch.cuda.Stream(device=dev)
+        self.bufs = [torch.empty(self.BUF_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.NBUF)]
+        self.free_ev: list = [None] * self.NBUF
+        self.next = 0
+        self.copy_pool = ThreadPoolExecutor(self.THREADS)
+        self.worker = ThreadPoolExecutor(1)
+
+    def submit(self, arrays: list[np.ndarray], dst: torch.Tensor, after: torch.cuda.Event) -> _Pending:
+        pend = _Pending()
+        dst.record_stream(self.stream)
+        self.worker.submit(self._run, arrays, dst, after, pend)
+        return pend
+
+    def _run(self, arrays: list[np.ndarray], dst: torch.Tensor, after: torch.cuda.Event, pend: _Pending) -> None:
+        try:
+            torch.cuda.set_device(self.dev)
+            self.stream.wait_event(after)  # the destination may be memory the caller's stream has only just released
+            shape = tuple(arrays[0].shape)
+            per = int(np.prod(shape)) * 4
+            with torch.cuda.stream(self.stream):
+                if per > self.BUF_BYTES:  # a single map larger than a staging buffer: plain copies
+                    for j, a in enumerate(arrays):
+                        dst[j].copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)))
+                else:
+                    n_buf = self.BUF_BYTES // per
+                    for j0 in range(0, len(arrays), n_buf):
+                        b = self.next
+                        self.next = (b + 1) % self.NBUF
+                        if self.free_ev[b] is not None:
+                            self.free_ev[b].synchronize()
+                        chunk = arrays[j0 : j0 + n_buf]
+                        view = self.bufs[b][: len(chunk) * per].view(torch.float32).view(len(chunk), *shape)
+                        host = view.numpy()
+
+                        def fill(lo: int, hi: int, host=host, chunk=chunk) -> None:
+                            for k in range(lo, hi):
+                                np.copyto(host[k], chunk[k], casting="same_kind")
+
+                        parts = min(self.THREADS, len(chunk))
+                        jobs = [self.copy_pool.submit(fill, len(chunk) * t // parts, len(chunk) * (t + 1) // parts) for t in range(parts)]
+                        for job in jobs:
+                            job.result()
+                        dst[j0 : j0 + len(chunk)].copy_(view, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self.stream)
+                        self.free_ev[b] = ev
+                done = torch.cuda.Event()
+                done.record(self.stream)
+            pend.cuda_event = done
+        except BaseException as exc:  # noqa: BLE001 - re-raised in the caller's thread by wait()
+            pend.error = exc
+        finally:
+            pend.flag.set()
+
+
 @dataclass
 class MapGroup:
     """Feature maps of one shape: ``maps [n, C, h, w]`` float32 on the device, ``ids`` = their
-    positions in the caller's list."""
+    positions in the caller's list.  ``pending``: an upload still in flight (``wait()`` before the maps are read)."""
 
     maps: torch.Tensor
     ids: torch.Tensor  # int64 [n], host
+    pending: _Pending | None = None
 
     @property
     def shape_hw(self) -> tuple[int, int]:
         return int(self.maps.shape[2]), int(self.maps.shape[3])
+
+    def wait(self) -> None:
+        if self.pending is not None:
+            self.pending.wait()
+            self.pending = None
 
 
 def transpose_maps(maps: torch.Tensor) -> torch.Tensor:
@@ -156,10 +263,12 @@ class MapSet:
     h2d_bytes: int = 0
 
     @staticmethod
-    def from_host(maps: list[np.ndarray]) -> "MapSet":
-        """Group a list of ``[C,h,w]`` float32 arrays by shape and upload them, one asynchronous copy
-        per map straight into the group's device tensor (no host-side staging copy; arrays that live
-        in pinned memory are copied without blocking the host)."""
+    def from_host(maps: list[np.ndarray], chunk: int | None = None, lazy: bool = False) -> "MapSet":
+        """Group a list of ``[C,h,w]`` float32 arrays by shape and upload them (``_Uploader``: pinned staging ring filled
+        by several threads, asynchronous DMA on a side stream).  ``chunk``: cut shape groups into pieces of at most that
+        many maps, each its own ``MapGroup``, so that the first piece can be used while the rest is still on its way;
+        ``lazy``: return before the copies have landed (every group carries its ``pending`` handle and must be
+        ``wait()``-ed for before its maps are read)."""
         dev = _require_cuda()
         if len(maps) == 0:
             raise ValueError("empty list of feature maps")
@@ -183,18 +292,33 @@ class MapSet:
         chans = {s[0] for s in by_shape}
         if len(chans) != 1:
             raise ValueError(f"feature maps disagree on the channel count: {sorted(chans)}")
-        groups, nbytes = [], 0
-        for shp, idx in by_shape.items():
+        for shp in by_shape:
             if shp[1] <= 2 * EDGE or shp[2] <= 2 * EDGE:
                 raise ValueError(f"feature map of shape {shp} vanishes after the 2-cell crop (similarity.py:92-93)")
-            dst = torch.empty((len(idx), *shp), dtype=torch.float32, device=dev)
-            for j, i in enumerate(idx):
+        # every destination is allocated before the first copy is queued: the side stream then only has to wait for what
+        # the caller's stream had queued up to here
+        pieces = []
+        for shp, idx in by_shape.items():
+            step = len(idx) if not chunk else max(1, chunk)
+            for s0 in range(0, len(idx), step):
+                part = idx[s0 : s0 + step]
+                pieces.append((part, torch.empty((len(part), *shp), dtype=torch.float32, device=dev)))
+        after = torch.cuda.Event()
+        after.record()
+        up = _Uploader.get(dev)
+        groups, nbytes = [], 0
+        for part, dst in pieces:
+            arrays = []
+            for i in part:
                 src = maps[i]
-                if src.dtype != np.float32 or not src.flags.c_contiguous:
-                    src = np.ascontiguousarray(src, dtype=np.float32)
-                dst[j].copy_(torch.from_numpy(src), non_blocking=True)
-            groups.append(MapGroup(dst, torch.tensor(idx, dtype=torch.int64)))
+                if src.dtype != np.float32:
+                    src = np.asarray(src, dtype=np.float32)
+                arrays.append(src)
+            groups.append(MapGroup(dst, torch.tensor(part, dtype=torch.int64), up.submit(arrays, dst, after)))
             nbytes += dst.numel() * 4
+        if not lazy:
+            for g in groups:
+                g.wait()
         return MapSet(groups, len(maps), chans.pop(), nbytes)
 
     @staticmethod
@@ -625,6 +749,7 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
     # large ones chunk by chunk inside every column block (packing is ~2 % of the correlation time)
     chunks: list[MapGroup] = []
     for grp in gallery.groups:
+        grp.wait()
         n = int(grp.maps.shape[0])
         per_map = grp.maps[0].numel() * 4
         step = max(1, min(n, gallery_chunk_bytes // max(per_map, 1)))
@@ -669,11 +794,13 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
             _score_block(blk, key, [GalleryOperands.pack(ch, keep32, with32)], [off], grouped, prec, approx)
 
     pending: dict[tuple[int, int], _Block] = {}
-    for rot, scale in variant_plan(rotations, scales):
-        for grp in probes.groups:
-            n_grp = int(grp.maps.shape[0])
-            for s0 in range(0, n_grp, col_block):  # a group wider than a column block is cut, so no block exceeds the cap
-                part = grp.maps[s0 : s0 + col_block]
+    plan = variant_plan(rotations, scales)
+    for grp in probes.groups:
+        grp.wait()  # a chunk that is still being uploaded: the kernels below queue behind its copy
+        n_grp = int(grp.maps.shape[0])
+        for s0 in range(0, n_grp, col_block):  # a group wider than a column block is cut, so no block exceeds the cap
+            part = grp.maps[s0 : s0 + col_block]
+            for rot, scale in plan:
                 v = make_variant(part, rot, scale)
                 key = (int(v.shape[2]), int(v.shape[3]))
                 blk = pending.setdefault(key, _Block())
@@ -683,9 +810,11 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
                 blk.maps.append(v)
                 blk.ids.append(grp.ids[s0 : s0 + col_block])
                 blk.ncols += int(v.shape[0])
-                if blk.ncols >= col_block:
-                    flush(blk, key)
-                    del pending[key]
+        # all variants of this group are in: blocks wide enough to run efficiently go now (the next group may still be
+        # on its way from the host), narrow ones keep collecting columns
+        if len(probes.groups) > 1:
+            for key in [k for k, b in pending.items() if b.ncols >= FLUSH_MIN_COLS]:
+                flush(pending.pop(key), key)
     # ragged probe sets leave many narrow blocks (a handful of columns per template shape): those share
     # column tiles through shape buckets instead of running one narrow launch each
     small = {k: b for k, b in pending.items() if b.ncols < bucket_below}
@@ -752,12 +881,13 @@ def compare(probe_maps, gallery_maps, matching_pairs, rotations=None, scales=Non
     its features came out of the feature cache -- is neither uploaded nor packed a second time."""
     global last_h2d_bytes
 
-    def ingest(maps):  # a FeatureMapList keeps its device copies only if it is passed through as is
+    def ingest(maps, chunk):  # a FeatureMapList keeps its device copies only if it is passed through as is
         if isinstance(maps, MapSet):
             return maps
-        return MapSet.from_host(maps if hasattr(maps, "device_copies") else list(maps))
+        return MapSet.from_host(maps if hasattr(maps, "device_copies") else list(maps), chunk=chunk, lazy=True)
 
-    probes, gallery = ingest(probe_maps), ingest(gallery_maps)
+    # the gallery goes first (it is needed by the first launch); probes travel in chunks that are scored as they arrive
+    gallery, probes = ingest(gallery_maps, None), ingest(probe_maps, PROBE_CHUNK)
     last_h2d_bytes = (probes.h2d_bytes, gallery.h2d_bytes)
     g_total = gallery.count
     tidx = np.asarray(matching_pairs, dtype=np.int64)

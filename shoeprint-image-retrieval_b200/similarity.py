@@ -109,8 +109,8 @@ def compare_maps(
             g0, g1 = sharding.shard_range(len(shoeprint_maps), world, rank)
             if g1 <= g0:
                 raise ValueError(f"{len(shoeprint_maps)} shoeprints cannot be shared among {world} ranks")
-            probes = engine.MapSet.from_host(_ingest(shoemark_maps))
-            shard = engine.MapSet.from_host(_ingest(shoeprint_maps[g0:g1]))
+            shard = engine.MapSet.from_host(_ingest(shoeprint_maps[g0:g1]), lazy=True)
+            probes = engine.MapSet.from_host(_ingest(shoemark_maps), chunk=engine.PROBE_CHUNK, lazy=True)
             engine.last_h2d_bytes = (probes.h2d_bytes, shard.h2d_bytes)
             d_ranks, tv, ti, scores = sharding.compare_sharded(probes, shard, pairs, g0, rotations, scales, precision, top_k)
             ranks = d_ranks.to("cpu").numpy().astype(np.int32)
