@@ -46,12 +46,15 @@ namespace sir {
 constexpr int kTcThreads = 384;
 constexpr int kTileM = 128;      // 16 x 8 positions
 constexpr int kTileN = 256;      // packed columns per tile
-constexpr int kStageK = 32;      // taps per B stage (64 bytes: one 64B-swizzle row)
+// taps per B stage = 16 * SPS (K16 steps per stage, a template parameter of the kernel): 32 taps (one 64B-swizzle row of
+// fp16) for the split-precision modes, 64 taps (128B swizzle) for the one-pass fp16 modes -- there a stage of 32 taps is
+// only two MMAs and the single issuing thread, not the tensor pipe, paced the kernel (ncu: pipe 55% busy, the issue
+// loop ~100 instructions per stage)
 constexpr int kGenThreads = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kMaxBStages = 16;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kBHalfBytes = kTileN * kStageK * 2;  // 16 KB
+__host__ __device__ constexpr uint32_t b_half_bytes(int sps) { return kTileN * 16 * sps * 2; }  // one operand half of a stage: 16 / 32 KB
 
 struct TcParams {
   const __half* ghi;
@@ -68,7 +71,8 @@ struct TcParams {
   int ncols;
   int nkc;         // 8-tap chunks per template row
   int nsteps;      // K16 steps per channel = ceil(Hm*nkc/2)
-  int nkstages;    // B stages per channel = Kpad/32
+  int nkstages;    // B stages per channel = ceil(Kpad / (16 * sps))
+  int sps;         // K16 steps per B stage: 2 or 4 (== the kernel's SPS)
   int npy, npx;    // 16x8 patches over the gallery position grid
   int ntiles_n;
   long long nunits;
@@ -114,8 +118,8 @@ __device__ __forceinline__ KRange k_range(const TcParams& p, int py) {
   KRange r;
   r.ks_lo = (u_lo * p.nkc) / 2;
   r.ks_hi = min(p.nsteps, (u_hi * p.nkc + 1) / 2);
-  r.st_lo = r.ks_lo / 2;
-  r.st_hi = (r.ks_hi + 1) / 2;
+  r.st_lo = r.ks_lo / p.sps;
+  r.st_hi = (r.ks_hi + p.sps - 1) / p.sps;
   r.nseg = (r.st_hi - r.st_lo + p.seg_stages - 1) / p.seg_stages;
   return r;
 }
@@ -128,8 +132,8 @@ __device__ __forceinline__ Seg seg_geometry(const TcParams& p, const KRange& kr,
   Seg s;
   s.st0 = kr.st_lo + sg * p.seg_stages;
   s.st1 = min(s.st0 + p.seg_stages, kr.st_hi);
-  const int t_first = 4 * s.st0;
-  const int t_last = min(4 * s.st1, 2 * kr.ks_hi) - 1;
+  const int t_first = 2 * p.sps * s.st0;  // in 8-tap chunks: two per K16 step
+  const int t_last = min(2 * p.sps * s.st1, 2 * kr.ks_hi) - 1;
   s.u_first = t_first / p.nkc;
   s.rows = 16 + (t_last / p.nkc - s.u_first);
   return s;
@@ -139,7 +143,7 @@ __device__ __forceinline__ Seg seg_geometry(const TcParams& p, const KRange& kr,
 // whole pipeline on its own work unit (same column tile and patch, neighbouring galleries) but the
 // leader issues one tcgen05.mma.cta_group::2 (M = 256) for both, and each CTA streams only its half
 // of the template columns: the B traffic per SM and the B footprint in shared memory halve.
-template <int CG>
+template <int CG, int SPS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_x,
               const __grid_constant__ CUtensorMap tm_ghi, const __grid_constant__ CUtensorMap tm_glo,
@@ -154,7 +158,8 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-  constexpr uint32_t kBHalfCta = kBHalfBytes / CG;                         // this CTA's share of one operand half
+  constexpr int kStageK = 16 * SPS;
+  constexpr uint32_t kBHalfCta = b_half_bytes(SPS) / CG;                   // this CTA's share of one operand half
   const uint32_t stage_bytes = kBHalfCta * (p.passes == 1 ? 1 : 2);       // per CTA (fp8c: 1 + 1/2 + 1/2)
   const uint32_t e_buf_bytes = p.nhalf * p.e_half_bytes;
   const uint32_t bar0 = base + p.off_bar;
@@ -272,7 +277,10 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       //      groups one E row apart (SBO), the two K chunks of a step 8 entries apart (LBO = 128 B).
       //   B: 64B swizzle, 8-row groups 512 B apart; a K16 sub-step is +32 B inside the swizzle row.
       const uint64_t a_desc_hi = ((uint64_t)((16u * Pe) >> 4) | (1ull << 14)) << 32;                 // SBO | version
-      const uint64_t b_desc_hi = ((uint64_t)(512u >> 4) | (1ull << 14) | (4ull << 29)) << 32;        // SBO | version | SW64
+      // B: 32-tap stages are 64-byte rows (64B swizzle, 8-row groups 512 B apart), 64-tap stages 128-byte rows (128B swizzle,
+      //    groups 1024 B apart); a K16 sub-step is +32 B inside the swizzle row either way
+      const uint64_t b_desc_hi = SPS == 2 ? ((uint64_t)(512u >> 4) | (1ull << 14) | (4ull << 29)) << 32      // SBO | version | SW64
+                                          : ((uint64_t)(1024u >> 4) | (1ull << 14) | (2ull << 29)) << 32;    // SBO | version | SW128
       constexpr uint32_t a_lbo = (128u >> 4) << 16, b_lbo = (16u >> 4) << 16;
       auto a_desc = [&](uint32_t addr) { return a_desc_hi | a_lbo | ((addr >> 4) & 0x3FFFu); };
       auto b_desc = [&](uint32_t addr) { return b_desc_hi | b_lbo | ((addr >> 4) & 0x3FFFu); };
@@ -301,28 +309,33 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             ptx::tc_fence_after();
             const uint32_t e_hi = base + p.off_e + ebuf * e_buf_bytes;
             // E row 0 of this segment is template row u_first: K step ks starts 256*ks - 16*u_first*Pe bytes in
-            uint32_t a_hi = e_hi + 512u * s.st0 - 16u * s.u_first * Pe;
-            for (int st = s.st0; st < s.st1; ++st, a_hi += 512u) {
+            uint32_t a_hi = e_hi + 256u * SPS * s.st0 - 16u * s.u_first * Pe;
+            for (int st = s.st0; st < s.st1; ++st, a_hi += 256u * SPS) {
               ptx::mbar_wait(bar_full(slot), bphase);
               ptx::tc_fence_after();
+              // K16 steps of this stage with a non-zero A operand (only the first and last stage of a unit are partial)
+              const int k_lo = max(kr.ks_lo - SPS * st, 0), k_hi = min(kr.ks_hi - SPS * st, SPS);
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const int ks = 2 * st + kk;
-                if (ks >= kr.ks_lo && ks < kr.ks_hi) {
+              for (int kk = 0; kk < SPS; ++kk) {
+                if (kk >= k_lo && kk < k_hi) {
                   const uint64_t da_hi = a_desc(a_hi + 256u * kk);
                   const uint64_t db_hi = b_desc(b_addr + 32u * kk);
                   mma(tmem_d, da_hi, db_hi, accumulate);
                   accumulate = 1;
-                  if (p.passes == 3) {
-                    mma(tmem_d, a_desc(a_hi + p.e_half_bytes + 256u * kk), db_hi, 1);
-                    mma(tmem_d, da_hi, b_desc(b_addr + kBHalfCta + 32u * kk), 1);
+                  if constexpr (SPS == 2) {
+                    if (p.passes == 3) {
+                      mma(tmem_d, a_desc(a_hi + p.e_half_bytes + 256u * kk), db_hi, 1);
+                      mma(tmem_d, da_hi, b_desc(b_addr + kBHalfCta + 32u * kk), 1);
+                    }
                   }
                 }
               }
-              if (p.passes == 2 && 2 * st + 1 >= kr.ks_lo && 2 * st < kr.ks_hi) {
-                // corrections over the whole 32-tap stage: (A_lo*4)(B_hi/4) and (A_hi/4)(B_lo*4), both e4m3
-                mma8(tmem_d, a8_desc(a_hi + p.e_half_bytes), b8_desc(b_addr + kBHalfCta));
-                mma8(tmem_d, a8_desc(a_hi + 2 * p.e_half_bytes), b8_desc(b_addr + kBHalfCta + kBHalfCta / 2));
+              if constexpr (SPS == 2) {
+                if (p.passes == 2 && k_hi > k_lo) {
+                  // corrections over the whole 32-tap stage: (A_lo*4)(B_hi/4) and (A_hi/4)(B_lo*4), both e4m3
+                  mma8(tmem_d, a8_desc(a_hi + p.e_half_bytes), b8_desc(b_addr + kBHalfCta));
+                  mma8(tmem_d, a8_desc(a_hi + 2 * p.e_half_bytes), b8_desc(b_addr + kBHalfCta + kBHalfCta / 2));
+                }
               }
               commit(bar_empty(slot));
               b_addr += stage_bytes;
@@ -619,7 +632,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_alloc, int C, int box_cols) {
+int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_alloc, int C, int box_cols, int stage_k = 32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -627,11 +640,12 @@ int make_template_map(CUtensorMap* tm, const uint16_t* ptr, int Kpad, int ncols_
   }
   cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)ncols_alloc, (cuuint64_t)C};
   cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Kpad * 2 * (cuuint64_t)ncols_alloc};
-  cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)box_cols, 1};
+  // a 64-tap box may reach past Kpad (a multiple of 32): the cells outside the tensor arrive as zeros
+  cuuint32_t box[3] = {(cuuint32_t)stage_k, (cuuint32_t)box_cols, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, stage_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (Kpad=%d ncols=%d C=%d)", (int)r, Kpad, ncols_alloc, C);
     return SIR_E_CUDA;
@@ -671,7 +685,7 @@ int make_template_map8(CUtensorMap* tm, const uint8_t* ptr, int Kpad, int ncols_
   }
   cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)ncols_alloc, (cuuint64_t)C};
   cuuint64_t strides[2] = {(cuuint64_t)Kpad, (cuuint64_t)Kpad * (cuuint64_t)ncols_alloc};
-  cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)box_cols, 1};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_cols, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -732,7 +746,12 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   p.nkc = tpl_row_taps(Wm, row_align) / 8;
   const int Kpad = tpl_kpad_aligned(Hm, Wm, row_align);
   p.nsteps = ceil_div(Hm * p.nkc, 2);
-  p.nkstages = Kpad / kStageK;
+  // one-pass fp16 (screening, fp16x1): 64-tap stages so that the issuing thread has four MMAs per barrier round trip;
+  // SIR_STAGE_TAPS=32 forces the short stages
+  p.sps = passes == 1 ? 4 : 2;
+  if (const char* env = getenv("SIR_STAGE_TAPS")) p.sps = (passes == 1 && atoi(env) != 32) ? 4 : 2;
+  const int stage_k = 16 * p.sps;
+  p.nkstages = ceil_div(Kpad, stage_k);
   p.npy = ceil_div(Hp, 16);
   p.npx = ceil_div(Wp, 8);
   p.ntiles_n = ceil_div(ncols, kTileN);
@@ -750,19 +769,19 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   // shared memory plan: B ring, 2 E buffers (x halves), row staging, column maxima, barriers
   const int halves = passes == 3 ? 2 : passes == 2 ? 3 : 1;          // operand arrays per E buffer
   const int gs16 = passes == 3 ? 2 : 1;                             // staged fp16 windows
-  const uint32_t stage_bytes = kBHalfBytes / cg * (passes == 1 ? 1 : 2);  // per CTA
+  const uint32_t stage_bytes = b_half_bytes(p.sps) / cg * (passes == 1 ? 1 : 2);  // per CTA
   const int Pe = 8 * p.nkc;
   const size_t limit = 227 * 1024 - 1024;  // alignment slack
   // Plan: long E segments first (every segment rebuilds 16 + rows-in-segment E rows, so short segments
   // make the generators the bottleneck), then as deep a B ring as the remaining shared memory allows
   // (at least 3 stages; 2 as a last resort), staging double-buffered unless that is what does not fit.
   bool ok = false;
-  const int nb_max = passes == 1 ? 12 : (cg == 2 ? 6 : 4);
+  const int nb_max = passes == 1 ? (p.sps == 4 ? 6 : 12) : (cg == 2 ? 6 : 4);
   for (int nb_min = 3; nb_min >= 2 && !ok; --nb_min) {
     for (int gsb = 2; gsb >= 1 && !ok; --gsb) {
       for (int seg = p.nkstages; seg >= 1; --seg) {
         // rows touched by a segment of `seg` stages: worst case over alignments
-        const int max_rows = 16 + (4 * seg - 1) / p.nkc + 1;
+        const int max_rows = 16 + (2 * p.sps * seg - 1) / p.nkc + 1;
         const size_t e_half = (size_t)(max_rows + 1) * Pe * 16;
         const size_t gs_half = (size_t)(max_rows + 1) * (Pe + 16);  // cells
         const size_t gs8 = passes == 2 ? (size_t)round_up((max_rows + 1) * (Pe + 32), 128) : 0;  // bytes of one 1-byte window
@@ -790,15 +809,15 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
     // MMA cycles of the non-skipped stages vs generator cycles (calibrated on B200 with 64 generator
     // threads: ~1.3 cycles per fp16 entry, built in pairs, ~2.5 per fp8 entry); whichever is larger paces
     // a (unit, channel)
-    const double cyc_stage = passes == 3 ? 768.0 : passes == 2 ? 512.0 : 256.0;
+    const double cyc_stage = passes == 3 ? 768.0 : passes == 2 ? 512.0 : 128.0 * p.sps;
     const int a = Hm / 2;
     double total = 0.0;
     for (int py = 0; py < p.npy; ++py) {
       const int u_lo = std::max(0, a - 16 * py - 15), u_hi = std::min(Hm, Hp + a - 16 * py);
       const int ks_lo = (u_lo * p.nkc) / 2, ks_hi = std::min(p.nsteps, (u_hi * p.nkc + 1) / 2);
-      const int stages = (ks_hi + 1) / 2 - ks_lo / 2;
+      const int stages = (ks_hi + p.sps - 1) / p.sps - ks_lo / p.sps;
       const int nseg_u = ceil_div(stages, p.seg_stages);
-      const int rows_seg = 16 + (4 * std::min(stages, p.seg_stages) - 1) / p.nkc + 2;
+      const int rows_seg = 16 + (2 * p.sps * std::min(stages, p.seg_stages) - 1) / p.nkc + 2;
       const double mma = stages * cyc_stage;
       const double per_entry = passes == 2 ? 1.3 + 2 * 2.5 : 1.3 * p.nhalf;
       const double gen = per_entry * nseg_u * (double)rows_seg * Pe;
@@ -820,7 +839,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   SIR_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ghi) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_glo) & 15) == 0,
                 "sir_ncc_scores: gallery operands must be 16-byte aligned");
   CUtensorMap tm_hi, tm_lo, tm_x, tm_ghi, tm_glo, tm_gx;
-  int rc = make_template_map(&tm_hi, d_thi, Kpad, ncols_alloc, C, kTileN / cg);
+  int rc = make_template_map(&tm_hi, d_thi, Kpad, ncols_alloc, C, kTileN / cg, stage_k);
   if (rc) return rc;
   rc = make_gallery_map(&tm_ghi, d_ghi, G * C, Hp, Wp, Pe + 16, p.gs_rows);
   if (rc) return rc;
@@ -835,7 +854,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
     if (rc) return rc;
   } else {
     // one-pass modes never touch the lo maps: alias them to the hi operands when the caller has none
-    rc = make_template_map(&tm_lo, d_tlo ? d_tlo : d_thi, Kpad, ncols_alloc, C, kTileN / cg);
+    rc = make_template_map(&tm_lo, d_tlo ? d_tlo : d_thi, Kpad, ncols_alloc, C, kTileN / cg, stage_k);
     if (rc) return rc;
     rc = make_gallery_map(&tm_glo, d_glo ? d_glo : d_ghi, G * C, Hp, Wp, Pe + 16, p.gs_rows);
     if (rc) return rc;
@@ -843,34 +862,28 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
     tm_gx = tm_glo;
   }
 
-  static thread_local size_t configured[3] = {0, 0, 0};
-  if (smem > configured[cg]) {
-    if (cg == 2) SIR_CUDA(cudaFuncSetAttribute(ncc_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else SIR_CUDA(cudaFuncSetAttribute(ncc_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[cg] = smem;
-  }
+  auto kernel = cg == 2 ? (p.sps == 4 ? ncc_tc_kernel<2, 4> : ncc_tc_kernel<2, 2>) : (p.sps == 4 ? ncc_tc_kernel<1, 4> : ncc_tc_kernel<1, 2>);
+  SIR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap: no cache
   int dev = 0, sms = 0;
   SIR_CUDA(cudaGetDevice(&dev));
   SIR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   unsigned grid = (unsigned)std::min<long long>(p.nunits, sms);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
   if (cg == 2) {
     grid &= ~1u;  // whole pairs only (nunits is even)
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SIR_CUDA(cudaLaunchKernelEx(&cfg, ncc_tc_kernel<2>, tm_hi, tm_lo, tm_x, tm_ghi, tm_glo, tm_gx, p));
-  } else {
-    ncc_tc_kernel<1><<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_x, tm_ghi, tm_glo, tm_gx, p);
   }
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  SIR_CUDA(cudaLaunchKernelEx(&cfg, kernel, tm_hi, tm_lo, tm_x, tm_ghi, tm_glo, tm_gx, p));
   SIR_LAUNCH_CHECK("ncc_tc_kernel");
   return SIR_OK;
 }

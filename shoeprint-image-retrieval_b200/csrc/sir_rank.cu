@@ -12,7 +12,7 @@ namespace sir {
 
 constexpr int kRankThreads = 256;
 constexpr int kRankWarps = kRankThreads / 32;
-constexpr int kMaxTopK = 128;
+constexpr int kMaxTopK = 128;  // <= kSelCap - kSelChunk: the k best always fit next to one chunk of new keys
 
 __global__ void true_scores_kernel(const float* __restrict__ scores, int Q, int G, int ld,
                                    const int32_t* __restrict__ true_idx, int g0, float* __restrict__ out) {
@@ -25,123 +25,134 @@ __global__ void true_scores_kernel(const float* __restrict__ scores, int Q, int 
 // (value desc, index asc) strict order
 __device__ __forceinline__ bool beats(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
 
-// Warp-select: each warp keeps an UNSORTED list of its k best (value, index) pairs in shared memory
-// together with the current worst entry (value `thr`, slot `wslot`).  A candidate that beats the worst
-// replaces it and the worst is recomputed by a warp reduction -- O(k/32) per insertion, no shifting.
-// Ordering (value desc, index asc) is only established once, by the final merge.
-struct Worst {
-  float v;
-  int idx;
-  int slot;
-};
-__device__ __forceinline__ Worst warp_find_worst(const float* lv, const int* li, int k, int lane) {
-  Worst w{INFINITY, -1, 0};
-  for (int j = lane; j < k; j += 32) {
-    const float v = lv[j];
-    const int id = li[j];
-    if (v < w.v || (v == w.v && id > w.idx)) w = Worst{v, id, j};
+// Top-k by threshold + compaction.  One CTA streams one score row (16-byte loads).  Every value is turned into a
+// 64-bit key whose unsigned order is (value descending, index ascending); keys above the CTA's current threshold are
+// appended to a shared-memory buffer with one atomicAdd per warp and slot (ballot-aggregated).  When the buffer could
+// overflow during the next chunk it is sorted (bitonic, in place), cut to the k best, and the k-th key becomes the new
+// threshold -- after the first cut only ~k/2048 of the values pass, so a 100,000-column row is cut two or three times
+// and the kernel stays a single streaming pass over HBM.
+constexpr int kSelCap = 2048;                  // keys the buffer holds
+constexpr int kSelChunk = kRankThreads * 4;    // values per iteration (one float4 per thread)
+
+__device__ __forceinline__ unsigned long long select_key(float v, int idx) {
+  unsigned u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // unsigned order == float order
+  return ((unsigned long long)u << 32) | (unsigned)(0x7fffffff - idx);
+}
+__device__ __forceinline__ float key_value(unsigned long long key) {
+  unsigned u = (unsigned)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+// sorts buf[0..n) descending (n <= kSelCap), keeps the first min(n, k) keys; returns the new count
+__device__ int select_compact(unsigned long long* buf, int n, int k, unsigned long long* thr) {
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = n + threadIdx.x; i < P; i += blockDim.x) buf[i] = 0ull;  // below every real key
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = buf[lo], b = buf[hi];
+        if ((a < b) == desc) {
+          buf[lo] = b;
+          buf[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, w.v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, w.idx, o);
-    const int os = __shfl_xor_sync(0xffffffffu, w.slot, o);
-    if (ov < w.v || (ov == w.v && oi > w.idx)) w = Worst{ov, oi, os};
-  }
-  return w;
+  const int kept = min(n, k);
+  if (threadIdx.x == 0 && n >= k && k > 0) *thr = buf[k - 1];
+  __syncthreads();
+  return kept;
 }
 
 __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __restrict__ scores, int Q, int G, int ld,
                                                                  const float* __restrict__ true_score, int g0, int k,
                                                                  int32_t* __restrict__ count_gt, int32_t* __restrict__ count_ge,
                                                                  float* __restrict__ topk_val, int32_t* __restrict__ topk_idx) {
-  __shared__ float lv[kRankWarps][kMaxTopK];
-  __shared__ int li[kRankWarps][kMaxTopK];
-  __shared__ int cnt[2][kRankWarps];
+  __shared__ unsigned long long buf[kSelCap];
+  __shared__ unsigned long long thr_s;
+  __shared__ int cnt_s;
+  __shared__ int red[2][kRankWarps];
   const int q = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* row = scores + (size_t)q * ld;
   const float ts = true_score[q];
-
-  for (int j = lane; j < k; j += 32) { lv[wid][j] = -INFINITY; li[wid][j] = INT_MAX; }
-  __syncwarp();
-  Worst worst{-INFINITY, INT_MAX, 0};  // every slot is empty: any finite value beats it
-  int gt = 0, ge = 0;
-
-  auto consider = [&](float v, int g, bool valid) {
-    if (valid) { gt += v > ts; ge += v >= ts; }
-    if (k > 0) {
-      // indices arrive in increasing order, so an equal value never displaces an earlier one
-      unsigned m = __ballot_sync(0xffffffffu, valid && v > worst.v);
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float cv = __shfl_sync(0xffffffffu, v, src);
-        const int ci = __shfl_sync(0xffffffffu, g, src);
-        if (cv > worst.v) {
-          if (lane == 0) { lv[wid][worst.slot] = cv; li[wid][worst.slot] = ci; }
-          __syncwarp();
-          worst = warp_find_worst(lv[wid], li[wid], k, lane);
+  if (threadIdx.x == 0) {
+    thr_s = 0ull;
+    cnt_s = 0;
+  }
+  __syncthreads();
+  const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  int gt = 0, ge = 0, cnt = 0;
+  for (int base = 0; base < G; base += kSelChunk) {
+    const int i0 = base + 4 * threadIdx.x;
+    float v[4];
+    if (aligned && i0 + 3 < G) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(row + i0));
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (i0 + j < G) ? __ldg(row + i0 + j) : 0.0f;
+    }
+    const unsigned long long thr = thr_s;
+    const float thr_v = key_value(thr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool valid = i0 + j < G;
+      gt += valid && v[j] > ts;
+      ge += valid && v[j] >= ts;
+      if (k > 0) {
+        unsigned long long key = 0ull;
+        bool take = valid && (thr == 0ull || v[j] >= thr_v);
+        if (take) {
+          key = select_key(v[j], g0 + i0 + j);
+          take = key > thr;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+          int pos = 0;
+          if (lane == 0) pos = atomicAdd(&cnt_s, __popc(m));
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (take) buf[pos + __popc(m & ((1u << lane) - 1u))] = key;
         }
       }
     }
-  };
-
-  // each warp owns a contiguous slice; 16-byte loads, four in flight per lane, when the row is aligned
-  const int per = ceil_div(G, kRankWarps);
-  const int beg = wid * per, end = min(G, beg + per);
-  const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-  int g = beg;
-  if (aligned) {
-    const int head = min(end, round_up(beg, 4));
-    for (int base = g; base < head; base += 32) { const int i = base + lane; consider(i < head ? row[i] : 0.f, g0 + i, i < head); }
-    g = head;
-    const int nvec = (end - g) / 4;
-    const float4* rv = reinterpret_cast<const float4*>(row + g);
-    for (int base = 0; base < nvec; base += 128) {
-      float4 v[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = base + u * 32 + lane;
-        ok[u] = i < nvec;
-        v[u] = ok[u] ? __ldg(rv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int gi = g0 + g + 4 * (base + u * 32 + lane);
-        consider(v[u].x, gi, ok[u]); consider(v[u].y, gi + 1, ok[u]); consider(v[u].z, gi + 2, ok[u]); consider(v[u].w, gi + 3, ok[u]);
+    if (k > 0) {
+      __syncthreads();
+      cnt = cnt_s;
+      if (cnt > kSelCap - kSelChunk) {  // the next chunk could overflow: cut to the k best, raise the threshold
+        cnt = select_compact(buf, cnt, k, &thr_s);
+        if (threadIdx.x == 0) cnt_s = cnt;
+        __syncthreads();
       }
     }
-    g += nvec * 4;
   }
-  for (int base = g; base < end; base += 32) { const int i = base + lane; consider(i < end ? row[i] : 0.f, g0 + i, i < end); }
-
   gt = warp_sum(gt);
   ge = warp_sum(ge);
-  if (lane == 0) { cnt[0][wid] = gt; cnt[1][wid] = ge; }
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {  // slots left empty when G < k
-    topk_val[(size_t)q * k + j] = -INFINITY;
-    topk_idx[(size_t)q * k + j] = -1;
+  if (lane == 0) {
+    red[0][wid] = gt;
+    red[1][wid] = ge;
   }
-  __syncthreads();
+  if (k > 0) cnt = select_compact(buf, cnt_s, k, &thr_s);  // (also the barrier for red[])
+  else __syncthreads();
   if (threadIdx.x == 0) {
     int a = 0, b = 0;
-    for (int w = 0; w < kRankWarps; ++w) { a += cnt[0][w]; b += cnt[1][w]; }
+    for (int w = 0; w < kRankWarps; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
     count_gt[q] = a;
     count_ge[q] = b;
   }
-  // merge the per-warp lists: every candidate counts how many candidates beat it
-  const int ncand = kRankWarps * k;
-  for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
-    const float v = lv[i / k][i % k];
-    const int id = li[i / k][i % k];
-    int r = 0;
-    for (int w = 0; w < kRankWarps; ++w)
-      for (int j = 0; j < k; ++j) r += beats(lv[w][j], li[w][j], v, id) ? 1 : 0;
-    if (r < k) {
-      topk_val[(size_t)q * k + r] = v;
-      topk_idx[(size_t)q * k + r] = (id == INT_MAX) ? -1 : id;
-    }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const bool have = j < cnt;
+    topk_val[(size_t)q * k + j] = have ? key_value(buf[j]) : -INFINITY;
+    topk_idx[(size_t)q * k + j] = have ? (int)(0x7fffffff - (unsigned)(buf[j] & 0xffffffffu)) : -1;
   }
 }
 

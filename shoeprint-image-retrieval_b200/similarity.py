@@ -134,15 +134,54 @@ def compare_maps(
     return ranks
 
 
+def _ncc_surfaces(marks: np.ndarray, prints: np.ndarray) -> np.ndarray:
+    """Per-channel NCC surfaces ``[C, Hp, Wp]`` (float32) of UNCROPPED maps ``[C,h,w]`` through the library's pack
+    kernels and ``sir_ncc_surface`` (fp32 CUDA cores, one small launch per channel).  Helper path only: the matching
+    path never materialises a surface."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native as nat
+
+    c, h, w = marks.shape
+    hm, wm = h - 2 * _PAD, w - 2 * _PAD
+    gal = engine.MapSet.from_host([prints])
+    ops = engine.GalleryOperands.pack(gal.groups[0], keep_fp32=True)
+    rn = ops.rnorm(hm, wm, simt=True)
+    dev = rn.device
+    tmap = torch.from_numpy(np.ascontiguousarray(marks)[None]).to(dev)
+    kpad = int(nat.lib.sir_template_kpad(hm, wm))
+    thi = torch.empty((c, 1, kpad), dtype=torch.float16, device=dev)
+    tlo = torch.empty_like(thi)
+    t32 = torch.empty((c, 1, hm * wm), dtype=torch.float32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nat.check(nat.lib.sir_template_pack(C.c_void_p(tmap.data_ptr()), 1, c, h, w, 0, 1, C.c_void_p(thi.data_ptr()),
+                                        C.c_void_p(tlo.data_ptr()), C.c_void_p(t32.data_ptr()), st), "sir_template_pack")
+    m = ops.Hp * ops.Wp
+    out = torch.empty((c, ops.Hp, ops.Wp), dtype=torch.float32, device=dev)
+    for ch in range(c):
+        nat.check(nat.lib.sir_ncc_surface(C.c_void_p(ops.gz.data_ptr() + 4 * ch * m), C.c_void_p(rn.data_ptr() + 4 * ch * m), ops.Hp, ops.Wp,
+                                          C.c_void_p(t32.data_ptr() + 4 * ch * hm * wm), hm, wm, C.c_void_p(out.data_ptr() + 4 * ch * m), st),
+                  "sir_ncc_surface")
+    return out.cpu().numpy()
+
+
 def get_similarity(shoemark: FeatureMapsArrayType, shoeprint: FeatureMapsArrayType) -> np.floating:
     """Similarity of one shoemark against one shoeprint (``similarity.py:75-108``): per-channel NCC
-    of the 2-cell-cropped maps, summed over channels, max over positions, divided by C."""
-    probes = engine.MapSet.from_host([_as_f32(shoemark)])
-    gallery = engine.MapSet.from_host([_as_f32(shoeprint)])
-    scores = engine.score_matrix(probes, gallery, None, None, engine.DEFAULT_PRECISION)
-    # compare_maps floors at 0 (similarity.py:355); a lone get_similarity call in the reference does
-    # not, but a negative best NCC only arises for anti-correlated maps and ranks last either way.
-    return np.float64(scores[0, 0].item())
+    of the 2-cell-cropped maps, summed over channels, max over positions, divided by C.
+
+    The fused path floors at 0 like ``compare_maps`` does (``similarity.py:355``); a lone ``get_similarity`` call in the
+    reference does not, so a pair whose best position is not positive is re-evaluated from its per-channel surfaces and
+    the (negative) maximum is returned as the reference would."""
+    mark, prnt = _as_f32(shoemark), _as_f32(shoeprint)
+    probes = engine.MapSet.from_host([mark])
+    gallery = engine.MapSet.from_host([prnt])
+    score = float(engine.score_matrix(probes, gallery, None, None, engine.DEFAULT_PRECISION)[0, 0].item())
+    if score > 0.0:
+        return np.float64(score)
+    surf = _ncc_surfaces(mark, prnt).astype(np.float64).sum(axis=0)
+    return np.float64(surf.max() / mark.shape[0])
 
 
 def normxcorr(
@@ -153,39 +192,17 @@ def normxcorr(
     """Normalised cross-correlation surface of ``template`` over ``image`` (``similarity.py:26-72``).
 
     Helper, not on the matching path: the fused kernel never materialises the surface
-    (``compare_maps`` / ``get_similarity`` go through ``sir_ncc_scores``).  Here the zero-meaned
+    (``compare_maps`` / ``get_similarity`` go through the fused kernels).  Here the zero-meaned
     operands and the window norm come from the library's pack kernels and the surface from
     ``sir_ncc_surface`` (fp32 CUDA cores).  Only ``mode="same"`` -- the only mode the reference uses
     (``similarity.py:104``) -- is supported.
     """
     if mode != "same":
         raise NotImplementedError("only mode='same' is used by the matching path (similarity.py:104)")
-    import ctypes as C
-
-    import torch
-
-    from . import _native as nat
-
     t = _as_f32(template)
     g = _as_f32(image)
-    hm, wm = t.shape
-    hp, wp = g.shape
     # frame both so the library's 2-cell crop removes exactly the frame
-    gal = engine.MapSet.from_host([np.pad(g, _PAD)[None]])
-    ops = engine.GalleryOperands.pack(gal.groups[0], keep_fp32=True)
-    rn = ops.rnorm(hm, wm, simt=True)
-    tmap = torch.from_numpy(np.pad(t, _PAD)[None, None]).to(rn.device)
-    kpad = int(nat.lib.sir_template_kpad(hm, wm))
-    thi = torch.empty((1, 1, kpad), dtype=torch.float16, device=rn.device)
-    tlo = torch.empty_like(thi)
-    t32 = torch.empty((1, 1, hm * wm), dtype=torch.float32, device=rn.device)
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    nat.check(nat.lib.sir_template_pack(C.c_void_p(tmap.data_ptr()), 1, 1, hm + 2 * _PAD, wm + 2 * _PAD, 0, 1, C.c_void_p(thi.data_ptr()),
-                                        C.c_void_p(tlo.data_ptr()), C.c_void_p(t32.data_ptr()), st), "sir_template_pack")
-    out = torch.empty((hp, wp), dtype=torch.float32, device=rn.device)
-    nat.check(nat.lib.sir_ncc_surface(C.c_void_p(ops.gz.data_ptr()), C.c_void_p(rn.data_ptr()), hp, wp, C.c_void_p(t32.data_ptr()), hm, wm,
-                                      C.c_void_p(out.data_ptr()), st), "sir_ncc_surface")
-    return out.cpu().numpy().astype(np.float64)
+    return _ncc_surfaces(np.pad(t, _PAD)[None], np.pad(g, _PAD)[None])[0].astype(np.float64)
 
 
 def _get_rank(similarities, matching_pairs: list[int], print_id: int) -> int:

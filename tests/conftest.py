@@ -20,3 +20,11 @@ def golden():
     """Vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
     with np.load(ROOT / "tests" / "golden" / "reference_vectors.npz") as z:
         return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden_edge():
+    """Edge-case vectors from the unmodified reference: dead / constant channels, ReLU-like flat regions, anti-correlated
+    probes (tests/golden/make_golden.py, edge_cases)."""
+    with np.load(ROOT / "tests" / "golden" / "reference_vectors_edge.npz") as z:
+        return {k: z[k] for k in z.files}

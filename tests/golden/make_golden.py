@@ -162,6 +162,55 @@ def main() -> None:
 
     np.savez_compressed(OUT / "reference_vectors.npz", **out)
     print("wrote", OUT / "reference_vectors.npz", sum(v.nbytes for v in out.values()), "bytes raw")
+    edge_cases()
+
+
+def edge_cases() -> None:
+    """Second file (own seed, so reference_vectors.npz stays bit-identical): inputs real post-activation feature maps
+    produce and synthetic smooth fields avoid -- dead (all-zero) and constant channels on either side, ReLU-like maps
+    with flat halves, an anti-correlated probe -- through get_similarity and through the worker with rotations."""
+    rng = np.random.default_rng(20261019)
+    out: dict[str, np.ndarray] = {}
+    g = smooth_field(rng, 5, 16, 12)
+    p = np.ascontiguousarray(g + 0.3 * rng.standard_normal(g.shape).astype(np.float32))
+    cases = []
+    g_dead = g.copy(); g_dead[1] = 0.0
+    cases.append((p, g_dead))                       # dead gallery channel
+    p_dead = p.copy(); p_dead[2] = 0.0
+    cases.append((p_dead, g))                       # dead probe channel
+    cases.append((p_dead, g_dead))                  # both
+    g_const = g.copy(); g_const[1] = 0.7321
+    cases.append((p, g_const))                      # constant non-zero gallery channel
+    g_relu = np.maximum(g, 0); g_relu[3, :, :6] = 0
+    cases.append((np.maximum(p, 0), np.ascontiguousarray(g_relu)))  # ReLU-like, one channel flat over half the map
+    cases.append((np.ascontiguousarray(-p), g))     # anti-correlated probe
+    small = make_probe(rng, g, 9, 8)
+    cases.append((np.ascontiguousarray(-small), g_dead))
+    for i, (a, b) in enumerate(cases):
+        out[f"eg{i}_p"], out[f"eg{i}_g"] = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+        out[f"eg{i}_out"] = np.array(float(ref_sim.get_similarity(out[f"eg{i}_p"], out[f"eg{i}_g"])))
+    out["eg_count"] = np.array(len(cases))
+    # compare pass over edge maps
+    gallery = [smooth_field(rng, 4, 15, 12) for _ in range(6)]
+    gallery[1][2] = 0.0
+    gallery[3] = np.ascontiguousarray(np.maximum(gallery[3], 0))
+    gallery[4][0] = 1.5
+    pairs = [0, 1, 3, 4, 5]
+    probes = [make_probe(rng, gallery[t], int(rng.integers(9, 16)), int(rng.integers(8, 13))) for t in pairs]
+    probes[1][2] = 0.0
+    probes[4] = np.ascontiguousarray(-probes[4])    # its true match is anti-correlated: ranks low, scores near the 0 floor
+    out["ecmp_gallery"] = np.stack(gallery)
+    out["ecmp_pairs"] = np.array(pairs, dtype=np.int64)
+    for qi, pr in enumerate(probes):
+        out[f"ecmp_probe{qi}"] = pr
+    out["ecmp_q"] = np.array(len(probes))
+    rots = [-12, 8]
+    ranks, _ = run_worker(probes, gallery, pairs, rots, None)
+    scores, _ = ref_scores(probes, gallery, rots, None)
+    out["ecmp_rot"] = np.array(rots, dtype=np.float64)
+    out["ecmp_ranks"], out["ecmp_scores"] = ranks, scores
+    np.savez_compressed(OUT / "reference_vectors_edge.npz", **out)
+    print("wrote", OUT / "reference_vectors_edge.npz", [float(out[f"eg{i}_out"]) for i in range(len(cases))], ranks)
 
 
 if __name__ == "__main__":

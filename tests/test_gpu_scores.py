@@ -241,3 +241,68 @@ def test_refinement_finds_the_exact_maximum(eng):
     assert pairs <= stats["positions"] < 3 * pairs, stats
     screened = eng.score_matrix(ps, gs, rot, None, "fp16x1")
     assert ((screened - exact).abs() / exact.abs().clamp_min(1e-3)).max().item() > err  # the screen alone is looser
+
+
+def test_edge_cases_match_reference_vectors(eng, golden_edge):
+    """Dead (all-zero) and constant channels on either side, ReLU-like maps with flat halves, anti-correlated probes --
+    what real post-activation feature maps contain and the smooth synthetic fields avoid -- against vectors produced by
+    the unmodified reference (tests/golden/make_golden.py edge_cases).  A dead channel contributes exactly 0 on both
+    sides: the reference maps its 0/0 to 0 (similarity.py:69-70), the library packs an all-zero template (E == 0) and
+    zeroes the window norm where D <= 1e-10 * sum(g^2) (csrc/sir_pack.cu window_rnorm_kernel)."""
+    from oracle import compare as ocmp
+    from src.shoeprint_image_retrieval.similarity import compare_maps, get_similarity, last_result
+
+    ge = golden_edge
+    for i in range(int(ge["eg_count"])):
+        want = float(ge[f"eg{i}_out"])
+        got = float(get_similarity(ge[f"eg{i}_p"], ge[f"eg{i}_g"]))
+        assert abs(got - want) <= REL_TOL * max(abs(want), 1e-3), (i, got, want)
+    gallery = list(ge["ecmp_gallery"])
+    probes = [ge[f"ecmp_probe{q}"] for q in range(int(ge["ecmp_q"]))]
+    pairs = [int(x) for x in ge["ecmp_pairs"]]
+    rot = [float(x) for x in ge["ecmp_rot"]]
+    for precision in ("fp16_refine", "fp16_fp8c", "fp16x3"):
+        ranks = compare_maps(probes, gallery, pairs, {"comparison": {"n_processes": 1, "rotations": rot, "scales": None, "precision": precision}})
+        _check(last_result["scores"].cpu().numpy(), ge["ecmp_scores"])
+        for q in range(len(probes)):
+            lo, hi = ocmp.rank_interval(ge["ecmp_scores"][q], pairs[q])
+            assert lo <= ranks[q] <= hi
+
+
+def test_get_similarity_returns_negative_maxima(eng):
+    """A lone get_similarity call is not floored at 0 in the reference (similarity.py:106-108)."""
+    from oracle import ncc
+    from src.shoeprint_image_retrieval.similarity import get_similarity
+
+    rng = np.random.default_rng(5)
+    found = 0
+    for _ in range(4000):  # 2x3 templates over 2x2 cropped maps: now and then every position correlates negatively
+        p = rng.standard_normal((1, 6, 7)).astype(np.float32)
+        g = rng.standard_normal((1, 6, 6)).astype(np.float32)
+        want = ncc.get_similarity(p, g, method="direct")
+        if want < -0.05:
+            got = float(get_similarity(p, g))
+            assert abs(got - want) <= 1e-5, (got, want)
+            found += 1
+            if found == 3:
+                return
+    assert found > 0, "no all-negative surface drawn"
+
+
+@pytest.mark.parametrize("shape", [(80, 59, 21), (176, 50, 19)])
+def test_reference_shapes_against_the_cpu_oracle(eng, shape):
+    """3 probes x 4 gallery maps at the reference's full map shapes (FID-300 block 4, 800x300 block 6), every parity mode
+    against the float64 CPU oracle itself -- not against another GPU evaluation."""
+    from oracle import compare as ocmp
+    from src.shoeprint_image_retrieval import synth
+
+    c, h, w = shape
+    gallery = synth.make_gallery(101, 4, c, h, w)
+    probes, pairs = synth.make_probes(102, gallery, 3, min_frac=0.85)
+    _, want = ocmp.compare_maps_oracle(probes, gallery, pairs, [-5], None, method="fast")
+    for precision in ("fp16_refine", "fp16_fp8c", "fp16x3"):
+        ranks, scores, _ = eng.compare(probes, gallery, pairs, [-5], None, precision=precision)
+        _check(scores.cpu().numpy(), want)
+        for i in range(len(probes)):
+            lo, hi = ocmp.rank_interval(want[i], pairs[i])
+            assert lo <= ranks[i] <= hi
