@@ -177,7 +177,13 @@ int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uin
 int sir_gallery_pack_f32(const float* d_gallery, int G, int C, int hg, int wg, uint16_t* d_ghi, uint16_t* d_glo, int32_t* d_gexp,
                          float* d_gz, float* d_g32, void* stream);
 int sir_template_pack_screen(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
-                             uint16_t* d_thi, float* d_t32p, void* stream);
+                             uint16_t* d_thi, float* d_t32p, const int32_t* d_gather, void* stream);
+/* d_gather (NULL = none): index map [h*w] from sir_variant_index_map.  The maps handed to sir_template_pack_screen
+ * are then the UNROTATED source maps (same number of cells); cell i of the h x w variant the columns show is source
+ * cell d_gather[i] (-1 = 0, Pillow's fill).  sir_variant_index_map(h, w, angle, transpose, ...) writes the map of
+ * Image.rotate(angle) on an h x w map (similarity.py:267), composed with a transposition when `transpose` != 0 (the
+ * variant is then w x h).  The rotated / transposed variant maps never exist in HBM. */
+int sir_variant_index_map(int h, int w, double angle, int transpose, int32_t* d_map, void* stream);
 long long sir_ncc_screen_rec_count(int G, int Hp, int Wp, int ncols);
 int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
                    const uint16_t* d_thi, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe, float* d_approx,

@@ -279,16 +279,9 @@ struct RotateCoeffs {
   long long a0, a1, a2, a3, a4, a5;
 };
 
-__global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
-                                                     long long planes, RotateCoeffs rc) {
-  // The source index depends only on (y, x): compute it once per thread, then walk the planes
-  // (channels x maps) with it -- the gather is shared by all channels and all probes of that shape.
-  const int hw = h * w;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= hw) return;
-  const int y = p / w, x = p - y * w;
+// source cell (row major index into the h x w map) of output cell (y, x), -1 = outside (filled with 0)
+__device__ __forceinline__ int rotate_source(const RotateCoeffs& rc, int h, int w, int y, int x) {
   int sy, sx;
-  bool ok = true;
   switch (rc.mode) {
     case 0: sy = y; sx = x; break;
     case 1: sy = h - 1 - y; sx = w - 1 - x; break;
@@ -297,12 +290,35 @@ __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ i
     default: {
       const long long xs = (rc.a2 + rc.a1 * y + rc.a0 * x) >> 16;
       const long long ys = (rc.a5 + rc.a4 * y + rc.a3 * x) >> 16;
-      ok = xs >= 0 && xs < w && ys >= 0 && ys < h;
+      if (!(xs >= 0 && xs < w && ys >= 0 && ys < h)) return -1;
       sx = (int)xs;
       sy = (int)ys;
     }
   }
-  const int src = ok ? sy * w + sx : 0;
+  return sy * w + sx;
+}
+
+// The rotation (and, with `transpose`, the change of orientation the host asks for) as an index map: cell p of the
+// OUTPUT map ([h][w], or [w][h] when transposed) reads source cell map[p] of the unrotated [h][w] map, -1 = zero fill.
+// The template pack applies it while it loads a plane, so the rotated / transposed variant maps are never written.
+__global__ void __launch_bounds__(256) rotate_index_map_kernel(int* __restrict__ map, int h, int w, RotateCoeffs rc, int transpose) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= h * w) return;
+  const int y = transpose ? p % h : p / w, x = transpose ? p / h : p % w;  // (y, x) of the rotated h x w map this output cell shows
+  map[p] = rotate_source(rc, h, w, y, x);
+}
+
+__global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                     long long planes, RotateCoeffs rc) {
+  // The source index depends only on (y, x): compute it once per thread, then walk the planes
+  // (channels x maps) with it -- the gather is shared by all channels and all probes of that shape.
+  const int hw = h * w;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hw) return;
+  const int y = p / w, x = p - y * w;
+  const int srci = rotate_source(rc, h, w, y, x);
+  const bool ok = srci >= 0;
+  const int src = ok ? srci : 0;
   for (long long plane = blockIdx.y; plane < planes; plane += gridDim.y) {
     const float v = ok ? __ldg(in + plane * hw + src) : 0.0f;
     out[plane * hw + p] = v;
@@ -329,21 +345,35 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
                                                        int h_in, int w_in, int h_out, int w_out, int axis,
                                                        const int* __restrict__ xmin, const int* __restrict__ cnt,
                                                        const double* __restrict__ kk, int ksize) {
-  const size_t total = (size_t)planes * h_out * w_out;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t plane = i / ((size_t)h_out * w_out);
-    const int p = (int)(i - plane * (size_t)h_out * w_out);
-    const int y = p / w_out, x = p - y * w_out;
-    const float* src = in + plane * (size_t)h_in * w_in;
-    const int o = axis ? x : y;
-    const int lo = xmin[o], n = cnt[o];
-    const double* k = kk + (size_t)o * ksize;
-    double ss = 0.0;
-    for (int j = 0; j < n; ++j) {
-      const float px = axis ? src[(size_t)y * w_in + lo + j] : src[(size_t)(lo + j) * w_in + x];
-      ss = __dadd_rn(ss, __dmul_rn((double)px, k[j]));
+  // One thread owns one output cell (y, x) and walks the planes (blockIdx.y strided): the tap range and the weights of
+  // its output index are fetched once and kept in registers (bicubic enlargement has at most 5 taps; longer filters
+  // fall back to reading them per plane).
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, hw_out = h_out * w_out, hw_in = h_in * w_in;
+  if (p >= hw_out) return;
+  const int y = p / w_out, x = p - y * w_out;
+  const int o = axis ? x : y;
+  const int lo = xmin[o], n = cnt[o];
+  const double* k = kk + (size_t)o * ksize;
+  const int src0 = axis ? y * w_in + lo : lo * w_in + x, step = axis ? 1 : w_in;
+  if (n <= 6) {
+    double kr[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) kr[j] = j < n ? k[j] : 0.0;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+      const float* src = in + (size_t)plane * hw_in + src0;
+      double ss = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j < n) ss = __dadd_rn(ss, __dmul_rn((double)__ldg(src + j * step), kr[j]));
+      out[(size_t)plane * hw_out + p] = (float)ss;
     }
-    out[i] = (float)ss;
+  } else {
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+      const float* src = in + (size_t)plane * hw_in + src0;
+      double ss = 0.0;
+      for (int j = 0; j < n; ++j) ss = __dadd_rn(ss, __dmul_rn((double)__ldg(src + j * step), k[j]));
+      out[(size_t)plane * hw_out + p] = (float)ss;
+    }
   }
 }
 
@@ -352,24 +382,30 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
 __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restrict__ maps, int C, int h, int w, int Hb, int Wb, int col0,
                                                             int ncols_alloc, int row_align, __half* __restrict__ thi,
                                                             __half* __restrict__ tlo, float* __restrict__ t32,
-                                                            uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l, float* __restrict__ t32p) {
+                                                            uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l, float* __restrict__ t32p,
+                                                            const int* __restrict__ gather) {
   __shared__ double sred[32];
   const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm;
   const int rowk = tpl_row_taps(Wb, row_align), Kpad = tpl_kpad_aligned(Hb, Wb, row_align);
   const int oy = Hb / 2 - Hm / 2, ox = Wb / 2 - Wm / 2;
   const int n = blockIdx.x / C, c = blockIdx.x - n * C;
   const float* src = maps + ((size_t)n * C + c) * (size_t)h * w;
+  auto cell = [&](int i) -> float {  // cell i of the (rotated / transposed) map this column shows
+    if (!gather) return src[i];
+    const int gi = __ldg(gather + i);
+    return gi >= 0 ? src[gi] : 0.0f;
+  };
 
   double acc = 0.0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     const int u = i / Wm, v = i - u * Wm;
-    acc += (double)src[(u + kEdge) * w + v + kEdge];
+    acc += (double)cell((u + kEdge) * w + v + kEdge);
   }
   const float mean = (float)(block_sum(acc, sred) / (double)K);
   double e = 0.0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     const int u = i / Wm, v = i - u * Wm;
-    const double z = (double)(src[(u + kEdge) * w + v + kEdge] - mean);
+    const double z = (double)(cell((u + kEdge) * w + v + kEdge) - mean);
     e += z * z;
   }
   e = block_sum(e, sred);
@@ -380,7 +416,7 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
     const int ub = k / rowk, u = ub - oy, v = k - ub * rowk - ox;
     float tn = 0.0f;
     if (u >= 0 && u < Hm && v >= 0 && v < Wm) {
-      tn = (float)((double)(src[(u + kEdge) * w + v + kEdge] - mean) * inv);
+      tn = (float)((double)(cell((u + kEdge) * w + v + kEdge) - mean) * inv);
       if (t32) t32[col * K + u * Wm + v] = tn;
     }
     const float s = ldexpf(tn, kTemplateScaleLog2);
@@ -402,7 +438,7 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
                                                                  __half* __restrict__ thi,
                                                                  __half* __restrict__ tlo, float* __restrict__ t32,
                                                                  uint8_t* __restrict__ t8b, uint8_t* __restrict__ t8l,
-                                                                 float* __restrict__ t32p) {
+                                                                 float* __restrict__ t32p, const int* __restrict__ gather) {
   extern __shared__ float slab[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int Hm = h - 2 * kEdge, Wm = w - 2 * kEdge, K = Hm * Wm, HW = h * w;
@@ -415,7 +451,14 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
   for (long long pc = (long long)blockIdx.x * nw + wid; pc < planes; pc += (long long)gridDim.x * nw) {
     const int n = (int)(pc / C), c = (int)(pc - (long long)n * C);
     const float* src = maps + pc * HW;
-    for (int i = lane; i < HW; i += 32) ch[i] = __ldg(src + i);
+    if (gather) {  // the variant (rotation / transposition) is applied on the way in: no variant map in HBM
+      for (int i = lane; i < HW; i += 32) {
+        const int gi = __ldg(gather + i);
+        ch[i] = gi >= 0 ? __ldg(src + gi) : 0.0f;
+      }
+    } else {
+      for (int i = lane; i < HW; i += 32) ch[i] = __ldg(src + i);
+    }
     __syncwarp();
     double acc = 0.0;
     for (int o = lane; o < Hm * m8; o += 32) {
@@ -583,12 +626,9 @@ static double round15(double v) {
 }
 static long long fix16(double v) { return (long long)std::floor(v * 65536.0 + 0.5); }
 
-extern "C" int sir_variant_rotate(const float* d_in, int N, int C, int h, int w, double angle, float* d_out,
-                                  void* stream) {
-  SIR_CHECK_ARG(d_in && d_out, "sir_variant_rotate: null pointer");
-  SIR_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0, "sir_variant_rotate: bad shape");
-  SIR_CHECK_ARG(h < 32768 && w < 32768, "sir_variant_rotate: map too large for the 16.16 fixed point walk");
-  RotateCoeffs rc{};
+// Pillow's rotate set-up (Image.rotate -> affine_fixed): mode + 16.16 fixed point coefficients for an h x w map.
+static int rotate_coeffs(int h, int w, double angle, sir::RotateCoeffs* out) {
+  sir::RotateCoeffs rc{};
   double a = std::fmod(angle, 360.0);
   if (a < 0) a += 360.0;  // Python's % on floats
   if (a == 0.0) rc.mode = 0;
@@ -608,6 +648,18 @@ extern "C" int sir_variant_rotate(const float* d_in, int N, int C, int h, int w,
     rc.a2 = fix16(m2 + m0 * 0.5 + m1 * 0.5);
     rc.a5 = fix16(m5 + m3 * 0.5 + m4 * 0.5);
   }
+  *out = rc;
+  return SIR_OK;
+}
+
+extern "C" int sir_variant_rotate(const float* d_in, int N, int C, int h, int w, double angle, float* d_out,
+                                  void* stream) {
+  SIR_CHECK_ARG(d_in && d_out, "sir_variant_rotate: null pointer");
+  SIR_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0, "sir_variant_rotate: bad shape");
+  SIR_CHECK_ARG(h < 32768 && w < 32768, "sir_variant_rotate: map too large for the 16.16 fixed point walk");
+  RotateCoeffs rc{};
+  int rcode = rotate_coeffs(h, w, angle, &rc);
+  if (rcode) return rcode;
   const long long planes = (long long)N * C;
   const unsigned bx = (unsigned)ceil_div(h * w, 256);
   const unsigned by = (unsigned)std::min<long long>(planes, std::max(1u, 148u * 16u / bx));
@@ -685,9 +737,9 @@ int run_pass(const float* in, float* out, int planes, int h_in, int w_in, int h_
   SIR_CUDA(cudaMemcpyAsync(d_xmin, c.xmin.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice, st));
   SIR_CUDA(cudaMemcpyAsync(d_cnt, c.cnt.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice, st));
   SIR_CUDA(cudaMemcpyAsync(d_kk, c.kk.data(), sizeof(double) * c.kk.size(), cudaMemcpyHostToDevice, st));
-  const size_t total = (size_t)planes * h_out * w_out;
-  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
-  resample_kernel<<<blocks, 256, 0, st>>>(in, out, planes, h_in, w_in, h_out, w_out, axis, d_xmin, d_cnt, d_kk, c.ksize);
+  const unsigned bx = (unsigned)ceil_div(h_out * w_out, 256);
+  const unsigned by = (unsigned)std::min<long long>(planes, std::max(1u, 148u * 16u / bx));
+  resample_kernel<<<dim3(bx, by), 256, 0, st>>>(in, out, planes, h_in, w_in, h_out, w_out, axis, d_xmin, d_cnt, d_kk, c.ksize);
   SIR_LAUNCH_CHECK("resample_kernel");
   SIR_CUDA(cudaFreeAsync(d_xmin, st));
   SIR_CUDA(cudaFreeAsync(d_cnt, st));
@@ -719,16 +771,17 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
 extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }
 
 static void launch_template_pack(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc, int row_align,
-                                 __half* thi, __half* tlo, float* t32, uint8_t* t8b, uint8_t* t8l, cudaStream_t st, float* t32p = nullptr) {
+                                 __half* thi, __half* tlo, float* t32, uint8_t* t8b, uint8_t* t8l, cudaStream_t st, float* t32p = nullptr,
+                                 const int* gather = nullptr) {
   const size_t slab = (size_t)h * w * sizeof(float);
   if (8 * slab <= 48 * 1024) {
     const long long planes = (long long)N * C;
     const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 148 * 8);
     template_pack_warp_kernel<<<blocks, 256, 8 * slab, st>>>(d_maps, planes, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32,
-                                                             t8b, t8l, t32p);
+                                                             t8b, t8l, t32p, gather);
   } else {
     template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, st>>>(d_maps, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32, t8b,
-                                                                    t8l, t32p);
+                                                                    t8l, t32p, gather);
   }
 }
 
@@ -790,19 +843,30 @@ extern "C" int sir_template_pack_embed(const float* d_maps, int N, int C, int h,
   return SIR_OK;
 }
 
+// Index map of a rotation (+ optional transposition) for sir_template_pack_screen's d_gather.
+extern "C" int sir_variant_index_map(int h, int w, double angle, int transpose, int32_t* d_map, void* stream) {
+  SIR_CHECK_ARG(d_map && h > 0 && w > 0 && h < 32768 && w < 32768, "sir_variant_index_map: bad argument");
+  RotateCoeffs rc{};
+  int rcode = rotate_coeffs(h, w, angle, &rc);
+  if (rcode) return rcode;
+  rotate_index_map_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(d_map, h, w, rc, transpose ? 1 : 0);
+  SIR_LAUNCH_CHECK("rotate_index_map_kernel");
+  return SIR_OK;
+}
+
 // Screen + refine operands (SIR_PREC_FP16_REFINE): d_thi as sir_template_pack (rows padded to 8 taps) for the tensor-core
 // screening pass and d_t32p [C][ncols_alloc][Kpad] float32 = (t - mean)/sqrt(E) * 2^10 in the same padded K layout for the
 // exact re-evaluation.  Hb x Wb >= the true template shape selects a bucket layout (anchor on anchor, zeros elsewhere) as in
 // sir_template_pack_embed; pass the true shape for a single-shape block.
 extern "C" int sir_template_pack_screen(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
-                                        uint16_t* d_thi, float* d_t32p, void* stream) {
+                                        uint16_t* d_thi, float* d_t32p, const int32_t* d_gather, void* stream) {
   SIR_CHECK_ARG(d_maps && d_thi && d_t32p, "sir_template_pack_screen: null pointer");
   SIR_CHECK_ARG(N > 0 && C > 0 && h > 2 * kEdge && w > 2 * kEdge, "sir_template_pack_screen: bad input shape");
   SIR_CHECK_ARG(Hb >= h - 2 * kEdge && Wb >= w - 2 * kEdge, "sir_template_pack_screen: bucket %dx%d smaller than template %dx%d", Hb, Wb,
                 h - 2 * kEdge, w - 2 * kEdge);
   SIR_CHECK_ARG(col0 >= 0 && col0 + N <= ncols_alloc, "sir_template_pack_screen: columns [%d,%d) outside %d", col0, col0 + N, ncols_alloc);
   launch_template_pack(d_maps, N, C, h, w, Hb, Wb, col0, ncols_alloc, 8, (__half*)d_thi, nullptr, nullptr, nullptr, nullptr,
-                       (cudaStream_t)stream, d_t32p);
+                       (cudaStream_t)stream, d_t32p, d_gather);
   SIR_LAUNCH_CHECK("template_pack_kernel");
   return SIR_OK;
 }

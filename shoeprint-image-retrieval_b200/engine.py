@@ -463,10 +463,45 @@ def make_variant(maps: torch.Tensor, rot: float | None, scale: float | None) -> 
 # --------------------------------------------------------------------------- scoring
 
 @dataclass
+class _Variant:
+    """Columns of one (probe group, variant).  ``maps [n,C,h,w]`` is the variant itself, or -- when ``rot`` is set -- the
+    UNROTATED maps: a rotation keeps the shape and is a pure gather (similarity.py:267, Pillow nearest), so the screening
+    mode lets the template pack apply it on the way in (``sir_variant_index_map``) and the rotated maps are never written."""
+
+    maps: torch.Tensor
+    rot: float | None = None
+
+    @property
+    def n(self) -> int:
+        return int(self.maps.shape[0])
+
+    def materialised(self) -> torch.Tensor:
+        return self.maps if self.rot is None else make_variant(self.maps, self.rot, None)
+
+
+_index_maps: dict = {}
+
+
+def _gather_map(dev, h: int, w: int, rot: float | None, flip: bool) -> torch.Tensor | None:
+    """Device index map of (rotation, transposition) for an ``h x w`` source map; None when it is the identity."""
+    if rot is None and not flip:
+        return None
+    key = (dev.index, h, w, 0.0 if rot is None else float(rot), flip)
+    if key not in _index_maps:
+        if len(_index_maps) > 256:
+            _index_maps.clear()
+        m = torch.empty(h * w, dtype=torch.int32, device=dev)
+        nat.check(nat.lib.sir_variant_index_map(h, w, key[3], 1 if flip else 0, _ptr(m), _stream()), "sir_variant_index_map")
+        launch_counter.add()
+        _index_maps[key] = m
+    return _index_maps[key]
+
+
+@dataclass
 class _Block:
     """Pending columns of one template shape."""
 
-    maps: list[torch.Tensor] = field(default_factory=list)
+    maps: list[_Variant] = field(default_factory=list)
     ids: list[torch.Tensor] = field(default_factory=list)
     ncols: int = 0
 
@@ -496,19 +531,18 @@ def _score_block(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperan
         if best_cost == float("inf"):
             raise nat.SirError(f"template {hm}x{wm} does not fit any shared-memory plan of the correlation kernel")
         plans.setdefault(best, []).append((ops, g0))
-    tblock = None
     for (mode, flip), members in plans.items():
-        if flip:
-            if tblock is None:
-                tblock = _Block([transpose_maps(m) for m in block.maps], block.ids, block.ncols)
-            _score_block_oriented(tblock, (w, h), [o.transposed() for o, _ in members], [g for _, g in members], scores, mode, approx)
-        else:
-            _score_block_oriented(block, (h, w), [o for o, _ in members], [g for _, g in members], scores, mode, approx)
+        ops = [o.transposed() if flip else o for o, _ in members]
+        _score_block_oriented(block, (h, w), flip, ops, [g for _, g in members], scores, mode, approx)
 
 
-def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[GalleryOperands], offsets: list[int],
+def _score_block_oriented(block: _Block, hw: tuple[int, int], flip: bool, gallery: list[GalleryOperands], offsets: list[int],
                           scores: torch.Tensor, precision: int, approx: torch.Tensor | None = None) -> None:
-    h, w = hw
+    """``hw``: shape of the block's variants as the caller holds them; ``flip``: the launch works on transposed maps
+    (``gallery`` already is).  The screening mode packs straight from the source maps through an index map; the other
+    modes materialise the rotated / transposed variant first."""
+    h0, w0 = hw
+    h, w = (w0, h0) if flip else (h0, w0)
     hm, wm = h - 2 * EDGE, w - 2 * EDGE
     dev = scores.device
     c = gallery[0].C
@@ -526,12 +560,18 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], gallery: list[Gall
     t8l = torch.empty_like(t8b) if fp8c else None
     t32 = torch.empty((c, ncols, hm * wm), dtype=torch.float32, device=dev) if simt else None
     col0 = 0
-    for m in block.maps:
-        n = int(m.shape[0])
+    for var in block.maps:
+        n = var.n
         if refine:
-            nat.check(nat.lib.sir_template_pack_screen(_ptr(m), n, c, h, w, hm, wm, col0, ncols, _ptr(thi), _ptr(t32p), _stream()),
-                      "sir_template_pack_screen")
-        elif fp8c:
+            nat.check(nat.lib.sir_template_pack_screen(_ptr(var.maps), n, c, h, w, hm, wm, col0, ncols, _ptr(thi), _ptr(t32p),
+                                                       _ptr(_gather_map(dev, h0, w0, var.rot, flip)), _stream()), "sir_template_pack_screen")
+            launch_counter.add()
+            col0 += n
+            continue
+        m = var.materialised()
+        if flip:
+            m = transpose_maps(m)
+        if fp8c:
             nat.check(
                 nat.lib.sir_template_pack_fp8c(_ptr(m), n, c, h, w, col0, ncols, _ptr(thi), _ptr(t8b), _ptr(t8l), _stream()),
                 "sir_template_pack_fp8c",
@@ -657,7 +697,10 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
     c = gops.C
     oriented = []
     for (h, w), blk in members:
-        maps = [transpose_maps(m) for m in blk.maps] if flip else blk.maps
+        if refine:  # packed straight from the source maps through an index map (rotation, transposition)
+            maps = [(v.maps, _gather_map(dev, h, w, v.rot, flip)) for v in blk.maps]
+        else:
+            maps = [(transpose_maps(v.materialised()) if flip else v.materialised(), None) for v in blk.maps]
         oriented.append(((w, h) if flip else (h, w), maps, blk))
     hb = max(hw[0] for hw, _, _ in oriented) - 2 * EDGE
     wb = max(hw[1] for hw, _, _ in oriented) - 2 * EDGE
@@ -684,10 +727,10 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
     for ((h, w), maps, blk), rn in zip(oriented, tables):
         hm, wm = h - 2 * EDGE, w - 2 * EDGE
         start = col0
-        for m in maps:
+        for m, gmap in maps:
             n = int(m.shape[0])
             if refine:
-                nat.check(nat.lib.sir_template_pack_screen(_ptr(m), n, c, h, w, hb, wb, col0, ncols, _ptr(thi), _ptr(t32p), _stream()),
+                nat.check(nat.lib.sir_template_pack_screen(_ptr(m), n, c, h, w, hb, wb, col0, ncols, _ptr(thi), _ptr(t32p), _ptr(gmap), _stream()),
                           "sir_template_pack_screen")
             else:
                 nat.check(nat.lib.sir_template_pack_embed(_ptr(m), n, c, h, w, hb, wb, col0, ncols, mode, _ptr(thi), _ptr(tlo), _ptr(t8b),
@@ -801,15 +844,18 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
         for s0 in range(0, n_grp, col_block):  # a group wider than a column block is cut, so no block exceeds the cap
             part = grp.maps[s0 : s0 + col_block]
             for rot, scale in plan:
-                v = make_variant(part, rot, scale)
-                key = (int(v.shape[2]), int(v.shape[3]))
+                if prec == nat.PREC_FP16_REFINE and scale is None:
+                    v = _Variant(part, rot)  # a rotation alone is applied by the template pack's gather
+                else:
+                    v = _Variant(make_variant(part, rot, scale))
+                key = (int(v.maps.shape[2]), int(v.maps.shape[3]))
                 blk = pending.setdefault(key, _Block())
-                if blk.ncols and blk.ncols + int(v.shape[0]) > col_block:
+                if blk.ncols and blk.ncols + v.n > col_block:
                     flush(blk, key)
                     blk = pending[key] = _Block()
                 blk.maps.append(v)
                 blk.ids.append(grp.ids[s0 : s0 + col_block])
-                blk.ncols += int(v.shape[0])
+                blk.ncols += v.n
         # all variants of this group are in: blocks wide enough to run efficiently go now (the next group may still be
         # on its way from the host), narrow ones keep collecting columns
         if len(probes.groups) > 1:
