@@ -163,6 +163,42 @@ def main() -> None:
     np.savez_compressed(OUT / "reference_vectors.npz", **out)
     print("wrote", OUT / "reference_vectors.npz", sum(v.nbytes for v in out.values()), "bytes raw")
     edge_cases()
+    loader_cases()
+
+
+def loader_cases() -> None:
+    """Third file: what the reference's Dataloader (dataloader.py:29-469) hands to the hot path for two generated
+    FID-300-shaped directories -- per cluster its scale, backbone block, file list, matching pairs and the loaded
+    (cropped, LANCZOS-resized) uint8 images."""
+    import hashlib
+    import tempfile
+
+    from src.shoeprint_image_retrieval.dataloader import Dataloader as RefLoader
+
+    sys.path.insert(0, str(OUT))
+    import synth_dataset
+
+    out: dict[str, np.ndarray] = {}
+    for name, seed, gsizes, qsizes, n_clusters in synth_dataset.CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            root = Path(tmp) / name
+            synth_dataset.write_dataset(root, seed, gsizes, qsizes)
+            loader = RefLoader(synth_dataset.config_for(root, n_clusters))
+            out[f"ld_{name}_nclusters"] = np.array(loader.num_clusters)
+            out[f"ld_{name}_scales"] = np.array(loader.scales, dtype=np.float64)
+            out[f"ld_{name}_blocks"] = np.array(loader.blocks, dtype=np.int64)
+            for k, (marks, prints, pairs, block) in enumerate(loader):
+                out[f"ld_{name}_c{k}_files"] = np.array(sorted(loader.clusters[k]))
+                out[f"ld_{name}_c{k}_pairs"] = np.array(pairs, dtype=np.int64)
+                out[f"ld_{name}_c{k}_block"] = np.array(block)
+                out[f"ld_{name}_c{k}_mark0"], out[f"ld_{name}_c{k}_print0"] = marks[0], prints[0]
+                digest = hashlib.sha256()
+                for im in list(marks) + list(prints):
+                    digest.update(repr(im.shape).encode() + np.ascontiguousarray(im).tobytes())
+                out[f"ld_{name}_c{k}_sha256"] = np.array(digest.hexdigest())
+                out[f"ld_{name}_c{k}_counts"] = np.array([len(marks), len(prints)])
+    np.savez_compressed(OUT / "reference_loader.npz", **out)
+    print("wrote", OUT / "reference_loader.npz", {k: v.tolist() for k, v in out.items() if k.endswith(("scales", "blocks", "nclusters"))})
 
 
 def edge_cases() -> None:

@@ -111,3 +111,44 @@ def test_feature_map_list_is_a_plain_list_without_device_copies():
     assert isinstance(maps, list) and len(maps) == 2 and maps.device_copies() is None
     for clone in (pickle.loads(pickle.dumps(maps)), copy.deepcopy(maps)):
         assert type(clone) is list and len(clone) == 2 and np.array_equal(clone[1], maps[1])
+
+
+@pytest.mark.parametrize("case", ["one", "two"])
+def test_dataloader_matches_the_reference_loader(tmp_path, case):
+    """What the loader hands to the hot path -- clusters, per-cluster scale and backbone block (incl. the reference's
+    _image_extremes quirks), matching pairs and the cropped / LANCZOS-resized uint8 images -- against
+    vectors recorded from the reference's own Dataloader on the same generated directories
+    (tests/golden/make_golden.py loader_cases; dataloader.py:29-469)."""
+    import hashlib
+    import sys
+
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import synth_dataset
+
+    from src.shoeprint_image_retrieval.dataloader import Dataloader
+
+    with np.load(ROOT / "tests" / "golden" / "reference_loader.npz") as z:
+        want = {k: z[k] for k in z.files}
+    name, seed, gsizes, qsizes, n_clusters = next(c for c in synth_dataset.CASES if c[0] == case)
+    root = tmp_path / name
+    synth_dataset.write_dataset(root, seed, gsizes, qsizes)
+    loader = Dataloader(synth_dataset.config_for(root, n_clusters))
+    assert loader.num_clusters == int(want[f"ld_{name}_nclusters"])
+    got = {}
+    for k, (marks, prints, pairs, block) in enumerate(loader):
+        digest = hashlib.sha256()
+        for im in list(marks) + list(prints):
+            digest.update(repr(im.shape).encode() + np.ascontiguousarray(im).tobytes())
+        got[tuple(sorted(loader.clusters[k]))] = (float(loader.scales[k]), int(block), list(pairs), marks[0], prints[0], digest.hexdigest(),
+                                                 [len(marks), len(prints)])
+    # the reference's KMeans is unseeded: clusters are matched by their file lists, not by their order
+    for k in range(loader.num_clusters):
+        files = tuple(str(f) for f in want[f"ld_{name}_c{k}_files"])
+        assert files in got, "cluster membership differs from the reference"
+        scale, block, pairs, mark0, print0, sha, counts = got[files]
+        assert scale == float(want[f"ld_{name}_scales"][k]) and block == int(want[f"ld_{name}_c{k}_block"])
+        assert pairs == [int(v) for v in want[f"ld_{name}_c{k}_pairs"]]
+        assert counts == [int(v) for v in want[f"ld_{name}_c{k}_counts"]]
+        np.testing.assert_array_equal(mark0, want[f"ld_{name}_c{k}_mark0"])
+        np.testing.assert_array_equal(print0, want[f"ld_{name}_c{k}_print0"])
+        assert sha == str(want[f"ld_{name}_c{k}_sha256"]), "loaded images differ from the reference loader's"
