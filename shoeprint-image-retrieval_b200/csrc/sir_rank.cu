@@ -45,6 +45,76 @@ __device__ __forceinline__ float key_value(unsigned long long key) {
   return __uint_as_float(u);
 }
 
+// Cuts buf[0..n) (n > k) to its k largest keys, unordered, and sets *thr to the smallest of them.  The k-th largest key
+// is found by 8-bit radix passes from the top (a 256-bin shared-memory histogram of the keys that still match the
+// prefix, a block scan from the top bin down); the walk stops as soon as the bin that holds the k-th key is needed
+// whole -- usually after two to four passes, never more than eight because keys are unique (they carry the index).
+// ~500 instructions per thread against ~2,600 for a bitonic sort of 2,048 keys.
+struct SelectScratch {
+  int hist[256];
+  int warp_tot[kRankWarps];
+  int bin, above, bin_cnt, kept_cnt;
+  unsigned long long kept_min;
+  unsigned long long tmp[kMaxTopK];
+};
+
+__device__ void select_cut(unsigned long long* buf, int n, int k, unsigned long long* thr, SelectScratch* sc) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned long long prefix = 0ull;
+  int need = k, shift = 56;
+  for (;; shift -= 8) {
+    sc->hist[tid] = 0;  // kRankThreads == 256 bins
+    __syncthreads();
+    for (int i = tid; i < n; i += kRankThreads) {
+      const unsigned long long key = buf[i];
+      if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&sc->hist[(int)((key >> shift) & 255ull)], 1);
+    }
+    __syncthreads();
+    // thread t owns bin 255 - t: inclusive prefix over t = number of matching keys in bins >= 255 - t
+    const int h = sc->hist[255 - tid];
+    int inc = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) sc->warp_tot[wid] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += sc->warp_tot[w];
+    inc += base;
+    if (inc >= need && inc - h < need) {  // exactly one thread: the bin that holds the need-th key from the top
+      sc->bin = 255 - tid;
+      sc->above = inc - h;
+      sc->bin_cnt = h;
+    }
+    __syncthreads();
+    prefix |= (unsigned long long)sc->bin << shift;
+    need -= sc->above;
+    const bool whole = sc->bin_cnt == need;  // every key of that bin is among the k best: the prefix is the boundary
+    __syncthreads();
+    if (whole || shift == 0) break;
+  }
+  // keep the keys >= prefix (exactly k of them)
+  if (tid == 0) {
+    sc->kept_cnt = 0;
+    sc->kept_min = ~0ull;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kRankThreads) {
+    const unsigned long long key = buf[i];
+    if (key >= prefix) {
+      const int pos = atomicAdd(&sc->kept_cnt, 1);
+      if (pos < kMaxTopK) sc->tmp[pos] = key;
+      atomicMin(&sc->kept_min, key);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += kRankThreads) buf[i] = sc->tmp[i];
+  if (tid == 0) *thr = sc->kept_min;
+  __syncthreads();
+}
+
 // sorts buf[0..n) descending (n <= kSelCap), keeps the first min(n, k) keys; returns the new count
 __device__ int select_compact(unsigned long long* buf, int n, int k, unsigned long long* thr) {
   int P = 1;
@@ -76,6 +146,7 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
                                                                  int32_t* __restrict__ count_gt, int32_t* __restrict__ count_ge,
                                                                  float* __restrict__ topk_val, int32_t* __restrict__ topk_idx) {
   __shared__ unsigned long long buf[kSelCap];
+  __shared__ SelectScratch scratch;
   __shared__ unsigned long long thr_s;
   __shared__ int cnt_s;
   __shared__ int red[2][kRankWarps];
@@ -126,7 +197,8 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
       __syncthreads();
       cnt = cnt_s;
       if (cnt > kSelCap - kSelChunk) {  // the next chunk could overflow: cut to the k best, raise the threshold
-        cnt = select_compact(buf, cnt, k, &thr_s);
+        select_cut(buf, cnt, k, &thr_s, &scratch);
+        cnt = k;
         if (threadIdx.x == 0) cnt_s = cnt;
         __syncthreads();
       }
@@ -138,8 +210,16 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
     red[0][wid] = gt;
     red[1][wid] = ge;
   }
-  if (k > 0) cnt = select_compact(buf, cnt_s, k, &thr_s);  // (also the barrier for red[])
-  else __syncthreads();
+  if (k > 0) {
+    cnt = cnt_s;
+    if (cnt > k) {
+      select_cut(buf, cnt, k, &thr_s, &scratch);
+      cnt = k;
+    }
+    cnt = select_compact(buf, cnt, k, &thr_s);  // order the (at most k) survivors; also the barrier for red[]
+  } else {
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     int a = 0, b = 0;
     for (int w = 0; w < kRankWarps; ++w) {
