@@ -18,6 +18,8 @@ A pair = one (probe, gallery print), all its variants included.
              FLOPs / mean launch time, from CUDA events around every launch
 * ``cpu_baseline`` the UNMODIFIED reference (``baseline/_ref``, its ``_comparison_worker`` in one forked
              process per host core; the oracle port when that copy is absent) on a bounded sample
+* ``config0`` BASELINE configs[0]: the default run.toml on a FID-300-shaped set (300 ragged probes x 1,175 gallery x 25
+             variants) through ``compare_maps`` -- the multi-shape bucket path real data takes (N = 1 only)
 * ``config4`` BASELINE configs[3]: 1,000 probes x 12,500 on-device gallery maps of 80x59x21 PER GPU (at N = 8
              that is the 1,000 x 100,000 target), V = 1 and V = 13, with the NCCL merge timed phase by phase
 * ``precision_study`` BASELINE configs[4]: 176x68x132 maps (1024x2048 inputs), every precision mode against the
@@ -380,6 +382,44 @@ def config4_block(args, world: int, rank: int, dist, torch) -> dict | None:
     return out if rank == 0 else None
 
 
+def config0_block(args) -> dict:
+    """BASELINE configs[0] / [2] shape of work: the default run.toml on a FID-300-shaped set -- 300 RAGGED probes (every probe
+    its own template shape, crops of 40-100 % of a print) x 1,175 gallery maps of 80x59x21 x 25 variants (7 rotations and
+    3 scales in the reference's combination), through ``similarity.compare_maps`` from host lists.  This is
+    the multi-shape bucket path (sir_template_pack_screen with a bucket layout + one window-norm table per 16 columns)."""
+    import torch
+
+    from src.shoeprint_image_retrieval import engine, similarity, synth
+
+    q, g, c, h, w = 300, 1175, 80, 59, 21
+    rot, scl = [-15, -9, -3, 3, 9, 15, 180], [1.02, 1.04, 1.08]
+    gallery = synth.make_gallery(1, g, c, h, w)
+    probes, pairs = synth.make_probes(2, gallery, q, min_frac=0.4)
+    cfg = {"comparison": {"n_processes": 1, "rotations": rot, "scales": scl, "precision": args.precision}}
+    # algorithmic work: 2*C*(gallery positions)*(template taps) per (variant, pair), template taps of the variant's true shape
+    taps = 0
+    for pm in probes:
+        for r, sc in engine.variant_plan(rot, scl):
+            hh, ww = pm.shape[1:]
+            if sc is not None:
+                hh, ww = engine.scaled_size(hh, ww, sc)
+            taps += (hh - 4) * (ww - 4)
+    flops = 2.0 * c * (h - 4) * (w - 4) * taps * g
+    times = []
+    for _ in range(2):
+        sink = io.StringIO()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):
+            ranks = similarity.compare_maps(probes, gallery, pairs, cfg)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = min(times)
+    return {"workload": "configs[0]: default run.toml, FID-300 shape, 300 ragged probes x 1,175 gallery x 25 variants, host lists through compare_maps",
+            "pairs_per_s": q * g / dt, "seconds": dt, "tflops_algorithmic_whole_pass": flops / dt / 1e12,
+            "template_shapes": len({p_.shape for p_ in probes}), "rank1_share": float((ranks == 1).mean())}
+
+
 def precision_block(args, world: int, rank: int, dist, torch) -> dict | None:
     """BASELINE configs[4]: 176x68x132 maps (1024x2048 inputs), 64 probes x 1,250 gallery maps per GPU (10,000 over 8).
     Every precision mode: pairs/s and max / mean relative score error against the float32 CUDA-core evaluation on a
@@ -559,6 +599,7 @@ def run_b200(args) -> None:
 
     c4 = config4_block(args, world, rank, dist, torch) if not args.no_config4 else None
     c5 = precision_block(args, world, rank, dist, torch) if not args.no_precision_study else None
+    c0 = config0_block(args) if (rank == 0 and world == 1 and not args.no_config4 and not args.quick) else None
     feat = feature_stage_numbers(args) if (rank == 0 and not args.no_features) else None
 
     if rank == 0:
@@ -597,6 +638,7 @@ def run_b200(args) -> None:
                        "positions_per_pair": rstats["positions"] / (args.steps * q_total * g_local) if rstats["positions"] else None,
                        "dense_records_per_step": rstats["dense_records"] / args.steps},
             "cpu_baseline": cb,
+            "config0": c0,
             "config4": c4,
             "precision_study": c5,
             "feature_stage": feat,

@@ -160,9 +160,7 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
   __syncthreads();
   const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
   int gt = 0, ge = 0, cnt = 0;
-  for (int base = 0; base < G; base += kSelChunk) {
-    const int i0 = base + 4 * threadIdx.x;
-    float v[4];
+  auto load4 = [&](int i0, float (&v)[4]) {
     if (aligned && i0 + 3 < G) {
       const float4 f = __ldg(reinterpret_cast<const float4*>(row + i0));
       v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
@@ -170,6 +168,15 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = (i0 + j < G) ? __ldg(row + i0 + j) : 0.0f;
     }
+  };
+  float vn[4];
+  load4(4 * threadIdx.x, vn);
+  for (int base = 0; base < G; base += kSelChunk) {
+    const int i0 = base + 4 * threadIdx.x;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = vn[j];
+    if (base + kSelChunk < G) load4(i0 + kSelChunk, vn);  // the next chunk is in flight across the barrier below
     const unsigned long long thr = thr_s;
     const float thr_v = key_value(thr);
 #pragma unroll
@@ -236,6 +243,56 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
   }
 }
 
+// k == 0: counts only -- no candidate buffer, so many rows are resident per SM and four 16-byte loads are in flight per thread.
+__global__ void __launch_bounds__(kRankThreads) rank_count_kernel(const float* __restrict__ scores, int Q, int G, int ld,
+                                                                  const float* __restrict__ true_score, int32_t* __restrict__ count_gt,
+                                                                  int32_t* __restrict__ count_ge) {
+  __shared__ int red[2][kRankWarps];
+  const int q = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float* row = scores + (size_t)q * ld;
+  const float ts = true_score[q];
+  int gt = 0, ge = 0, g = 0;
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const int nvec = G / 4;
+    const float4* rv = reinterpret_cast<const float4*>(row);
+    for (int base = 0; base < nvec; base += 4 * kRankThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * kRankThreads + threadIdx.x;
+        v[u] = i < nvec ? __ldg(rv + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        gt += (v[u].x > ts) + (v[u].y > ts) + (v[u].z > ts) + (v[u].w > ts);
+        ge += (v[u].x >= ts) + (v[u].y >= ts) + (v[u].z >= ts) + (v[u].w >= ts);
+      }
+    }
+    g = nvec * 4;
+  }
+  for (int i = g + threadIdx.x; i < G; i += kRankThreads) {
+    const float v = __ldg(row + i);
+    gt += v > ts;
+    ge += v >= ts;
+  }
+  gt = warp_sum(gt);
+  ge = warp_sum(ge);
+  if (lane == 0) {
+    red[0][wid] = gt;
+    red[1][wid] = ge;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int w = 0; w < kRankWarps; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    count_gt[q] = a;
+    count_ge[q] = b;
+  }
+}
+
 // K9 final step: [P][Q][k] gathered lists -> global [Q][k].  Empty slots carry idx -1 / -inf.
 __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int P,
                                                          int Q, int k, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
@@ -298,8 +355,12 @@ extern "C" int sir_rank_topk(const float* d_scores, int Q, int G, int score_ld, 
   SIR_CHECK_ARG(Q > 0 && G > 0 && score_ld >= G, "sir_rank_topk: bad shape Q=%d G=%d ld=%d", Q, G, score_ld);
   SIR_CHECK_ARG(k >= 0 && k <= kMaxTopK, "sir_rank_topk: k=%d outside [0,%d]", k, kMaxTopK);
   SIR_CHECK_ARG(k == 0 || (d_topk_val && d_topk_idx), "sir_rank_topk: k>0 needs output lists");
-  rank_topk_kernel<<<Q, kRankThreads, 0, (cudaStream_t)stream>>>(d_scores, Q, G, score_ld, d_true_score, g0, k,
-                                                                 d_count_gt, d_count_ge, d_topk_val, d_topk_idx);
+  if (k == 0) {
+    rank_count_kernel<<<Q, kRankThreads, 0, (cudaStream_t)stream>>>(d_scores, Q, G, score_ld, d_true_score, d_count_gt, d_count_ge);
+  } else {
+    rank_topk_kernel<<<Q, kRankThreads, 0, (cudaStream_t)stream>>>(d_scores, Q, G, score_ld, d_true_score, g0, k,
+                                                                   d_count_gt, d_count_ge, d_topk_val, d_topk_idx);
+  }
   SIR_LAUNCH_CHECK("rank_topk_kernel");
   return SIR_OK;
 }
