@@ -167,7 +167,8 @@ int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uin
  * (caller zeroes it first).  tau must cover twice the screening error.  d_rnorm (one template shape) or d_rnorm_tab
  * (multi-shape bucket, one table pointer per 16-column chunk as in sir_ncc_scores_multi): exactly one is non-NULL;
  * Hb x Wb is the K layout of the packed templates (= Hm x Wm for a single shape), rows padded to 8 taps.
- * d_stats: NULL or 4 device counters ([0] positions evaluated, [1] records with more than 3 rows, [2] tiles with
+ * variants_hint: about how many columns of the block belong to one probe (>= 1; sizes the refinement's tiles: with V
+ * variants roughly one (column, gallery) cell in V has a candidate).  d_stats: NULL or 4 device counters ([0] positions evaluated, [1] records with more than 3 rows, [2] tiles with
  * work), accumulated.  sir_ncc_screen_rec_count: number of 8-byte records d_rec must hold.
  *
  * sir_gallery_pack_f32: sir_gallery_pack that also writes d_g32 [G][C][Hp][WP] float32 = (g - mean) * 2^e, rows
@@ -191,7 +192,7 @@ int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const float* con
 int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
                    const float* d_t32p, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe,
                    const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel, float tau_abs, const void* d_rec,
-                   unsigned long long* d_stats, void* stream);
+                   int variants_hint, unsigned long long* d_stats, void* stream);
 /* cudaMemsetAsync(d_ptr, 0, bytes) on `stream`: the path zeroes its score / operand buffers through the library. */
 int sir_memset_zero(void* d_ptr, size_t bytes, void* stream);
 

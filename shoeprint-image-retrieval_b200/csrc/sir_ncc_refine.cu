@@ -13,14 +13,19 @@
 // maximum is always among the candidates; if it ever were not, the result would still be an exactly evaluated
 // correlation value within 2 * (screening error) of the true maximum.
 //
-// One CTA owns a tile of TN columns x TG gallery prints.  Per channel the tile's template columns and gallery
-// planes that have work are staged in shared memory by plain bulk copies (cp.async.bulk, one per plane, issued by
-// a producer warp, lanes in parallel, into a two-stage ring guarded by full/empty mbarriers: channel c+1 lands while
-// channel c is being multiplied), so every operand byte is read once per tile instead of once per candidate.  Each
-// of the eight consumer warps takes one candidate at a time, lanes spread over (template row, tap); template rows
-// that only meet the "same"-mode zero padding are skipped.  The work list is built without
-// atomics (block scan over per-thread counts): every run evaluates the same candidates in the same order.
+// Every position needs a template plane and a gallery plane per channel (~6 KB for ~700 multiply-adds), so what
+// the kernel has to organise is operand reuse.  One CTA owns TN columns x TGB gallery prints.  Per channel the
+// template planes of its columns that have work are staged ONCE (double buffered over channels) and the gallery
+// planes stream past them in sub-chunks of TGS prints through a small ring -- plain bulk copies (cp.async.bulk, one
+// per plane, issued by the lanes of a producer warp), full/empty mbarriers, no block barrier in the loop.  With
+// several variants per probe only about one (column, gallery) cell in ten has a candidate, so a gallery plane is
+// shared by ~TN/10 positions and a template plane by all its column's positions; with one variant every cell has
+// one.  Sixteen consumer warps take one position at a time, lanes spread over (template row, tap); template rows
+// that only meet the "same"-mode zero padding are skipped.  The work list is built without atomics (block scan over
+// per-thread counts, in gallery-major order so that a sub-chunk's positions are contiguous): every run evaluates the
+// same candidates in the same order.
 #include <algorithm>
+#include <cstdlib>
 
 #include "sir_common.cuh"
 #include "sir_ptx.cuh"
@@ -29,7 +34,9 @@ namespace sir {
 
 constexpr int kRefWarps = 16;                      // consumer warps (one candidate position at a time each)
 constexpr int kRefThreads = 32 * (kRefWarps + 1);  // + one producer warp issuing the bulk copies
-constexpr int kRefStages = 2;
+constexpr int kRefMaxStages = 4;                   // gallery sub-chunk ring (depth chosen by the host)
+constexpr int kRefMaxSub = 128;                    // sub-chunks per tile
+constexpr int kRefMaxTgb = 2048;                   // gallery prints per tile
 
 struct RefineParams {
   const float* g32;
@@ -42,7 +49,7 @@ struct RefineParams {
   const uint2* rec;
   unsigned long long* stats;  // optional: [0] positions evaluated, [1] records that listed more than 3 rows, [2] tiles with work
   int G, C, Hp, Wp, WP, Hb, Wb, rowk, Kpad, ncols, ncols_alloc, npx, NP, score_ld, g0;
-  int TN, TG, cap, tiles_g;
+  int TN, TGS, TGB, NS, ST, cap, tiles_g;
   int vl, ru, rv;  // lane mapping: vl lanes along a template row, the 32 / vl lane groups split ru ways over rows, rv ways over row chunks
   float tau_rel, tau_abs, inv_scale;
 };
@@ -69,24 +76,27 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* to
 
 __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefineParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int PG = p.Hp * p.WP;                           // cells of one packed gallery plane
-  const size_t buf_floats = (size_t)p.TN * p.Kpad + (size_t)p.TG * PG;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // full[kRefStages], empty[kRefStages]
-  float* bufs = reinterpret_cast<float*>(smem_raw + 128);           // [kRefStages][ [TN][Kpad] + [TG][PG] ]
-  uint2* list = reinterpret_cast<uint2*>(bufs + kRefStages * buf_floats);  // [cap] (j | i << 8, y | x << 16)
+  const int PG = p.Hp * p.WP;                                      // cells of one packed gallery plane
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // full_g[ST], empty_g[ST], empty_t[2]
+  float* tplbuf = reinterpret_cast<float*>(smem_raw + 128);         // [2][TN][Kpad]   templates of channel c in buffer c & 1
+  float* galbuf = tplbuf + 2 * (size_t)p.TN * p.Kpad;               // [ST][TGS][PG]
+  uint2* list = reinterpret_cast<uint2*>(galbuf + (size_t)p.ST * p.TGS * PG);  // [cap] (j | i << 8, y | x << 16)
   float* acc = reinterpret_cast<float*>(list + p.cap);              // [cap]
-  int* flags = reinterpret_cast<int*>(acc + p.cap);                 // [TN + TG]
-  int* scratch = flags + p.TN + p.TG;                               // [warps]
+  int* flags = reinterpret_cast<int*>(acc + p.cap);                 // [TN + TGB]
+  int* seg = flags + p.TN + p.TGB;                                  // [NS + 1] first list entry of every sub-chunk
+  int* scratch = seg + p.NS + 1;                                    // [warps]
 
+  const int kRefStages = p.ST;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n0 = (blockIdx.x / p.tiles_g) * p.TN, gt0 = (blockIdx.x % p.tiles_g) * p.TG;
+  const int n0 = (blockIdx.x / p.tiles_g) * p.TN, gt0 = (blockIdx.x % p.tiles_g) * p.TGB;
   const int M = p.Hp * p.Wp;
-  const int items = p.TN * p.TG * p.NP;
+  const int items = p.TGB * p.TN * p.NP;  // (gallery i, column j, patch), gallery major
+  const int ipt = (items + kRefThreads - 1) / kRefThreads, item0 = min(items, tid * ipt), item1 = min(items, item0 + ipt);
 
   // candidate rows of one record: 0 when the record cannot hold the pair's maximum
   auto expand = [&](int item, uint32_t* info_out, int* py_out, int* px_out, int* j_out, int* i_out) -> int {
     const int pidx = item % p.NP, pair = item / p.NP;
-    const int i = pair % p.TG, j = pair / p.TG;
+    const int j = pair % p.TN, i = pair / p.TN;
     const int n = n0 + j, g = gt0 + i;
     if (n >= p.ncols || g >= p.G) return 0;
     const float a = __ldg(p.approx + (size_t)__ldg(p.col2probe + n) * p.score_ld + p.g0 + g);
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
   };
 
   int mine = 0;
-  for (int item = tid; item < items; item += kRefThreads) {
+  for (int item = item0; item < item1; ++item) {
     uint32_t info;
     int py, px, j, i;
     mine += expand(item, &info, &py, &px, &j, &i);
@@ -118,6 +128,8 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
       ptx::mbar_init(ptx::smem_u32(bars + st), 1);                      // full: the producer's expect_tx arrival + the bytes
       ptx::mbar_init(ptx::smem_u32(bars + kRefStages + st), kRefWarps);  // empty: one arrival per consumer warp
     }
+    ptx::mbar_init(ptx::smem_u32(bars + 2 * kRefStages), kRefWarps);     // template buffers free again
+    ptx::mbar_init(ptx::smem_u32(bars + 2 * kRefStages + 1), kRefWarps);
     ptx::fence_barrier_init();
     if (p.stats) {
       atomicAdd(p.stats + 0, (unsigned long long)total);
@@ -130,14 +142,15 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
   // vl-tap chunks of a row (rv), whichever split gives the longest inner loop for this shape (chosen by the host)
   const int vl = p.vl, lv = lane % vl, grp = lane / vl, gu = grp % p.ru, gv = grp / p.ru, nchunk = p.rowk / vl;
   const uint32_t tbytes = (uint32_t)p.Kpad * 4u, gbytes = (uint32_t)PG * 4u;
-  uint32_t it = 0;  // channel iterations so far (stage = it % kRefStages, barrier parity = (it / kRefStages) & 1)
+  uint32_t it = 0;   // gallery steps so far   (stage = it % kRefStages, barrier parity = (it / kRefStages) & 1)
+  uint32_t cit = 0;  // channels so far        (template buffer = cit & 1, barrier parity = (cit >> 1) & 1)
 
   for (int r0 = 0; r0 < total; r0 += p.cap) {
     const int nl = min(p.cap, total - r0);
-    // ---- this round's slice of the work list, in scan order
+    // ---- this round's slice of the work list, in scan (= gallery-major) order
     if (base < r0 + p.cap && base + mine > r0) {
       int o = base;
-      for (int item = tid; item < items; item += kRefThreads) {
+      for (int item = item0; item < item1; ++item) {
         uint32_t info;
         int py, px, j, i;
         const int cnt = expand(item, &info, &py, &px, &j, &i);
@@ -159,91 +172,122 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
         }
       }
     }
-    for (int k = tid; k < p.TN + p.TG; k += kRefThreads) flags[k] = 0;
+    for (int k = tid; k < p.TN + p.TGB; k += kRefThreads) flags[k] = 0;
+    for (int k = tid; k <= p.NS; k += kRefThreads) seg[k] = -1;
     __syncthreads();
     for (int e = tid; e < nl; e += kRefThreads) {
       acc[e] = 0.0f;
+      const int i = list[e].x >> 8;
       flags[list[e].x & 0xff] = 1;
-      flags[p.TN + (list[e].x >> 8)] = 1;
+      flags[p.TN + i] = 1;
+      const int s = i / p.TGS;
+      if (e == 0 || (int)(list[e - 1].x >> 8) / p.TGS != s) seg[s] = e;  // the list is gallery major: first entry of sub-chunk s
+    }
+    __syncthreads();
+    if (tid == 0) {  // empty sub-chunks start where the next one starts
+      seg[p.NS] = nl;
+      for (int s = p.NS - 1; s >= 0; --s)
+        if (seg[s] < 0) seg[s] = seg[s + 1];
     }
     __syncthreads();
 
     if (warp == kRefWarps) {
-      // ---- producer warp: per channel, one bulk copy per flagged plane (lanes issue in parallel) into the next free stage
-      uint32_t bytes = 0;
-      for (int k = 0; k < p.TN + p.TG; ++k) bytes += flags[k] ? (k < p.TN ? tbytes : gbytes) : 0u;
-      for (int c = 0; c < p.C; ++c, ++it) {
-        const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
-        const uint32_t full = ptx::smem_u32(bars + st);
-        ptx::mbar_wait(ptx::smem_u32(bars + kRefStages + st), par ^ 1u);  // consumers are done with this stage
-        float* dst = bufs + st * buf_floats;
-        if (lane == 0) {
-          ptx::fence_proxy_async_smem();  // the consumers' generic reads of this stage precede the async writes
-          ptx::mbar_arrive_expect_tx(full, bytes);
-        }
-        __syncwarp();
-        for (int k = lane; k < p.TN + p.TG; k += 32) {
-          if (!flags[k]) continue;
-          if (k < p.TN)
-            ptx::bulk_load(ptx::smem_u32(dst + (size_t)k * p.Kpad), p.t32 + ((size_t)c * p.ncols_alloc + n0 + k) * p.Kpad, tbytes, full);
-          else
-            ptx::bulk_load(ptx::smem_u32(dst + (size_t)p.TN * p.Kpad + (size_t)(k - p.TN) * PG),
-                           p.g32 + ((size_t)(gt0 + k - p.TN) * p.C + c) * PG, gbytes, full);
+      // ---- producer warp: per channel the flagged template planes once, then the flagged gallery planes sub-chunk by sub-chunk
+      uint32_t tpl_bytes = 0;
+      for (int j = 0; j < p.TN; ++j) tpl_bytes += flags[j] ? tbytes : 0u;
+      for (int c = 0; c < p.C; ++c, ++cit) {
+        bool first = true;
+        float* tdst = tplbuf + (cit & 1u) * (size_t)p.TN * p.Kpad;
+        for (int s = 0; s < p.NS; ++s) {
+          if (seg[s + 1] == seg[s]) continue;  // no position in this sub-chunk
+          const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
+          const uint32_t full = ptx::smem_u32(bars + st);
+          ptx::mbar_wait(ptx::smem_u32(bars + kRefStages + st), par ^ 1u);  // consumers are done with this gallery stage
+          if (first) ptx::mbar_wait(ptx::smem_u32(bars + 2 * kRefStages + (cit & 1u)), ((cit >> 1) & 1u) ^ 1u);  // and with this template buffer
+          float* gdst = galbuf + (size_t)st * p.TGS * PG;
+          uint32_t bytes = first ? tpl_bytes : 0u;
+          for (int k = 0; k < p.TGS; ++k) bytes += flags[p.TN + s * p.TGS + k] ? gbytes : 0u;
+          if (lane == 0) {
+            ptx::fence_proxy_async_smem();  // the consumers' generic reads of these buffers precede the async writes
+            ptx::mbar_arrive_expect_tx(full, bytes);
+          }
+          __syncwarp();
+          for (int k = lane; k < p.TGS; k += 32) {
+            const int i = s * p.TGS + k;
+            if (flags[p.TN + i]) ptx::bulk_load(ptx::smem_u32(gdst + (size_t)k * PG), p.g32 + ((size_t)(gt0 + i) * p.C + c) * PG, gbytes, full);
+          }
+          if (first) {
+            for (int j = lane; j < p.TN; j += 32)
+              if (flags[j]) ptx::bulk_load(ptx::smem_u32(tdst + (size_t)j * p.Kpad), p.t32 + ((size_t)c * p.ncols_alloc + n0 + j) * p.Kpad, tbytes, full);
+            first = false;
+          }
+          ++it;
         }
       }
     } else {
       // ---- consumer warps: one candidate position at a time
-      constexpr int kSlots = 4;  // entries of a warp held per lane: covers cap <= kRefWarps * 32 * kSlots
-      for (int c = 0; c < p.C; ++c, ++it) {
-        const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
-        // this channel's window norms of the warp's entries, one gather before the wait (entry warp + kRefWarps * t in lane t % 32)
-        float rnv[kSlots];
-#pragma unroll
-        for (int s4 = 0; s4 < kSlots; ++s4) {
-          const int e = warp + kRefWarps * (lane + 32 * s4);
-          rnv[s4] = 0.0f;
-          if (e < nl) {
-            const uint2 en = list[e];
-            const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en.x & 0xff)) >> 4] : p.rnorm;
-            rnv[s4] = __ldg(table + ((size_t)(gt0 + (int)(en.x >> 8)) * p.C + c) * M + (en.y & 0xffff) * p.Wp + (en.y >> 16));
-          }
-        }
-        ptx::mbar_wait(ptx::smem_u32(bars + st), par);
-        const float* tpl = bufs + st * buf_floats;
-        const float* gal = tpl + (size_t)p.TN * p.Kpad;
-        int t = 0;
-        for (int e = warp; e < nl; e += kRefWarps, ++t) {
-          const uint2 en = list[e];
-          const int j = en.x & 0xff, i = en.x >> 8, y = en.y & 0xffff, x = en.y >> 16;
-          const int u_lo = max(0, a - y), u_hi = min(p.Hb, p.Hp + a - y);  // template rows that meet the map
-          const float* T = tpl + (size_t)j * p.Kpad;
-          const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
-          float part0 = 0.0f, part1 = 0.0f;
-          const int ts = p.ru * p.rowk, gs = p.ru * p.WP;
-          for (int ch = gv; ch < nchunk; ch += p.rv) {
-            const int v = ch * vl + lv, gx = x + v - b;
-            if (gx >= 0 && gx < p.Wp) {
-              const float* tp = T + (u_lo + gu) * p.rowk + v;
-              const float* gp = Gs + (u_lo + gu) * p.WP + v;
-              int u = u_lo + gu;
-              for (; u + 3 * p.ru < u_hi; u += 4 * p.ru, tp += 4 * ts, gp += 4 * gs) {
-                part0 = fmaf(tp[0], gp[0], part0);
-                part1 = fmaf(tp[ts], gp[gs], part1);
-                part0 = fmaf(tp[2 * ts], gp[2 * gs], part0);
-                part1 = fmaf(tp[3 * ts], gp[3 * gs], part1);
-              }
-              for (; u < u_hi; u += p.ru, tp += ts, gp += gs) part0 = fmaf(*tp, *gp, part0);
+      for (int c = 0; c < p.C; ++c, ++cit) {
+        const float* tpl = tplbuf + (cit & 1u) * (size_t)p.TN * p.Kpad;
+        for (int s = 0; s < p.NS; ++s) {
+          const int e0 = seg[s], e1 = seg[s + 1];
+          if (e1 == e0) continue;
+          const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
+          // this channel's window norms of the warp's positions in the sub-chunk, one gather before the wait (entry e0 + warp +
+          // kRefWarps * t in lane t)
+          float rnv = 0.0f;
+          {
+            const int e = e0 + warp + kRefWarps * lane;
+            if (e < e1) {
+              const uint2 en = list[e];
+              const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en.x & 0xff)) >> 4] : p.rnorm;
+              rnv = __ldg(table + ((size_t)(gt0 + (int)(en.x >> 8)) * p.C + c) * M + (en.y & 0xffff) * p.Wp + (en.y >> 16));
             }
           }
-          const float part = warp_sum(part0 + part1);
-          float rn = rnv[0];
-#pragma unroll
-          for (int s4 = 1; s4 < kSlots; ++s4) rn = (t >> 5) == s4 ? rnv[s4] : rn;
-          rn = __shfl_sync(0xffffffffu, rn, t & 31);
-          if (lane == 0) acc[e] = fmaf(part, rn, acc[e]);
+          ptx::mbar_wait(ptx::smem_u32(bars + st), par);
+          const float* gal = galbuf + (size_t)st * p.TGS * PG;
+          int t = 0;
+          for (int e = e0 + warp; e < e1; e += kRefWarps, ++t) {
+            const uint2 en = list[e];
+            const int j = en.x & 0xff, i = (int)(en.x >> 8) - s * p.TGS, y = en.y & 0xffff, x = en.y >> 16;
+            if ((t & 31) == 0 && t) {  // more than 32 positions of this warp in one sub-chunk: fetch the next 32 norms
+              const int e2 = e + kRefWarps * lane;
+              rnv = 0.0f;
+              if (e2 < e1) {
+                const uint2 en2 = list[e2];
+                const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en2.x & 0xff)) >> 4] : p.rnorm;
+                rnv = __ldg(table + ((size_t)(gt0 + (int)(en2.x >> 8)) * p.C + c) * M + (en2.y & 0xffff) * p.Wp + (en2.y >> 16));
+              }
+            }
+            const int u_lo = max(0, a - y), u_hi = min(p.Hb, p.Hp + a - y);  // template rows that meet the map
+            const float* T = tpl + (size_t)j * p.Kpad;
+            const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
+            float part0 = 0.0f, part1 = 0.0f;
+            const int ts = p.ru * p.rowk, gs = p.ru * p.WP;
+            for (int ch = gv; ch < nchunk; ch += p.rv) {
+              const int v = ch * vl + lv, gx = x + v - b;
+              if (gx >= 0 && gx < p.Wp) {
+                const float* tp = T + (u_lo + gu) * p.rowk + v;
+                const float* gp = Gs + (u_lo + gu) * p.WP + v;
+                int u = u_lo + gu;
+                for (; u + 3 * p.ru < u_hi; u += 4 * p.ru, tp += 4 * ts, gp += 4 * gs) {
+                  part0 = fmaf(tp[0], gp[0], part0);
+                  part1 = fmaf(tp[ts], gp[gs], part1);
+                  part0 = fmaf(tp[2 * ts], gp[2 * gs], part0);
+                  part1 = fmaf(tp[3 * ts], gp[3 * gs], part1);
+                }
+                for (; u < u_hi; u += p.ru, tp += ts, gp += gs) part0 = fmaf(*tp, *gp, part0);
+              }
+            }
+            const float part = warp_sum(part0 + part1);
+            const float rn = __shfl_sync(0xffffffffu, rnv, t & 31);
+            if (lane == 0) acc[e] = fmaf(part, rn, acc[e]);
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + kRefStages + st));
+          ++it;
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + kRefStages + st));
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + 2 * kRefStages + (cit & 1u)));  // this channel's templates are no longer needed
       }
     }
     __syncthreads();
@@ -262,7 +306,7 @@ using namespace sir;
 extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
                               const float* d_t32p, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe,
                               const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel, float tau_abs, const void* d_rec,
-                              unsigned long long* d_stats, void* stream) {
+                              int variants_hint, unsigned long long* d_stats, void* stream) {
   SIR_CHECK_ARG((d_rnorm != nullptr) != (d_rnorm_tab != nullptr), "sir_ncc_refine: give d_rnorm or d_rnorm_tab, not both");
   SIR_CHECK_ARG(d_g32 && d_t32p && d_col2probe && d_approx && d_scores && d_rec, "sir_ncc_refine: null pointer");
   SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0 && Hb > 0 && Wb > 0 && ncols > 0 && ncols <= ncols_alloc, "sir_ncc_refine: bad shape");
@@ -290,19 +334,37 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
   p.tau_rel = tau_rel; p.tau_abs = tau_abs;
   p.inv_scale = 1.0f / ((float)C * (float)(1 << kTemplateScaleLog2));
   p.cap = 1024;
-  // tile: as many (column, gallery) pairs per CTA as two staged channel buffers allow (every operand byte is then
-  // read once per tile); ties go to more columns because consecutive CTAs walk the gallery tiles of one column tile
-  const size_t budget = 220 * 1024, fixed = 128 + (size_t)p.cap * 12 + 4 * (32 + 32 + kRefThreads / 32) + 64;
+  // Tile: TN resident template columns (two channel buffers) + a ring of kRefStages x TGS gallery planes.  More columns =
+  // every gallery plane serves more positions; TGS only has to keep a step long enough to hide the copies.
+  const size_t budget = 220 * 1024;
   const size_t tbytes = (size_t)p.Kpad * 4, gbytes = (size_t)Hp * p.WP * 4;
-  int best_tn = 0, best_tg = 0;
-  for (int tn = 32; tn >= 1; tn >>= 1)
-    for (int tg = 32; tg >= 1; tg >>= 1)
-      if (fixed + kRefStages * (tn * tbytes + tg * gbytes) <= budget && (tn * tg > best_tn * best_tg || (tn * tg == best_tn * best_tg && tn > best_tn))) {
-        best_tn = tn;
-        best_tg = tg;
-      }
-  SIR_CHECK_ARG(best_tn > 0, "sir_ncc_refine: template %dx%d / map %dx%d do not fit shared memory", Hb, Wb, Hp, Wp);
-  static_assert(kRefWarps * 32 * 4 >= 1024, "every list entry of a warp needs a lane slot for its window norm");
+  const size_t fixed = 128 + (size_t)p.cap * 12 + 4 * (size_t)(32 + kRefMaxTgb + kRefMaxSub + 1 + kRefThreads / 32) + 64;
+  p.TN = 0;
+  p.ST = 2;
+  int tgs_first = 8;
+  if (const char* env = getenv("SIR_REFINE_STAGES")) p.ST = std::max(2, std::min(kRefMaxStages, atoi(env)));
+  if (const char* env = getenv("SIR_REFINE_TGS")) tgs_first = std::max(1, std::min(32, atoi(env)));
+  const int kRefStages = p.ST;
+  for (int tgs = tgs_first; tgs >= 1 && p.TN == 0; tgs >>= 1) {
+    if (fixed + kRefStages * tgs * gbytes + 2 * tbytes > budget) continue;
+    int tn = (int)std::min<size_t>(32, (budget - fixed - kRefStages * tgs * gbytes) / (2 * tbytes));
+    if (const char* env = getenv("SIR_REFINE_TN")) tn = std::max(1, std::min(tn, atoi(env)));
+    if (tn >= std::min(8, ncols) || tgs == 1) {
+      p.TN = tn >= 8 ? tn / 8 * 8 : tn;
+      p.TGS = tgs;
+    }
+  }
+  SIR_CHECK_ARG(p.TN > 0, "sir_ncc_refine: template %dx%d / map %dx%d do not fit shared memory", Hb, Wb, Hp, Wp);
+  p.TN = std::min(p.TN, ncols);
+  // gallery prints per tile: as many as keep the expected work list (about 1.3 positions per (probe, gallery) pair, i.e.
+  // 1.3 / variants per (column, gallery) cell) inside one round of `cap` entries
+  const int variants = std::max(1, variants_hint);
+  long long tgb = (long long)p.cap * variants * 10 / (13LL * p.TN);
+  tgb = std::min<long long>({tgb, (long long)p.TGS * kRefMaxSub, (long long)kRefMaxTgb, (long long)round_up(G, p.TGS)});
+  tgb = std::max<long long>(tgb, p.TGS);
+  p.TGB = (int)(tgb / p.TGS * p.TGS);
+  p.NS = p.TGB / p.TGS;
+  p.tiles_g = ceil_div(G, p.TGB);
   // lane mapping: the inner loop walks template rows; estimated instructions per (position, channel) for a split of the lane
   // groups over rows (ru) and row chunks (rv): chunk rounds x (set-up + rows per lane x ~3.3)
   p.vl = (p.rowk % 32 == 0) ? 32 : (p.rowk % 16 == 0) ? 16 : 8;
@@ -319,10 +381,9 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
       }
     }
   }
-  p.TN = best_tn;
-  p.TG = best_tg;
-  p.tiles_g = ceil_div(G, p.TG);
-  const size_t smem = fixed + kRefStages * (p.TN * tbytes + p.TG * gbytes);
+  const size_t smem = 128 + 2 * p.TN * tbytes + (size_t)kRefStages * p.TGS * gbytes + (size_t)p.cap * 12 +
+                      4 * (size_t)(p.TN + p.TGB + p.NS + 1 + kRefThreads / 32) + 64;
+  SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_refine: shared-memory plan overflow (%zu bytes)", smem);
   SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   const long long blocks = (long long)ceil_div(ncols, p.TN) * p.tiles_g;
   SIR_CHECK_ARG(blocks < (1ll << 31), "sir_ncc_refine: too many tiles");

@@ -583,7 +583,9 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], flip: bool, galler
             )
         launch_counter.add()
         col0 += n
-    col2probe = torch.cat(block.ids).to(torch.int32).to(dev, non_blocking=True)
+    ids_all = torch.cat(block.ids)
+    variants_hint = max(1, int(ids_all.numel()) // max(1, int(ids_all.unique().numel())))  # columns per probe in this block
+    col2probe = ids_all.to(torch.int32).to(dev, non_blocking=True)
     for ops, g0 in zip(gallery, offsets):
         rn = ops.rnorm(hm, wm, simt)
         if kernel_events is not None:
@@ -631,8 +633,8 @@ def _score_block_oriented(block: _Block, hw: tuple[int, int], flip: bool, galler
             nat.check(
                 nat.lib.sir_ncc_refine(
                     _ptr(ops.g32), _ptr(rn), None, ops.G, ops.C, ops.Hp, ops.Wp, _ptr(t32p), ncols, ncols, hm, wm,
-                    _ptr(col2probe), _ptr(approx), _ptr(scores), int(scores.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec), _stats_ptr(),
-                    _stream(),
+                    _ptr(col2probe), _ptr(approx), _ptr(scores), int(scores.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec), variants_hint,
+                    _stats_ptr(), _stream(),
                 ),
                 "sir_ncc_refine",
             )
@@ -756,7 +758,8 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
         nat.check(
             nat.lib.sir_ncc_refine(
                 _ptr(gops.g32), None, _ptr(d_tab), gops.G, gops.C, gops.Hp, gops.Wp, _ptr(t32p), ncols, ncols, hb, wb,
-                _ptr(d_c2p), _ptr(approx), _ptr(scores), int(scores.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec), _stats_ptr(), _stream(),
+                _ptr(d_c2p), _ptr(approx), _ptr(scores), int(scores.stride(0)), g0, TAU_REL, TAU_ABS, _ptr(rec),
+                max(1, int(col2probe.numel()) // max(1, int(col2probe.unique().numel()))), _stats_ptr(), _stream(),
             ),
             "sir_ncc_refine",
         )
