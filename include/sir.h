@@ -12,8 +12,8 @@
  *   - every function returns 0 on success, a negative SIR_E_* code otherwise; the message is
  *     available from sir_last_error() (thread local);
  *   - pointers named d_* are DEVICE pointers owned by the caller (PyTorch tensors in this
- *     repository); h_* are host pointers; nothing is allocated or freed behind the caller's back
- *     except small per-call index tables, released before the call returns (stream ordered);
+ *     repository); h_* are host pointers; nothing is allocated or freed behind the caller's back:
+ *     calls that need scratch take a caller workspace sized by a *_workspace_bytes query;
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised;
  *   - feature maps are float32, row major [count][C][h][w]; a call handles maps of ONE shape,
  *     the host groups ragged inputs by shape (dataloader.py never pads);
@@ -80,10 +80,13 @@ int sir_gallery_window_rnorm_multi(const uint16_t* d_ghi, const uint16_t* d_glo,
  * d_in [N][C][h][w] f32 -> d_out [N][C][h2][w2] f32.
  * rotate: angle in degrees (counter clockwise), same size, zero fill, 16.16 fixed point walk.
  * resize: bicubic a=-0.5, horizontal pass first, double accumulation; d_tmp [N][C][h][w2] f32
- * scratch (may be NULL when w2 == w or h2 == h). */
+ * scratch (may be NULL when w2 == w or h2 == h); d_ws: caller-owned device workspace (16-byte aligned) of at least
+ * sir_variant_resize_workspace_bytes(h, w, h2, w2) bytes for the tap tables of the passes (nothing is allocated
+ * inside; the tables are written stream ordered, so the workspace may be reused by the next call on the same stream). */
 int sir_variant_rotate(const float* d_in, int N, int C, int h, int w, double angle, float* d_out, void* stream);
+size_t sir_variant_resize_workspace_bytes(int h, int w, int h2, int w2);
 int sir_variant_resize(const float* d_in, int N, int C, int h, int w, int h2, int w2,
-                       float* d_out, float* d_tmp, void* stream);
+                       float* d_out, float* d_tmp, void* d_ws, size_t ws_bytes, void* stream);
 
 /* [N][C][h][w] -> [N][C][w][h].  Scores are invariant under transposing probe and gallery maps alike; the
  * host uses this to present the correlation kernel with the orientation that pads less. */

@@ -33,7 +33,8 @@ SIGNATURES = {
     "sir_gallery_window_rnorm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "sir_gallery_window_rnorm_multi": (_i, [_p, _p, _i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), _p]),
     "sir_variant_rotate": (_i, [_p, _i, _i, _i, _i, C.c_double, _p, _p]),
-    "sir_variant_resize": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "sir_variant_resize_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "sir_variant_resize": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, C.c_size_t, _p]),
     "sir_maps_transpose": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "sir_template_kpad": (_i, [_i, _i]),
     "sir_template_pack": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

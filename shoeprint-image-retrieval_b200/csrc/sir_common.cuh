@@ -40,6 +40,14 @@ void set_error(const char* fmt, ...);
     }                                                                                       \
   } while (0)
 
+// cudaFuncSetAttribute state is per DEVICE: call sites cache "already opted in" per (thread, device), so a host thread
+// that drives a second GPU opts in there too.
+inline int current_device_slot() {
+  int dev = 0;
+  (void)cudaGetDevice(&dev);
+  return dev & 63;
+}
+
 constexpr int kEdge = 2;           // similarity.py:92-93 crop
 constexpr int kTemplateScaleLog2 = 10;  // packed templates are (t-mean)/sqrt(E) * 2^10
 constexpr int kGalleryPeakLog2 = 10;    // packed gallery channels have max|v| in [2^9, 2^10)

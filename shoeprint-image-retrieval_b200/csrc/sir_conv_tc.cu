@@ -573,7 +573,8 @@ int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, c
   return SIR_OK;
 }
 int sm_count() {
-  static int n = 0;
+  static int per_dev[64] = {};
+  int& n = per_dev[current_device_slot()];
   if (!n) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
@@ -903,7 +904,8 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
     if (rc) return rc;
     rc = encode(&hxl, d_xlo, 5, dims, strides, box, 0, "activation lo (halo)");
     if (rc) return rc;
-    static thread_local bool halo_configured[3] = {false, false, false};
+    static thread_local bool halo_configured_dev[64][3] = {};
+    bool* halo_configured = halo_configured_dev[current_device_slot()];
     const void* hfn = act == 0 ? (const void*)conv_halo_kernel<0> : act == 1 ? (const void*)conv_halo_kernel<1> : (const void*)conv_halo_kernel<2>;
     if (!halo_configured[act]) {
       SIR_CUDA(cudaFuncSetAttribute(hfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024)));
@@ -931,7 +933,8 @@ extern "C" int sir_feat_conv(const uint16_t* d_xhi, const uint16_t* d_xlo, const
   if (rc) return rc;
   rc = encode(&txl, d_xlo, 4, dims, strides, box, bk, "activation lo", stride);
   if (rc) return rc;
-  static thread_local bool configured[3] = {false, false, false};
+  static thread_local bool configured_dev[64][3] = {};
+  bool* configured = configured_dev[current_device_slot()];
   const void* fn = act == 0 ? (const void*)conv_tc_kernel<0> : act == 1 ? (const void*)conv_tc_kernel<1> : (const void*)conv_tc_kernel<2>;
   if (!configured[act]) {
     SIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024)));

@@ -93,7 +93,8 @@ int launch_ncc_simt(const float* d_gz, const float* d_rnorm, int G, int C, int H
   SIR_CHECK_ARG(d_gz && d_t32, "sir_ncc_scores(FP32_SIMT): needs d_gz and d_t32");
   const size_t smem = sizeof(float) * ((size_t)(Hp + Hm - 1) * (Wp + Wm - 1) + (size_t)Hm * Wm);
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_scores(FP32_SIMT): maps too large for shared memory");
-  static thread_local size_t configured = 0;
+  static thread_local size_t configured_dev[64] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
     SIR_CUDA(cudaFuncSetAttribute(ncc_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -580,7 +580,8 @@ extern "C" int sir_gallery_window_rnorm(const uint16_t* d_ghi, const uint16_t* d
   SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0 && Hm > 0 && Wm > 0, "sir_gallery_window_rnorm: bad shape");
   const size_t smem = 2 * (size_t)(Hp + 1) * (Wp + 1) * sizeof(double);
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_gallery_window_rnorm: map %dx%d too large for the smem SAT", Hp, Wp);
-  static thread_local size_t configured = 0;
+  static thread_local size_t configured_dev[64] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
     SIR_CUDA(cudaFuncSetAttribute(window_rnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -597,7 +598,8 @@ extern "C" int sir_gallery_window_rnorm_multi(const uint16_t* d_ghi, const uint1
   SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0 && nshapes > 0, "sir_gallery_window_rnorm_multi: bad shape");
   const size_t smem = 2 * (size_t)(Hp + 1) * (Wp + 1) * sizeof(double);
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_gallery_window_rnorm_multi: map %dx%d too large for the smem SAT", Hp, Wp);
-  static thread_local size_t configured = 0;
+  static thread_local size_t configured_dev[64] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
     SIR_CUDA(cudaFuncSetAttribute(window_rnorm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -724,15 +726,20 @@ Coeffs precompute(int n_in, int n_out) {
   return c;
 }
 
-int run_pass(const float* in, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int axis,
+// bytes of one pass's tap tables in the workspace: xmin, cnt (int per output index) + weights (double, ksize per index)
+size_t pass_ws_bytes(int n_in, int n_out) {
+  const double scale = (double)n_in / n_out, fscale = scale < 1.0 ? 1.0 : scale;
+  const int ksize = (int)std::ceil(2.0 * fscale) * 2 + 1;
+  return (size_t)round_up(2 * n_out * (int)sizeof(int), 16) + (size_t)n_out * ksize * sizeof(double);
+}
+
+int run_pass(const float* in, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int axis, void* d_ws,
              cudaStream_t st) {
   const Coeffs c = precompute(axis ? w_in : h_in, axis ? w_out : h_out);
   const int n_out = axis ? w_out : h_out;
-  int *d_xmin = nullptr, *d_cnt = nullptr;
-  double* d_kk = nullptr;
-  SIR_CUDA(cudaMallocAsync(&d_xmin, sizeof(int) * n_out, st));
-  SIR_CUDA(cudaMallocAsync(&d_cnt, sizeof(int) * n_out, st));
-  SIR_CUDA(cudaMallocAsync(&d_kk, sizeof(double) * c.kk.size(), st));
+  int* d_xmin = reinterpret_cast<int*>(d_ws);
+  int* d_cnt = d_xmin + n_out;
+  double* d_kk = reinterpret_cast<double*>(reinterpret_cast<char*>(d_ws) + round_up(2 * n_out * (int)sizeof(int), 16));
   // pageable sources: the runtime stages them before returning, so the vectors may die here
   SIR_CUDA(cudaMemcpyAsync(d_xmin, c.xmin.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice, st));
   SIR_CUDA(cudaMemcpyAsync(d_cnt, c.cnt.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice, st));
@@ -741,15 +748,20 @@ int run_pass(const float* in, float* out, int planes, int h_in, int w_in, int h_
   const unsigned by = (unsigned)std::min<long long>(planes, std::max(1u, 148u * 16u / bx));
   resample_kernel<<<dim3(bx, by), 256, 0, st>>>(in, out, planes, h_in, w_in, h_out, w_out, axis, d_xmin, d_cnt, d_kk, c.ksize);
   SIR_LAUNCH_CHECK("resample_kernel");
-  SIR_CUDA(cudaFreeAsync(d_xmin, st));
-  SIR_CUDA(cudaFreeAsync(d_cnt, st));
-  SIR_CUDA(cudaFreeAsync(d_kk, st));
   return SIR_OK;
 }
 }  // namespace
 
+extern "C" size_t sir_variant_resize_workspace_bytes(int h, int w, int h2, int w2) {
+  if (h <= 0 || w <= 0 || h2 <= 0 || w2 <= 0) return 0;
+  size_t n = 0;
+  if (w2 != w) n += round_up((int)pass_ws_bytes(w, w2), 256);
+  if (h2 != h) n += round_up((int)pass_ws_bytes(h, h2), 256);
+  return n;
+}
+
 extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w, int h2, int w2, float* d_out,
-                                  float* d_tmp, void* stream) {
+                                  float* d_tmp, void* d_ws, size_t ws_bytes, void* stream) {
   SIR_CHECK_ARG(d_in && d_out, "sir_variant_resize: null pointer");
   SIR_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && h2 > 0 && w2 > 0, "sir_variant_resize: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -758,14 +770,18 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
     SIR_CUDA(cudaMemcpyAsync(d_out, d_in, sizeof(float) * (size_t)planes * h * w, cudaMemcpyDeviceToDevice, st));
     return SIR_OK;
   }
+  SIR_CHECK_ARG(d_ws && ws_bytes >= sir_variant_resize_workspace_bytes(h, w, h2, w2) && (reinterpret_cast<uintptr_t>(d_ws) & 15) == 0,
+                "sir_variant_resize: workspace of %zu bytes (16-byte aligned) needed, see sir_variant_resize_workspace_bytes",
+                sir_variant_resize_workspace_bytes(h, w, h2, w2));
+  char* ws = reinterpret_cast<char*>(d_ws);
   if (w2 != w && h2 != h) {
     SIR_CHECK_ARG(d_tmp, "sir_variant_resize: two-pass resize needs d_tmp");
-    int rc = run_pass(d_in, d_tmp, planes, h, w, h, w2, 1, st);
+    int rc = run_pass(d_in, d_tmp, planes, h, w, h, w2, 1, ws, st);
     if (rc) return rc;
-    return run_pass(d_tmp, d_out, planes, h, w2, h2, w2, 0, st);
+    return run_pass(d_tmp, d_out, planes, h, w2, h2, w2, 0, ws + round_up((int)pass_ws_bytes(w, w2), 256), st);
   }
-  if (w2 != w) return run_pass(d_in, d_out, planes, h, w, h, w2, 1, st);
-  return run_pass(d_in, d_out, planes, h, w, h2, w, 0, st);
+  if (w2 != w) return run_pass(d_in, d_out, planes, h, w, h, w2, 1, ws, st);
+  return run_pass(d_in, d_out, planes, h, w, h2, w, 0, ws, st);
 }
 
 extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }

@@ -451,8 +451,10 @@ def make_variant(maps: torch.Tensor, rot: float | None, scale: float | None) -> 
             resized = torch.empty((n, c, h2, w2), dtype=torch.float32, device=maps.device)
             two_pass = h2 != h and w2 != w
             tmp = torch.empty((n, c, h, w2), dtype=torch.float32, device=maps.device) if two_pass else None
+            ws_bytes = int(nat.lib.sir_variant_resize_workspace_bytes(h, w, h2, w2))
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=maps.device)  # tap tables of the passes
             nat.check(
-                nat.lib.sir_variant_resize(_ptr(out), n, c, h, w, h2, w2, _ptr(resized), _ptr(tmp), _stream()),
+                nat.lib.sir_variant_resize(_ptr(out), n, c, h, w, h2, w2, _ptr(resized), _ptr(tmp), _ptr(ws), ws_bytes, _stream()),
                 "sir_variant_resize",
             )
             launch_counter.add(2 if two_pass else 1)

@@ -318,7 +318,18 @@ class FeatureMapList(list):
             ids, parts = by_shape.setdefault(shp, ([], []))
             ids.extend(idx)
             parts.append(maps)
-        self.device_groups = [(torch.cat(parts) if len(parts) > 1 else parts[0], ids) for ids, parts in by_shape.values()]
+        groups = []
+        for ids, parts in by_shape.values():
+            if len(parts) == 1:
+                groups.append((parts[0], ids))
+                continue
+            whole = torch.empty((sum(int(t.shape[0]) for t in parts), *parts[0].shape[1:]), dtype=parts[0].dtype, device=parts[0].device)
+            at = 0
+            for t in parts:  # device-to-device copies (cudaMemcpyAsync), no torch kernel
+                whole[at : at + int(t.shape[0])].copy_(t)
+                at += int(t.shape[0])
+            groups.append((whole, ids))
+        self.device_groups = groups
         self._ids = tuple(id(a) for a in self)
 
     def __reduce__(self):  # pickles (and deep-copies) as the plain list of arrays; the device copies stay behind
