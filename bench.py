@@ -216,6 +216,35 @@ def run_reference(args) -> None:
 
 
 # ----------------------------------------------------------------------------- feature stage (side measurement)
+def feature_stage_parallel(world: int, rank: int, dist, torch) -> dict:
+    """Feature stage data-parallel over the GPUs (images are independent): every rank pushes its own 64-image
+    batches of 800x300 prints through the backbone, device-resident; aggregate images/s from the slowest rank."""
+    import numpy as np
+
+    from src.shoeprint_image_retrieval import network
+
+    cfg = {"model": {"type": "EfficientNetV2_M", "clahe_clip_limit": 2.0, "clahe_tile_grid_size": [8, 8]}}
+    model = network.Model(cfg, 6, random_init_seed=0)
+    rng = np.random.default_rng(100 + rank)
+    d_batch = torch.from_numpy(rng.integers(0, 256, size=(64, 800, 300), dtype=np.uint8)).cuda()
+    model._forward_device(d_batch, apply_clahe=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 4
+    for _ in range(reps):
+        model._forward_device(d_batch, apply_clahe=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"n_gpus": world, "images_per_s": world * reps * 64 / (float(ms.item()) * 1e-3), "per_gpu_batch": 64,
+            "note": "device-resident uint8 prints -> [C,h,w] maps, CLAHE included; one process per GPU, no collective"}
+
+
 def feature_stage_numbers(args) -> dict:
     """images/s of the backbone (EfficientNetV2-M cut at block 6, seeded random init, synthetic 800x300
     uint8 prints): through ``Model.get_multiple_feature_maps`` (H2D, GPU CLAHE, kernels, D2H) and
@@ -600,7 +629,10 @@ def run_b200(args) -> None:
     c4 = config4_block(args, world, rank, dist, torch) if not args.no_config4 else None
     c5 = precision_block(args, world, rank, dist, torch) if not args.no_precision_study else None
     c0 = config0_block(args) if (rank == 0 and world == 1 and not args.no_config4 and not args.quick) else None
+    feat_par = feature_stage_parallel(world, rank, dist, torch) if (world > 1 and not args.no_features) else None
     feat = feature_stage_numbers(args) if (rank == 0 and not args.no_features) else None
+    if feat is not None and feat_par is not None:
+        feat["data_parallel"] = feat_par
 
     if rank == 0:
         peaks = _peaks()

@@ -152,7 +152,8 @@ class _Uploader:
 
     BUF_BYTES = 64 << 20
     NBUF = 3
-    THREADS = max(2, min(8, (os.cpu_count() or 2) // 2))
+    # copy threads per process: half the host cores, shared among the ranks of the box (torchrun sets LOCAL_WORLD_SIZE)
+    THREADS = max(2, min(8, (os.cpu_count() or 2) // (2 * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))))
     _instances: dict = {}
 
     @classmethod
