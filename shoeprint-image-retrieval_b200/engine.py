@@ -797,11 +797,19 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
     # norms: ~3x the chunk's float32 bytes) stay bounded; small galleries are packed once up front,
     # large ones chunk by chunk inside every column block (packing is ~2 % of the correlation time)
     chunks: list[MapGroup] = []
+    n_variants = len(variant_plan(rotations, scales))
     for grp in gallery.groups:
         grp.wait()
         n = int(grp.maps.shape[0])
         per_map = grp.maps[0].numel() * 4
         step = max(1, min(n, gallery_chunk_bytes // max(per_map, 1)))
+        if with32:
+            # the screening pass leaves 8 bytes per (column, gallery print, 16x8 patch): keep that record buffer under
+            # ~16 GB for the widest column block this call can produce
+            hp, wp = int(grp.maps.shape[2]) - 2 * EDGE, int(grp.maps.shape[3]) - 2 * EDGE
+            patches = max(-(-hp // 16) * -(-wp // 8), -(-wp // 16) * -(-hp // 8))
+            cols = min(max(col_block, 32768), max(1, probes.count * n_variants))
+            step = max(1, min(step, (16 << 30) // (8 * patches * cols)))
         for s0 in range(0, n, step):
             chunks.append(MapGroup(grp.maps[s0 : s0 + step], grp.ids[s0 : s0 + step]))
     offsets, g0 = [], 0
