@@ -810,6 +810,7 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
             patches = max(-(-hp // 16) * -(-wp // 8), -(-wp // 16) * -(-hp // 8))
             cols = min(max(col_block, 32768), max(1, probes.count * n_variants))
             step = max(1, min(step, (16 << 30) // (8 * patches * cols)))
+        step = -(-n // -(-n // step))  # equal chunks
         for s0 in range(0, n, step):
             chunks.append(MapGroup(grp.maps[s0 : s0 + step], grp.ids[s0 : s0 + step]))
     offsets, g0 = [], 0
