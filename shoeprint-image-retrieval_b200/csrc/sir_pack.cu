@@ -13,6 +13,20 @@
 
 namespace sir {
 
+// One warp copies a plane of n floats into its shared-memory slab with eight independent loads in flight per lane: with a
+// plain one-load-per-iteration loop the pack kernels kept ~20 KB in flight per SM and reached 45 % of the HBM rate.
+__device__ __forceinline__ void warp_load_plane(float* __restrict__ dst, const float* __restrict__ src, int n, int lane) {
+  int i = lane;
+  for (; i + 7 * 32 < n; i += 8 * 32) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(src + i + 32 * j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[i + 32 * j] = v[j];
+  }
+  for (; i < n; i += 32) dst[i] = __ldg(src + i);
+}
+
 __device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
 
 // ------------------------------------------------------------------------------------------
@@ -80,7 +94,7 @@ __global__ void __launch_bounds__(256) gallery_pack_warp_kernel(const float* __r
   const int c8 = WP / 8, n8 = Hp * c8;
   for (long long gc = (long long)blockIdx.x * nw + wid; gc < planes; gc += (long long)gridDim.x * nw) {
     const float* src = gal + gc * HW;
-    for (int i = lane; i < HW; i += 32) ch[i] = __ldg(src + i);
+    warp_load_plane(ch, src, HW, lane);
     __syncwarp();
     double acc = 0.0;
     for (int o = lane; o < n8; o += 32) {
@@ -457,7 +471,7 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
         ch[i] = gi >= 0 ? __ldg(src + gi) : 0.0f;
       }
     } else {
-      for (int i = lane; i < HW; i += 32) ch[i] = __ldg(src + i);
+      warp_load_plane(ch, src, HW, lane);
     }
     __syncwarp();
     double acc = 0.0;
