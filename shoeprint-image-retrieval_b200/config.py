@@ -5,7 +5,7 @@ Same keys and the same normalisation as the reference: an empty string for
 ``None`` (``config.py:60-63``).  Extra, optional keys understood by this implementation
 (absent -> reference behaviour):
 
-* ``comparison.precision``  ``"fp16_fp8c"`` (default, parity grade) | ``"fp16x3"`` | ``"fp16x1"`` | ``"fp32_simt"``
+* ``comparison.precision``  ``"fp16_refine"`` (default, parity grade) | ``"fp16_fp8c"`` | ``"fp16x3"`` | ``"fp16x1"`` | ``"fp32_simt"``
 * ``comparison.top_k``      length of the per-probe candidate list kept next to the ranks
 """
 

@@ -1,14 +1,19 @@
 """Device-side orchestration of the matching path (PyTorch owns memory and streams; every
 kernel is in ``libsir.so``).
 
-Flow (reference call sites in brackets):
+Flow of the default precision mode (reference call sites in brackets):
 
-    gallery maps --sir_gallery_pack--> fp16 hi/lo operands            [similarity.py:92,49]
-    probe maps --sir_variant_rotate/resize--> variant maps            [similarity.py:262-276, 321-353]
-               --sir_template_pack--> column blocks per template shape [similarity.py:92,48,67]
-    per (template shape, gallery shape): sir_gallery_window_rnorm     [similarity.py:57-65]
-                                         sir_ncc_scores (max-fused)   [similarity.py:53-55,68,100-108,355-367]
-    scores --sir_true_scores / sir_rank_topk--> ranks, top-k          [similarity.py:378-386]
+    gallery maps --sir_gallery_pack_f32--> fp16 operands + float32 copy        [similarity.py:92,49]
+    probe maps --sir_variant_resize (scaled variants only)--> variant maps     [similarity.py:262-276, 321-353]
+               --sir_template_pack_screen (rotation / transposition through an index map)--> column blocks
+                                                                               [similarity.py:267,92,48,67]
+    per (template shape, gallery shape): sir_gallery_window_rnorm              [similarity.py:57-65]
+        sir_ncc_screen (fp16 tensor-core surface, max-fused, candidate records) [similarity.py:53-55,68,100-108,355-367]
+        sir_ncc_refine (exact float32 value at the candidate positions)
+    scores --sir_true_scores / sir_rank_topk--> ranks, top-k                   [similarity.py:378-386]
+
+The single-pass modes (``fp16_fp8c``, ``fp16x3``, ``fp16x1``, ``fp32_simt``) materialise every variant
+(sir_variant_rotate / resize), pack with sir_template_pack[_fp8c] and score with sir_ncc_scores[_fp8c].
 
 Ragged inputs are grouped by shape on the host (the reference never pads: dataloader.py:231-237).
 """
