@@ -27,7 +27,7 @@ __device__ __forceinline__ bool beats(float va, int ia, float vb, int ib) { retu
 
 // Top-k by threshold + compaction.  One CTA streams one score row (16-byte loads).  Every value is turned into a
 // 64-bit key whose unsigned order is (value descending, index ascending); keys above the CTA's current threshold are
-// appended to a shared-memory buffer with one atomicAdd per warp and slot (ballot-aggregated).  When the buffer could
+// appended to a shared-memory buffer (one shared-memory atomicAdd per candidate; candidates are rare after the first cut).  When the buffer could
 // overflow during the next chunk it is sorted (bitonic, in place), cut to the k best, and the k-th key becomes the new
 // threshold -- after the first cut only ~k/2048 of the values pass, so a 100,000-column row is cut two or three times
 // and the kernel stays a single streaming pass over HBM.
@@ -141,6 +141,12 @@ __device__ int select_compact(unsigned long long* buf, int n, int k, unsigned lo
   return kept;
 }
 
+// Streaming loop of the top-k kernel.  Until the first cut every value is a candidate, so the row is walked one chunk
+// (kSelChunk values) per barrier.  Afterwards only ~k/2048 of the values pass the threshold and the loop takes kSelSpan
+// chunks per barrier with all of their 16-byte loads in flight at once; should more candidates arrive than the buffer
+// holds (a row that keeps improving, e.g. sorted ascending) the span is discarded and redone chunk by chunk.
+constexpr int kSelSpan = 8;
+
 __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __restrict__ scores, int Q, int G, int ld,
                                                                  const float* __restrict__ true_score, int g0, int k,
                                                                  int32_t* __restrict__ count_gt, int32_t* __restrict__ count_ge,
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
   __shared__ unsigned long long buf[kSelCap];
   __shared__ SelectScratch scratch;
   __shared__ unsigned long long thr_s;
-  __shared__ int cnt_s;
+  __shared__ int cnt_s, overflow_s;
   __shared__ int red[2][kRankWarps];
   const int q = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* row = scores + (size_t)q * ld;
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
   if (threadIdx.x == 0) {
     thr_s = 0ull;
     cnt_s = 0;
+    overflow_s = 0;
   }
   __syncthreads();
   const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
@@ -169,46 +176,71 @@ __global__ void __launch_bounds__(kRankThreads) rank_topk_kernel(const float* __
       for (int j = 0; j < 4; ++j) v[j] = (i0 + j < G) ? __ldg(row + i0 + j) : 0.0f;
     }
   };
-  float vn[4];
-  load4(4 * threadIdx.x, vn);
-  for (int base = 0; base < G; base += kSelChunk) {
-    const int i0 = base + 4 * threadIdx.x;
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = vn[j];
-    if (base + kSelChunk < G) load4(i0 + kSelChunk, vn);  // the next chunk is in flight across the barrier below
-    const unsigned long long thr = thr_s;
-    const float thr_v = key_value(thr);
+  // candidates of one float4 against the threshold the span started with; appends beyond the buffer set the overflow flag
+  auto consider4 = [&](const float (&v)[4], int i0, unsigned long long thr, float thr_v, int& gts, int& ges) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool valid = i0 + j < G;
-      gt += valid && v[j] > ts;
-      ge += valid && v[j] >= ts;
-      if (k > 0) {
-        unsigned long long key = 0ull;
-        bool take = valid && (thr == 0ull || v[j] >= thr_v);
-        if (take) {
-          key = select_key(v[j], g0 + i0 + j);
-          take = key > thr;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, take);
-        if (m) {
-          int pos = 0;
-          if (lane == 0) pos = atomicAdd(&cnt_s, __popc(m));
-          pos = __shfl_sync(0xffffffffu, pos, 0);
-          if (take) buf[pos + __popc(m & ((1u << lane) - 1u))] = key;
+      gts += valid && v[j] > ts;
+      ges += valid && v[j] >= ts;
+      if (valid && (thr == 0ull || v[j] >= thr_v)) {
+        const unsigned long long key = select_key(v[j], g0 + i0 + j);
+        if (key > thr) {
+          const int pos = atomicAdd(&cnt_s, 1);
+          if (pos < kSelCap) buf[pos] = key;
+          else overflow_s = 1;
         }
       }
     }
-    if (k > 0) {
-      __syncthreads();
-      cnt = cnt_s;
-      if (cnt > kSelCap - kSelChunk) {  // the next chunk could overflow: cut to the k best, raise the threshold
-        select_cut(buf, cnt, k, &thr_s, &scratch);
-        cnt = k;
-        if (threadIdx.x == 0) cnt_s = cnt;
-        __syncthreads();
+  };
+  int slow_left = 0;  // chunks still to be walked one per barrier after an overflow
+  for (int base = 0; base < G;) {
+    const unsigned long long thr = thr_s;
+    const float thr_v = key_value(thr);
+    const bool fast = thr != 0ull && slow_left == 0 && k > 0;
+    const int span = fast ? kSelSpan : 1;
+    int gts = 0, ges = 0;
+    if (fast) {
+      float v[kSelSpan][4];
+#pragma unroll
+      for (int c = 0; c < kSelSpan; ++c) load4(base + c * kSelChunk + 4 * threadIdx.x, v[c]);
+#pragma unroll
+      for (int c = 0; c < kSelSpan; ++c) consider4(v[c], base + c * kSelChunk + 4 * threadIdx.x, thr, thr_v, gts, ges);
+    } else {
+      float v[4];
+      load4(base + 4 * threadIdx.x, v);
+      if (k > 0) {
+        consider4(v, base + 4 * threadIdx.x, thr, thr_v, gts, ges);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool valid = base + 4 * threadIdx.x + j < G;
+          gts += valid && v[j] > ts;
+          ges += valid && v[j] >= ts;
+        }
       }
+    }
+    __syncthreads();
+    if (overflow_s) {  // block-uniform: forget this span and walk it again one chunk per barrier
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        cnt_s = cnt;
+        overflow_s = 0;
+      }
+      slow_left = kSelSpan;
+      __syncthreads();
+      continue;
+    }
+    gt += gts;
+    ge += ges;
+    base += span * kSelChunk;
+    if (slow_left > 0) --slow_left;
+    cnt = min(cnt_s, kSelCap);
+    if (k > 0 && cnt > kSelCap - kSelChunk) {  // the next chunk could overflow: cut to the k best, raise the threshold
+      select_cut(buf, cnt, k, &thr_s, &scratch);
+      cnt = k;
+      if (threadIdx.x == 0) cnt_s = cnt;
+      __syncthreads();
     }
   }
   gt = warp_sum(gt);

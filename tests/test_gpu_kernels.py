@@ -148,6 +148,28 @@ def test_rank_topk_matches_numpy(eng):
                 assert np.all(ti2.cpu().numpy()[:, g:] == -1)
 
 
+def test_rank_topk_long_rows(eng):
+    """Rows long enough for the multi-chunk fast path of the threshold select (sir_rank.cu), including the rows it has to
+    redo: ascending values (every value beats the threshold: the candidate buffer overflows), descending, constant, and
+    blocks of exact ties."""
+    rng = np.random.default_rng(44)
+    g = 50000
+    rows = [rng.random(g), np.sort(rng.random(g)), np.sort(rng.random(g))[::-1], np.full(g, 0.25), np.repeat(rng.random(g // 100), 100),
+            np.concatenate([rng.random(g // 2), np.sort(rng.random(g - g // 2))])]
+    s = np.stack(rows).astype(np.float32)
+    true = rng.integers(0, g, size=len(rows))
+    d = torch.from_numpy(s).cuda()
+    for k in (64, 128, 5):
+        gt, ge, tv, ti, _ = eng.rank_true_matches(d, true, k, g0=7)
+        ts_np = s[np.arange(len(rows)), true - 0]
+        gt2, ge2, tv2, ti2, _ = eng.rank_true_matches(d, true + 7, k, g0=7)
+        np.testing.assert_array_equal(gt2.cpu().numpy(), (s > ts_np[:, None]).sum(1))
+        np.testing.assert_array_equal(ge2.cpu().numpy(), (s >= ts_np[:, None]).sum(1))
+        order = np.lexsort((np.arange(g)[None, :].repeat(len(rows), 0), -s), axis=1)[:, :k]
+        np.testing.assert_array_equal(ti2.cpu().numpy(), order + 7)
+        np.testing.assert_array_equal(tv2.cpu().numpy(), np.take_along_axis(s, order, 1))
+
+
 def test_merge_topk(eng):
     from src.shoeprint_image_retrieval import _native as nat
 
