@@ -16,7 +16,7 @@ for c, h, w, g, q in [(176, 50, 19, 24, 16), (80, 59, 21, 24, 16)]:
     ref32 = engine.score_matrix(ps, gs, rot, None, "fp32_simt").cpu().numpy()
     sub_q, sub_g = 3, 4
     _, want = ocmp.compare_maps_oracle([m for m in prb[:sub_q].cpu().numpy()], [m for m in gal[:sub_g].cpu().numpy()], [0] * sub_q, rot, None)
-    for mode in ("fp16x3", "fp16_fp8c", "fp16x1"):
+    for mode in ("fp16_refine", "fp16x3", "fp16_fp8c", "fp16x1"):
         s = engine.score_matrix(ps, gs, rot, None, mode).cpu().numpy()
         e32 = np.abs(s - ref32) / np.maximum(np.abs(ref32), 1e-3)
         e64 = np.abs(s[:sub_q, :sub_g] - want) / np.maximum(np.abs(want), 1e-3)

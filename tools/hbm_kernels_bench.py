@@ -57,4 +57,4 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 report("template_pack fp8c (K5t)", n * c * (4 * h * w + 4 * kpad),
        timed(lambda: nat.check(nat.lib.sir_template_pack_fp8c(C.c_void_p(maps.data_ptr()), n, c, h, w, 0, n, C.c_void_p(thi.data_ptr()), C.c_void_p(t8b.data_ptr()), C.c_void_p(t8l.data_ptr()), st))))
 Path("gpurun_out").mkdir(exist_ok=True)
-Path("gpurun_out/hbm_kernels_r01.json").write_text(json.dumps(rows, indent=1))
+Path("gpurun_out/r02_hbm_kernels.json").write_text(json.dumps(rows, indent=1))
