@@ -32,8 +32,10 @@
 
 namespace sir {
 
-constexpr int kRefWarps = 16;                      // consumer warps (one candidate position at a time each)
-constexpr int kRefThreads = 32 * (kRefWarps + 1);  // + one producer warp issuing the bulk copies
+// consumer warps (one candidate position at a time each) + one producer warp issuing the bulk copies: 16 consumers when
+// few (column, gallery) cells have a candidate (several variants per probe: a step holds about one position per warp and
+// more warps only add barrier traffic), 31 when every cell has one (one variant per probe: 79 -> 65 ms per 2.08 M positions)
+constexpr int kRefMaxThreads = 1024;
 constexpr int kRefMaxStages = 4;                   // gallery sub-chunk ring (depth chosen by the host)
 constexpr int kRefMaxSub = 128;                    // sub-chunks per tile
 constexpr int kRefMaxTgb = 2048;                   // gallery prints per tile
@@ -54,6 +56,7 @@ struct RefineParams {
   float tau_rel, tau_abs, inv_scale;
 };
 
+template <int kRefThreads>
 __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int inc = v;
@@ -74,7 +77,9 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* to
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefineParams p) {
+template <int kRefWarps>
+__global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const RefineParams p) {
+  constexpr int kRefThreads = 32 * (kRefWarps + 1);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int PG = p.Hp * p.WP;                                      // cells of one packed gallery plane
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // full_g[ST], empty_g[ST], empty_t[2]
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(kRefThreads) ncc_refine_kernel(const RefinePar
     mine += expand(item, &info, &py, &px, &j, &i);
   }
   int total = 0;
-  const int base = block_exclusive_scan(mine, scratch, &total);
+  const int base = block_exclusive_scan<kRefThreads>(mine, scratch, &total);
   if (total == 0) return;
   if (tid == 0) {
     for (int st = 0; st < kRefStages; ++st) {
@@ -338,7 +343,7 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
   // every gallery plane serves more positions; TGS only has to keep a step long enough to hide the copies.
   const size_t budget = 220 * 1024;
   const size_t tbytes = (size_t)p.Kpad * 4, gbytes = (size_t)Hp * p.WP * 4;
-  const size_t fixed = 128 + (size_t)p.cap * 12 + 4 * (size_t)(32 + kRefMaxTgb + kRefMaxSub + 1 + kRefThreads / 32) + 64;
+  const size_t fixed = 128 + (size_t)p.cap * 12 + 4 * (size_t)(32 + kRefMaxTgb + kRefMaxSub + 1 + kRefMaxThreads / 32) + 64;
   p.TN = 0;
   p.ST = 2;
   int tgs_first = 8;
@@ -382,12 +387,17 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
     }
   }
   const size_t smem = 128 + 2 * p.TN * tbytes + (size_t)kRefStages * p.TGS * gbytes + (size_t)p.cap * 12 +
-                      4 * (size_t)(p.TN + p.TGB + p.NS + 1 + kRefThreads / 32) + 64;
+                      4 * (size_t)(p.TN + p.TGB + p.NS + 1 + kRefMaxThreads / 32) + 64;
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_refine: shared-memory plan overflow (%zu bytes)", smem);
-  SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   const long long blocks = (long long)ceil_div(ncols, p.TN) * p.tiles_g;
   SIR_CHECK_ARG(blocks < (1ll << 31), "sir_ncc_refine: too many tiles");
-  ncc_refine_kernel<<<(unsigned)blocks, kRefThreads, smem, (cudaStream_t)stream>>>(p);
+  if (variants <= 2) {
+    SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    ncc_refine_kernel<31><<<(unsigned)blocks, 32 * 32, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    ncc_refine_kernel<16><<<(unsigned)blocks, 32 * 17, smem, (cudaStream_t)stream>>>(p);
+  }
   SIR_LAUNCH_CHECK("ncc_refine_kernel");
   return SIR_OK;
 }
