@@ -88,6 +88,15 @@ size_t sir_variant_resize_workspace_bytes(int h, int w, int h2, int w2);
 int sir_variant_resize(const float* d_in, int N, int C, int h, int w, int h2, int w2,
                        float* d_out, float* d_tmp, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Loader resize on the device (dataloader.py:231-237, Image.resize(size, LANCZOS) of the cropped 8-bit prints): Pillow's
+ * 8 bits-per-channel resampler, bit exact (LANCZOS support 3, coefficients rounded to 22 fractional bits, horizontal
+ * pass first into an 8-bit intermediate).  d_in uint8 [N][h][w][ch] (ch = 1 grayscale, 3 RGB) -> d_out [N][h2][w2][ch];
+ * d_tmp [N][h][w2][ch] scratch (may be NULL when only one axis changes); d_ws: caller workspace of
+ * sir_image_resize_workspace_bytes(h, w, h2, w2) bytes, 16-byte aligned. */
+size_t sir_image_resize_workspace_bytes(int h, int w, int h2, int w2);
+int sir_image_resize_lanczos(const uint8_t* d_in, int N, int h, int w, int ch, int h2, int w2, uint8_t* d_out, uint8_t* d_tmp,
+                             void* d_ws, size_t ws_bytes, void* stream);
+
 /* [N][C][h][w] -> [N][C][w][h].  Scores are invariant under transposing probe and gallery maps alike; the
  * host uses this to present the correlation kernel with the orientation that pads less. */
 int sir_maps_transpose(const float* d_in, int N, int C, int h, int w, float* d_out, void* stream);

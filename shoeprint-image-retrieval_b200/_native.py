@@ -35,6 +35,8 @@ SIGNATURES = {
     "sir_variant_rotate": (_i, [_p, _i, _i, _i, _i, C.c_double, _p, _p]),
     "sir_variant_resize_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "sir_variant_resize": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, C.c_size_t, _p]),
+    "sir_image_resize_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "sir_image_resize_lanczos": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, C.c_size_t, _p]),
     "sir_maps_transpose": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "sir_template_kpad": (_i, [_i, _i]),
     "sir_template_pack": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

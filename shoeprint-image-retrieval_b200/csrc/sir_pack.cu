@@ -391,6 +391,29 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
   }
 }
 
+// Loader resize (dataloader.py:231-237: Image.resize(size, LANCZOS) on 8-bit images): one pass of Pillow's 8 bits-per-channel
+// resampler -- integer coefficients of 22 fractional bits, int32 accumulation from 1 << 21, arithmetic shift, clip to 0..255
+// (Resample.c ImagingResampleHorizontal_8bpc / Vertical_8bpc, normalize_coeffs_8bpc).  axis 1: along w; axis 0: along h.
+// in [planes][h_in][w_in][ch] uint8 -> out [planes][h_out][w_out][ch]; bit exact with Pillow.
+__global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int planes, int h_in,
+                                                          int w_in, int h_out, int w_out, int ch, int axis, const int* __restrict__ xmin,
+                                                          const int* __restrict__ cnt, const int* __restrict__ kk, int ksize) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, hwc_out = h_out * w_out * ch;
+  if (p >= hwc_out) return;
+  const int c = p % ch, x = (p / ch) % w_out, y = p / (ch * w_out);
+  const int o = axis ? x : y;
+  const int lo = xmin[o], n = cnt[o];
+  const int* k = kk + (size_t)o * ksize;
+  const int src0 = axis ? (y * w_in + lo) * ch + c : (lo * w_in + x) * ch + c, step = axis ? ch : w_in * ch;
+  for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+    const uint8_t* src = in + (size_t)plane * h_in * w_in * ch + src0;
+    int ss = 1 << 21;
+    for (int j = 0; j < n; ++j) ss += (int)__ldg(src + (size_t)j * step) * k[j];
+    ss >>= 22;
+    out[(size_t)plane * hwc_out + p] = (uint8_t)min(255, max(0, ss));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K5 templates: one CTA per (map n, channel c).
 __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restrict__ maps, int C, int h, int w, int Hb, int Wb, int col0,
@@ -707,12 +730,18 @@ double bicubic(double x) {
   if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
   return 0.0;
 }
-// Pillow Resample.c precompute_coeffs, bicubic (support 2.0).
-Coeffs precompute(int n_in, int n_out) {
+double sinc_filter(double x) {
+  if (x == 0.0) return 1.0;
+  x = x * M_PI;
+  return std::sin(x) / x;
+}
+double lanczos3(double x) { return (-3.0 <= x && x < 3.0) ? sinc_filter(x) * sinc_filter(x / 3) : 0.0; }  // truncated sinc
+// Pillow Resample.c precompute_coeffs: bicubic (support 2.0) or, with `lanczos`, LANCZOS (support 3.0).
+Coeffs precompute(int n_in, int n_out, bool lanczos = false) {
   Coeffs c;
   const double scale = (double)n_in / n_out;
   const double fscale = scale < 1.0 ? 1.0 : scale;
-  const double support = 2.0 * fscale;
+  const double support = (lanczos ? 3.0 : 2.0) * fscale;
   c.ksize = (int)std::ceil(support) * 2 + 1;
   c.xmin.assign(n_out, 0);
   c.cnt.assign(n_out, 0);
@@ -728,7 +757,7 @@ Coeffs precompute(int n_in, int n_out) {
     double* k = &c.kk[(size_t)xx * c.ksize];
     double ww = 0.0;
     for (int i = 0; i < n; ++i) {
-      const double wgt = bicubic((i + lo - center + 0.5) * ss);
+      const double wgt = lanczos ? lanczos3((i + lo - center + 0.5) * ss) : bicubic((i + lo - center + 0.5) * ss);
       k[i] = wgt;
       ww += wgt;
     }
@@ -796,6 +825,63 @@ extern "C" int sir_variant_resize(const float* d_in, int N, int C, int h, int w,
   }
   if (w2 != w) return run_pass(d_in, d_out, planes, h, w, h, w2, 1, ws, st);
   return run_pass(d_in, d_out, planes, h, w, h2, w, 0, ws, st);
+}
+
+namespace {
+size_t pass_u8_ws_bytes(int n_in, int n_out) {
+  const double scale = (double)n_in / n_out, fscale = scale < 1.0 ? 1.0 : scale;
+  const int ksize = (int)std::ceil(3.0 * fscale) * 2 + 1;
+  return (size_t)round_up((2 + ksize) * n_out * (int)sizeof(int), 256);
+}
+int run_pass_u8(const uint8_t* in, uint8_t* out, int planes, int h_in, int w_in, int h_out, int w_out, int ch, int axis, void* d_ws,
+                cudaStream_t st) {
+  const Coeffs c = precompute(axis ? w_in : h_in, axis ? w_out : h_out, true);
+  const int n_out = axis ? w_out : h_out;
+  std::vector<int> tab((size_t)(2 + c.ksize) * n_out);
+  for (int i = 0; i < n_out; ++i) {
+    tab[i] = c.xmin[i];
+    tab[n_out + i] = c.cnt[i];
+  }
+  for (size_t i = 0; i < c.kk.size(); ++i) {  // normalize_coeffs_8bpc
+    const double v = c.kk[i];
+    tab[2 * (size_t)n_out + i] = v < 0 ? (int)(-0.5 + v * (double)(1 << 22)) : (int)(0.5 + v * (double)(1 << 22));
+  }
+  int* d_tab = reinterpret_cast<int*>(d_ws);
+  SIR_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, st));  // pageable: staged before returning
+  const unsigned bx = (unsigned)ceil_div(h_out * w_out * ch, 256);
+  const unsigned by = (unsigned)std::min<long long>(planes, std::max(1u, 148u * 16u / bx));
+  resample_u8_kernel<<<dim3(bx, by), 256, 0, st>>>(in, out, planes, h_in, w_in, h_out, w_out, ch, axis, d_tab, d_tab + n_out, d_tab + 2 * n_out,
+                                                   c.ksize);
+  SIR_LAUNCH_CHECK("resample_u8_kernel");
+  return SIR_OK;
+}
+}  // namespace
+
+extern "C" size_t sir_image_resize_workspace_bytes(int h, int w, int h2, int w2) {
+  if (h <= 0 || w <= 0 || h2 <= 0 || w2 <= 0) return 0;
+  return (w2 != w ? pass_u8_ws_bytes(w, w2) : 0) + (h2 != h ? pass_u8_ws_bytes(h, h2) : 0);
+}
+
+extern "C" int sir_image_resize_lanczos(const uint8_t* d_in, int N, int h, int w, int ch, int h2, int w2, uint8_t* d_out, uint8_t* d_tmp,
+                                        void* d_ws, size_t ws_bytes, void* stream) {
+  SIR_CHECK_ARG(d_in && d_out, "sir_image_resize_lanczos: null pointer");
+  SIR_CHECK_ARG(N > 0 && h > 0 && w > 0 && h2 > 0 && w2 > 0 && ch >= 1 && ch <= 4, "sir_image_resize_lanczos: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h2 == h && w2 == w) {
+    SIR_CUDA(cudaMemcpyAsync(d_out, d_in, (size_t)N * h * w * ch, cudaMemcpyDeviceToDevice, st));
+    return SIR_OK;
+  }
+  SIR_CHECK_ARG(d_ws && ws_bytes >= sir_image_resize_workspace_bytes(h, w, h2, w2) && (reinterpret_cast<uintptr_t>(d_ws) & 15) == 0,
+                "sir_image_resize_lanczos: workspace of %zu bytes (16-byte aligned) needed", sir_image_resize_workspace_bytes(h, w, h2, w2));
+  char* ws = reinterpret_cast<char*>(d_ws);
+  if (w2 != w && h2 != h) {  // horizontal pass first, 8-bit intermediate, as ImagingResample does
+    SIR_CHECK_ARG(d_tmp, "sir_image_resize_lanczos: two-pass resize needs d_tmp [N][h][w2][ch]");
+    int rc = run_pass_u8(d_in, d_tmp, N, h, w, h, w2, ch, 1, ws, st);
+    if (rc) return rc;
+    return run_pass_u8(d_tmp, d_out, N, h, w2, h2, w2, ch, 0, ws + pass_u8_ws_bytes(w, w2), st);
+  }
+  if (w2 != w) return run_pass_u8(d_in, d_out, N, h, w, h, w2, ch, 1, ws, st);
+  return run_pass_u8(d_in, d_out, N, h, w, h2, w, ch, 0, ws, st);
 }
 
 extern "C" int sir_gallery_pitch(int Wp) { return Wp > 0 ? gal_pitch(Wp) : 0; }

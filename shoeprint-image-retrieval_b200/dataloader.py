@@ -14,6 +14,11 @@ the unchanged entry point.  What is kept exactly, because it decides the inputs 
 * clusters whose scales differ by at most ``cluster_minimise_tolerance`` and share a block merge
   (``:329-364``).
 
+Optional (``SIR_DEVICE_RESIZE=1``, off by default): the LANCZOS resize of a cluster's images runs on the GPU
+(``engine.resize_images_lanczos`` -> ``sir_image_resize_lanczos``, bit exact with Pillow's 8-bit resampler); decode and crop stay
+on the host threads.  It is off by default because the loader hands numpy arrays to the caller, so the resized images
+travel back to the host and the round trip costs more than Pillow's own resize saves.
+
 Deliberate differences: KMeans is seeded (the reference's is not, ``:284``, so its clustering
 varies run to run); files are decoded by a thread pool and every file is loaded (the reference's
 process chunking drops or misplaces files when ``len % n_processes`` is 1, ``:137-146``).
@@ -80,19 +85,31 @@ class Dataloader:
         return marks, prints, pairs, self.blocks[k]
 
     # ------------------------------------------------------------------ loading
-    def _load_one(self, directory: Path, name: str, scale: float) -> np.ndarray:
+    def _load_one(self, directory: Path, name: str, scale: float, resize: bool = True) -> np.ndarray:
         crop = self.config["dataset"]["crop"]
         with Image.open(directory / name) as image:
             ch, cw = floor(image.height * crop[0]), floor(image.width * crop[1])
             image = image.crop((cw, ch, image.width - cw, image.height - ch))
+            if not resize:
+                return np.array(image)
             size = (int(image.width * scale), int(image.height * scale))
             return np.array(image.resize(size, Image.Resampling.LANCZOS))
 
     def _load_images(self, image_files: list[str], image_directory: Path, scale: float) -> tuple[list[np.ndarray], list[int]]:
         image_files.sort()  # in place, like the reference (dataloader.py:133): gallery order = name order
         workers = max(1, min(int(self.config["dataset"]["n_processes"]), os.cpu_count() or 1, len(image_files) or 1))
+        device_resize = os.environ.get("SIR_DEVICE_RESIZE", "") == "1"
         with ThreadPoolExecutor(workers) as pool:
-            images = list(pool.map(lambda n: self._load_one(image_directory, n, scale), image_files))
+            images = list(pool.map(lambda n: self._load_one(image_directory, n, scale, not device_resize), image_files))
+        if device_resize:  # decode + crop on the host, LANCZOS on the GPU (bit exact with Pillow)
+            from . import engine
+
+            usable = [im.dtype == np.uint8 and im.ndim in (2, 3) for im in images]
+            sizes = [(int(im.shape[0] * scale), int(im.shape[1] * scale)) for im in images]
+            if all(usable):
+                images = engine.resize_images_lanczos(images, sizes)
+            else:  # 16-bit / palette images: Pillow's own path
+                images = [np.array(Image.fromarray(im).resize((hw[1], hw[0]), Image.Resampling.LANCZOS)) for im, hw in zip(images, sizes)]
         ids = [_file_id(n, self.config["dataset"]["type"]) for n in image_files]
         return images, ids
 

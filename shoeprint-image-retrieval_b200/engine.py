@@ -468,6 +468,32 @@ def make_variant(maps: torch.Tensor, rot: float | None, scale: float | None) -> 
     return out
 
 
+def resize_images_lanczos(images: list[np.ndarray], sizes: list[tuple[int, int]]) -> list[np.ndarray]:
+    """``np.array(Image.fromarray(im).resize((w2, h2), LANCZOS))`` for uint8 images on the device (``sir_image_resize_lanczos``,
+    bit exact with Pillow's 8-bit resampler; ``dataloader.py:231-237``).  ``sizes[i] = (h2, w2)``.  Images that share source
+    and target size travel as one batch."""
+    dev = _require_cuda()
+    out: list = [None] * len(images)
+    batches: dict[tuple, list[int]] = {}
+    for i, (im, hw) in enumerate(zip(images, sizes)):
+        batches.setdefault((tuple(im.shape), tuple(hw)), []).append(i)
+    for (shape, (h2, w2)), idx in batches.items():
+        h, w = shape[:2]
+        ch = 1 if len(shape) == 2 else int(shape[2])
+        src = torch.from_numpy(np.stack([np.ascontiguousarray(images[i]) for i in idx])).to(dev, non_blocking=True)
+        dst = torch.empty((len(idx), h2, w2) + ((ch,) if len(shape) == 3 else ()), dtype=torch.uint8, device=dev)
+        tmp = torch.empty((len(idx), h, w2, ch), dtype=torch.uint8, device=dev) if (h2 != h and w2 != w) else None
+        ws_bytes = int(nat.lib.sir_image_resize_workspace_bytes(h, w, h2, w2))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        nat.check(nat.lib.sir_image_resize_lanczos(_ptr(src), len(idx), h, w, ch, h2, w2, _ptr(dst), _ptr(tmp), _ptr(ws), ws_bytes, _stream()),
+                  "sir_image_resize_lanczos")
+        launch_counter.add(2 if tmp is not None else 1)
+        host = dst.cpu().numpy()
+        for j, i in enumerate(idx):
+            out[i] = host[j]
+    return out
+
+
 # --------------------------------------------------------------------------- scoring
 
 @dataclass

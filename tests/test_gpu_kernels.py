@@ -1,9 +1,12 @@
 """GPU parity tests of the individual libsir kernels against the CPU oracle / Pillow."""
 
 import ctypes as C
+from pathlib import Path
 
 import numpy as np
 import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
 
 pytestmark = pytest.mark.gpu
 
@@ -188,3 +191,50 @@ def test_merge_topk(eng):
         cand = sorted(((-vals[pp, qq, j], idx[pp, qq, j]) for pp in range(p) for j in range(k) if idx[pp, qq, j] >= 0))[:k]
         np.testing.assert_array_equal(oi.cpu().numpy()[qq], [c[1] for c in cand])
         np.testing.assert_array_equal(ov.cpu().numpy()[qq], [-c[0] for c in cand])
+
+
+def test_device_lanczos_resize_bit_exact_vs_pillow(eng):
+    """sir_image_resize_lanczos (the loader's resize on the device) against Pillow itself and the CPU restatement."""
+    from PIL import Image
+
+    from oracle.loader import resize_lanczos_u8
+
+    rng = np.random.default_rng(9)
+    images, sizes = [], []
+    for t in range(24):
+        h, w = (int(rng.integers(20, 200)), int(rng.integers(20, 120))) if t % 6 else (586, 270)
+        s = float(rng.uniform(0.4, 1.5))
+        images.append(rng.integers(0, 256, size=(h, w) if t % 4 else (h, w, 3), dtype=np.uint8))
+        sizes.append((max(1, int(h * s)) if t % 5 else h, max(1, int(w * s))))
+    images += [images[1].copy(), images[1].copy()]  # a batch of three with equal sizes
+    sizes += [sizes[1], sizes[1]]
+    got = eng.resize_images_lanczos(images, sizes)
+    for im, (h2, w2), g in zip(images, sizes, got):
+        want = np.array(Image.fromarray(im).resize((w2, h2), Image.Resampling.LANCZOS))
+        np.testing.assert_array_equal(g, want)
+        np.testing.assert_array_equal(resize_lanczos_u8(im, h2, w2), want)
+
+
+def test_loader_with_device_resize_equals_host_loader(eng, tmp_path, monkeypatch):
+    """Dataloader with SIR_DEVICE_RESIZE=1 (LANCZOS on the GPU) returns exactly what the host loader returns, on a directory
+    whose prints are large enough to be scaled down (dataloader.py:408-417: scale = maximum_dim / largest)."""
+    import sys
+
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import synth_dataset
+
+    from src.shoeprint_image_retrieval.dataloader import Dataloader
+
+    root = tmp_path / "big"
+    synth_dataset.write_dataset(root, 21, [(1800, 800)] * 4, [(1200 + 40 * i, 560 + 10 * i) for i in range(5)])
+    cfg = synth_dataset.config_for(root, 1)
+    monkeypatch.delenv("SIR_DEVICE_RESIZE", raising=False)
+    host = list(Dataloader(cfg))
+    monkeypatch.setenv("SIR_DEVICE_RESIZE", "1")
+    dev = list(Dataloader(cfg))
+    assert len(host) == len(dev) == 1
+    assert Dataloader(cfg).scales[0] < 1.0
+    for (m0, p0, pairs0, b0), (m1, p1, pairs1, b1) in zip(host, dev):
+        assert pairs0 == pairs1 and b0 == b1
+        for a, b in zip(m0 + p0, m1 + p1):
+            np.testing.assert_array_equal(a, b)

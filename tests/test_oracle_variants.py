@@ -37,3 +37,22 @@ def test_resize_bit_exact_random_cases():
         got = variants.resize_maps(m, s)
         assert got.shape == want.shape
         np.testing.assert_array_equal(got, want)
+
+
+def test_loader_lanczos_restatement_is_bit_exact_vs_pillow():
+    """oracle.loader.resize_lanczos_u8 == Image.resize(size, LANCZOS) on 8-bit images (dataloader.py:231-237): gray and RGB,
+    enlargement and reduction, one or both axes."""
+    import numpy as np
+    from PIL import Image
+
+    from oracle.loader import resize_lanczos_u8
+
+    rng = np.random.default_rng(0)
+    for t in range(40):
+        h, w = int(rng.integers(5, 90)), int(rng.integers(5, 90))
+        s = float(rng.uniform(0.3, 1.6))
+        h2 = max(1, int(h * s)) if t % 5 else h
+        w2 = max(1, int(w * (s if t % 3 else rng.uniform(0.3, 1.6))))
+        img = rng.integers(0, 256, size=(h, w) if t % 4 else (h, w, 3), dtype=np.uint8)
+        want = np.array(Image.fromarray(img).resize((w2, h2), Image.Resampling.LANCZOS))
+        np.testing.assert_array_equal(resize_lanczos_u8(img, h2, w2), want)
