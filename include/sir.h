@@ -208,6 +208,11 @@ int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const float* const*
 /* cudaMemsetAsync(d_ptr, 0, bytes) on `stream`: the path zeroes its score / operand buffers through the library. */
 int sir_memset_zero(void* d_ptr, size_t bytes, void* stream);
 
+/* Test aid: one CTA per SM fills the SM's whole shared-memory carve-out with `byte`.  Shared memory is not cleared between
+ * kernels; the parity tests run the correlation kernels after a 0xFF fill (NaN as fp16 / e4m3 / float32) to prove that no
+ * MMA or reduction reads a cell the kernel itself has not written. */
+int sir_debug_fill_shared_memory(int byte, void* stream);
+
 /* Planning aid (host only, nothing is launched): estimated SM cycles per (gallery, 256-column tile, channel)
  * of the tensor-core kernel for this shape and precision mode -- the larger of the MMA time of the
  * non-skipped K stages and the shifted-entry generation time under the shared-memory plan the launch

@@ -96,6 +96,28 @@ extern "C" int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const
                        d_col2probe, d_approx, score_ld, g0, 1, (cudaStream_t)stream, nullptr, d_rnorm_tab, (uint2*)d_rec, tau_rel, tau_abs);
 }
 
+namespace {
+__global__ void __launch_bounds__(256) smem_fill_kernel(uint32_t word, int words) {
+  extern __shared__ uint32_t fill_area[];
+  for (int i = threadIdx.x; i < words; i += blockDim.x) fill_area[i] = word;
+  __syncthreads();
+  if (fill_area[(threadIdx.x * 7) % words] != word) __trap();  // keeps the stores alive
+}
+}  // namespace
+
+extern "C" int sir_debug_fill_shared_memory(int byte, void* stream) {
+  SIR_CHECK_ARG(byte >= 0 && byte <= 255, "sir_debug_fill_shared_memory: byte %d", byte);
+  int dev = 0, sms = 0, smem = 0;
+  SIR_CUDA(cudaGetDevice(&dev));
+  SIR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SIR_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  SIR_CUDA(cudaFuncSetAttribute(smem_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t word = 0x01010101u * (uint32_t)byte;
+  smem_fill_kernel<<<sms, 256, smem, (cudaStream_t)stream>>>(word, smem / 4);  // one CTA per SM: it owns the whole carve-out
+  SIR_LAUNCH_CHECK("smem_fill_kernel");
+  return SIR_OK;
+}
+
 extern "C" int sir_memset_zero(void* d_ptr, size_t bytes, void* stream) {
   SIR_CHECK_ARG(d_ptr || bytes == 0, "sir_memset_zero: null pointer");
   if (bytes) SIR_CUDA(cudaMemsetAsync(d_ptr, 0, bytes, (cudaStream_t)stream));

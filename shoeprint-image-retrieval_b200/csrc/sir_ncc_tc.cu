@@ -198,6 +198,12 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     if constexpr (CG == 2) ptx::tmem_alloc_2cta(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
     else ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)));
   }
+  // The E buffers start from zeros: an MMA over a partial stage (the K32 fp8 corrections, the odd last K16 step) reads
+  // entry rows no generator pass of this segment has written.  Their B taps are zero, but whatever an earlier kernel
+  // left in shared memory may decode to NaN / Inf (0x7F / 0xFF as e4m3), and NaN * 0 poisons the position.
+  for (uint32_t o = p.off_e + 16u * threadIdx.x; o < p.off_gs; o += 16u * blockDim.x)
+    *reinterpret_cast<uint4*>(base_ptr + o) = make_uint4(0u, 0u, 0u, 0u);
+  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (CG == 2) ptx::cluster_sync();  // the peer's barriers are initialised before anyone signals them

@@ -469,7 +469,13 @@ __global__ void __launch_bounds__(128) template_pack_kernel(const float* __restr
   }
 }
 
-// Warp-per-(map, channel) version of the template pack, same idea as gallery_pack_warp_kernel.
+// Warp-per-(map, channel) version of the template pack, same idea as gallery_pack_warp_kernel.  The kernel is bound by
+// instruction issue, not by HBM (ncu: ~2 warp instructions per cycle and SM, DRAM < 50 %), so it is specialised per operand
+// set (MODE 0: screening, hi + float32 taps; 1: hi + lo [+ t32]; 2: hi + the two fp8 companions), divides by multiplication
+// and does the per-cell arithmetic in float32 (the mean and the energy are still accumulated in float64).
+__device__ __forceinline__ int div_small(int n, unsigned magic) { return (int)(((unsigned)n * magic) >> 24); }  // n < 2^16, d < 2^8
+
+template <int MODE>
 __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __restrict__ maps, long long planes, int C, int h, int w,
                                                                  int Hb, int Wb, int col0, int ncols_alloc, int row_align,
                                                                  __half* __restrict__ thi,
@@ -485,6 +491,7 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
   const int oy = Hb / 2 - Hm / 2, ox = Wb / 2 - Wm / 2;
   float* ch = slab + (size_t)wid * HW;
   const int c8 = rowk / 8, n8 = Kpad / 8, m8 = (Wm + 7) / 8;
+  const unsigned magic_c8 = (1u << 24) / (unsigned)c8 + 1, magic_m8 = (1u << 24) / (unsigned)m8 + 1;
   for (long long pc = (long long)blockIdx.x * nw + wid; pc < planes; pc += (long long)gridDim.x * nw) {
     const int n = (int)(pc / C), c = (int)(pc - (long long)n * C);
     const float* src = maps + pc * HW;
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
     __syncwarp();
     double acc = 0.0;
     for (int o = lane; o < Hm * m8; o += 32) {
-      const int u = o / m8, v0 = (o - u * m8) * 8;
+      const int u = div_small(o, magic_m8), v0 = (o - u * m8) * 8;
       const float* row = ch + (u + kEdge) * w + kEdge + v0;
       float part = 0.0f;
 #pragma unroll
@@ -509,49 +516,56 @@ __global__ void __launch_bounds__(256) template_pack_warp_kernel(const float* __
     const float mean = (float)(warp_sum(acc) / (double)K);
     double e = 0.0;
     for (int o = lane; o < Hm * m8; o += 32) {
-      const int u = o / m8, v0 = (o - u * m8) * 8;
+      const int u = div_small(o, magic_m8), v0 = (o - u * m8) * 8;
       const float* row = ch + (u + kEdge) * w + kEdge + v0;
+      float part = 0.0f;  // eight squares in float32 (all positive: ~1e-7 relative), the 100+ partials in float64
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const double z = (v0 + j < Wm) ? (double)(row[j] - mean) : 0.0;
-        e += z * z;
+        const float z = (v0 + j < Wm) ? row[j] - mean : 0.0f;
+        part = fmaf(z, z, part);
       }
+      e += (double)part;
     }
     e = warp_sum(e);
     const double inv = e > 0.0 ? 1.0 / sqrt(e) : 0.0;
+    const float inv_f = (float)inv;
+    const float inv_scaled = (float)ldexp(inv, kTemplateScaleLog2);  // a power of two: same rounding as scaling afterwards
     const size_t col = (size_t)c * ncols_alloc + col0 + n;
     for (int o = lane; o < n8; o += 32) {
-      const int ub = o / c8, vb0 = (o - ub * c8) * 8;  // bucket coordinates of this 8-tap chunk
+      const int ub = div_small(o, magic_c8), vb0 = (o - ub * c8) * 8;  // bucket coordinates of this 8-tap chunk
       const int u = ub - oy;
+      const bool row_in = u >= 0 && u < Hm;
+      const float* row = ch + (u + kEdge) * w + kEdge - ox + vb0;
       __align__(16) __half h8[8];
-      __align__(16) __half l8[8];
-      __align__(8) uint8_t b8[8];
-      __align__(8) uint8_t q8[8];
       __align__(16) float s8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int v = vb0 + j - ox;
-        float tn = 0.0f;
-        if (u >= 0 && u < Hm && v >= 0 && v < Wm) {
-          tn = (float)((double)(ch[(u + kEdge) * w + kEdge + v] - mean) * inv);
-          if (t32) t32[col * K + u * Wm + v] = tn;
-        }
-        const float sc = ldexpf(tn, kTemplateScaleLog2);
-        s8[j] = sc;
-        h8[j] = __float2half_rn(sc);
-        const float lo = sc - __half2float(h8[j]);
-        l8[j] = __float2half_rn(lo);
-        b8[j] = to_e4m3(__half2float(h8[j]) * kFp8HiScale);
-        q8[j] = to_e4m3(lo * kFp8LoScale);
+        const bool in = row_in && v >= 0 && v < Wm;
+        const float z = in ? row[j] - mean : 0.0f;
+        s8[j] = z * inv_scaled;
+        h8[j] = __float2half_rn(s8[j]);
+        if (MODE == 1 && t32 && in) t32[col * K + u * Wm + v] = z * inv_f;
       }
       *reinterpret_cast<uint4*>(thi + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(h8);
-      if (t32p) {
+      if (MODE == 0) {
         float4* d = reinterpret_cast<float4*>(t32p + col * Kpad + (size_t)o * 8);
         d[0] = *reinterpret_cast<const float4*>(s8);
         d[1] = *reinterpret_cast<const float4*>(s8 + 4);
-      }
-      if (tlo) *reinterpret_cast<uint4*>(tlo + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(l8);
-      if (t8b) {
+      } else if (MODE == 1) {
+        if (!tlo) continue;
+        __align__(16) __half l8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) l8[j] = __float2half_rn(s8[j] - __half2float(h8[j]));
+        *reinterpret_cast<uint4*>(tlo + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint4*>(l8);
+      } else {  // fp8 copies for the correction MMAs: (B_hi / 64) and (B_lo * 64), see sir_ncc_tc.cu
+        __align__(8) uint8_t b8[8];
+        __align__(8) uint8_t q8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          b8[j] = to_e4m3(__half2float(h8[j]) * kFp8HiScale);
+          q8[j] = to_e4m3((s8[j] - __half2float(h8[j])) * kFp8LoScale);
+        }
         *reinterpret_cast<uint2*>(t8b + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint2*>(b8);
         *reinterpret_cast<uint2*>(t8l + col * Kpad + (size_t)o * 8) = *reinterpret_cast<const uint2*>(q8);
       }
@@ -893,8 +907,8 @@ static void launch_template_pack(const float* d_maps, int N, int C, int h, int w
   if (8 * slab <= 48 * 1024) {
     const long long planes = (long long)N * C;
     const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 148 * 8);
-    template_pack_warp_kernel<<<blocks, 256, 8 * slab, st>>>(d_maps, planes, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32,
-                                                             t8b, t8l, t32p, gather);
+    auto kern = t32p ? template_pack_warp_kernel<0> : (t8b ? template_pack_warp_kernel<2> : template_pack_warp_kernel<1>);
+    kern<<<blocks, 256, 8 * slab, st>>>(d_maps, planes, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32, t8b, t8l, t32p, gather);
   } else {
     template_pack_kernel<<<(unsigned)((size_t)N * C), 128, 0, st>>>(d_maps, C, h, w, Hb, Wb, col0, ncols_alloc, row_align, thi, tlo, t32, t8b,
                                                                     t8l, t32p, gather);

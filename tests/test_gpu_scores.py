@@ -302,7 +302,57 @@ def test_reference_shapes_against_the_cpu_oracle(eng, shape):
     _, want = ocmp.compare_maps_oracle(probes, gallery, pairs, [-5], None, method="fast")
     for precision in ("fp16_refine", "fp16_fp8c", "fp16x3"):
         ranks, scores, _ = eng.compare(probes, gallery, pairs, [-5], None, precision=precision)
-        _check(scores.cpu().numpy(), want)
+        try:
+            _check(scores.cpu().numpy(), want)
+        except AssertionError as exc:
+            raise AssertionError(f"{precision}: {exc}") from None
         for i in range(len(probes)):
             lo, hi = ocmp.rank_interval(want[i], pairs[i])
-            assert lo <= ranks[i] <= hi
+            assert lo <= ranks[i] <= hi, precision
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("byte", [0xFF, 0x7F, 0x7C])
+def test_stale_shared_memory_does_not_leak_into_scores(eng, byte):
+    """Shared memory keeps what the previous kernel left there.  An MMA over a partial K stage reads operand rows the kernel has
+    not written in this pass (their partner taps are zero), so leftovers that decode to NaN / Inf (0xFF, 0x7F as e4m3 and
+    float, 0x7C7C = +Inf as fp16) used to poison a position now and then.  Fill every SM's shared memory with such a
+    pattern right before each scoring call (ragged probes: the multi-shape bucket path) and compare with the oracle."""
+    import ctypes as C
+    import torch
+    from oracle import compare as ocmp
+    from src.shoeprint_image_retrieval import _native as nat, synth
+
+    gallery = synth.make_gallery(101, 4, 80, 59, 21)
+    probes, pairs = synth.make_probes(102, gallery, 3, min_frac=0.85)
+    _, want = ocmp.compare_maps_oracle(probes, gallery, pairs, [-5], None, method="fast")
+    uniform = [g[:, 2:-2, 1:-1].copy() for g in gallery[:3]]
+    _, want_u = ocmp.compare_maps_oracle(uniform, gallery, [0, 1, 2], [-5], None, method="fast")
+    real = nat.lib
+
+    def poisoned(name):
+        fn = getattr(real, name)
+
+        def call(*args):
+            nat.check(real.sir_debug_fill_shared_memory(byte, args[-1]), "sir_debug_fill_shared_memory")
+            return fn(*args)
+
+        return call
+
+    class _Lib:  # the engine's kernels, each preceded by the fill on the same stream
+        def __getattr__(self, name):
+            if name in ("sir_ncc_screen", "sir_ncc_refine", "sir_ncc_scores", "sir_ncc_scores_multi", "sir_ncc_scores_fp8c"):
+                return poisoned(name)
+            return getattr(real, name)
+
+    nat.lib = _Lib()
+    try:
+        for precision in ("fp16_refine", "fp16_fp8c", "fp16x3"):
+            for p, w, pr in ((probes, want, pairs), (uniform, want_u, [0, 1, 2])):
+                _, scores, _ = eng.compare(p, gallery, pr, [-5], None, precision=precision)
+                try:
+                    _check(scores.cpu().numpy(), w)
+                except AssertionError as exc:
+                    raise AssertionError(f"{precision}, fill {byte:#x}: {exc}") from None
+    finally:
+        nat.lib = real

@@ -46,6 +46,8 @@ ops = engine.GalleryOperands.pack(grp, keep_fp32=False)
 hp, wp = h - 4, w - 4
 wpitch = ops.ghi.shape[3]
 report("gallery_pack (K5g)", n * c * (4 * h * w + 4 * hp * wpitch), timed(lambda: engine.GalleryOperands.pack(grp, keep_fp32=False)))
+report("gallery_pack_f32 (K5g, default mode)", n * c * (4 * h * w + 8 * hp * wpitch),
+       timed(lambda: engine.GalleryOperands.pack(grp, keep_fp32=False, with_f32=True)))
 def rn():
     ops._rnorm.clear(); ops.rnorm(hp, wp, False)
 report("window_rnorm (K6)", n * c * (4 * hp * wpitch + 4 * hp * wp), timed(rn))
@@ -56,5 +58,13 @@ thi = torch.empty((c, n, kpad), dtype=torch.float16, device="cuda"); t8b = torch
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 report("template_pack fp8c (K5t)", n * c * (4 * h * w + 4 * kpad),
        timed(lambda: nat.check(nat.lib.sir_template_pack_fp8c(C.c_void_p(maps.data_ptr()), n, c, h, w, 0, n, C.c_void_p(thi.data_ptr()), C.c_void_p(t8b.data_ptr()), C.c_void_p(t8l.data_ptr()), st))))
+for rot in (None, 7.0):
+    gm = engine._gather_map(maps.device, h, w, rot, False)
+    from src.shoeprint_image_retrieval.engine import _ptr
+    kp = int(nat.lib.sir_template_kpad(hp, wp))
+    th = torch.empty((c, n, kp), dtype=torch.float16, device="cuda"); t32p = torch.empty((c, n, kp), dtype=torch.float32, device="cuda")
+    report(f"template_pack_screen rot={rot} (K5t, default mode)", n * c * (4 * h * w + 6 * kp),
+           timed(lambda: nat.check(nat.lib.sir_template_pack_screen(C.c_void_p(maps.data_ptr()), n, c, h, w, hp, wp, 0, n, C.c_void_p(th.data_ptr()),
+                                                                    C.c_void_p(t32p.data_ptr()), _ptr(gm), st))))
 Path("gpurun_out").mkdir(exist_ok=True)
 Path("gpurun_out/r02_hbm_kernels.json").write_text(json.dumps(rows, indent=1))
