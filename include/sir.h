@@ -153,10 +153,12 @@ int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, const uint8
 
 /* Multi-shape column tiles (ragged probe sets: every probe / scale variant its own template shape).
  * Templates of different true shapes are packed into the K layout of one BUCKET shape Hb x Wb, anchor on
- * anchor, zeros elsewhere (the numerator is unchanged); each 16-column chunk of the block holds templates
- * of one true shape and d_rnorm_tab[chunk] points at that shape's window-norm table (similarity.py:57-65
- * depends on the TRUE template size).  d_rnorm_tab: device array of device pointers, 16 per 256-column
- * tile, every entry valid.  precision: SIR_PREC_FP16X3 (d_glo, d_tlo) or SIR_PREC_FP16_FP8C (e4m3 operands). */
+ * anchor, zeros elsewhere (the numerator is unchanged); each chunk of sir_ncc_norm_chunk() (= 8) columns of the
+ * block holds templates of one true shape and d_rnorm_tab[chunk] points at that shape's window-norm table
+ * (similarity.py:57-65 depends on the TRUE template size).  d_rnorm_tab: device array of device pointers, 256 /
+ * sir_ncc_norm_chunk() per 256-column tile, every entry valid (also those of the last tile's absent columns).
+ * precision: SIR_PREC_FP16X3 (d_glo, d_tlo) or SIR_PREC_FP16_FP8C (e4m3 operands). */
+int sir_ncc_norm_chunk(void);
 int sir_template_pack_embed(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
                             int precision, uint16_t* d_thi, uint16_t* d_tlo, uint8_t* d_t8b, uint8_t* d_t8l, void* stream);
 int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sir_ncc_screen": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, C.c_float, C.c_float, _p, _p]),
     "sir_ncc_refine": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, C.c_float, C.c_float, _p, _i, _p, _p]),
     "sir_memset_zero": (_i, [_p, C.c_size_t, _p]),
+    "sir_ncc_norm_chunk": (_i, []),
     "sir_debug_fill_shared_memory": (_i, [_i, _p]),
     "sir_ncc_cost": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
     "sir_true_scores": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),

@@ -55,7 +55,7 @@ extern "C" int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, 
 
 // Multi-shape column tiles: the columns of the block were packed with sir_template_pack_embed into the K
 // layout of a bucket shape Hb x Wb; every 16-column chunk holds templates of ONE true shape and
-// d_rnorm_tab[chunk] (device array of device pointers, 16 per 256-column tile, every entry valid) is the
+// d_rnorm_tab[chunk] (device array of device pointers, one per sir_ncc_norm_chunk() columns, every entry valid) is the
 // window-norm table of that shape.  precision: SIR_PREC_FP16X3 or SIR_PREC_FP16_FP8C.
 extern "C" int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l,
                                     const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp, const uint16_t* d_thi,
@@ -117,6 +117,8 @@ extern "C" int sir_debug_fill_shared_memory(int byte, void* stream) {
   SIR_LAUNCH_CHECK("smem_fill_kernel");
   return SIR_OK;
 }
+
+extern "C" int sir_ncc_norm_chunk(void) { return sir::kNormChunkCols; }
 
 extern "C" int sir_memset_zero(void* d_ptr, size_t bytes, void* stream) {
   SIR_CHECK_ARG(d_ptr || bytes == 0, "sir_memset_zero: null pointer");

@@ -49,6 +49,7 @@ inline int current_device_slot() {
 }
 
 constexpr int kEdge = 2;           // similarity.py:92-93 crop
+constexpr int kNormChunkCols = 8;  // multi-shape column tiles: columns that share one window-norm table (sir_ncc_norm_chunk)
 constexpr int kTemplateScaleLog2 = 10;  // packed templates are (t-mean)/sqrt(E) * 2^10
 constexpr int kGalleryPeakLog2 = 10;    // packed gallery channels have max|v| in [2^9, 2^10)
 // fp8 (e4m3: 2^-9 .. 448) companions of the fp16 operands for the correction MMAs: hi / 64 (peak 16) and

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
             const int e = e0 + warp + kRefWarps * lane;
             if (e < e1) {
               const uint2 en = list[e];
-              const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en.x & 0xff)) >> 4] : p.rnorm;
+              const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en.x & 0xff)) / kNormChunkCols] : p.rnorm;
               rnv = __ldg(table + ((size_t)(gt0 + (int)(en.x >> 8)) * p.C + c) * M + (en.y & 0xffff) * p.Wp + (en.y >> 16));
             }
           }
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
               rnv = 0.0f;
               if (e2 < e1) {
                 const uint2 en2 = list[e2];
-                const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en2.x & 0xff)) >> 4] : p.rnorm;
+                const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en2.x & 0xff)) / kNormChunkCols] : p.rnorm;
                 rnv = __ldg(table + ((size_t)(gt0 + (int)(en2.x >> 8)) * p.C + c) * M + (en2.y & 0xffff) * p.Wp + (en2.y >> 16));
               }
             }

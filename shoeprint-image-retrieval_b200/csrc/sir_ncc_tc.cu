@@ -60,7 +60,7 @@ struct TcParams {
   const __half* ghi;
   const __half* glo;
   const float* rnorm;
-  // multi-shape column tiles: one window-norm table per 16-column chunk (16 per 256-column tile), NULL
+  // multi-shape column tiles: one window-norm table per kNormChunkCols-column chunk (32 per 256-column tile), NULL
   // when every column of the launch has the same true template shape
   const float* const* rnorm_tab;
   const int32_t* col2probe;
@@ -506,24 +506,31 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       const int y = 16 * py + mh, x = 8 * px + ml;
       const bool valid = (y < p.Hp) && (x < p.Wp);
       const int ncol_half = tile_cols(p, nt) - half * 128;  // columns of this warp's half that exist
-      // window-norm rows of this thread's position, one per 16-column chunk of its column half: with
-      // multi-shape tiles the chunks of a tile may belong to templates of different true shapes
+      // window-norm rows of this thread's position, one per kNormChunkCols-column chunk of its column half: with
+      // multi-shape tiles the chunks of a tile may belong to templates of different true shapes (the table pointers are
+      // warp-uniform loads, re-read per channel rather than held in 2 x 16 registers)
+      constexpr int kChunks = 128 / kNormChunkCols;
       const size_t roff = (size_t)g * p.C * M + (valid ? y * p.Wp + x : 0);
-      const float* rrow[8];
+      const float* const* tabp = p.rnorm_tab ? p.rnorm_tab + ((size_t)nt * (kTileN / kNormChunkCols) + half * kChunks) : nullptr;
+      auto load_norms = [&](float (&r)[kChunks], int c) {
+        if (tabp) {
 #pragma unroll
-      for (int j8 = 0; j8 < 8; ++j8)
-        rrow[j8] = (p.rnorm_tab ? p.rnorm_tab[(size_t)nt * 16 + half * 8 + j8] : p.rnorm) + roff;
+          for (int j = 0; j < kChunks; ++j)
+            r[j] = (valid && c < p.C && j * kNormChunkCols < ncol_half) ? __ldg(tabp[j] + roff + (size_t)c * M) : 0.0f;
+        } else {
+          const float v = (valid && c < p.C) ? __ldg(p.rnorm + roff + (size_t)c * M) : 0.0f;
+#pragma unroll
+          for (int j = 0; j < kChunks; ++j) r[j] = v;
+        }
+      };
 
       float total[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) total[j] = 0.0f;
-      float r_cur[8], r_next[8];
-#pragma unroll
-      for (int j8 = 0; j8 < 8; ++j8) r_cur[j8] = (valid && j8 * 16 < ncol_half) ? __ldg(rrow[j8]) : 0.0f;
+      float r_cur[kChunks], r_next[kChunks];
+      load_norms(r_cur, 0);
       for (int c = 0; c < p.C; ++c, ++cs) {
-#pragma unroll
-        for (int j8 = 0; j8 < 8; ++j8)
-          r_next[j8] = (valid && c + 1 < p.C && j8 * 16 < ncol_half) ? __ldg(rrow[j8] + (size_t)(c + 1) * M) : 0.0f;
+        load_norms(r_next, c + 1);
         const int buf = cs & 1;
         ptx::mbar_wait(bar_accfull(buf), (cs >> 1) & 1);
         ptx::tc_fence_after();
@@ -536,7 +543,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            total[j4 * 32 + j] = fmaf(r_cur[2 * j4 + (j >> 4)], __uint_as_float(v[j]), total[j4 * 32 + j]);
+            total[j4 * 32 + j] = fmaf(r_cur[(32 / kNormChunkCols) * j4 + j / kNormChunkCols], __uint_as_float(v[j]), total[j4 * 32 + j]);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -545,7 +552,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
           else ptx::mbar_arrive(bar_accempty(buf));
         }
 #pragma unroll
-        for (int j8 = 0; j8 < 8; ++j8) r_cur[j8] = r_next[j8];
+        for (int j = 0; j < kChunks; ++j) r_cur[j] = r_next[j];
       }
       // max over the tile's valid positions, then over the 4 lane quarters, then into scores
       if (p.rec == nullptr) {

@@ -690,16 +690,80 @@ def _best_plan(ops: GalleryOperands, hm: int, wm: int, precision: int) -> tuple[
     return best[0], best[1], best_cost
 
 
+# Cost of one multi-shape launch, in the unit of ``plan_cost`` (SM cycles per gallery map, 256-column tile and channel),
+# fitted on a B200 to 31 bucket launches of the configs[0] workload (``tools/ragged_buckets.py``): time = 0.62 us * (plan cost
+# * column tiles + BUCKET_FIXED_COST) * G * C / (1175 * 80).  A partial tile still pays for the narrow MMA (~61 cycles whatever
+# the width below 120 columns) and for the whole entry generation; the fixed part is the summed-area pass of the window
+# norms, the refinement's start-up and the tail of the correlation kernel.
+BUCKET_FIXED_COST = 29000.0
+PARTIAL_TILE_FLOOR = 0.47
+
+
+def _norm_chunk() -> int:
+    return int(nat.lib.sir_ncc_norm_chunk())
+
+
+def _pad_cols(n: int) -> int:
+    """Columns of one true template shape inside a multi-shape block: whole window-norm chunks."""
+    chunk = _norm_chunk()
+    return -(-n // chunk) * chunk
+
+
+def _tiles_equiv(cols: int) -> float:
+    full, rest = divmod(cols, 256)
+    return full + (max(PARTIAL_TILE_FLOOR, rest / 256) if rest else 0.0)
+
+
+def _merge_buckets(buckets: dict[tuple, list], cost_of, max_cols: int, max_shapes: int) -> dict[tuple, list]:
+    """Agglomerate the fine buckets ``(mode, flip, rows, cols) -> members``: two buckets of one mode and orientation are merged
+    (bucket shape = the element-wise maximum, so the smaller templates carry more zero taps) whenever the model above says the
+    merged launch is cheaper than the two -- few-column buckets cost almost as much as a full tile on their own."""
+    def launch_cost(key, members) -> float:
+        cols = sum(_pad_cols(blk.ncols) for _, blk in members)
+        launches = max(1, -(-cols // max_cols), -(-len(members) // max_shapes))
+        unit = cost_of(key)
+        if unit == float("inf"):
+            return unit
+        return unit * (_tiles_equiv(cols) + PARTIAL_TILE_FLOOR * (launches - 1)) + launches * BUCKET_FIXED_COST
+
+    items = {k: list(v) for k, v in buckets.items()}
+    costs = {k: launch_cost(k, v) for k, v in items.items()}
+    while len(items) > 1:
+        best = None
+        keys = list(items)
+        for i, ka in enumerate(keys):
+            for kb in keys[i + 1:]:
+                if ka[:2] != kb[:2]:
+                    continue
+                km = (ka[0], ka[1], max(ka[2], kb[2]), max(ka[3], kb[3]))
+                merged = launch_cost(km, items[ka] + items[kb])
+                gain = costs[ka] + costs[kb] - merged
+                if gain > 0 and (best is None or gain > best[0]):
+                    best = (gain, ka, kb, km, merged)
+        if best is None:
+            break
+        _, ka, kb, km, merged = best
+        members = items.pop(ka) + items.pop(kb)
+        costs.pop(ka), costs.pop(kb)
+        if km in items:  # the merged shape is an existing bucket: join it
+            members = items.pop(km) + members
+            merged = launch_cost(km, members)
+        items[km], costs[km] = members, merged
+    return items
+
+
 def _score_buckets(blocks: dict[tuple[int, int], _Block], gallery: list[GalleryOperands], offsets: list[int],
-                   scores: torch.Tensor, precision: int, max_cols: int = 8192, table_budget: int = 12 << 30,
+                   scores: torch.Tensor, precision: int, max_cols: int = 8192, table_budget: int | None = None,
                    approx: torch.Tensor | None = None) -> None:
     """Multi-shape column tiles (``sir_template_pack_embed`` + ``sir_ncc_scores_multi``).
 
     Template shapes that round to the same bucket (rows to 8, columns to the mode's row alignment, in
     the orientation the planner prefers) are packed into one K layout, anchor on anchor; each shape's
-    columns are padded to a multiple of 16 so that every 16-column chunk has one true shape and hence
-    one window-norm table."""
+    columns are padded to a multiple of ``sir_ncc_norm_chunk()`` (8) so that every such chunk has one true shape and
+    hence one window-norm table.  Buckets are then merged while the launch-cost model gains (``_merge_buckets``)."""
     dev = scores.device
+    if table_budget is None:  # window-norm tables of one launch: a quarter of what is free now, at most 24 GB
+        table_budget = int(min(24 << 30, max(4 << 30, torch.cuda.mem_get_info(dev)[0] // 4)))
     for ops, g0 in zip(gallery, offsets):
         buckets: dict[tuple, list] = {}
         for (h, w), blk in blocks.items():
@@ -711,13 +775,21 @@ def _score_buckets(blocks: dict[tuple[int, int], _Block], gallery: list[GalleryO
             align = 16 if mode == nat.PREC_FP16_FP8C else 8
             buckets.setdefault((mode, flip, -(-oh // 8) * 8, -(-ow // align) * align), []).append(((h, w), blk))
         table_bytes = ops.G * ops.C * ops.Hp * ops.Wp * 4
+        max_shapes = max(1, table_budget // table_bytes)
+
+        def cost_of(key, ops=ops) -> float:
+            mode, flip, bh, bw = key
+            return plan_cost(mode, ops.G, *((ops.Wp, ops.Hp) if flip else (ops.Hp, ops.Wp)), bh, bw)
+
+        if os.environ.get("SIR_BUCKET_MERGE", "1") != "0":
+            buckets = _merge_buckets(buckets, cost_of, max_cols, max_shapes)
         for (mode, flip, _, _), members in buckets.items():
             gops = ops.transposed() if flip else ops
             batch: list = []
             cols = 0
             for item in members:
-                n32 = -(-item[1].ncols // 16) * 16
-                if batch and (cols + n32 > max_cols or (len(batch) + 1) * table_bytes > table_budget):
+                n32 = _pad_cols(item[1].ncols)
+                if batch and (cols + n32 > max_cols or len(batch) + 1 > max_shapes):
                     _score_one_bucket(batch, gops, g0, scores, mode, flip, dev, approx)
                     batch, cols = [], 0
                 batch.append(item)
@@ -740,7 +812,7 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
         oriented.append(((w, h) if flip else (h, w), maps, blk))
     hb = max(hw[0] for hw, _, _ in oriented) - 2 * EDGE
     wb = max(hw[1] for hw, _, _ in oriented) - 2 * EDGE
-    ncols = sum(-(-blk.ncols // 16) * 16 for _, _, blk in oriented)
+    ncols = sum(_pad_cols(blk.ncols) for _, _, blk in oriented)
     kpad = int(nat.lib.sir_template_kpad_fp8c(hb, wb) if fp8c else nat.lib.sir_template_kpad(hb, wb))
     thi = _zeros((c, ncols, kpad), torch.float16, dev)
     tlo = None if (fp8c or refine) else _zeros((c, ncols, kpad), torch.float16, dev)
@@ -749,7 +821,8 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
     t8l = _zeros((c, ncols, kpad), torch.uint8, dev) if fp8c else None
     col2probe = torch.zeros(ncols, dtype=torch.int32)
     ntiles = -(-ncols // 256)
-    tab = torch.zeros(ntiles * 16, dtype=torch.int64)
+    chunk = _norm_chunk()
+    tab = torch.zeros(ntiles * (256 // chunk), dtype=torch.int64)
     # one pass over the gallery builds the window-norm tables of every member shape
     tables = [torch.empty((gops.G, gops.C, gops.Hp * gops.Wp), dtype=torch.float32, device=dev) for _ in oriented]
     ns = len(oriented)
@@ -774,9 +847,9 @@ def _score_one_bucket(members: list, gops: GalleryOperands, g0: int, scores: tor
             launch_counter.add()
             col0 += n
         col2probe[start:col0] = torch.cat(blk.ids).to(torch.int32)
-        col0 = start + -(-blk.ncols // 16) * 16
-        tab[start // 16 : col0 // 16] = rn.data_ptr()
-    tab[col0 // 16 :] = tables[-1].data_ptr()
+        col0 = start + _pad_cols(blk.ncols)
+        tab[start // chunk : col0 // chunk] = rn.data_ptr()
+    tab[col0 // chunk :] = tables[-1].data_ptr()
     d_tab = tab.to(dev, non_blocking=True)
     d_c2p = col2probe.to(dev, non_blocking=True)
     g8a, g8l = gops.fp8_companions() if fp8c else (None, None)
