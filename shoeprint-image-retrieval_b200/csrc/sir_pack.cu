@@ -155,21 +155,36 @@ __global__ void __launch_bounds__(256) gallery_pack_warp_kernel(const float* __r
 // ------------------------------------------------------------------------------------------
 // K6: window inverse norm through float64 summed-area tables held in shared memory.
 // One CTA per (gallery, channel); dynamic smem = 2 * (Hp+1)*(Wp+1) doubles.
-__global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo,
-                                                           const float* __restrict__ gz, int Hp, int Wp, int Hm, int Wm,
-                                                           float* __restrict__ rnorm) {
-  extern __shared__ double sat[];
-  const int W1 = Wp + 1, M = Hp * Wp;
-  double* s1 = sat;
-  double* s2 = sat + (size_t)(Hp + 1) * W1;
-  const size_t gc = blockIdx.x;
+// The kernels are bound by instruction issue (ncu: 6.6 k warp instructions per 55x17 plane, FP64 pipe 7 % busy), so the
+// per-cell loops carry their (row, column) along instead of dividing, and the table value is one MUFU.RSQ of the float64
+// window energy (2 ulp of float32).
+struct CellWalk {  // cell i = tid, tid + nthreads, ... of a rows x cols grid as (y, x)
+  int y, x, dy, dx, cols;
+  __device__ __forceinline__ CellWalk(int tid, int nthreads, int cols_) : cols(cols_) {
+    y = tid / cols;
+    x = tid - y * cols;
+    dy = nthreads / cols;
+    dx = nthreads - dy * cols;
+  }
+  __device__ __forceinline__ void next() {
+    y += dy;
+    x += dx;
+    if (x >= cols) {
+      x -= cols;
+      ++y;
+    }
+  }
+};
 
-  for (int i = threadIdx.x; i < (Hp + 1) * W1; i += blockDim.x) {
-    const int y = i / W1, x = i - y * W1;
+__device__ __forceinline__ void build_sat(const __half* __restrict__ ghi, const __half* __restrict__ glo, const float* __restrict__ gz,
+                                          size_t gc, int Hp, int Wp, double* s1, double* s2) {
+  const int W1 = Wp + 1, M = Hp * Wp, WP = gal_pitch(Wp);
+  CellWalk cw(threadIdx.x, blockDim.x, W1);
+  for (int i = threadIdx.x; i < (Hp + 1) * W1; i += blockDim.x, cw.next()) {
     double v = 0.0;
-    if (y > 0 && x > 0) {
-      const size_t j = gc * M + (size_t)(y - 1) * Wp + (x - 1);
-      const size_t jp = (gc * Hp + (size_t)(y - 1)) * gal_pitch(Wp) + (x - 1);
+    if (cw.y > 0 && cw.x > 0) {
+      const size_t j = gc * M + (size_t)(cw.y - 1) * Wp + (cw.x - 1);
+      const size_t jp = (gc * Hp + (size_t)(cw.y - 1)) * WP + (cw.x - 1);
       v = gz ? (double)gz[j] : (double)__half2float(ghi[jp]) + (double)__half2float(glo[jp]);
     }
     s1[i] = v;
@@ -196,24 +211,38 @@ __global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restr
     }
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void rnorm_from_sat(const double* s1, const double* s2, size_t gc, int Hp, int Wp, int Hm, int Wm,
+                                               float* __restrict__ rnorm) {
+  const int W1 = Wp + 1, M = Hp * Wp;
   const int a = Hm / 2, b = Wm / 2;
   const double inv_n = 1.0 / ((double)Hm * (double)Wm);
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    const int y = i / Wp, x = i - y * Wp;
-    const int r0 = max(y - a, 0), r1 = min(y - a + Hm, Hp);
-    const int c0 = max(x - b, 0), c1 = min(x - b + Wm, Wp);
+  float* out = rnorm + gc * M;
+  CellWalk cw(threadIdx.x, blockDim.x, Wp);
+  for (int i = threadIdx.x; i < M; i += blockDim.x, cw.next()) {
+    const int r0 = max(cw.y - a, 0) * W1, r1 = min(cw.y - a + Hm, Hp) * W1;
+    const int c0 = max(cw.x - b, 0), c1 = min(cw.x - b + Wm, Wp);
     float r = 0.0f;
     if (r1 > r0 && c1 > c0) {
-      const double t1 = s1[r1 * W1 + c1] - s1[r0 * W1 + c1] - s1[r1 * W1 + c0] + s1[r0 * W1 + c0];
-      const double t2 = s2[r1 * W1 + c1] - s2[r0 * W1 + c1] - s2[r1 * W1 + c0] + s2[r0 * W1 + c0];
+      const double t1 = s1[r1 + c1] - s1[r0 + c1] - s1[r1 + c0] + s1[r0 + c0];
+      const double t2 = s2[r1 + c1] - s2[r0 + c1] - s2[r1 + c0] + s2[r0 + c0];
       const double d = t2 - t1 * t1 * inv_n;
       // A window that is flat up to SAT round-off is the reference's "division by ~0" case
       // (similarity.py:69-70 zeroes the non-finite results; FFT noise decides the rest): call it 0.
-      // the table is float32: an IEEE float sqrt + divide of the float64 window energy is exact enough
-      if (d > 1e-10 * t2) r = __fdiv_rn(1.0f, __fsqrt_rn((float)d));
+      if (d > 1e-10 * t2) r = rsqrtf((float)d);
     }
-    rnorm[gc * M + i] = r;
+    out[i] = r;
   }
+}
+
+__global__ void __launch_bounds__(256) window_rnorm_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo,
+                                                           const float* __restrict__ gz, int Hp, int Wp, int Hm, int Wm,
+                                                           float* __restrict__ rnorm) {
+  extern __shared__ double sat[];
+  double* s2 = sat + (size_t)(Hp + 1) * (Wp + 1);
+  build_sat(ghi, glo, gz, blockIdx.x, Hp, Wp, sat, s2);
+  rnorm_from_sat(sat, s2, blockIdx.x, Hp, Wp, Hm, Wm, rnorm);
 }
 
 // Several template shapes at once: the float64 summed-area tables of a channel are built once and every
@@ -227,62 +256,9 @@ struct RnormShapes {
 __global__ void __launch_bounds__(256) window_rnorm_multi_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo,
                                                                  const float* __restrict__ gz, int Hp, int Wp, RnormShapes sh) {
   extern __shared__ double sat[];
-  const int W1 = Wp + 1, M = Hp * Wp;
-  double* s1 = sat;
-  double* s2 = sat + (size_t)(Hp + 1) * W1;
-  const size_t gc = blockIdx.x;
-
-  for (int i = threadIdx.x; i < (Hp + 1) * W1; i += blockDim.x) {
-    const int y = i / W1, x = i - y * W1;
-    double v = 0.0;
-    if (y > 0 && x > 0) {
-      const size_t j = gc * M + (size_t)(y - 1) * Wp + (x - 1);
-      const size_t jp = (gc * Hp + (size_t)(y - 1)) * gal_pitch(Wp) + (x - 1);
-      v = gz ? (double)gz[j] : (double)__half2float(ghi[jp]) + (double)__half2float(glo[jp]);
-    }
-    s1[i] = v;
-    s2[i] = v * v;
-  }
-  __syncthreads();
-  for (int y = 1 + threadIdx.x; y <= Hp; y += blockDim.x) {  // prefix along x
-    double a = 0.0, b = 0.0;
-    for (int x = 1; x <= Wp; ++x) {
-      a += s1[y * W1 + x];
-      b += s2[y * W1 + x];
-      s1[y * W1 + x] = a;
-      s2[y * W1 + x] = b;
-    }
-  }
-  __syncthreads();
-  for (int x = 1 + threadIdx.x; x <= Wp; x += blockDim.x) {  // prefix along y
-    double a = 0.0, b = 0.0;
-    for (int y = 1; y <= Hp; ++y) {
-      a += s1[y * W1 + x];
-      b += s2[y * W1 + x];
-      s1[y * W1 + x] = a;
-      s2[y * W1 + x] = b;
-    }
-  }
-  __syncthreads();
-  for (int si = 0; si < sh.n; ++si) {
-    const int Hm = sh.hm[si], Wm = sh.wm[si];
-    float* __restrict__ rnorm = sh.out[si];
-    const int a = Hm / 2, b = Wm / 2;
-    const double inv_n = 1.0 / ((double)Hm * (double)Wm);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-      const int y = i / Wp, x = i - y * Wp;
-      const int r0 = max(y - a, 0), r1 = min(y - a + Hm, Hp);
-      const int c0 = max(x - b, 0), c1 = min(x - b + Wm, Wp);
-      float r = 0.0f;
-      if (r1 > r0 && c1 > c0) {
-        const double t1 = s1[r1 * W1 + c1] - s1[r0 * W1 + c1] - s1[r1 * W1 + c0] + s1[r0 * W1 + c0];
-        const double t2 = s2[r1 * W1 + c1] - s2[r0 * W1 + c1] - s2[r1 * W1 + c0] + s2[r0 * W1 + c0];
-        const double d = t2 - t1 * t1 * inv_n;
-        if (d > 1e-10 * t2) r = __fdiv_rn(1.0f, __fsqrt_rn((float)d));
-      }
-      rnorm[gc * M + i] = r;
-    }
-  }
+  double* s2 = sat + (size_t)(Hp + 1) * (Wp + 1);
+  build_sat(ghi, glo, gz, blockIdx.x, Hp, Wp, sat, s2);
+  for (int si = 0; si < sh.n; ++si) rnorm_from_sat(sat, s2, blockIdx.x, Hp, Wp, sh.hm[si], sh.wm[si], sh.out[si]);
 }
 
 // ------------------------------------------------------------------------------------------
