@@ -95,7 +95,7 @@ def _peaks() -> dict:
 
 def _ncu_traffic() -> tuple[float | None, str | None]:
     """DRAM bytes of one ncc_tc_kernel launch from the committed `ncu --set full` capture (profiles/)."""
-    for name in ("r02_ncu_full_ncc_tc_kernel_screen.txt", "r01_ncu_full_ncc_tc_kernel_final.txt"):
+    for name in ("r02_ncu_full_ncc_tc_kernel_final.txt", "r02_ncu_full_ncc_tc_kernel_screen.txt", "r01_ncu_full_ncc_tc_kernel_final.txt"):
         f = ROOT / "profiles" / name
         if not f.exists():
             continue

@@ -268,6 +268,15 @@ int sir_scatter_columns(const float* d_in, int Q, int G, int ld_in, const int32_
 int sir_feat_clahe_to_nhwc(const uint8_t* d_img, int B, int H, int W, double clip_limit, int tiles_x, int tiles_y,
                            const float* h_mean, const float* h_std, uint8_t* d_lut, uint8_t* d_clahe_u8, float* d_out,
                            float* d_amax_out, void* stream);
+/* sir_feat_clahe_rgb_to_nhwc: the RGB branch of Model._clahe (network.py:199-204: cv2 RGB2LAB, CLAHE on L, LAB2RGB) on uint8
+ * [B][H][W][3], bit exact, fused with ToTensor / Normalize.  d_rgb2lab / d_lab2rgb: the two 8-bit colour conversions as
+ * 2^24-entry tables (uint32 c0 | c1 << 8 | c2 << 16 at index c0 << 16 | c1 << 8 | c2; the host builds them once with
+ * cv2.cvtColor over all 2^24 pixels).  Scratch: d_l_plane [B][H][W] bytes, d_ab_plane [B][H][W] uint16, d_lut as above;
+ * d_rgb_out [B][H][W][3] or NULL receives the equalised uint8 image. */
+int sir_feat_clahe_rgb_to_nhwc(const uint8_t* d_rgb, int B, int H, int W, double clip_limit, int tiles_x, int tiles_y,
+                               const float* h_mean, const float* h_std, const uint32_t* d_rgb2lab, const uint32_t* d_lab2rgb,
+                               uint8_t* d_l_plane, uint16_t* d_ab_plane, uint8_t* d_lut, uint8_t* d_rgb_out, float* d_out,
+                               float* d_amax_out, void* stream);
 int sir_feat_image_to_nhwc(const uint8_t* d_img, int B, int H, int W, int in_ch, const float* h_mean, const float* h_std,
                            float* d_out, float* d_amax_out, void* stream);
 int sir_feat_im2col_split(const float* d_in, const float* d_amax_in, int B, int H, int W, int C, int kh, int kw, int stride,

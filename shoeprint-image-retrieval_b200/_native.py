@@ -64,6 +64,8 @@ SIGNATURES = {
     "sir_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "sir_scatter_columns": (_i, [_p, _i, _i, _i, _p, _p, _i, _p]),
     "sir_feat_clahe_to_nhwc": (_i, [_p, _i, _i, _i, C.c_double, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p, _p, _p]),
+    "sir_feat_clahe_rgb_to_nhwc": (_i, [_p, _i, _i, _i, C.c_double, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p, _p, _p, _p, _p,
+                                        _p, _p]),
     "sir_feat_image_to_nhwc": (_i, [_p, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p]),
     "sir_feat_im2col_split": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     "sir_feat_conv_tile_n": (_i, [_i]),

@@ -109,6 +109,25 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
   lut[((size_t)b * gridDim.x + tile) * 256 + t] = (uint8_t)min(max(v, 0), 255);
 }
 
+// the equalised value of pixel (x, y) of image b: bilinear blend of the four nearest tiles' LUT entries for value v
+__device__ __forceinline__ int clahe_interpolate(int v, int x, int y, int b, int tiles_x, int tiles_y, float inv_tw, float inv_th,
+                                                 const uint8_t* __restrict__ lut) {
+  const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+  const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+  const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+  const int tx2 = min(tx1 + 1, tiles_x - 1), ty2 = min(ty1 + 1, tiles_y - 1);
+  tx1 = max(tx1, 0);
+  ty1 = max(ty1, 0);
+  const uint8_t* lb = lut + (size_t)b * tiles_x * tiles_y * 256 + v;
+  const float l11 = lb[(ty1 * tiles_x + tx1) * 256], l12 = lb[(ty1 * tiles_x + tx2) * 256];
+  const float l21 = lb[(ty2 * tiles_x + tx1) * 256], l22 = lb[(ty2 * tiles_x + tx2) * 256];
+  const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+  const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  return min(max(__float2int_rn(res), 0), 255);
+}
+
 // CLAHE interpolation fused with ToTensor / grayscale repeat / Normalize: uint8 in, float32 NHWC(3) out.
 __global__ void __launch_bounds__(256) clahe_apply_to_nhwc_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int tiles_x,
                                                                   int tiles_y, float inv_tw, float inv_th, const uint8_t* __restrict__ lut,
@@ -121,24 +140,55 @@ __global__ void __launch_bounds__(256) clahe_apply_to_nhwc_kernel(const uint8_t*
     const int x = (int)(i % W);
     const size_t r = i / W;
     const int y = (int)(r % H), b = (int)(r / H);
-    const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
-    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
-    const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
-    const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
-    const int tx2 = min(tx1 + 1, tiles_x - 1), ty2 = min(ty1 + 1, tiles_y - 1);
-    tx1 = max(tx1, 0);
-    ty1 = max(ty1, 0);
-    const int v = img[i];
-    const uint8_t* lb = lut + (size_t)b * tiles_x * tiles_y * 256 + v;
-    const float l11 = lb[(ty1 * tiles_x + tx1) * 256], l12 = lb[(ty1 * tiles_x + tx2) * 256];
-    const float l21 = lb[(ty2 * tiles_x + tx1) * 256], l22 = lb[(ty2 * tiles_x + tx2) * 256];
-    const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-    const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-    const int q = min(max(__float2int_rn(res), 0), 255);
+    const int q = clahe_interpolate(img[i], x, y, b, tiles_x, tiles_y, inv_tw, inv_th, lut);
     if (clahe_out) clahe_out[i] = (uint8_t)q;
     const float g = __fdiv_rn((float)q, 255.0f);
     const float o0 = __fdiv_rn(g - m0, s0), o1 = __fdiv_rn(g - m1, s1), o2 = __fdiv_rn(g - m2, s2);
+    out[3 * i] = o0;
+    out[3 * i + 1] = o1;
+    out[3 * i + 2] = o2;
+    local = fmaxf(local, fmaxf(fabsf(o0), fmaxf(fabsf(o1), fabsf(o2))));
+  }
+  local = warp_max(local);
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(amax, local);
+}
+
+// CLAHE of RGB prints (network.py:199-204): RGB -> LAB, CLAHE on L, LAB -> RGB.  OpenCV's 8-bit colour conversions are pure
+// functions of the 24-bit pixel, so both are 2^24-entry tables (built once on the host by cv2.cvtColor itself, packed
+// c0 | c1 << 8 | c2 << 16, indexed c0 << 16 | c1 << 8 | c2): bit exact by construction, one gather per pixel.
+__global__ void __launch_bounds__(256) rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t pixels, const uint32_t* __restrict__ rgb2lab,
+                                                         uint8_t* __restrict__ l_plane, uint16_t* __restrict__ ab_plane) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pixels; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t key = ((uint32_t)rgb[3 * i] << 16) | ((uint32_t)rgb[3 * i + 1] << 8) | rgb[3 * i + 2];
+    const uint32_t lab = __ldg(rgb2lab + key);
+    l_plane[i] = (uint8_t)(lab & 0xffu);
+    ab_plane[i] = (uint16_t)(lab >> 8);
+  }
+}
+
+__global__ void __launch_bounds__(256) clahe_apply_rgb_to_nhwc_kernel(const uint8_t* __restrict__ l_plane, const uint16_t* __restrict__ ab_plane,
+                                                                      int B, int H, int W, int tiles_x, int tiles_y, float inv_tw,
+                                                                      float inv_th, const uint8_t* __restrict__ lut,
+                                                                      const uint32_t* __restrict__ lab2rgb, float m0, float m1, float m2,
+                                                                      float s0, float s1, float s2, uint8_t* __restrict__ rgb_out,
+                                                                      float* __restrict__ out, float* __restrict__ amax) {
+  const size_t total = (size_t)B * H * W;
+  float local = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const size_t r = i / W;
+    const int y = (int)(r % H), b = (int)(r / H);
+    const int q = clahe_interpolate(l_plane[i], x, y, b, tiles_x, tiles_y, inv_tw, inv_th, lut);
+    const uint32_t ab = ab_plane[i];
+    const uint32_t px = __ldg(lab2rgb + (((uint32_t)q << 16) | ((ab & 0xffu) << 8) | (ab >> 8)));
+    const int c0 = px & 0xff, c1 = (px >> 8) & 0xff, c2 = (px >> 16) & 0xff;
+    if (rgb_out) {
+      rgb_out[3 * i] = (uint8_t)c0;
+      rgb_out[3 * i + 1] = (uint8_t)c1;
+      rgb_out[3 * i + 2] = (uint8_t)c2;
+    }
+    const float o0 = __fdiv_rn(__fdiv_rn((float)c0, 255.0f) - m0, s0), o1 = __fdiv_rn(__fdiv_rn((float)c1, 255.0f) - m1, s1),
+                o2 = __fdiv_rn(__fdiv_rn((float)c2, 255.0f) - m2, s2);
     out[3 * i] = o0;
     out[3 * i + 1] = o1;
     out[3 * i + 2] = o2;
@@ -719,6 +769,35 @@ extern "C" int sir_feat_clahe_to_nhwc(const uint8_t* d_img, int B, int H, int W,
                                                                           h_mean[1], h_mean[2], h_std[0], h_std[1], h_std[2], d_clahe_u8,
                                                                           d_out, d_amax);
   SIR_LAUNCH_CHECK("clahe_apply_to_nhwc_kernel");
+  return SIR_OK;
+}
+
+extern "C" int sir_feat_clahe_rgb_to_nhwc(const uint8_t* d_rgb, int B, int H, int W, double clip_limit, int tiles_x, int tiles_y,
+                                          const float* h_mean, const float* h_std, const uint32_t* d_rgb2lab, const uint32_t* d_lab2rgb,
+                                          uint8_t* d_l_plane, uint16_t* d_ab_plane, uint8_t* d_lut, uint8_t* d_rgb_out, float* d_out,
+                                          float* d_amax, void* stream) {
+  SIR_CHECK_ARG(d_rgb && d_rgb2lab && d_lab2rgb && d_l_plane && d_ab_plane && d_lut && d_out && d_amax && h_mean && h_std,
+                "sir_feat_clahe_rgb_to_nhwc: null pointer");
+  SIR_CHECK_ARG(B > 0 && H > 1 && W > 1 && tiles_x > 0 && tiles_y > 0 && tiles_x * tiles_y <= 65535, "sir_feat_clahe_rgb_to_nhwc: bad shape");
+  const int eh = H % tiles_y == 0 && W % tiles_x == 0 ? H : H + (tiles_y - H % tiles_y);
+  const int ew = H % tiles_y == 0 && W % tiles_x == 0 ? W : W + (tiles_x - W % tiles_x);
+  const int th = eh / tiles_y, tw = ew / tiles_x;
+  SIR_CHECK_ARG(eh - H < H && ew - W < W, "sir_feat_clahe_rgb_to_nhwc: image %dx%d too small for a %dx%d tile grid", H, W, tiles_y, tiles_x);
+  const int area = th * tw;
+  const float lut_scale = 255.0f / (float)area;
+  int clip = 0;
+  if (clip_limit > 0.0) clip = std::max((int)(clip_limit * area / 256), 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pixels = (size_t)B * H * W;
+  rgb_to_lab_kernel<<<grid_for(pixels), 256, 0, st>>>(d_rgb, pixels, d_rgb2lab, d_l_plane, d_ab_plane);
+  SIR_LAUNCH_CHECK("rgb_to_lab_kernel");
+  clahe_lut_kernel<<<dim3((unsigned)(tiles_x * tiles_y), (unsigned)B), 256, 0, st>>>(d_l_plane, H, W, tiles_x, th, tw, clip, lut_scale, d_lut);
+  SIR_LAUNCH_CHECK("clahe_lut_kernel");
+  const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+  clahe_apply_rgb_to_nhwc_kernel<<<grid_for(pixels), 256, 0, st>>>(d_l_plane, d_ab_plane, B, H, W, tiles_x, tiles_y, inv_tw, inv_th, d_lut,
+                                                                   d_lab2rgb, h_mean[0], h_mean[1], h_mean[2], h_std[0], h_std[1], h_std[2],
+                                                                   d_rgb_out, d_out, d_amax);
+  SIR_LAUNCH_CHECK("clahe_apply_rgb_to_nhwc_kernel");
   return SIR_OK;
 }
 

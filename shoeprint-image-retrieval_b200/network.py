@@ -297,6 +297,28 @@ def _images_digest(images: list[np.ndarray]) -> bytes:
     return h.digest()
 
 
+_LAB_TABLES: dict = {}
+
+
+def _lab_tables(dev: torch.device) -> tuple[torch.Tensor, torch.Tensor]:
+    """OpenCV's 8-bit RGB -> LAB and LAB -> RGB conversions as device tables over all 2^24 pixels (``sir_feat_clahe_rgb_to_nhwc``).
+    Both are pure per-pixel functions, so tabulating them with ``cv2.cvtColor`` itself (0.7 s, once per process and device;
+    2 x 64 MB) makes the GPU path bit exact with ``network.py:200,204`` whatever OpenCV's fixed-point recipe is."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _LAB_TABLES:
+        import cv2
+
+        idx = np.arange(1 << 24, dtype=np.uint32)
+        px = np.stack([(idx >> 16) & 255, (idx >> 8) & 255, idx & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+        out = []
+        for code in (cv2.COLOR_RGB2LAB, cv2.COLOR_LAB2RGB):
+            conv = cv2.cvtColor(px, code).reshape(-1, 3).astype(np.uint32)
+            packed = conv[:, 0] | (conv[:, 1] << 8) | (conv[:, 2] << 16)
+            out.append(torch.from_numpy(packed.view(np.int32)).to(dev))
+        _LAB_TABLES[key] = tuple(out)
+    return _LAB_TABLES[key]
+
+
 class FeatureMapList(list):
     """What ``get_multiple_feature_maps`` returns: the reference's list of ``[C,h,w]`` float32 arrays
     (``network.py:246-269``) that also remembers the device-resident copies the maps were read back from.
@@ -745,12 +767,21 @@ class Model:
         mean = (C.c_float * 3)(*self.mean)
         std = (C.c_float * 3)(*self.std)
         if apply_clahe:
-            assert in_ch == 1
             tx, ty = (int(v) for v in self.config["model"]["clahe_tile_grid_size"])
+            clip = float(self.config["model"]["clahe_clip_limit"])
             lut = torch.empty((b, tx * ty, 256), dtype=torch.uint8, device=self.device)
-            nat.check(nat.lib.sir_feat_clahe_to_nhwc(_ptr(d_img), b, h, w, float(self.config["model"]["clahe_clip_limit"]), tx, ty, mean, std,
-                                                     _ptr(lut), None, _ptr(x0), _ptr(amax0), _stream()), "sir_feat_clahe_to_nhwc")
-            launch_counter.add(2)
+            if in_ch == 1:
+                nat.check(nat.lib.sir_feat_clahe_to_nhwc(_ptr(d_img), b, h, w, clip, tx, ty, mean, std, _ptr(lut), None, _ptr(x0), _ptr(amax0),
+                                                         _stream()), "sir_feat_clahe_to_nhwc")
+                launch_counter.add(2)
+            else:  # RGB prints: LAB round trip through the tabulated OpenCV conversions (network.py:199-204)
+                rgb2lab, lab2rgb = _lab_tables(self.device)
+                l_plane = torch.empty((b, h, w), dtype=torch.uint8, device=self.device)
+                ab_plane = torch.empty((b, h, w), dtype=torch.int16, device=self.device)
+                nat.check(nat.lib.sir_feat_clahe_rgb_to_nhwc(_ptr(d_img), b, h, w, clip, tx, ty, mean, std, _ptr(rgb2lab), _ptr(lab2rgb),
+                                                             _ptr(l_plane), _ptr(ab_plane), _ptr(lut), None, _ptr(x0), _ptr(amax0), _stream()),
+                          "sir_feat_clahe_rgb_to_nhwc")
+                launch_counter.add(3)
         else:
             nat.check(nat.lib.sir_feat_image_to_nhwc(_ptr(d_img), b, h, w, in_ch, mean, std, _ptr(x0), _ptr(amax0), _stream()),
                       "sir_feat_image_to_nhwc")
@@ -801,7 +832,7 @@ class Model:
 
     def get_feature_maps(self, img: np.ndarray) -> np.ndarray:
         """One image (uint8 ``[H,W]`` or ``[H,W,3]``) -> ``[C,h,w]`` float32 (``network.py:210-244``)."""
-        if img.ndim == 2 and not self._host_clahe:
+        if img.ndim in (2, 3) and img.dtype == np.uint8 and not self._host_clahe:
             out = self._forward_uint8(img[None], apply_clahe=True)
         else:
             out = self._forward_uint8(self._clahe(img)[None])
@@ -862,7 +893,7 @@ class Model:
         step = 0
         for shp, idx in by_shape.items():
             limit = self._batch_limit(shp[0], shp[1])
-            gpu_clahe = len(shp) == 2 and not self._host_clahe
+            gpu_clahe = not self._host_clahe and all(images[i].dtype == np.uint8 for i in idx)
             for s in range(0, len(idx), limit):
                 chunk = idx[s : s + limit]
                 stage = self._pinned("in", step % 2, (limit, *shp), torch.uint8)[: len(chunk)]

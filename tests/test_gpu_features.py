@@ -139,6 +139,66 @@ def test_model_gpu_clahe_path_matches_host_clahe_path(monkeypatch):
     np.testing.assert_array_equal(a, b)
 
 
+def test_gpu_rgb_clahe_bit_exact_vs_opencv():
+    """sir_feat_clahe_rgb_to_nhwc against the reference's RGB branch (network.py:199-204): cv2 RGB2LAB, CLAHE on L, LAB2RGB.
+    The equalised uint8 image must be identical and the fused output equal to ToTensor + Normalize of it."""
+    import ctypes as C
+
+    import cv2
+
+    from src.shoeprint_image_retrieval import _native as nat, network
+
+    rng = np.random.default_rng(11)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    rgb2lab, lab2rgb = network._lab_tables(torch.device("cuda", 0))
+    p = lambda t: C.c_void_p(t.data_ptr())
+    for (h, w), clip, tiles in [((470, 162), 2.0, (8, 8)), ((123, 77), 4.0, (4, 6)), ((64, 64), 0.0, (8, 8))]:
+        smooth = np.stack([np.stack([_image(int(rng.integers(1 << 30)), h, w) for _ in range(3)], -1) for _ in range(2)])
+        noise = rng.integers(0, 256, size=(1, h, w, 3), dtype=np.uint8)  # every corner of the colour cube
+        imgs = np.concatenate([smooth, noise])
+        n = len(imgs)
+        d = torch.from_numpy(imgs).cuda()
+        lut = torch.empty((n, tiles[0] * tiles[1], 256), dtype=torch.uint8, device="cuda")
+        l_plane = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+        ab_plane = torch.empty((n, h, w), dtype=torch.int16, device="cuda")
+        u8 = torch.empty_like(d)
+        out = torch.empty((n, h, w, 3), dtype=torch.float32, device="cuda")
+        amax = torch.zeros(1, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nat.check(nat.lib.sir_feat_clahe_rgb_to_nhwc(p(d), n, h, w, clip, tiles[0], tiles[1], (C.c_float * 3)(*mean), (C.c_float * 3)(*std),
+                                                     p(rgb2lab), p(lab2rgb), p(l_plane), p(ab_plane), p(lut), p(u8), p(out), p(amax), st))
+        cl = cv2.createCLAHE(clipLimit=clip, tileGridSize=tiles)
+        want = []
+        for im in imgs:
+            l_ch, a_ch, b_ch = cv2.split(cv2.cvtColor(im, cv2.COLOR_RGB2LAB))
+            want.append(cv2.cvtColor(cv2.merge((cl.apply(l_ch), a_ch, b_ch)), cv2.COLOR_LAB2RGB))
+        want = np.stack(want)
+        np.testing.assert_array_equal(u8.cpu().numpy(), want, err_msg=f"{h}x{w} clip {clip} tiles {tiles}")
+        ref = (torch.from_numpy(want).float().div(255) - torch.tensor(mean)) / torch.tensor(std)
+        np.testing.assert_array_equal(out.cpu().numpy(), ref.numpy())
+        assert abs(float(amax) - float(ref.abs().max())) < 1e-6
+
+
+def test_model_rgb_prints_gpu_clahe_matches_host_clahe():
+    """RGB prints through the Model: CLAHE on the device (tabulated LAB round trip) and on the host (cv2) give identical maps,
+    single image and batched."""
+    from src.shoeprint_image_retrieval import network
+
+    imgs = [np.stack([_image(31 + 3 * i + c, 300, 130) for c in range(3)], -1) for i in range(3)]
+    model = network.Model(_config("EfficientNetV2_M"), 4, random_init_seed=2)
+    a = model.get_feature_maps(imgs[0])
+    many = model.get_multiple_feature_maps(imgs, progress=False)
+    model._host_clahe = True
+    network.clear_caches()
+    b = model.get_feature_maps(imgs[0])
+    many_host = model.get_multiple_feature_maps(imgs, progress=False)
+    np.testing.assert_array_equal(a, b)
+    for x, y in zip(many, many_host):
+        np.testing.assert_array_equal(x, y)
+    # a batch shares one running |max| for the operand scaling, so batched and single maps agree to rounding only
+    assert np.linalg.norm(many[0] - a) <= 1e-5 * np.linalg.norm(a)
+
+
 def test_device_resident_handoff_to_compare():
     """maps returned by get_multiple_feature_maps keep device copies; compare uses them (no H2D) and gives
     the same ranks and scores as the host lists.  Replacing an element falls back to the host path."""
