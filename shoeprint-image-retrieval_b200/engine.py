@@ -60,8 +60,8 @@ TAU_ABS = 2.0e-5
 
 #: probes uploaded from host lists travel in chunks of this many maps; a chunk's columns are launched once at least
 #: FLUSH_MIN_COLS of one template shape have accumulated, while the next chunk is still being copied
-PROBE_CHUNK = 512
-FLUSH_MIN_COLS = 4096
+PROBE_CHUNK = int(os.environ.get("SIR_PROBE_CHUNK", "512"))
+FLUSH_MIN_COLS = int(os.environ.get("SIR_FLUSH_MIN_COLS", "1024"))
 
 
 class _LaunchCounter:
@@ -305,10 +305,14 @@ class MapSet:
         # the caller's stream had queued up to here
         pieces = []
         for shp, idx in by_shape.items():
-            step = len(idx) if not chunk else max(1, chunk)
-            for s0 in range(0, len(idx), step):
+            # the first pieces are smaller (chunk/4, chunk/2): the consumer's first launch waits for the first piece only
+            s0, step = 0, (len(idx) if not chunk else max(1, chunk // 4))
+            while s0 < len(idx):
                 part = idx[s0 : s0 + step]
                 pieces.append((part, torch.empty((len(part), *shp), dtype=torch.float32, device=dev)))
+                s0 += step
+                if chunk:
+                    step = min(max(1, chunk), 2 * step)
         after = torch.cuda.Event()
         after.record()
         up = _Uploader.get(dev)
