@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
   constexpr int kRefThreads = 32 * (kRefWarps + 1);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int PG = p.Hp * p.WP;                                      // cells of one packed gallery plane
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // full_g[ST], empty_g[ST], empty_t[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // full_g[ST], empty_g[ST], empty_t[2], full_t[2]
   float* tplbuf = reinterpret_cast<float*>(smem_raw + 128);         // [2][TN][Kpad]   templates of channel c in buffer c & 1
   float* galbuf = tplbuf + 2 * (size_t)p.TN * p.Kpad;               // [ST][TGS][PG]
   uint2* list = reinterpret_cast<uint2*>(galbuf + (size_t)p.ST * p.TGS * PG);  // [cap] (j | i << 8, y | x << 16)
@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
     }
     ptx::mbar_init(ptx::smem_u32(bars + 2 * kRefStages), kRefWarps);     // template buffers free again
     ptx::mbar_init(ptx::smem_u32(bars + 2 * kRefStages + 1), kRefWarps);
+    ptx::mbar_init(ptx::smem_u32(bars + 2 * kRefStages + 2), 1);             // template buffers filled (own barriers: the planes of
+    ptx::mbar_init(ptx::smem_u32(bars + 2 * kRefStages + 3), 1);             // channel c + 1 travel while channel c is being consumed)
     ptx::fence_barrier_init();
     if (p.stats) {
       atomicAdd(p.stats + 0, (unsigned long long)total);
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
   // vl-tap chunks of a row (rv), whichever split gives the longest inner loop for this shape (chosen by the host)
   const int vl = p.vl, lv = lane % vl, grp = lane / vl, gu = grp % p.ru, gv = grp / p.ru, nchunk = p.rowk / vl;
   const uint32_t tbytes = (uint32_t)p.Kpad * 4u, gbytes = (uint32_t)PG * 4u;
-  uint32_t it = 0;   // gallery steps so far   (stage = it % kRefStages, barrier parity = (it / kRefStages) & 1)
+  uint32_t gst = 0, gpar = 0;  // gallery ring: current stage and the parity of its barriers (both roles step them alike)
   uint32_t cit = 0;  // channels so far        (template buffer = cit & 1, barrier parity = (cit >> 1) & 1)
 
   for (int r0 = 0; r0 < total; r0 += p.cap) {
@@ -197,20 +199,32 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
     __syncthreads();
 
     if (warp == kRefWarps) {
-      // ---- producer warp: per channel the flagged template planes once, then the flagged gallery planes sub-chunk by sub-chunk
+      // ---- producer warp: per channel the flagged template planes once, then the flagged gallery planes sub-chunk by sub-chunk.
+      // The template planes of channel c + 1 are requested at the START of channel c (their buffer was released at the end
+      // of channel c - 1), so that burst (TN planes) never sits in front of a gallery step.
       uint32_t tpl_bytes = 0;
       for (int j = 0; j < p.TN; ++j) tpl_bytes += flags[j] ? tbytes : 0u;
-      for (int c = 0; c < p.C; ++c, ++cit) {
-        bool first = true;
-        float* tdst = tplbuf + (cit & 1u) * (size_t)p.TN * p.Kpad;
+      auto request_templates = [&](int c, uint32_t cc) {  // cc: channels so far, this one included in the count of its buffer
+        const uint32_t buf = cc & 1u, full_t = ptx::smem_u32(bars + 2 * kRefStages + 2 + buf);
+        ptx::mbar_wait(ptx::smem_u32(bars + 2 * kRefStages + buf), ((cc >> 1) & 1u) ^ 1u);  // the consumers are done with this buffer
+        if (lane == 0) {
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive_expect_tx(full_t, tpl_bytes);
+        }
+        __syncwarp();
+        float* tdst = tplbuf + buf * (size_t)p.TN * p.Kpad;
+        for (int j = lane; j < p.TN; j += 32)
+          if (flags[j]) ptx::bulk_load(ptx::smem_u32(tdst + (size_t)j * p.Kpad), p.t32 + ((size_t)c * p.ncols_alloc + n0 + j) * p.Kpad, tbytes, full_t);
+      };
+      request_templates(0, cit);
+      for (int c = 0; c < p.C; ++c) {
+        if (c + 1 < p.C) request_templates(c + 1, cit + (uint32_t)c + 1u);
         for (int s = 0; s < p.NS; ++s) {
           if (seg[s + 1] == seg[s]) continue;  // no position in this sub-chunk
-          const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
-          const uint32_t full = ptx::smem_u32(bars + st);
-          ptx::mbar_wait(ptx::smem_u32(bars + kRefStages + st), par ^ 1u);  // consumers are done with this gallery stage
-          if (first) ptx::mbar_wait(ptx::smem_u32(bars + 2 * kRefStages + (cit & 1u)), ((cit >> 1) & 1u) ^ 1u);  // and with this template buffer
-          float* gdst = galbuf + (size_t)st * p.TGS * PG;
-          uint32_t bytes = first ? tpl_bytes : 0u;
+          const uint32_t full = ptx::smem_u32(bars + gst);
+          ptx::mbar_wait(ptx::smem_u32(bars + kRefStages + gst), gpar ^ 1u);  // consumers are done with this gallery stage
+          float* gdst = galbuf + (size_t)gst * p.TGS * PG;
+          uint32_t bytes = 0u;
           for (int k = 0; k < p.TGS; ++k) bytes += flags[p.TN + s * p.TGS + k] ? gbytes : 0u;
           if (lane == 0) {
             ptx::fence_proxy_async_smem();  // the consumers' generic reads of these buffers precede the async writes
@@ -221,79 +235,98 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
             const int i = s * p.TGS + k;
             if (flags[p.TN + i]) ptx::bulk_load(ptx::smem_u32(gdst + (size_t)k * PG), p.g32 + ((size_t)(gt0 + i) * p.C + c) * PG, gbytes, full);
           }
-          if (first) {
-            for (int j = lane; j < p.TN; j += 32)
-              if (flags[j]) ptx::bulk_load(ptx::smem_u32(tdst + (size_t)j * p.Kpad), p.t32 + ((size_t)c * p.ncols_alloc + n0 + j) * p.Kpad, tbytes, full);
-            first = false;
+          if (++gst == (uint32_t)kRefStages) {
+            gst = 0;
+            gpar ^= 1u;
           }
-          ++it;
         }
       }
+      cit += (uint32_t)p.C;
     } else {
       // ---- consumer warps: one candidate position at a time
-      for (int c = 0; c < p.C; ++c, ++cit) {
-        const float* tpl = tplbuf + (cit & 1u) * (size_t)p.TN * p.Kpad;
-        for (int s = 0; s < p.NS; ++s) {
-          const int e0 = seg[s], e1 = seg[s + 1];
-          if (e1 == e0) continue;
-          const uint32_t st = it % kRefStages, par = (it / kRefStages) & 1u;
-          // this channel's window norms of the warp's positions in the sub-chunk, one gather before the wait (entry e0 + warp +
-          // kRefWarps * t in lane t)
-          float rnv = 0.0f;
-          {
-            const int e = e0 + warp + kRefWarps * lane;
-            if (e < e1) {
-              const uint2 en = list[e];
-              const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en.x & 0xff)) / kNormChunkCols] : p.rnorm;
-              rnv = __ldg(table + ((size_t)(gt0 + (int)(en.x >> 8)) * p.C + c) * M + (en.y & 0xffff) * p.Wp + (en.y >> 16));
+      // window norm of list entry e in channel c (0 past the end of the sub-chunk)
+      auto norm_of = [&](int e, int e1, int c) -> float {
+        if (e >= e1) return 0.0f;
+        const uint2 en = list[e];
+        const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en.x & 0xff)) / kNormChunkCols] : p.rnorm;
+        return __ldg(table + ((size_t)(gt0 + (int)(en.x >> 8)) * p.C + c) * M + (en.y & 0xffff) * p.Wp + (en.y >> 16));
+      };
+      // The norms of a step are gathered ONE STEP AHEAD (lane t holds the norm of the warp's t-th position of the step): a
+      // step holds about one position per warp, so a gather issued inside the step would put a global-load latency on
+      // every one of the C * NS steps.
+      auto next_step = [&](int& c, int& s) {  // the next (channel, sub-chunk) with positions; c == p.C when there is none
+        for (++s;; ++s) {
+          if (s >= p.NS) {
+            s = 0;
+            if (++c >= p.C) return;
+          }
+          if (seg[s + 1] != seg[s]) return;
+        }
+      };
+      int c = 0, s = -1;
+      next_step(c, s);
+      float rnv = c < p.C ? norm_of(seg[s] + warp + kRefWarps * lane, seg[s + 1], c) : 0.0f;
+      int c_seen = 0;  // channels whose template buffer this warp has released
+      int c_ready = -1;  // channel whose template planes this warp has waited for
+      while (c < p.C) {
+        int cn = c, sn = s;
+        next_step(cn, sn);
+        const float rnv_next = cn < p.C ? norm_of(seg[sn] + warp + kRefWarps * lane, seg[sn + 1], cn) : 0.0f;
+        const uint32_t cc = cit + (uint32_t)c;
+        const float* tpl = tplbuf + (cc & 1u) * (size_t)p.TN * p.Kpad;
+        const int e0 = seg[s], e1 = seg[s + 1];
+        if (c != c_ready) {  // first step of a channel: its template planes have landed
+          ptx::mbar_wait(ptx::smem_u32(bars + 2 * kRefStages + 2 + (cc & 1u)), (cc >> 1) & 1u);
+          c_ready = c;
+        }
+        const uint32_t st = gst;
+        ptx::mbar_wait(ptx::smem_u32(bars + st), gpar);
+        const float* gal = galbuf + (size_t)st * p.TGS * PG;
+        int t = 0;
+        for (int e = e0 + warp; e < e1; e += kRefWarps, ++t) {
+          const uint2 en = list[e];
+          const int j = en.x & 0xff, i = (int)(en.x >> 8) - s * p.TGS, y = en.y & 0xffff, x = en.y >> 16;
+          if ((t & 31) == 0 && t) rnv = norm_of(e + kRefWarps * lane, e1, c);  // more than 32 positions of this warp in one sub-chunk
+          const int u_lo = max(0, a - y), u_hi = min(p.Hb, p.Hp + a - y);  // template rows that meet the map
+          const float* T = tpl + (size_t)j * p.Kpad;
+          const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
+          float part0 = 0.0f, part1 = 0.0f;
+          const int ts = p.ru * p.rowk, gs = p.ru * p.WP;
+          for (int ch = gv; ch < nchunk; ch += p.rv) {
+            const int v = ch * vl + lv, gx = x + v - b;
+            if (gx >= 0 && gx < p.Wp) {
+              const float* tp = T + (u_lo + gu) * p.rowk + v;
+              const float* gp = Gs + (u_lo + gu) * p.WP + v;
+              int u = u_lo + gu;
+              for (; u + 3 * p.ru < u_hi; u += 4 * p.ru, tp += 4 * ts, gp += 4 * gs) {
+                part0 = fmaf(tp[0], gp[0], part0);
+                part1 = fmaf(tp[ts], gp[gs], part1);
+                part0 = fmaf(tp[2 * ts], gp[2 * gs], part0);
+                part1 = fmaf(tp[3 * ts], gp[3 * gs], part1);
+              }
+              for (; u < u_hi; u += p.ru, tp += ts, gp += gs) part0 = fmaf(*tp, *gp, part0);
             }
           }
-          ptx::mbar_wait(ptx::smem_u32(bars + st), par);
-          const float* gal = galbuf + (size_t)st * p.TGS * PG;
-          int t = 0;
-          for (int e = e0 + warp; e < e1; e += kRefWarps, ++t) {
-            const uint2 en = list[e];
-            const int j = en.x & 0xff, i = (int)(en.x >> 8) - s * p.TGS, y = en.y & 0xffff, x = en.y >> 16;
-            if ((t & 31) == 0 && t) {  // more than 32 positions of this warp in one sub-chunk: fetch the next 32 norms
-              const int e2 = e + kRefWarps * lane;
-              rnv = 0.0f;
-              if (e2 < e1) {
-                const uint2 en2 = list[e2];
-                const float* table = p.rnorm_tab ? p.rnorm_tab[(n0 + (int)(en2.x & 0xff)) / kNormChunkCols] : p.rnorm;
-                rnv = __ldg(table + ((size_t)(gt0 + (int)(en2.x >> 8)) * p.C + c) * M + (en2.y & 0xffff) * p.Wp + (en2.y >> 16));
-              }
-            }
-            const int u_lo = max(0, a - y), u_hi = min(p.Hb, p.Hp + a - y);  // template rows that meet the map
-            const float* T = tpl + (size_t)j * p.Kpad;
-            const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
-            float part0 = 0.0f, part1 = 0.0f;
-            const int ts = p.ru * p.rowk, gs = p.ru * p.WP;
-            for (int ch = gv; ch < nchunk; ch += p.rv) {
-              const int v = ch * vl + lv, gx = x + v - b;
-              if (gx >= 0 && gx < p.Wp) {
-                const float* tp = T + (u_lo + gu) * p.rowk + v;
-                const float* gp = Gs + (u_lo + gu) * p.WP + v;
-                int u = u_lo + gu;
-                for (; u + 3 * p.ru < u_hi; u += 4 * p.ru, tp += 4 * ts, gp += 4 * gs) {
-                  part0 = fmaf(tp[0], gp[0], part0);
-                  part1 = fmaf(tp[ts], gp[gs], part1);
-                  part0 = fmaf(tp[2 * ts], gp[2 * gs], part0);
-                  part1 = fmaf(tp[3 * ts], gp[3 * gs], part1);
-                }
-                for (; u < u_hi; u += p.ru, tp += ts, gp += gs) part0 = fmaf(*tp, *gp, part0);
-              }
-            }
-            const float part = warp_sum(part0 + part1);
-            const float rn = __shfl_sync(0xffffffffu, rnv, t & 31);
-            if (lane == 0) acc[e] = fmaf(part, rn, acc[e]);
-          }
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + kRefStages + st));
-          ++it;
+          const float part = warp_sum(part0 + part1);
+          const float rn = __shfl_sync(0xffffffffu, rnv, t & 31);
+          if (lane == 0) acc[e] = fmaf(part, rn, acc[e]);
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + 2 * kRefStages + (cit & 1u)));  // this channel's templates are no longer needed
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + kRefStages + st));
+        if (++gst == (uint32_t)kRefStages) {
+          gst = 0;
+          gpar ^= 1u;
+        }
+        if (cn != c) {  // last sub-chunk of channel c: its templates are no longer needed (nor those of skipped-over channels)
+          __syncwarp();
+          for (; c_seen < min(cn, p.C); ++c_seen)
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(bars + 2 * kRefStages + ((cit + (uint32_t)c_seen) & 1u)));
+        }
+        c = cn;
+        s = sn;
+        rnv = rnv_next;
       }
+      cit += (uint32_t)p.C;
     }
     __syncthreads();
     for (int e = tid; e < nl; e += kRefThreads) {
