@@ -403,6 +403,7 @@ def config4_block(args, world: int, rank: int, dist, torch) -> dict | None:
             "refine_kernel_ms": r_ms,
             "prepare_ms": phases.get("scores", 0.0) - k_ms - r_ms,  # gallery / template pack, variants, window norms
             "merge_ms": {k: phases.get(k, 0.0) for k in ("true_score", "allreduce_max", "rank_topk", "allreduce_sum", "allgather", "merge_topk")},
+            "rank_skew_ms": phases.get("rank_skew", 0.0),
             "rank1_share": float((ranks == 1).float().mean().item()),
             "ranks_match_gathered_rows": ok_ranks, "topk_matches_gathered_rows": ok_topk,
             "peak_device_gib": torch.cuda.max_memory_allocated() / 2**30, "gpu_launches": engine.launch_counter.n - launches0,

@@ -24,7 +24,7 @@ import torch.distributed as dist
 __all__ = ["shard_range", "merge_ranks", "compare_sharded", "phase_events"]
 
 #: when set to a dict, every phase of the sharded rank appends a (start, end) CUDA-event pair under its name
-#: ("scores", "true_score", "allreduce_max", "rank_topk", "allreduce_sum", "allgather", "merge_topk"); bench.py reads it
+#: ("scores", "true_score", "rank_skew", "allreduce_max", "rank_topk", "allreduce_sum", "allgather", "merge_topk"); bench.py reads it
 phase_events: dict | None = None
 
 
@@ -121,6 +121,11 @@ def compare_sharded(probes, gallery_shard, true_idx, g0: int, rotations=None, sc
         )
         engine.launch_counter.add()
     if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if phase_events is not None:
+            # measuring only: the first collective of the merge otherwise absorbs the wait for the slowest rank's scoring
+            # pass (tens of ms of clock skew between GPUs at 1,000 x 12,500 per rank); time that wait on its own
+            with _Phase("rank_skew"):
+                dist.all_reduce(torch.zeros(1, dtype=torch.float32, device=dev), group=group)
         with _Phase("allreduce_max"):
             dist.all_reduce(true_score, op=dist.ReduceOp.MAX, group=group)
     with _Phase("rank_topk"):
