@@ -157,7 +157,11 @@ int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, const uint8
  * block holds templates of one true shape and d_rnorm_tab[chunk] points at that shape's window-norm table
  * (similarity.py:57-65 depends on the TRUE template size).  d_rnorm_tab: device array of device pointers, 256 /
  * sir_ncc_norm_chunk() per 256-column tile, every entry valid (also those of the last tile's absent columns).
- * precision: SIR_PREC_FP16X3 (d_glo, d_tlo) or SIR_PREC_FP16_FP8C (e4m3 operands). */
+ * precision: SIR_PREC_FP16X3 (d_glo, d_tlo) or SIR_PREC_FP16_FP8C (e4m3 operands).
+ * d_tile_rows (optional, NULL = none): int32 [tiles][2], per 256-column tile the rows [lo, hi) of the bucket's K layout that
+ * hold a non-zero tap in ANY column of the tile (always including the anchor row Hb / 2); rows outside are skipped by
+ * every role of the kernel exactly like the rows that only meet the "same" padding.  With the columns sorted by true
+ * template height a tile of short templates costs what its own tallest template costs, not what the bucket's does. */
 int sir_ncc_norm_chunk(void);
 int sir_template_pack_embed(const float* d_maps, int N, int C, int h, int w, int Hb, int Wb, int col0, int ncols_alloc,
                             int precision, uint16_t* d_thi, uint16_t* d_tlo, uint8_t* d_t8b, uint8_t* d_t8l, void* stream);
@@ -165,7 +169,7 @@ int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uin
                          const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
                          const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
                          int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe, float* d_scores,
-                         int score_ld, int g0, int precision, void* stream);
+                         int score_ld, int g0, int precision, const int32_t* d_tile_rows, void* stream);
 
 /* Screen + refine (SIR_PREC_FP16_REFINE).  The reference needs ONE number per (probe, gallery): the maximum of the
  * correlation surface over positions and variants (similarity.py:106-108, 365-367).  sir_ncc_screen computes the
@@ -202,7 +206,7 @@ int sir_variant_index_map(int h, int w, double angle, int transpose, int32_t* d_
 long long sir_ncc_screen_rec_count(int G, int Hp, int Wp, int ncols);
 int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
                    const uint16_t* d_thi, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe, float* d_approx,
-                   int score_ld, int g0, float tau_rel, float tau_abs, void* d_rec, void* stream);
+                   int score_ld, int g0, float tau_rel, float tau_abs, void* d_rec, const int32_t* d_tile_rows, void* stream);
 int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp,
                    const float* d_t32p, int ncols, int ncols_alloc, int Hb, int Wb, const int32_t* d_col2probe,
                    const float* d_approx, float* d_scores, int score_ld, int g0, float tau_rel, float tau_abs, const void* d_rec,

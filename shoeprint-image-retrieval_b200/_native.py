@@ -48,12 +48,12 @@ SIGNATURES = {
     "sir_template_pack_fp8c": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sir_ncc_scores_fp8c": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "sir_template_pack_embed": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
-    "sir_ncc_scores_multi": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+    "sir_ncc_scores_multi": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
     "sir_ncc_screen_rec_count": (C.c_longlong, [_i, _i, _i, _i]),
     "sir_gallery_pack_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "sir_template_pack_screen": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "sir_variant_index_map": (_i, [_i, _i, C.c_double, _i, _p, _p]),
-    "sir_ncc_screen": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, C.c_float, C.c_float, _p, _p]),
+    "sir_ncc_screen": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, C.c_float, C.c_float, _p, _p, _p]),
     "sir_ncc_refine": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, C.c_float, C.c_float, _p, _i, _p, _p]),
     "sir_memset_zero": (_i, [_p, C.c_size_t, _p]),
     "sir_ncc_norm_chunk": (_i, []),

@@ -9,7 +9,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
                   int C, int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
                   int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
                   int passes, cudaStream_t st, double* cost_out, const float* const* d_rnorm_tab, uint2* d_rec, float tau_rel,
-                  float tau_abs);
+                  float tau_abs, const int32_t* d_tile_rows = nullptr);
 }  // namespace sir
 
 using namespace sir;
@@ -56,19 +56,21 @@ extern "C" int sir_ncc_scores_fp8c(const uint16_t* d_ghi, const uint8_t* d_g8a, 
 // Multi-shape column tiles: the columns of the block were packed with sir_template_pack_embed into the K
 // layout of a bucket shape Hb x Wb; every 16-column chunk holds templates of ONE true shape and
 // d_rnorm_tab[chunk] (device array of device pointers, one per sir_ncc_norm_chunk() columns, every entry valid) is the
-// window-norm table of that shape.  precision: SIR_PREC_FP16X3 or SIR_PREC_FP16_FP8C.
+// window-norm table of that shape.  precision: SIR_PREC_FP16X3 or SIR_PREC_FP16_FP8C.  d_tile_rows (optional): per 256-column tile
+// the rows [lo, hi) of the bucket layout that hold a non-zero tap in any column of the tile; the other rows are skipped.
 extern "C" int sir_ncc_scores_multi(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d_g8a, const uint8_t* d_g8l,
                                     const float* const* d_rnorm_tab, int G, int C, int Hp, int Wp, const uint16_t* d_thi,
                                     const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l, int ncols, int ncols_alloc, int Hb,
                                     int Wb, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0, int precision,
-                                    void* stream) {
+                                    const int32_t* d_tile_rows, void* stream) {
   SIR_CHECK_ARG(d_rnorm_tab && d_col2probe && d_scores, "sir_ncc_scores_multi: null pointer");
   SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0, "sir_ncc_scores_multi: empty gallery");
   SIR_CHECK_ARG(Hb > 0 && Wb > 0 && ncols > 0 && ncols <= ncols_alloc, "sir_ncc_scores_multi: bad template block");
   SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_scores_multi: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
   SIR_CHECK_ARG(precision == SIR_PREC_FP16X3 || precision == SIR_PREC_FP16_FP8C, "sir_ncc_scores_multi: precision %d not supported", precision);
   return launch_ncc_tc(d_ghi, d_glo, d_g8a, d_g8l, nullptr, G, C, Hp, Wp, d_thi, d_tlo, d_t8b, d_t8l, ncols, ncols_alloc, Hb, Wb, d_col2probe,
-                       d_scores, score_ld, g0, precision == SIR_PREC_FP16X3 ? 3 : 2, (cudaStream_t)stream, nullptr, d_rnorm_tab, nullptr, 0.0f, 0.0f);
+                       d_scores, score_ld, g0, precision == SIR_PREC_FP16X3 ? 3 : 2, (cudaStream_t)stream, nullptr, d_rnorm_tab, nullptr, 0.0f, 0.0f,
+                       d_tile_rows);
 }
 
 // Screening pass of SIR_PREC_FP16_REFINE: the correlation with plain fp16 operands (one MMA per K step, the tensor
@@ -85,7 +87,7 @@ extern "C" long long sir_ncc_screen_rec_count(int G, int Hp, int Wp, int ncols) 
 extern "C" int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const float* const* d_rnorm_tab, int G, int C,
                               int Hp, int Wp, const uint16_t* d_thi, int ncols, int ncols_alloc, int Hb, int Wb,
                               const int32_t* d_col2probe, float* d_approx, int score_ld, int g0, float tau_rel, float tau_abs,
-                              void* d_rec, void* stream) {
+                              void* d_rec, const int32_t* d_tile_rows, void* stream) {
   SIR_CHECK_ARG((d_rnorm != nullptr) != (d_rnorm_tab != nullptr), "sir_ncc_screen: give d_rnorm or d_rnorm_tab, not both");
   SIR_CHECK_ARG(d_col2probe && d_approx && d_rec, "sir_ncc_screen: null pointer");
   SIR_CHECK_ARG(G > 0 && C > 0 && Hp > 0 && Wp > 0, "sir_ncc_screen: empty gallery");
@@ -93,7 +95,7 @@ extern "C" int sir_ncc_screen(const uint16_t* d_ghi, const float* d_rnorm, const
   SIR_CHECK_ARG(score_ld >= g0 + G, "sir_ncc_screen: score row (%d) shorter than g0+G (%d)", score_ld, g0 + G);
   SIR_CHECK_ARG(tau_rel >= 0.0f && tau_abs >= 0.0f, "sir_ncc_screen: negative candidate margin");
   return launch_ncc_tc(d_ghi, nullptr, nullptr, nullptr, d_rnorm, G, C, Hp, Wp, d_thi, nullptr, nullptr, nullptr, ncols, ncols_alloc, Hb, Wb,
-                       d_col2probe, d_approx, score_ld, g0, 1, (cudaStream_t)stream, nullptr, d_rnorm_tab, (uint2*)d_rec, tau_rel, tau_abs);
+                       d_col2probe, d_approx, score_ld, g0, 1, (cudaStream_t)stream, nullptr, d_rnorm_tab, (uint2*)d_rec, tau_rel, tau_abs, d_tile_rows);
 }
 
 namespace {

@@ -12,7 +12,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace sir
 
 extern "C" const char* sir_last_error(void) { return sir::g_err; }
-extern "C" int sir_abi_version(void) { return 2; }
+extern "C" int sir_abi_version(void) { return 3; }
 
 extern "C" int sir_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

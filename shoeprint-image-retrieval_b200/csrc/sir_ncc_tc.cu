@@ -95,6 +95,9 @@ struct TcParams {
   uint2* rec;
   float tau_rel, tau_abs;  // candidate margin tau(m) = tau_rel * |m| + tau_abs, in accumulator units
   uint32_t off_mask;       // [4][256] candidate-row masks next to the column maxima
+  // multi-shape column tiles: rows [x, y) of the bucket's K layout that hold a non-zero tap in ANY column of tile nt (the
+  // templates sit anchor on anchor, so the range always contains the anchor row Hm/2); NULL = all Hm rows
+  const int2* tile_rows;
 };
 
 struct Seg {
@@ -111,10 +114,15 @@ struct KRange {
   int nseg;
 };
 
-__device__ __forceinline__ KRange k_range(const TcParams& p, int py) {
+__device__ __forceinline__ KRange k_range(const TcParams& p, int py, int nt) {
   const int a = p.Hm / 2;
-  const int u_lo = max(0, a - 16 * py - 15);
-  const int u_hi = min(p.Hm, p.Hp + a - 16 * py);
+  int u_lo = max(0, a - 16 * py - 15);
+  int u_hi = min(p.Hm, p.Hp + a - 16 * py);
+  if (p.tile_rows) {  // rows that are zero in every column of this tile are skipped like the "same" padding
+    const int2 tr = p.tile_rows[nt];
+    u_lo = max(u_lo, tr.x);
+    u_hi = min(u_hi, tr.y);
+  }
   KRange r;
   r.ks_lo = (u_lo * p.nkc) / 2;
   r.ks_hi = min(p.nsteps, (u_hi * p.nkc + 1) / 2);
@@ -228,7 +236,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       uint32_t slot = 0, par = 0;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const int nt = (int)(unit / per_tile);
-        const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx);
+        const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx, nt);
         for (int c = 0; c < p.C; ++c) {
           for (int st = kr.st_lo; st < kr.st_hi; ++st) {
             ptx::mbar_wait(bar_empty(slot), par ^ 1);
@@ -300,7 +308,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       uint32_t b_addr = base + p.off_b;
       const uint32_t b_end = b_addr + p.nbstages * stage_bytes;
       for (long long unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-        const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx);
+        const KRange kr = k_range(p, (int)((unit % per_tile) / p.Gp) / p.npx, (int)(unit / per_tile));
         idesc = ptx::make_idesc_f16(kTileM * CG, tile_cols(p, (int)(unit / per_tile)));
         for (int c = 0; c < p.C; ++c, ++cs) {
           const int buf = cs & 1;
@@ -383,7 +391,7 @@ ncc_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
       cu.g = min((int)(rem % p.Gp), p.G - 1);
       cu.py = pidx / p.npx;
       cu.px = pidx % p.npx;
-      cu.kr = k_range(p, cu.py);
+      cu.kr = k_range(p, cu.py, (int)(cu.unit / per_tile));
     };
     auto advance = [&](Cursor& cu) {
       if (++cu.sg < cu.kr.nseg) return;
@@ -737,7 +745,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
                   int C, int Hp, int Wp, const uint16_t* d_thi, const uint16_t* d_tlo, const uint8_t* d_t8b, const uint8_t* d_t8l,
                   int ncols, int ncols_alloc, int Hm, int Wm, const int32_t* d_col2probe, float* d_scores, int score_ld, int g0,
                   int passes, cudaStream_t st, double* cost_out, const float* const* d_rnorm_tab, uint2* d_rec, float tau_rel,
-                  float tau_abs) {
+                  float tau_abs, const int32_t* d_tile_rows) {
   // cost_out != NULL: dry run -- plan only, report the estimated SM cycles per (gallery, 256-column tile,
   // channel) and return without touching any pointer (sir_ncc_cost)
   SIR_CHECK_ARG(d_ghi && d_thi, "sir_ncc_scores(tcgen05): needs packed fp16 operands");
@@ -749,6 +757,7 @@ int launch_ncc_tc(const uint16_t* d_ghi, const uint16_t* d_glo, const uint8_t* d
   p.glo = (const __half*)d_glo;
   p.rnorm = d_rnorm;
   p.rnorm_tab = d_rnorm_tab;
+  p.tile_rows = reinterpret_cast<const int2*>(d_tile_rows);
   p.col2probe = d_col2probe;
   p.scores = d_scores;
   p.score_ld = score_ld;
@@ -911,5 +920,5 @@ extern "C" int sir_ncc_cost(int precision, int G, int Hp, int Wp, int Hm, int Wm
   alignas(16) static const uint16_t dummy16[8] = {0};
   alignas(16) static const uint8_t dummy8[16] = {0};
   return sir::launch_ncc_tc(dummy16, dummy16, dummy8, dummy8, nullptr, G, 1, Hp, Wp, dummy16, dummy16, dummy8, dummy8, 256, 256, Hm, Wm,
-                            nullptr, nullptr, 0, 0, passes, nullptr, h_cost, nullptr, nullptr, 0.0f, 0.0f);
+                            nullptr, nullptr, 0, 0, passes, nullptr, h_cost, nullptr, nullptr, 0.0f, 0.0f, nullptr);
 }

@@ -356,3 +356,37 @@ def test_stale_shared_memory_does_not_leak_into_scores(eng, byte):
                     raise AssertionError(f"{precision}, fill {byte:#x}: {exc}") from None
     finally:
         nat.lib = real
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp16_refine", "fp16_fp8c", "fp16x3"])
+def test_multi_tile_buckets_with_per_tile_row_ranges(eng, precision, monkeypatch):
+    """Ragged probes whose merged shape buckets span several 256-column tiles: the columns are laid out tallest template
+    first and the correlation kernel is told per tile which rows of the bucket layout are occupied (d_tile_rows), so tiles of
+    short templates skip the rest.  Scores must equal the per-shape float32 CUDA-core evaluation (no buckets, no skipping),
+    and a 3 x 4 subsample the float64 CPU oracle."""
+    from oracle import compare as ocmp
+    from src.shoeprint_image_retrieval import synth
+
+    gallery = synth.make_gallery(201, 4, 12, 59, 21)
+    probes, pairs = synth.make_probes(202, gallery, 100, min_frac=0.4)
+    rotations = [r for r in range(-12, 13, 2) if r]
+    seen = []
+    real = eng._score_one_bucket
+
+    def spy(members, gops, g0, scores, mode, flip, dev, approx=None):
+        heights = {(hw[1] if flip else hw[0]) for hw, _ in members}
+        seen.append((sum(eng._pad_cols(blk.ncols) for _, blk in members), len(heights)))
+        return real(members, gops, g0, scores, mode, flip, dev, approx)
+
+    monkeypatch.setattr(eng, "_score_one_bucket", spy)
+    _, got, _ = eng.compare(probes, gallery, pairs, rotations, None, precision=precision)
+    assert any(cols > 256 and nh > 4 for cols, nh in seen), f"no multi-tile bucket of mixed heights was launched: {seen}"
+    monkeypatch.setattr(eng, "_score_one_bucket", real)
+    _, want, _ = eng.compare(probes, gallery, pairs, rotations, None, precision="fp32_simt")
+    try:
+        _check(got.cpu().numpy(), want.cpu().numpy(), 2e-5 if precision == "fp16_refine" else REL_TOL)
+        _, exact = ocmp.compare_maps_oracle(probes[:3], gallery, pairs[:3], rotations, None, method="fast")
+        _check(got.cpu().numpy()[:3], exact)
+    except AssertionError as exc:
+        raise AssertionError(f"{precision}: {exc}") from None

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
     for name in declared:
         assert hasattr(nat.lib, name)
-    assert nat.lib.sir_abi_version() == 2
+    assert nat.lib.sir_abi_version() == 3
 
 
 def test_kpad_matches_layout_rule():
