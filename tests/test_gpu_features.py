@@ -199,6 +199,42 @@ def test_model_rgb_prints_gpu_clahe_matches_host_clahe():
     assert np.linalg.norm(many[0] - a) <= 1e-5 * np.linalg.norm(a)
 
 
+def test_feature_stage_ignores_stale_shared_memory():
+    """Every feature-stage kernel after a 0xFF fill of all shared memory (NaN as fp16 / fp32): the maps must be bit-identical
+    to a normal run, i.e. no MMA, halo or reduction reads a shared-memory cell the kernel has not written itself."""
+    from src.shoeprint_image_retrieval import _native as nat, network
+
+    imgs = [_image(71 + i, 300, 130) for i in range(3)]
+    rgb = [np.stack([_image(81 + c, 200, 100) for c in range(3)], -1)]
+    for name, block in (("EfficientNetV2_M", 5), ("VGG16", 5)):
+        model = network.Model(_config(name), block, random_init_seed=4)
+        network.clear_caches()
+        want = [m.copy() for m in model.get_multiple_feature_maps(imgs, progress=False)] + [model.get_feature_maps(rgb[0])]
+        real = nat.lib
+
+        class _Lib:
+            def __getattr__(self, fn_name):
+                fn = getattr(real, fn_name)
+                if not fn_name.startswith("sir_feat_") or fn_name.endswith(("_plan", "_tile_n", "_parts", "_bytes")):
+                    return fn
+
+                def call(*args):
+                    nat.check(real.sir_debug_fill_shared_memory(0xFF, args[-1]), "sir_debug_fill_shared_memory")
+                    return fn(*args)
+
+                return call
+
+        nat.lib = _Lib()
+        try:
+            network.clear_caches()
+            got = [m.copy() for m in model.get_multiple_feature_maps(imgs, progress=False)] + [model.get_feature_maps(rgb[0])]
+        finally:
+            nat.lib = real
+        for a, b in zip(got, want):
+            assert np.isfinite(a).all()
+            np.testing.assert_array_equal(a, b, err_msg=name)
+
+
 def test_device_resident_handoff_to_compare():
     """maps returned by get_multiple_feature_maps keep device copies; compare uses them (no H2D) and gives
     the same ranks and scores as the host lists.  Replacing an element falls back to the host path."""
