@@ -200,8 +200,9 @@ def test_model_rgb_prints_gpu_clahe_matches_host_clahe():
 
 
 def test_feature_stage_ignores_stale_shared_memory():
-    """Every feature-stage kernel after a 0xFF fill of all shared memory (NaN as fp16 / fp32): the maps must be bit-identical
-    to a normal run, i.e. no MMA, halo or reduction reads a shared-memory cell the kernel has not written itself."""
+    """Every feature-stage kernel after a 0xFF fill of all shared memory (NaN as fp16 / fp32), every ``torch.empty`` device
+    buffer pre-filled with 0xFF: the maps must be bit-identical to a normal run, i.e. no MMA, halo or reduction reads a
+    shared-memory or global cell the stage has not written itself."""
     from src.shoeprint_image_retrieval import _native as nat, network
 
     imgs = [_image(71 + i, 300, 130) for i in range(3)]
@@ -224,12 +225,22 @@ def test_feature_stage_ignores_stale_shared_memory():
 
                 return call
 
+        real_empty = torch.empty
+
+        def poisoned_empty(*args, **kwargs):  # and every device buffer the stage allocates starts as 0xFF bytes
+            t = real_empty(*args, **kwargs)
+            if t.is_cuda and t.numel() and t.is_contiguous():
+                t.view(torch.uint8).fill_(0xFF)
+            return t
+
         nat.lib = _Lib()
+        torch.empty = poisoned_empty
         try:
             network.clear_caches()
             got = [m.copy() for m in model.get_multiple_feature_maps(imgs, progress=False)] + [model.get_feature_maps(rgb[0])]
         finally:
             nat.lib = real
+            torch.empty = real_empty
         for a, b in zip(got, want):
             assert np.isfinite(a).all()
             np.testing.assert_array_equal(a, b, err_msg=name)

@@ -390,3 +390,33 @@ def test_multi_tile_buckets_with_per_tile_row_ranges(eng, precision, monkeypatch
         _check(got.cpu().numpy()[:3], exact)
     except AssertionError as exc:
         raise AssertionError(f"{precision}: {exc}") from None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp16_refine", "fp16_fp8c", "fp16x3"])
+def test_uninitialised_device_buffers_do_not_leak_into_scores(eng, precision, monkeypatch):
+    """``torch.empty`` hands out whatever the allocator has; every device buffer the path allocates that way is filled
+    with 0xFF (NaN in every format) here before use.  Scores of a uniform and of a ragged probe set (single-shape blocks
+    and multi-shape buckets, rotations and scales) must be bit-identical to a normal run."""
+    import torch
+    from src.shoeprint_image_retrieval import synth
+
+    gallery = synth.make_gallery(301, 5, 8, 40, 17)
+    uniform, pairs_u = synth.make_probes(302, gallery, 24)
+    ragged, pairs_r = synth.make_probes(303, gallery, 24, min_frac=0.5)
+    cases = [(uniform, pairs_u, [-6, 6], None), (ragged, pairs_r, [-6, 6], [1.08]), (ragged, pairs_r, None, None)]
+    want = [eng.compare(p, gallery, pr, rot, scl, precision=precision)[1].cpu().numpy() for p, pr, rot, scl in cases]
+    real_empty = torch.empty
+
+    def poisoned_empty(*args, **kwargs):
+        t = real_empty(*args, **kwargs)
+        if t.is_cuda and t.numel():
+            t.view(torch.uint8).fill_(0xFF) if t.is_contiguous() else None
+        return t
+
+    monkeypatch.setattr(torch, "empty", poisoned_empty)
+    got = [eng.compare(p, gallery, pr, rot, scl, precision=precision)[1].cpu().numpy() for p, pr, rot, scl in cases]
+    monkeypatch.setattr(torch, "empty", real_empty)
+    for g, w in zip(got, want):
+        assert np.isfinite(g).all()
+        np.testing.assert_array_equal(g, w)
