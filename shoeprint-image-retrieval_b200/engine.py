@@ -119,7 +119,15 @@ def _ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_current_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> C.c_void_p:
+    """The current CUDA stream as a ``cudaStream_t``.  Ragged passes make ~17,000 library calls; ``torch.cuda.current_stream()``
+    builds a Python Stream object (14 us) per call, the raw accessor is ~0.3 us."""
+    if _raw_stream is not None and _current_device is not None:
+        return C.c_void_p(_raw_stream(_current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -502,19 +510,51 @@ def resize_images_lanczos(images: list[np.ndarray], sizes: list[tuple[int, int]]
 
 @dataclass
 class _Variant:
-    """Columns of one (probe group, variant).  ``maps [n,C,h,w]`` is the variant itself, or -- when ``rot`` is set -- the
-    UNROTATED maps: a rotation keeps the shape and is a pure gather (similarity.py:267, Pillow nearest), so the screening
-    mode lets the template pack apply it on the way in (``sir_variant_index_map``) and the rotated maps are never written."""
+    """Columns of one (probe group, variant), generated on demand.
 
-    maps: torch.Tensor
-    rot: float | None = None
+    ``source [n,C,h,w]`` are the probe maps; the variant is rotate(``rot``) then resize(``scale``) of them
+    (similarity.py:267-274).  A rotation alone keeps the shape and is a pure gather (Pillow nearest), so with ``gather`` the
+    screening mode lets the template pack apply it on the way in (``sir_variant_index_map``) and the rotated maps are never
+    written: ``maps`` is then the source and ``rot`` the rotation still to apply.  Everything else is materialised the first
+    time ``maps`` is read -- inside the block / bucket that scores it, so the thousands of small variant kernels of a ragged
+    probe set are queued bucket by bucket behind each other's correlation launches instead of all up front."""
+
+    source: torch.Tensor
+    rot_angle: float | None = None
+    scale: float | None = None
+    gather: bool = False
+    _made: torch.Tensor | None = None
+
+    def __post_init__(self) -> None:
+        n, c, h, w = (int(v) for v in self.source.shape)
+        self.n = n
+        self.shape_hw = (h, w)
+        if self.scale is not None:
+            self.shape_hw = scaled_size(h, w, self.scale)
+            if self.shape_hw[0] < 1 or self.shape_hw[1] < 1:
+                raise ValueError(f"scale {self.scale} shrinks a {h}x{w} map to nothing")
+        self.gather = self.gather and self.scale is None
 
     @property
-    def n(self) -> int:
-        return int(self.maps.shape[0])
+    def rot(self) -> float | None:
+        """The rotation the template pack still has to apply (gather variants only)."""
+        return self.rot_angle if self.gather else None
+
+    @property
+    def maps(self) -> torch.Tensor:
+        if self.gather or (self.rot_angle is None and self.scale is None):
+            return self.source
+        if self._made is None:
+            self._made = make_variant(self.source, self.rot_angle, self.scale)
+        return self._made
 
     def materialised(self) -> torch.Tensor:
-        return self.maps if self.rot is None else make_variant(self.maps, self.rot, None)
+        """The variant as a tensor, whatever the mode (the single-pass modes pack from materialised maps)."""
+        if self.gather and self.rot_angle is not None:
+            if self._made is None:
+                self._made = make_variant(self.source, self.rot_angle, None)
+            return self._made
+        return self.maps
 
 
 _index_maps: dict = {}
@@ -1017,11 +1057,10 @@ def score_matrix(probes: MapSet, gallery: MapSet, rotations=None, scales=None, p
         for s0 in range(0, n_grp, col_block):  # a group wider than a column block is cut, so no block exceeds the cap
             part = grp.maps[s0 : s0 + col_block]
             for rot, scale in plan:
-                if prec == nat.PREC_FP16_REFINE and scale is None:
-                    v = _Variant(part, rot)  # a rotation alone is applied by the template pack's gather
-                else:
-                    v = _Variant(make_variant(part, rot, scale))
-                key = (int(v.maps.shape[2]), int(v.maps.shape[3]))
+                # a rotation alone is applied by the screening mode's template pack (gather); everything else is
+                # materialised when its block is scored
+                v = _Variant(part, rot, scale, gather=prec == nat.PREC_FP16_REFINE)
+                key = v.shape_hw
                 blk = pending.setdefault(key, _Block())
                 if blk.ncols and blk.ncols + v.n > col_block:
                     flush(blk, key)
