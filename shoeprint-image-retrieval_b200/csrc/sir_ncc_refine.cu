@@ -379,7 +379,9 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
   const size_t fixed = 128 + (size_t)p.cap * 12 + 4 * (size_t)(32 + kRefMaxTgb + kRefMaxSub + 1 + kRefMaxThreads / 32) + 64;
   p.TN = 0;
   p.ST = 2;
-  int tgs_first = 8;
+  // time follows the number of (channel, sub-chunk) steps: 16 prints per sub-chunk when that still leaves 16 resident columns
+  // (configs[1]: 45.5 -> 41.6 ms), else 8 and down
+  int tgs_first = 16;
   if (const char* env = getenv("SIR_REFINE_STAGES")) p.ST = std::max(2, std::min(kRefMaxStages, atoi(env)));
   if (const char* env = getenv("SIR_REFINE_TGS")) tgs_first = std::max(1, std::min(32, atoi(env)));
   const int kRefStages = p.ST;
@@ -387,7 +389,7 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
     if (fixed + kRefStages * tgs * gbytes + 2 * tbytes > budget) continue;
     int tn = (int)std::min<size_t>(32, (budget - fixed - kRefStages * tgs * gbytes) / (2 * tbytes));
     if (const char* env = getenv("SIR_REFINE_TN")) tn = std::max(1, std::min(tn, atoi(env)));
-    if (tn >= std::min(8, ncols) || tgs == 1) {
+    if (tn >= std::min(tgs == 16 ? 16 : 8, ncols) || tgs == 1) {
       p.TN = tn >= 8 ? tn / 8 * 8 : tn;
       p.TGS = tgs;
     }
