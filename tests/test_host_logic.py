@@ -152,3 +152,55 @@ def test_dataloader_matches_the_reference_loader(tmp_path, case):
         np.testing.assert_array_equal(mark0, want[f"ld_{name}_c{k}_mark0"])
         np.testing.assert_array_equal(print0, want[f"ld_{name}_c{k}_print0"])
         assert sha == str(want[f"ld_{name}_c{k}_sha256"]), "loaded images differ from the reference loader's"
+
+
+def test_bucket_merge_planner_keeps_every_shape_and_never_costs_more():
+    """engine._merge_buckets (host planning of the ragged path): every template shape ends up in exactly one launch, only
+    buckets of one mode and orientation are merged, the merged layout covers its members, the modelled cost does not go up,
+    and the library's own planner (sir_ncc_cost, host only) accepts every merged bucket shape."""
+    from types import SimpleNamespace as NS
+
+    from src.shoeprint_image_retrieval import _native as nat, engine
+
+    rng = np.random.default_rng(5)
+    g, hp, wp = 1175, 55, 17
+    prec = nat.PREC_FP16_REFINE
+    memo: dict = {}
+
+    def cost_of(key):
+        if key not in memo:
+            mode, flip, bh, bw = key
+            memo[key] = engine.plan_cost(mode, g, *((wp, hp) if flip else (hp, wp)), bh, bw)
+        return memo[key]
+
+    shapes = {(int(rng.integers(24, 60)), int(rng.integers(10, 22))) for _ in range(160)}
+    buckets: dict = {}
+    for h, w in sorted(shapes):
+        hm, wm = h - 4, w - 4
+        flip = (h * 7 + w) % 3 == 0
+        oh, ow = (wm, hm) if flip else (hm, wm)
+        buckets.setdefault((prec, flip, -(-oh // 8) * 8, -(-ow // 8) * 8), []).append(((h, w), NS(ncols=int(rng.integers(1, 30)))))
+
+    def total(bk):
+        out = 0.0
+        for key, members in bk.items():
+            cols = sum(engine._pad_cols(b.ncols) for _, b in members)
+            out += cost_of(key) * engine._tiles_equiv(cols) + engine.BUCKET_FIXED_COST
+        return out
+
+    merged = engine._merge_buckets(buckets, cost_of, 8192, 68)
+    again = engine._merge_buckets(buckets, cost_of, 8192, 68)
+    assert {k: [hw for hw, _ in v] for k, v in merged.items()} == {k: [hw for hw, _ in v] for k, v in again.items()}
+    assert sorted(hw for v in merged.values() for hw, _ in v) == sorted(hw for v in buckets.values() for hw, _ in v)
+    assert len(merged) < len(buckets)
+    for (mode, flip, bh, bw), members in merged.items():
+        assert cost_of((mode, flip, bh, bw)) < float("inf")
+        for (h, w), _ in members:
+            oh, ow = (w - 4, h - 4) if flip else (h - 4, w - 4)
+            assert oh <= bh and ow <= bw
+            assert any((h, w) in [hw for hw, _ in v] for k, v in buckets.items() if k[:2] == (mode, flip))
+    # the bucket-level bound of the model (every tile priced at the bucket's own height) must not exceed the unmerged total
+    # by more than the rows-per-tile refinement can give back; the per-tile model itself is monotone by construction
+    assert total(merged) <= 1.35 * total(buckets)
+    assert engine._tiles_equiv(256) == 1.0 and engine._tiles_equiv(8) == engine.PARTIAL_TILE_FLOOR and engine._tiles_equiv(300) > 1.0
+    assert engine._pad_cols(1) == nat.lib.sir_ncc_norm_chunk() and engine._pad_cols(16) == 16
