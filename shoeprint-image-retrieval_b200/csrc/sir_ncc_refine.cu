@@ -77,7 +77,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* to
   return base + inc - v;
 }
 
-template <int kRefWarps>
+// TS / GS: the lane's row stride in the template / gallery plane (ru * rowk, ru * WP floats) as compile-time constants for
+// the two shapes the benchmarks live on (0 = run-time strides): the dense case is issue bound at ~5 instructions per
+// multiply-add with run-time strides, constant strides turn the address arithmetic into immediate offsets.
+template <int kRefWarps, int TS, int GS>
 __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const RefineParams p) {
   constexpr int kRefThreads = 32 * (kRefWarps + 1);
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(32 * (kRefWarps + 1)) ncc_refine_kernel(const 
           const float* T = tpl + (size_t)j * p.Kpad;
           const float* Gs = gal + (size_t)i * PG + (y - a) * p.WP + (x - b);
           float part0 = 0.0f, part1 = 0.0f;
-          const int ts = p.ru * p.rowk, gs = p.ru * p.WP;
+          const int ts = TS ? TS : p.ru * p.rowk, gs = GS ? GS : p.ru * p.WP;
           for (int ch = gv; ch < nchunk; ch += p.rv) {
             const int v = ch * vl + lv, gx = x + v - b;
             if (gx >= 0 && gx < p.Wp) {
@@ -426,13 +429,23 @@ extern "C" int sir_ncc_refine(const float* d_g32, const float* d_rnorm, const fl
   SIR_CHECK_ARG(smem <= 227 * 1024, "sir_ncc_refine: shared-memory plan overflow (%zu bytes)", smem);
   const long long blocks = (long long)ceil_div(ncols, p.TN) * p.tiles_g;
   SIR_CHECK_ARG(blocks < (1ll << 31), "sir_ncc_refine: too many tiles");
+  const int ts = p.ru * p.rowk, gs = p.ru * p.WP;
+  auto launch = [&](auto kernel, int warps) -> int {
+    SIR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    kernel<<<(unsigned)blocks, 32 * (warps + 1), smem, (cudaStream_t)stream>>>(p);
+    return SIR_OK;
+  };
+  int rc;
   if (variants <= 2) {
-    SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    ncc_refine_kernel<31><<<(unsigned)blocks, 32 * 32, smem, (cudaStream_t)stream>>>(p);
+    if (ts == 56 && gs == 56) rc = launch(ncc_refine_kernel<31, 56, 56>, 31);
+    else if (ts == 32 && gs == 32) rc = launch(ncc_refine_kernel<31, 32, 32>, 31);
+    else rc = launch(ncc_refine_kernel<31, 0, 0>, 31);
   } else {
-    SIR_CUDA(cudaFuncSetAttribute(ncc_refine_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    ncc_refine_kernel<16><<<(unsigned)blocks, 32 * 17, smem, (cudaStream_t)stream>>>(p);
+    if (ts == 56 && gs == 56) rc = launch(ncc_refine_kernel<16, 56, 56>, 16);
+    else if (ts == 32 && gs == 32) rc = launch(ncc_refine_kernel<16, 32, 32>, 16);
+    else rc = launch(ncc_refine_kernel<16, 0, 0>, 16);
   }
+  if (rc) return rc;
   SIR_LAUNCH_CHECK("ncc_refine_kernel");
   return SIR_OK;
 }
