@@ -18,6 +18,7 @@ A pair = one (probe, gallery print), all its variants included.
              FLOPs / mean launch time, from CUDA events around every launch
 * ``cpu_baseline`` the UNMODIFIED reference (``baseline/_ref``, its ``_comparison_worker`` in one forked
              process per host core; the oracle port when that copy is absent) on a bounded sample
+* ``config2`` BASELINE configs[2]: the same images at block 6 (176x30x11 maps), 40 variants, same path as ``config0``
 * ``config0`` BASELINE configs[0]: the default run.toml on a FID-300-shaped set (300 ragged probes x 1,175 gallery x 25
              variants) through ``compare_maps`` -- the multi-shape bucket path real data takes (N = 1 only)
 * ``config4`` BASELINE configs[3]: 1,000 probes x 12,500 on-device gallery maps of 80x59x21 PER GPU (at N = 8
@@ -412,24 +413,36 @@ def config4_block(args, world: int, rank: int, dist, torch) -> dict | None:
     return out if rank == 0 else None
 
 
-def config0_block(args) -> dict:
-    """BASELINE configs[0] / [2] shape of work: the default run.toml on a FID-300-shaped set -- 300 RAGGED probes (every probe
-    its own template shape, crops of 40-100 % of a print) x 1,175 gallery maps of 80x59x21 x 25 variants (7 rotations and
-    3 scales in the reference's combination), through ``similarity.compare_maps`` from host lists.  This is
-    the multi-shape bucket path (sir_template_pack_screen with a bucket layout + one window-norm table per 16 columns)."""
+def config0_block(args, which: int = 0) -> dict:
+    """BASELINE configs[0] / [2] shape of work through ``similarity.compare_maps`` from host lists -- the multi-shape bucket
+    path (sir_template_pack_screen with a bucket layout + one window-norm table per 8 columns + per-tile row ranges).
+
+    which = 0: the default run.toml on a FID-300-shaped set -- 300 RAGGED probes (every probe its own template shape, crops of
+    40-100 % of a print) x 1,175 gallery maps of 80x59x21 (block 4) x 25 variants (7 rotations and 3 scales in the
+    reference's combination).
+    which = 2: the deeper cut of configs[2] -- block 6 on the same images, 176x30x11 maps, 12 rotations (+-30 step 5) and 3
+    scales = 40 variants."""
     import torch
 
     from src.shoeprint_image_retrieval import engine, similarity, synth
 
-    q, g, c, h, w = 300, 1175, 80, 59, 21
-    rot, scl = [-15, -9, -3, 3, 9, 15, 180], [1.02, 1.04, 1.08]
+    if which == 0:
+        q, g, c, h, w = 300, 1175, 80, 59, 21
+        rot, scl = [-15, -9, -3, 3, 9, 15, 180], [1.02, 1.04, 1.08]
+        name = "configs[0]: default run.toml, FID-300 shape, 300 ragged probes x 1,175 gallery x 25 variants, host lists through compare_maps"
+    else:
+        q, g, c, h, w = 300, 1175, 176, 30, 11
+        rot, scl = [a for a in range(-30, 31, 5) if a], [1.02, 1.04, 1.08]
+        name = ("configs[2]: FID-300 shape at block 6 (176x30x11 maps), 300 ragged probes x 1,175 gallery x 40 variants "
+                "(12 rotations x 3 scales + the unscaled set), host lists through compare_maps")
     gallery = synth.make_gallery(1, g, c, h, w)
-    probes, pairs = synth.make_probes(2, gallery, q, min_frac=0.4)
+    probes, pairs = synth.make_probes(2, gallery, q, min_frac=0.4 if which == 0 else 0.6)
     cfg = {"comparison": {"n_processes": 1, "rotations": rot, "scales": scl, "precision": args.precision}}
     # algorithmic work: 2*C*(gallery positions)*(template taps) per (variant, pair), template taps of the variant's true shape
     taps = 0
+    plan = engine.variant_plan(rot, scl)
     for pm in probes:
-        for r, sc in engine.variant_plan(rot, scl):
+        for r, sc in plan:
             hh, ww = pm.shape[1:]
             if sc is not None:
                 hh, ww = engine.scaled_size(hh, ww, sc)
@@ -445,7 +458,7 @@ def config0_block(args) -> dict:
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     dt = min(times)
-    return {"workload": "configs[0]: default run.toml, FID-300 shape, 300 ragged probes x 1,175 gallery x 25 variants, host lists through compare_maps",
+    return {"workload": name, "variants": len(plan),
             "pairs_per_s": q * g / dt, "seconds": dt, "tflops_algorithmic_whole_pass": flops / dt / 1e12,
             "template_shapes": len({p_.shape for p_ in probes}), "rank1_share": float((ranks == 1).mean())}
 
@@ -630,6 +643,7 @@ def run_b200(args) -> None:
     c4 = config4_block(args, world, rank, dist, torch) if not args.no_config4 else None
     c5 = precision_block(args, world, rank, dist, torch) if not args.no_precision_study else None
     c0 = config0_block(args) if (rank == 0 and world == 1 and not args.no_config4 and not args.quick) else None
+    c2 = config0_block(args, 2) if c0 is not None else None
     feat_par = feature_stage_parallel(world, rank, dist, torch) if (world > 1 and not args.no_features) else None
     feat = feature_stage_numbers(args) if (rank == 0 and not args.no_features) else None
     if feat is not None and feat_par is not None:
@@ -672,6 +686,7 @@ def run_b200(args) -> None:
                        "dense_records_per_step": rstats["dense_records"] / args.steps},
             "cpu_baseline": cb,
             "config0": c0,
+            "config2": c2,
             "config4": c4,
             "precision_study": c5,
             "feature_stage": feat,
