@@ -204,3 +204,34 @@ def test_bucket_merge_planner_keeps_every_shape_and_never_costs_more():
     assert total(merged) <= 1.35 * total(buckets)
     assert engine._tiles_equiv(256) == 1.0 and engine._tiles_equiv(8) == engine.PARTIAL_TILE_FLOOR and engine._tiles_equiv(300) > 1.0
     assert engine._pad_cols(1) == nat.lib.sir_ncc_norm_chunk() and engine._pad_cols(16) == 16
+
+
+def test_variants_are_described_without_being_generated(monkeypatch):
+    """engine._Variant: shape and column count are known at construction (similarity.py:267-274: a rotation keeps the shape,
+    a scale gives (int(h*s), int(w*s))), nothing is launched until ``maps`` is read -- the ragged path relies on that to
+    queue variant kernels bucket by bucket -- and a scale that shrinks a map to nothing fails immediately."""
+    import torch
+
+    from src.shoeprint_image_retrieval import engine
+
+    made = []
+    monkeypatch.setattr(engine, "make_variant", lambda maps, rot, scale: made.append((rot, scale)) or torch.zeros(1))
+    src = torch.zeros((3, 4, 20, 9))
+    plain = engine._Variant(src, None, None, gather=True)
+    rotated = engine._Variant(src, 7.0, None, gather=True)
+    scaled = engine._Variant(src, 7.0, 1.08, gather=True)
+    single_pass = engine._Variant(src, 7.0, None, gather=False)
+    assert [v.n for v in (plain, rotated, scaled, single_pass)] == [3, 3, 3, 3]
+    assert plain.shape_hw == rotated.shape_hw == single_pass.shape_hw == (20, 9)
+    assert scaled.shape_hw == engine.scaled_size(20, 9, 1.08) == (21, 9)
+    assert made == []
+    assert plain.maps is src and rotated.maps is src and rotated.rot == 7.0 and plain.rot is None
+    assert made == []  # a rotation alone is left to the template pack's gather
+    assert scaled.rot is None and scaled.maps is not src and made == [(7.0, 1.08)]
+    scaled.maps  # noqa: B018 - cached
+    assert made == [(7.0, 1.08)]
+    assert single_pass.rot is None and single_pass.maps is not src and made[-1] == (7.0, None)
+    rotated.materialised()
+    assert made[-1] == (7.0, None) and len(made) == 3
+    with pytest.raises(ValueError):
+        engine._Variant(torch.zeros((1, 4, 20, 9)), None, 0.01)
